@@ -1,0 +1,174 @@
+/*
+ * memex_b200.h -- C ABI of the B200-native embedding + vector-search hot path of memex.
+ *
+ * This is the drop-in boundary: a Rust (cxx / extern "C") shim binds exactly these symbols
+ * (INTEGRATION.md shows it) and keeps memex's own surfaces unchanged above them:
+ *
+ *   trait VectorStore           reference lib/libmemex/src/storage/mod.rs:54-66
+ *   HnswStore (file store)      reference lib/libmemex/src/storage/local.rs:21-166
+ *   SentenceEmbedder runner     reference lib/libmemex/src/llm/embedding.rs:94-135
+ *                               (the one line `model.encode(&segments)`, :109)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; handles are opaque; all buffers are caller-owned.
+ *   - every call returns an int32 status: MX_OK or a negative code that maps 1:1 onto the
+ *     reference's VectorStoreError / EmbeddingError variants (storage/mod.rs:30-48,
+ *     llm/embedding.rs:10-16).  Nothing aborts or unwinds across the boundary (the reference
+ *     panics at local.rs:31 and :80-83; this ABI returns MX_ERR_UNSUPPORTED / MX_ERR_SEARCH).
+ *   - mx_last_error(handle) gives the message for the last failing call on that handle
+ *     (valid until the next call on it); mx_last_error(NULL) the last create/load failure
+ *     on the calling thread.
+ *   - a handle is not re-entrant (memex already serialises a store behind a tokio Mutex,
+ *     storage/mod.rs:70-92, and owns the embedder on one thread, embedding.rs:84-91);
+ *     distinct handles may be driven from different threads -- each owns a CUDA stream.
+ *   - row ids are 1-based and contiguous in insertion order, as `next_id = len + 1`
+ *     (local.rs:63); the uuid strings stay on the host side of the binding.
+ *   - there is NO CPU fallback: every entry point that computes needs a CUDA device
+ *     (sm_100a cubins only) and fails with MX_ERR_CONNECTION without one.
+ */
+#ifndef MEMEX_B200_H
+#define MEMEX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MX_ABI_VERSION 1
+
+/* status codes <-> reference error variants */
+#define MX_OK 0
+#define MX_ERR_CONNECTION (-1)  /* VectorStoreError::ConnectionError  (no device / CUDA failure)   */
+#define MX_ERR_DELETE (-2)      /* VectorStoreError::DeleteError                                  */
+#define MX_ERR_FILE_IO (-3)     /* VectorStoreError::FileIOError                                  */
+#define MX_ERR_INSERTION (-4)   /* VectorStoreError::InsertionError (non-finite input, OOM, ...)   */
+#define MX_ERR_SEARCH (-5)      /* VectorStoreError::SearchError                                  */
+#define MX_ERR_SERDE (-6)       /* VectorStoreError::SerdeError    (bad file header)              */
+#define MX_ERR_SAVE (-7)        /* VectorStoreError::SaveError                                    */
+#define MX_ERR_UNSUPPORTED (-8) /* VectorStoreError::Unsupported   (also single-row delete)       */
+#define MX_ERR_INVALID (-9)     /* bad argument: null pointer, dim mismatch, k == 0                */
+#define MX_ERR_ENCODE (-10)     /* EmbeddingError::EncodingFailure                                */
+#define MX_ERR_SETUP (-11)      /* EmbeddingError::SetupError      (bad config / missing weight)   */
+
+#define MX_DTYPE_F32 0u
+#define MX_DTYPE_F16 1u
+#define MX_METRIC_COSINE 0u /* score = 1 - DistCosine, as local.rs:86 */
+#define MX_METRIC_DOT 1u    /* score = dot product (north_star's dot-product scan) */
+
+#define MX_MAX_K 256u
+
+typedef struct mx_store mx_store;
+typedef struct mx_embedder mx_embedder;
+
+/* ------------------------------------------------------------------------------------------
+ * vector store -- replaces HnswStore's use of hnsw_rs (local.rs:48,65,76,101,127-129,150-153)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mx_store_cfg {
+    uint32_t dim;       /* vector dimension (384 for the MiniLM models, storage/mod.rs:126)  */
+    uint32_t dtype;     /* MX_DTYPE_*: how rows are kept in HBM                               */
+    uint32_t metric;    /* MX_METRIC_*                                                        */
+    int32_t device;     /* CUDA ordinal                                                       */
+    uint64_t capacity;  /* rows to preallocate; the store grows geometrically beyond it        */
+    uint64_t id_offset; /* ids reported = id_offset + local_row * id_stride + 1 (row sharding) */
+    uint64_t id_stride; /* 0 is read as 1                                                     */
+} mx_store_cfg;
+
+/* HnswStore::new (local.rs:95-108) */
+int32_t mx_store_create(const mx_store_cfg *cfg, mx_store **out);
+void mx_store_destroy(mx_store *s);
+
+/* HnswStore::insert / bulk_insert (local.rs:55-69): appends n rows [n, dim] f32 row-major from
+ * HOST memory; *first_id_out (may be NULL) receives the 1-based id of the first new row. */
+int32_t mx_store_add(mx_store *s, const float *vecs, uint64_t n, uint64_t *first_id_out);
+/* same, rows already in DEVICE memory (ingest straight from the embedder's output) */
+int32_t mx_store_add_device(mx_store *s, const float *vecs_dev, uint64_t n, uint64_t *first_id_out);
+
+/* HnswStore::search (local.rs:71-91) for nq queries at once.  HOST buffers.
+ *   ids_out [nq, k], scores_out [nq, k] best first, counts_out [nq] = min(k, len).
+ * Ranking is the EXACT (distance asc, id asc) order the reference's HNSW walk approximates;
+ * scores are bit-identical to DistCosine + local.rs:86 evaluated on the stored rows. */
+int32_t mx_store_search(mx_store *s, const float *queries, uint32_t nq, uint32_t k,
+                        uint64_t *ids_out, float *scores_out, uint32_t *counts_out);
+/* same with DEVICE buffers, asynchronous on `cuda_stream` (a cudaStream_t; NULL = the store's
+ * own stream).  dists_out (may be NULL) receives the raw sort keys (cosine distance, or -dot)
+ * that mx_merge_topk_device consumes. */
+int32_t mx_store_search_device(mx_store *s, const float *queries_dev, uint32_t nq, uint32_t k,
+                               uint64_t *ids_dev, float *scores_dev, float *dists_dev,
+                               uint32_t *counts_dev, void *cuda_stream);
+
+/* merge of G per-shard results (after the all-gather): inputs [G, nq, k] / [G, nq], DEVICE
+ * buffers, ordered by (key asc, id asc) -> [nq, k].  metric picks the key -> score map. */
+int32_t mx_merge_topk_device(const uint64_t *ids_dev, const float *dists_dev,
+                             const uint32_t *counts_dev, uint32_t n_shards, uint32_t nq, uint32_t k,
+                             uint32_t metric, uint64_t *ids_out_dev, float *scores_out_dev,
+                             uint32_t *counts_out_dev, int32_t device, void *cuda_stream);
+
+int32_t mx_store_len(mx_store *s, uint64_t *n_out); /* hnsw.get_nb_point(), local.rs:238 */
+int32_t mx_store_clear(mx_store *s);                /* delete_all's index reset, local.rs:48-50 */
+int32_t mx_store_delete(mx_store *s, uint64_t id);  /* local.rs:29-32: always MX_ERR_UNSUPPORTED */
+/* HnswStore::save / load (local.rs:115-165): one flat file `vectors.b200.bin` in `dir`
+ * (the id map `vectors.meta.json` is written by the host side of the binding). */
+int32_t mx_store_save(mx_store *s, const char *dir);
+int32_t mx_store_load(const char *dir, int32_t device, mx_store **out);
+int32_t mx_store_has_file(const char *dir); /* 1 / 0 */
+int32_t mx_store_remove_file(const char *dir);
+/* stored rows [first_row, first_row + n) widened to f32 into HOST memory (tests, migration) */
+int32_t mx_store_get_rows(mx_store *s, uint64_t first_row, uint64_t n, float *out);
+int32_t mx_store_sync(mx_store *s);
+int32_t mx_store_info(mx_store *s, uint32_t *dim, uint32_t *dtype, uint32_t *metric,
+                      uint64_t *capacity);
+/* which scan kernel mx_store_search* will use for (nq, k): 0 = fp32 CUDA-core stream,
+ * 1 = fp16 CUDA-core stream, 2 = fp16 tcgen05.  force >= 0 pins a path (tests / bench). */
+int32_t mx_store_scan_path(mx_store *s, uint32_t nq, uint32_t k, int32_t force);
+
+/* device-side timing of the store's own kernels (CUDA events on the launching stream) */
+int32_t mx_store_set_timing(mx_store *s, int32_t on);
+int32_t mx_store_get_timing(mx_store *s, double *scan_ms_total, uint64_t *scan_launches,
+                            double *other_ms_total, uint64_t *other_launches);
+
+/* ------------------------------------------------------------------------------------------
+ * sentence embedder -- replaces rust-bert's SentenceEmbeddingsModel::encode (embedding.rs:109)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mx_model_cfg {
+    uint32_t layers, hidden, heads, ffn, vocab, max_pos, type_vocab;
+    float ln_eps;
+    uint32_t normalize;  /* sentence-transformers Normalize module present (all-MiniLM: 1) */
+    uint32_t precision;  /* 0 = bf16 activations on tcgen05 (product path), 1 = fp32 CUDA-core
+                            validation path (same kernels' math in fp32) */
+    uint32_t max_tokens; /* workspace bound: max B*S per encode call */
+} mx_model_cfg;
+
+/* weights by HF BertModel name ("embeddings.word_embeddings.weight",
+ * "encoder.layer.0.attention.self.query.weight", ...), f32, Linear weights [out, in] */
+typedef struct mx_tensor {
+    const char *name;
+    const float *data;
+    uint64_t numel;
+} mx_tensor;
+
+int32_t mx_embedder_create(const mx_model_cfg *cfg, const mx_tensor *weights, uint32_t n_weights,
+                           int32_t device, mx_embedder **out);
+void mx_embedder_destroy(mx_embedder *e);
+/* ids [B, S] int32 padded, lens [B] (tokens beyond lens[b] are ignored), out [B, hidden] f32;
+ * HOST buffers. */
+int32_t mx_embedder_encode(mx_embedder *e, const int32_t *ids, const int32_t *lens, uint32_t B,
+                           uint32_t S, float *out);
+/* ids / out in DEVICE memory, lens on the HOST; asynchronous on cuda_stream (NULL = own) */
+int32_t mx_embedder_encode_device(mx_embedder *e, const int32_t *ids_dev, const int32_t *lens,
+                                  uint32_t B, uint32_t S, float *out_dev, void *cuda_stream);
+int32_t mx_embedder_sync(mx_embedder *e);
+int32_t mx_embedder_set_timing(mx_embedder *e, int32_t on);
+int32_t mx_embedder_get_timing(mx_embedder *e, double *gemm_ms_total, uint64_t *gemm_launches,
+                               double *other_ms_total, uint64_t *other_launches);
+
+/* ------------------------------------------------------------------------------------------ */
+const char *mx_last_error(const void *handle);
+uint64_t mx_launch_count(void);     /* kernels this library has launched in this process */
+int32_t mx_device_count(void);
+int32_t mx_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEMEX_B200_H */

@@ -1,0 +1,252 @@
+// common.cuh -- shared host/device helpers for libmemex_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/memex_b200.h"
+
+namespace mx {
+
+constexpr int kNumSMsDefault = 148;
+
+extern std::atomic<uint64_t> g_launches;      // kernels launched by this library
+extern thread_local std::string g_last_error;  // last create/load failure on this thread
+
+// Every handle starts with this so mx_last_error(handle) works for both kinds.
+struct HandleBase {
+    uint32_t magic = 0;
+    std::string last_error;
+};
+constexpr uint32_t kStoreMagic = 0x4d585354;     // "MXST"
+constexpr uint32_t kEmbedderMagic = 0x4d58454d;  // "MXEM"
+
+inline int32_t fail(HandleBase *h, int32_t code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h)
+        h->last_error = buf;
+    else
+        g_last_error = buf;
+    return code;
+}
+
+#define MX_CUDA(h, code, expr)                                                                  \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return ::mx::fail((h), (code), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                              __FILE__, __LINE__);                                              \
+    } while (0)
+
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// CUDA-event timing of the library's own kernels on the launching stream.
+struct KernelTimer {
+    bool on = false;
+    struct Span {
+        cudaEvent_t a, b;
+        int kind;
+    };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    double total_ms[2] = {0, 0};
+    uint64_t launches[2] = {0, 0};
+
+    cudaEvent_t get()
+    {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    // kind 0 = dominant kernel (scan / GEMM), 1 = everything else
+    void begin(cudaStream_t st, int kind)
+    {
+        if (!on) return;
+        Span s{get(), get(), kind};
+        cudaEventRecord(s.a, st);
+        spans.push_back(s);
+    }
+    void end(cudaStream_t st)
+    {
+        if (!on) return;
+        cudaEventRecord(spans.back().b, st);
+    }
+    void collect()
+    {
+        for (Span &s : spans) {
+            cudaEventSynchronize(s.b);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, s.a, s.b);
+            total_ms[s.kind] += ms;
+            launches[s.kind] += 1;
+            pool.push_back(s.a);
+            pool.push_back(s.b);
+        }
+        spans.clear();
+    }
+    void reset()
+    {
+        collect();
+        total_ms[0] = total_ms[1] = 0;
+        launches[0] = launches[1] = 0;
+    }
+    ~KernelTimer()
+    {
+        for (Span &s : spans) {
+            cudaEventDestroy(s.a);
+            cudaEventDestroy(s.b);
+        }
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    }
+};
+
+template <typename T>
+inline T ceil_div(T a, T b)
+{
+    return (a + b - 1) / b;
+}
+
+}  // namespace mx
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace mx {
+
+constexpr float kNegInf = -__builtin_huge_valf();
+constexpr uint32_t kNoRow = 0xffffffffu;
+
+// 128-bit streaming load: read-only path, do not allocate in L1 (rows are touched once)
+__device__ __forceinline__ float4 ldg_stream_f4(const float4 *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// "a ranks before b" for approximate candidates: higher score first, ties -> lower row
+__device__ __forceinline__ bool cand_before(float sa, uint32_t ra, float sb, uint32_t rb)
+{
+    return sa > sb || (sa == sb && ra < rb);
+}
+
+// A top-(32*E) list spread over the lanes of one warp: lane l holds E entries.  Unordered; the
+// warp-uniform (thr_s, thr_r) is the entry that would be evicted next.
+template <int E>
+struct WarpTopK {
+    float s[E];
+    uint32_t r[E];
+    float thr_s;
+    uint32_t thr_r;
+
+    __device__ __forceinline__ void init()
+    {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            s[e] = kNegInf;
+            r[e] = kNoRow;
+        }
+        thr_s = kNegInf;
+        thr_r = kNoRow;
+    }
+    __device__ __forceinline__ bool accepts(float v, uint32_t row) const
+    {
+        return cand_before(v, row, thr_s, thr_r);
+    }
+    // cheap pre-filter used in hot loops
+    __device__ __forceinline__ bool maybe(float v) const { return v >= thr_s; }
+
+    // warp-uniform call: (v, row) identical on all lanes, accepts(v,row) already true
+    __device__ __forceinline__ void insert(float v, uint32_t row)
+    {
+        bool mine = false;
+#pragma unroll
+        for (int e = 0; e < E; ++e) mine |= (s[e] == thr_s && r[e] == thr_r);
+        uint32_t holders = __ballot_sync(0xffffffffu, mine);
+        int holder = __ffs(holders) - 1;
+        if ((int)lane_id() == holder) {
+            bool done = false;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                if (!done && s[e] == thr_s && r[e] == thr_r) {
+                    s[e] = v;
+                    r[e] = row;
+                    done = true;
+                }
+            }
+        }
+        refresh();
+    }
+    // recompute the eviction entry: minimal score, ties -> maximal row
+    __device__ __forceinline__ void refresh()
+    {
+        float ms = s[0];
+        uint32_t mr = r[0];
+#pragma unroll
+        for (int e = 1; e < E; ++e) {
+            if (cand_before(ms, mr, s[e], r[e])) {
+                ms = s[e];
+                mr = r[e];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            float os = __shfl_xor_sync(0xffffffffu, ms, o);
+            uint32_t orow = __shfl_xor_sync(0xffffffffu, mr, o);
+            if (cand_before(ms, mr, os, orow)) {
+                ms = os;
+                mr = orow;
+            }
+        }
+        thr_s = ms;
+        thr_r = mr;
+    }
+    // offer one candidate per lane (flag = this lane has one); lanes are drained in lane order
+    __device__ __forceinline__ void offer(bool flag, float v, uint32_t row)
+    {
+        uint32_t m = __ballot_sync(0xffffffffu, flag && accepts(v, row));
+        while (m) {
+            int src = __ffs(m) - 1;
+            float cv = __shfl_sync(0xffffffffu, v, src);
+            uint32_t cr = __shfl_sync(0xffffffffu, row, src);
+            if (accepts(cv, cr)) insert(cv, cr);
+            m &= m - 1;
+            // the threshold moved: drop lanes that no longer qualify
+            m &= __ballot_sync(0xffffffffu, flag && accepts(v, row));
+        }
+    }
+};
+
+}  // namespace mx
+#endif

@@ -1,0 +1,404 @@
+// rerank.cu -- candidate merge + exact re-scoring, shard merge, ingest and small data movers.
+//
+// The scan kernels rank rows by an fp32 / tensor-core approximation of the score.  This file
+// turns their per-CTA candidate lists into the final answer with the REFERENCE'S arithmetic:
+//
+//   hnsw_rs 0.1.20 DistCosine::eval  (called under reference storage/local.rs:76):
+//       products a*b, a*a, b*b in f32, widened to f64, folded left to right in f64;
+//       d = max(0, 1 - ab / sqrt(aa * bb)) as f32; either norm zero -> d = 0
+//   reference storage/local.rs:86:   similarity = 1.0 - (1.0 / (1.0 / d))   in f32
+//   reference storage/local.rs:63:   ids are 1-based in insertion order
+//
+// Every operation is the IEEE round-to-nearest one (explicit __fmul_rn / __dadd_rn / __fdiv_rn,
+// double sqrt and division are correctly rounded on the device), evaluated in the same order,
+// so scores are bit-identical to oracle/cosine_oracle.c and ordering is (d asc, id asc).
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace mx {
+
+__device__ __forceinline__ float load_elem(const void *rows, uint32_t dtype, size_t idx)
+{
+    return dtype == MX_DTYPE_F32 ? reinterpret_cast<const float *>(rows)[idx]
+                                 : __half2float(reinterpret_cast<const __half *>(rows)[idx]);
+}
+
+// exact key of (query, row): cosine distance, or -dot for the dot metric
+__device__ float exact_key(const float *q, const void *rows, uint32_t dtype, uint32_t metric, size_t row_off,
+                           uint32_t dim, double *aa_out)
+{
+    double ab = 0.0, aa = 0.0, bb = 0.0;
+    if (dtype == MX_DTYPE_F32) {
+        const float *r = reinterpret_cast<const float *>(rows) + row_off;
+        for (uint32_t i = 0; i < dim; ++i) {
+            const float a = q[i], b = r[i];
+            ab = __dadd_rn(ab, (double)__fmul_rn(a, b));
+            aa = __dadd_rn(aa, (double)__fmul_rn(a, a));
+            bb = __dadd_rn(bb, (double)__fmul_rn(b, b));
+        }
+    } else {
+        const __half *r = reinterpret_cast<const __half *>(rows) + row_off;
+        for (uint32_t i = 0; i < dim; ++i) {
+            const float a = q[i], b = __half2float(r[i]);
+            ab = __dadd_rn(ab, (double)__fmul_rn(a, b));
+            aa = __dadd_rn(aa, (double)__fmul_rn(a, a));
+            bb = __dadd_rn(bb, (double)__fmul_rn(b, b));
+        }
+    }
+    if (aa_out) *aa_out = aa;
+    if (metric == MX_METRIC_DOT) return -(float)ab;
+    if (aa > 0.0 && bb > 0.0) {
+        const double du = __dsub_rn(1.0, __ddiv_rn(ab, __dsqrt_rn(__dmul_rn(aa, bb))));
+        return (float)fmax(du, 0.0);
+    }
+    return 0.f;
+}
+
+__device__ __forceinline__ float key_to_score(float key, uint32_t metric)
+{
+    if (metric == MX_METRIC_DOT) return -key;
+    return __fsub_rn(1.0f, __fdiv_rn(1.0f, __fdiv_rn(1.0f, key)));  // local.rs:86
+}
+
+constexpr int kRerankThreads = 512;
+constexpr int kRerankWarps = kRerankThreads / 32;
+
+template <int E>
+__global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
+{
+    constexpr int kList = 32 * E;
+    constexpr int kMaxEntries = kList + (int)MX_MAX_K;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *qs = reinterpret_cast<float *>(smem_raw);                 // [ldq]
+    float *ws = qs + p.ldq;                                          // [warps][kList] scores
+    uint32_t *wr = reinterpret_cast<uint32_t *>(ws + kRerankWarps * kList);
+    float *ekey = reinterpret_cast<float *>(wr + kRerankWarps * kList);  // [kMaxEntries]
+    uint32_t *erow = reinterpret_cast<uint32_t *>(ekey + kMaxEntries);
+    __shared__ uint32_t n_entries_s;
+    __shared__ int zero_query_s;
+
+    const uint32_t q = blockIdx.x;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < p.ldq; i += blockDim.x) qs[i] = p.queries[(size_t)q * p.ldq + i];
+
+    // 1. every warp folds a slice of the candidate lists into its own list
+    WarpTopK<E> top;
+    top.init();
+    for (uint32_t l = warp; l < p.n_lists; l += kRerankWarps) {
+        const size_t o = ((size_t)q * p.n_lists + l) * p.lcap;
+        for (uint32_t e = 0; e < p.lcap / 32; ++e) {
+            const float v = p.cand_s[o + e * 32 + lane];
+            const uint32_t r = p.cand_r[o + e * 32 + lane];
+            top.offer(r != kNoRow, v, r);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        ws[warp * kList + e * 32 + lane] = top.s[e];
+        wr[warp * kList + e * 32 + lane] = top.r[e];
+    }
+    __syncthreads();
+    // 2. warp 0 folds the warp lists; appends the lowest-id zero-norm rows (cosine: d = 0)
+    if (warp == 0) {
+        for (int w = 1; w < kRerankWarps; ++w)
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const float v = ws[w * kList + e * 32 + lane];
+                const uint32_t r = wr[w * kList + e * 32 + lane];
+                top.offer(r != kNoRow, v, r);
+            }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            ekey[e * 32 + lane] = 0.f;
+            erow[e * 32 + lane] = top.r[e];
+        }
+        uint32_t n = kList;
+        if (p.metric == MX_METRIC_COSINE) {
+            const uint32_t nz = min(min(*p.n_zero, p.k), (uint32_t)MX_MAX_K);
+            for (uint32_t i = lane; i < nz; i += 32) {
+                ekey[kList + i] = 0.f;
+                erow[kList + i] = p.zero_rows[i];
+            }
+            n += nz;
+        }
+        if (lane == 0) n_entries_s = n;
+    }
+    __syncthreads();
+    const uint32_t n_entries = n_entries_s;
+
+    // 3. exact key per entry (one thread each)
+    double aa = 1.0;
+    for (uint32_t j = threadIdx.x; j < n_entries; j += blockDim.x) {
+        const uint32_t row = erow[j];
+        if (row != kNoRow && row < p.n_rows)
+            ekey[j] = exact_key(qs, p.rows, p.dtype, p.metric, (size_t)row * p.ld, p.dim, &aa);
+        else
+            erow[j] = kNoRow;
+    }
+    if (threadIdx.x == 0) {
+        // the query's own norm decides the degenerate case (DistCosine: aa == 0 -> d = 0 for all)
+        double a2 = 0.0;
+        for (uint32_t i = 0; i < p.dim; ++i) a2 = __dadd_rn(a2, (double)__fmul_rn(qs[i], qs[i]));
+        zero_query_s = (p.metric == MX_METRIC_COSINE && !(a2 > 0.0)) ? 1 : 0;
+    }
+    __syncthreads();
+
+    const uint32_t count = min(p.k, p.n_rows);
+    if (zero_query_s) {
+        // all distances are 0 -> (d asc, id asc) is simply the first rows
+        for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) {
+            const bool ok = j < count;
+            p.ids_out[(size_t)q * p.k + j] = ok ? p.id_offset + (uint64_t)j * p.id_stride + 1 : 0;
+            p.scores_out[(size_t)q * p.k + j] = ok ? key_to_score(0.f, p.metric) : 0.f;
+            if (p.dists_out) p.dists_out[(size_t)q * p.k + j] = 0.f;
+        }
+        if (threadIdx.x == 0) p.counts_out[q] = count;
+        return;
+    }
+
+    // 4. drop duplicates (a zero row can also arrive through the scan), then rank-sort
+    for (uint32_t j = threadIdx.x; j < n_entries; j += blockDim.x) {
+        const uint32_t row = erow[j];
+        bool dup = false;
+        if (row != kNoRow)
+            for (uint32_t i = 0; i < j; ++i) dup |= (erow[i] == row);
+        if (dup) ekey[j] = __int_as_float(0x7fc00000);  // mark; row cleared after the barrier
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < n_entries; j += blockDim.x)
+        if (ekey[j] != ekey[j]) erow[j] = kNoRow;
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) {
+        if (j >= count) {
+            p.ids_out[(size_t)q * p.k + j] = 0;
+            p.scores_out[(size_t)q * p.k + j] = 0.f;
+            if (p.dists_out) p.dists_out[(size_t)q * p.k + j] = 0.f;
+        }
+    }
+    for (uint32_t j = threadIdx.x; j < n_entries; j += blockDim.x) {
+        const uint32_t row = erow[j];
+        if (row == kNoRow) continue;
+        const float key = ekey[j];
+        uint32_t rank = 0;
+        for (uint32_t i = 0; i < n_entries; ++i) {
+            const uint32_t ri = erow[i];
+            if (ri == kNoRow) continue;
+            const float ki = ekey[i];
+            rank += (ki < key || (ki == key && ri < row)) ? 1u : 0u;
+        }
+        if (rank < count) {
+            p.ids_out[(size_t)q * p.k + rank] = p.id_offset + (uint64_t)row * p.id_stride + 1;
+            p.scores_out[(size_t)q * p.k + rank] = key_to_score(key, p.metric);
+            if (p.dists_out) p.dists_out[(size_t)q * p.k + rank] = key;
+        }
+    }
+    if (threadIdx.x == 0) p.counts_out[q] = count;
+}
+
+cudaError_t launch_rerank(const RerankParams &p, cudaStream_t st)
+{
+    const uint32_t E = p.lcap / 32;
+    const size_t smem = (size_t)p.ldq * 4 + (size_t)kRerankWarps * p.lcap * 8 + (size_t)(p.lcap + MX_MAX_K) * 8;
+#define MX_RR(EE)                                                                                  \
+    {                                                                                              \
+        auto kern = rerank_kernel<EE>;                                                             \
+        if (smem > 48 * 1024) {                                                                    \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                        \
+        }                                                                                          \
+        kern<<<p.nq, kRerankThreads, smem, st>>>(p);                                               \
+    }
+    switch (E) {
+        case 1: MX_RR(1) break;
+        case 2: MX_RR(2) break;
+        case 4: MX_RR(4) break;
+        case 8: MX_RR(8) break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef MX_RR
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 tail: merge of G shard answers after the all-gather.  One CTA per query, rank-sort of
+// G*k entries by (key asc, id asc).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) merge_kernel(MergeParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t T = p.n_shards * p.k;
+    float *key = reinterpret_cast<float *>(smem_raw);
+    uint64_t *id = reinterpret_cast<uint64_t *>(smem_raw + (((size_t)T * 4 + 7) & ~(size_t)7));
+    __shared__ uint32_t total_s;
+    const uint32_t q = blockIdx.x;
+    if (threadIdx.x == 0) total_s = 0;
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
+        const uint32_t g = j / p.k, e = j - g * p.k;
+        const uint32_t c = p.counts[(size_t)g * p.nq + q];
+        const bool ok = e < c;
+        key[j] = ok ? p.dists[((size_t)g * p.nq + q) * p.k + e] : 0.f;
+        id[j] = ok ? p.ids[((size_t)g * p.nq + q) * p.k + e] : 0;
+        if (ok) atomicAdd(&total_s, 1u);
+    }
+    __syncthreads();
+    const uint32_t count = min(p.k, total_s);
+    for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x)
+        if (j >= count) {
+            p.ids_out[(size_t)q * p.k + j] = 0;
+            p.scores_out[(size_t)q * p.k + j] = 0.f;
+        }
+    for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
+        const uint64_t mine = id[j];
+        if (mine == 0) continue;
+        const float kj = key[j];
+        uint32_t rank = 0;
+        for (uint32_t i = 0; i < T; ++i) {
+            const uint64_t oi = id[i];
+            if (oi == 0) continue;
+            const float ki = key[i];
+            rank += (ki < kj || (ki == kj && oi < mine)) ? 1u : 0u;
+        }
+        if (rank < count) {
+            p.ids_out[(size_t)q * p.k + rank] = mine;
+            p.scores_out[(size_t)q * p.k + rank] = key_to_score(kj, p.metric);
+        }
+    }
+    if (threadIdx.x == 0) p.counts_out[q] = count;
+}
+
+cudaError_t launch_merge(const MergeParams &p, cudaStream_t st)
+{
+    const size_t T = (size_t)p.n_shards * p.k;
+    const size_t smem = ((T * 4 + 7) & ~(size_t)7) + T * 8;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    merge_kernel<<<p.nq, 256, smem, st>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// ingest: one warp per row.  f32 source -> stored dtype (round to nearest even, as numpy's
+// astype(float16)), inv_norm from the STORED values, flags for zero-norm / non-finite rows.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ingest_kernel(IngestParams p)
+{
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (row >= p.n) return;
+    const uint32_t lane = lane_id();
+    const float *src = p.src + row * p.dim;
+    const uint64_t dst_row = p.first_row + row;
+    float ss = 0.f;
+    bool bad = false;
+    for (uint32_t c = lane; c < p.ld; c += 32) {
+        float v = c < p.dim ? src[c] : 0.f;
+        if (p.dtype == MX_DTYPE_F16) {
+            const __half h = __float2half_rn(v);
+            reinterpret_cast<__half *>(p.rows)[dst_row * p.ld + c] = h;
+            v = __half2float(h);
+        } else {
+            reinterpret_cast<float *>(p.rows)[dst_row * p.ld + c] = v;
+        }
+        bad |= !isfinite(v);
+        ss = fmaf(v, v, ss);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    bad = __any_sync(0xffffffffu, bad) || !isfinite(ss);
+    if (lane == 0) {
+        if (bad) atomicOr(p.bad_flag, 1u);
+        const bool zero = !(ss > 0.f);
+        p.inv_norm[dst_row] = zero ? 0.f : 1.0f / sqrtf(ss);
+        if (zero && p.metric == MX_METRIC_COSINE) atomicOr(p.bad_flag, 2u);
+    }
+}
+
+cudaError_t launch_ingest(const IngestParams &p, cudaStream_t st)
+{
+    if (p.n == 0) return cudaSuccess;
+    const uint32_t rows_per_cta = 256 / 32;
+    ingest_kernel<<<(unsigned)ceil_div<uint64_t>(p.n, rows_per_cta), 256, 0, st>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// the k lowest zero-norm rows matter for cosine (d = 0 -> score 1.0): ordered compaction of the
+// first MX_MAX_K rows with inv_norm == 0, one CTA, early exit.
+__global__ void __launch_bounds__(1024) collect_zero_rows_kernel(const float *inv_norm, uint64_t n,
+                                                                 uint32_t *zero_rows, uint32_t *n_zero)
+{
+    __shared__ uint32_t warp_cnt[32];
+    __shared__ uint32_t found_s;
+    if (threadIdx.x == 0) found_s = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < n; base += blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        const bool z = i < n && inv_norm[i] == 0.f;
+        const uint32_t m = __ballot_sync(0xffffffffu, z);
+        const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+        if (lane == 0) warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        uint32_t before = found_s;
+        for (uint32_t w = 0; w < warp; ++w) before += warp_cnt[w];
+        const uint32_t pos = before + __popc(m & ((1u << lane) - 1));
+        if (z && pos < MX_MAX_K) zero_rows[pos] = (uint32_t)i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = found_s;
+            for (uint32_t w = 0; w < blockDim.x / 32; ++w) t += warp_cnt[w];
+            found_s = t;
+        }
+        __syncthreads();
+        if (found_s >= MX_MAX_K) break;
+    }
+    if (threadIdx.x == 0) *n_zero = min(found_s, (uint32_t)MX_MAX_K);
+}
+
+cudaError_t launch_collect_zero_rows(const float *inv_norm, uint64_t n, uint32_t *zero_rows, uint32_t *n_zero,
+                                     cudaStream_t st)
+{
+    collect_zero_rows_kernel<<<1, 1024, 0, st>>>(inv_norm, n, zero_rows, n_zero);
+    count_launch();
+    return cudaGetLastError();
+}
+
+__global__ void export_rows_kernel(const void *rows, uint32_t dtype, uint32_t ld, uint32_t dim, uint64_t first_row,
+                                   uint64_t n, float *out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * dim) return;
+    const uint64_t r = i / dim;
+    const uint32_t c = (uint32_t)(i - r * dim);
+    out[i] = load_elem(rows, dtype, (size_t)(first_row + r) * ld + c);
+}
+
+cudaError_t launch_export_rows(const void *rows, uint32_t dtype, uint32_t ld, uint32_t dim, uint64_t first_row,
+                               uint64_t n, float *out, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    export_rows_kernel<<<(unsigned)ceil_div<uint64_t>(n * dim, 256), 256, 0, st>>>(rows, dtype, ld, dim, first_row, n,
+                                                                                   out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+__global__ void stage_queries_kernel(const float *q, uint32_t nq, uint32_t dim, uint32_t ldq, float *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * ldq) return;
+    const uint32_t r = i / ldq, c = i - r * ldq;
+    out[i] = c < dim ? q[(size_t)r * dim + c] : 0.f;
+}
+
+cudaError_t launch_stage_queries(const float *q, uint32_t nq, uint32_t dim, uint32_t ldq, float *out, cudaStream_t st)
+{
+    stage_queries_kernel<<<ceil_div<uint32_t>(nq * ldq, 256), 256, 0, st>>>(q, nq, dim, ldq, out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace mx

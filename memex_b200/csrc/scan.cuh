@@ -1,0 +1,76 @@
+// scan.cuh -- interfaces between the store and its scan / rerank kernels.
+#pragma once
+#include "common.cuh"
+
+namespace mx {
+
+// One approximate-scan launch: every query in [0, nq) against rows [0, n_rows).
+// Output: cand_s / cand_r [nq][n_lists][lcap] -- per (query, CTA) unordered top lists, padded
+// with (-inf, kNoRow).
+struct ScanParams {
+    const void *rows;        // [capacity, ld] in the stored dtype
+    const float *inv_norm;   // [capacity] 1 / |row|  (cosine), 0 for zero rows
+    const float *queries;    // [nq, ldq] f32, zero padded to ldq
+    float *cand_s;
+    uint32_t *cand_r;
+    uint32_t n_rows;
+    uint32_t ld;             // elements per stored row (multiple of 16 bytes)
+    uint32_t ldq;            // floats per staged query (>= ld, multiple of 8)
+    uint32_t nq;
+    uint32_t n_lists;        // lists per query (= CTAs of the scan grid)
+    uint32_t use_inv;        // 1 = cosine (scale by inv_norm), 0 = dot
+};
+
+uint32_t scan_stream_lcap(uint32_t k);
+uint32_t scan_stream_nq_per_pass(uint32_t nq, uint32_t k);
+cudaError_t launch_scan_stream(const ScanParams &p, uint32_t dtype, uint32_t k, uint32_t n_ctas,
+                               cudaStream_t st);
+
+// merge of the candidate lists + exact re-scoring with the reference's arithmetic
+struct RerankParams {
+    const void *rows;
+    const float *queries;     // [nq, ldq] f32 (the caller's values, unrounded)
+    const float *cand_s;
+    const uint32_t *cand_r;
+    const uint32_t *zero_rows;  // first <= MX_MAX_K rows whose norm is zero (cosine only)
+    const uint32_t *n_zero;     // device scalar
+    uint64_t *ids_out;          // [nq, k]
+    float *scores_out;          // [nq, k]
+    float *dists_out;           // [nq, k] or nullptr
+    uint32_t *counts_out;       // [nq]
+    uint64_t id_offset, id_stride;
+    uint32_t n_rows, ld, ldq, dim, nq, k;
+    uint32_t n_lists, lcap;
+    uint32_t dtype, metric;
+};
+cudaError_t launch_rerank(const RerankParams &p, cudaStream_t st);
+
+struct MergeParams {
+    const uint64_t *ids;     // [G, nq, k]
+    const float *dists;      // [G, nq, k]
+    const uint32_t *counts;  // [G, nq]
+    uint64_t *ids_out;
+    float *scores_out;
+    uint32_t *counts_out;
+    uint32_t n_shards, nq, k, metric;
+};
+cudaError_t launch_merge(const MergeParams &p, cudaStream_t st);
+
+// ingest: f32 rows -> stored dtype (+ inv_norm, zero-row list, non-finite flag)
+struct IngestParams {
+    const float *src;     // [n, dim]
+    void *rows;           // stored matrix base
+    float *inv_norm;
+    uint32_t *zero_rows;
+    uint32_t *n_zero;
+    uint32_t *bad_flag;
+    uint64_t first_row, n;
+    uint32_t dim, ld, dtype, metric;
+};
+cudaError_t launch_ingest(const IngestParams &p, cudaStream_t st);
+cudaError_t launch_export_rows(const void *rows, uint32_t dtype, uint32_t ld, uint32_t dim,
+                               uint64_t first_row, uint64_t n, float *out, cudaStream_t st);
+cudaError_t launch_stage_queries(const float *q, uint32_t nq, uint32_t dim, uint32_t ldq, float *out,
+                                 cudaStream_t st);
+
+}  // namespace mx

@@ -1,0 +1,734 @@
+// store.cu -- mx_store: the device-resident flat vector store behind memex's VectorStore surface.
+//
+// Host-side bookkeeping mirrors HnswStore (reference lib/libmemex/src/storage/local.rs:21-166):
+// rows are appended in insertion order and identified by 1-based ids (local.rs:63); search returns
+// (id, score) best first (local.rs:71-91); delete of one row is unsupported (local.rs:29-32);
+// clear resets the index (local.rs:48-50); save/load persist one flat file next to the host
+// side's vectors.meta.json (local.rs:115-165).
+//
+// HBM layout: rows [capacity, ld] in the stored dtype (ld = dim rounded up to 16 bytes, zero
+// padded), inv_norm [capacity] f32.  Search = approximate scan (scan_stream.cu or scan_tc.cu)
+// -> candidate merge + exact re-score (rerank.cu).  There is no CPU path.
+#include <cerrno>
+#include <cmath>
+#include <cstring>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace mx {
+
+std::atomic<uint64_t> g_launches{0};
+thread_local std::string g_last_error;
+
+cudaError_t launch_collect_zero_rows(const float *inv_norm, uint64_t n, uint32_t *zero_rows, uint32_t *n_zero,
+                                     cudaStream_t st);
+
+static const char kFileName[] = "vectors.b200.bin";
+static const char kFileMagic[8] = {'M', 'X', 'B', '2', '0', '0', 'V', '1'};
+
+struct FileHeader {
+    char magic[8];
+    uint32_t dim, dtype, metric, ld;
+    uint64_t n;
+    uint64_t reserved[4];
+};
+
+}  // namespace mx
+
+using namespace mx;
+
+struct mx_store : HandleBase {
+    mx_store_cfg cfg{};
+    cudaStream_t stream = nullptr;
+    int sm_count = kNumSMsDefault;
+    uint32_t ld = 0;      // elements per stored row
+    uint32_t ldq = 0;     // floats per staged query
+    size_t elem = 4;
+    uint64_t n = 0, capacity = 0;
+    void *rows = nullptr;
+    float *inv_norm = nullptr;
+    uint32_t *zero_rows = nullptr;  // [MX_MAX_K]
+    uint32_t *n_zero = nullptr;     // device scalar
+    uint32_t *flags = nullptr;      // device scalar: bit0 non-finite, bit1 zero row seen
+    bool zero_dirty = false;
+    int32_t force_path = -1;
+    // scratch
+    float *q_stage = nullptr;
+    size_t q_stage_cap = 0;  // floats
+    float *cand_s = nullptr;
+    uint32_t *cand_r = nullptr;
+    size_t cand_cap = 0;  // entries
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+    void *dev_io = nullptr;
+    size_t dev_io_cap = 0;
+    TcScanState *tc = nullptr;
+    KernelTimer timer;
+};
+
+namespace {
+
+int32_t set_device(mx_store *s) { MX_CUDA(s, MX_ERR_CONNECTION, cudaSetDevice(s->cfg.device)); return MX_OK; }
+
+int32_t ensure_pinned(mx_store *s, size_t bytes)
+{
+    if (bytes <= s->pinned_cap) return MX_OK;
+    if (s->pinned) cudaFreeHost(s->pinned);
+    s->pinned = nullptr;
+    s->pinned_cap = 0;
+    MX_CUDA(s, MX_ERR_CONNECTION, cudaMallocHost(&s->pinned, bytes));
+    s->pinned_cap = bytes;
+    return MX_OK;
+}
+
+int32_t ensure_dev_io(mx_store *s, size_t bytes)
+{
+    if (bytes <= s->dev_io_cap) return MX_OK;
+    if (s->dev_io) cudaFree(s->dev_io);
+    s->dev_io = nullptr;
+    s->dev_io_cap = 0;
+    MX_CUDA(s, MX_ERR_CONNECTION, cudaMalloc(&s->dev_io, bytes));
+    s->dev_io_cap = bytes;
+    return MX_OK;
+}
+
+int32_t reserve(mx_store *s, uint64_t want, int32_t err_code)
+{
+    if (want <= s->capacity) return MX_OK;
+    uint64_t cap = s->capacity ? s->capacity : 1024;
+    while (cap < want) cap = cap + cap / 2 + 1024;
+    if (cap > 0xfffffff0ull) {
+        if (want > 0xfffffff0ull) return fail(s, err_code, "store is limited to 2^32 - 16 rows per device");
+        cap = 0xfffffff0ull;
+    }
+    void *nrows = nullptr;
+    float *ninv = nullptr;
+    MX_CUDA(s, err_code, cudaMalloc(&nrows, cap * s->ld * s->elem));
+    cudaError_t e = cudaMalloc(&ninv, cap * sizeof(float));
+    if (e != cudaSuccess) {
+        cudaFree(nrows);
+        return fail(s, err_code, "cudaMalloc(inv_norm) failed: %s", cudaGetErrorString(e));
+    }
+    if (s->n) {
+        cudaMemcpyAsync(nrows, s->rows, s->n * s->ld * s->elem, cudaMemcpyDeviceToDevice, s->stream);
+        cudaMemcpyAsync(ninv, s->inv_norm, s->n * sizeof(float), cudaMemcpyDeviceToDevice, s->stream);
+    }
+    MX_CUDA(s, err_code, cudaStreamSynchronize(s->stream));
+    cudaFree(s->rows);
+    cudaFree(s->inv_norm);
+    s->rows = nrows;
+    s->inv_norm = ninv;
+    s->capacity = cap;
+    if (s->tc) tc_scan_invalidate(s->tc);
+    return MX_OK;
+}
+
+// rows already on the device as f32 [n, dim]
+int32_t ingest_device(mx_store *s, const float *src_dev, uint64_t n, cudaStream_t st)
+{
+    IngestParams ip{};
+    ip.src = src_dev;
+    ip.rows = s->rows;
+    ip.inv_norm = s->inv_norm;
+    ip.zero_rows = s->zero_rows;
+    ip.n_zero = s->n_zero;
+    ip.bad_flag = s->flags;
+    ip.first_row = s->n;
+    ip.n = n;
+    ip.dim = s->cfg.dim;
+    ip.ld = s->ld;
+    ip.dtype = s->cfg.dtype;
+    ip.metric = s->cfg.metric;
+    s->timer.begin(st, 1);
+    MX_CUDA(s, MX_ERR_INSERTION, launch_ingest(ip, st));
+    s->timer.end(st);
+    return MX_OK;
+}
+
+int32_t finish_add(mx_store *s, uint64_t n, cudaStream_t st, uint64_t *first_id_out)
+{
+    uint32_t flags = 0;
+    MX_CUDA(s, MX_ERR_INSERTION, cudaMemcpyAsync(&flags, s->flags, 4, cudaMemcpyDeviceToHost, st));
+    MX_CUDA(s, MX_ERR_INSERTION, cudaStreamSynchronize(st));
+    if (flags) {
+        cudaMemsetAsync(s->flags, 0, 4, st);
+        cudaStreamSynchronize(st);
+    }
+    if (flags & 1u) return fail(s, MX_ERR_INSERTION, "non-finite value in inserted vectors (batch of %llu rejected)",
+                                (unsigned long long)n);
+    if (flags & 2u) s->zero_dirty = true;
+    if (first_id_out) *first_id_out = s->cfg.id_offset + s->n * s->cfg.id_stride + 1;
+    s->n += n;
+    return MX_OK;
+}
+
+uint32_t pick_path(mx_store *s, uint32_t nq, uint32_t k)
+{
+    if (s->force_path >= 0) return (uint32_t)s->force_path;
+    if (s->cfg.dtype == MX_DTYPE_F16 && s->tc && tc_scan_supports(s->tc, k) && nq >= 8) return 2;
+    return s->cfg.dtype == MX_DTYPE_F16 ? 1 : 0;
+}
+
+int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_t k, uint64_t *ids_dev,
+                           float *scores_dev, float *dists_dev, uint32_t *counts_dev, cudaStream_t st)
+{
+    if (!q_dev || !ids_dev || !scores_dev || !counts_dev) return fail(s, MX_ERR_INVALID, "null buffer");
+    if (k == 0 || k > MX_MAX_K) return fail(s, MX_ERR_INVALID, "k must be in [1, %u]", MX_MAX_K);
+    if (nq == 0) return MX_OK;
+    if (s->n == 0) {
+        // empty index: HnswStore::search returns no neighbours (local.rs:76-90)
+        MX_CUDA(s, MX_ERR_SEARCH, cudaMemsetAsync(counts_dev, 0, sizeof(uint32_t) * nq, st));
+        MX_CUDA(s, MX_ERR_SEARCH, cudaMemsetAsync(ids_dev, 0, sizeof(uint64_t) * nq * k, st));
+        MX_CUDA(s, MX_ERR_SEARCH, cudaMemsetAsync(scores_dev, 0, sizeof(float) * nq * k, st));
+        if (dists_dev) MX_CUDA(s, MX_ERR_SEARCH, cudaMemsetAsync(dists_dev, 0, sizeof(float) * nq * k, st));
+        return MX_OK;
+    }
+    if (s->zero_dirty) {
+        MX_CUDA(s, MX_ERR_SEARCH, launch_collect_zero_rows(s->inv_norm, s->n, s->zero_rows, s->n_zero, st));
+        s->zero_dirty = false;
+    }
+    const uint32_t path = pick_path(s, nq, k);
+    if (path == 2 && !(s->cfg.dtype == MX_DTYPE_F16 && s->tc && tc_scan_supports(s->tc, k)))
+        return fail(s, MX_ERR_UNSUPPORTED, "tcgen05 scan needs an fp16 store and k <= %u", tc_scan_max_k());
+    if ((path == 0) != (s->cfg.dtype == MX_DTYPE_F32))
+        return fail(s, MX_ERR_UNSUPPORTED, "scan path %u does not match the store dtype", path);
+
+    // stage queries: [nq, ldq] f32 zero padded
+    const size_t qfloats = (size_t)nq * s->ldq;
+    if (qfloats > s->q_stage_cap) {
+        if (s->q_stage) cudaFree(s->q_stage);
+        s->q_stage = nullptr;
+        s->q_stage_cap = 0;
+        MX_CUDA(s, MX_ERR_SEARCH, cudaMalloc(&s->q_stage, qfloats * sizeof(float)));
+        s->q_stage_cap = qfloats;
+    }
+    s->timer.begin(st, 1);
+    MX_CUDA(s, MX_ERR_SEARCH, launch_stage_queries(q_dev, nq, s->cfg.dim, s->ldq, s->q_stage, st));
+    s->timer.end(st);
+
+    uint32_t n_lists, lcap;
+    if (path == 2) {
+        n_lists = tc_scan_lists(s->tc, s->n);
+        lcap = tc_scan_lcap(k);
+    } else {
+        const uint64_t rows_per_cta = 16 * 16;  // a CTA iteration covers at least this many rows
+        n_lists = (uint32_t)std::min<uint64_t>((uint64_t)s->sm_count, ceil_div<uint64_t>(s->n, rows_per_cta));
+        lcap = scan_stream_lcap(k);
+    }
+    const size_t cand = (size_t)nq * n_lists * lcap;
+    if (cand > s->cand_cap) {
+        if (s->cand_s) cudaFree(s->cand_s);
+        if (s->cand_r) cudaFree(s->cand_r);
+        s->cand_s = nullptr;
+        s->cand_r = nullptr;
+        s->cand_cap = 0;
+        MX_CUDA(s, MX_ERR_SEARCH, cudaMalloc(&s->cand_s, cand * sizeof(float)));
+        MX_CUDA(s, MX_ERR_SEARCH, cudaMalloc(&s->cand_r, cand * sizeof(uint32_t)));
+        s->cand_cap = cand;
+    }
+
+    ScanParams sp{};
+    sp.rows = s->rows;
+    sp.inv_norm = s->inv_norm;
+    sp.queries = s->q_stage;
+    sp.cand_s = s->cand_s;
+    sp.cand_r = s->cand_r;
+    sp.n_rows = (uint32_t)s->n;
+    sp.ld = s->ld;
+    sp.ldq = s->ldq;
+    sp.nq = nq;
+    sp.n_lists = n_lists;
+    sp.use_inv = s->cfg.metric == MX_METRIC_COSINE ? 1u : 0u;
+    if (path == 2) {
+        const char *why = nullptr;
+        cudaError_t e = tc_scan_launch(s->tc, sp, s->capacity, k, &s->timer, st, &why);
+        if (e != cudaSuccess)
+            return fail(s, MX_ERR_SEARCH, "tcgen05 scan failed: %s (%s)", cudaGetErrorString(e), why ? why : "");
+    } else {
+        s->timer.begin(st, 0);
+        MX_CUDA(s, MX_ERR_SEARCH, launch_scan_stream(sp, s->cfg.dtype, k, n_lists, st));
+        s->timer.end(st);
+    }
+
+    RerankParams rp{};
+    rp.rows = s->rows;
+    rp.queries = s->q_stage;
+    rp.cand_s = s->cand_s;
+    rp.cand_r = s->cand_r;
+    rp.zero_rows = s->zero_rows;
+    rp.n_zero = s->n_zero;
+    rp.ids_out = ids_dev;
+    rp.scores_out = scores_dev;
+    rp.dists_out = dists_dev;
+    rp.counts_out = counts_dev;
+    rp.id_offset = s->cfg.id_offset;
+    rp.id_stride = s->cfg.id_stride;
+    rp.n_rows = (uint32_t)s->n;
+    rp.ld = s->ld;
+    rp.ldq = s->ldq;
+    rp.dim = s->cfg.dim;
+    rp.nq = nq;
+    rp.k = k;
+    rp.n_lists = n_lists;
+    rp.lcap = lcap;
+    rp.dtype = s->cfg.dtype;
+    rp.metric = s->cfg.metric;
+    s->timer.begin(st, 1);
+    MX_CUDA(s, MX_ERR_SEARCH, launch_rerank(rp, st));
+    s->timer.end(st);
+    return MX_OK;
+}
+
+bool dir_join(const char *dir, std::string &out)
+{
+    if (!dir) return false;
+    out = dir;
+    if (!out.empty() && out.back() != '/') out += '/';
+    out += kFileName;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t mx_abi_version(void) { return MX_ABI_VERSION; }
+uint64_t mx_launch_count(void) { return g_launches.load(); }
+int32_t mx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *mx_last_error(const void *handle)
+{
+    if (!handle) return g_last_error.c_str();
+    return static_cast<const HandleBase *>(handle)->last_error.c_str();
+}
+
+int32_t mx_store_create(const mx_store_cfg *cfg, mx_store **out)
+{
+    if (!cfg || !out) return fail(nullptr, MX_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->dim == 0 || cfg->dim > 65536) return fail(nullptr, MX_ERR_INVALID, "dim must be in [1, 65536]");
+    if (cfg->dtype > MX_DTYPE_F16) return fail(nullptr, MX_ERR_UNSUPPORTED, "unknown dtype %u", cfg->dtype);
+    if (cfg->metric > MX_METRIC_DOT) return fail(nullptr, MX_ERR_UNSUPPORTED, "unknown metric %u", cfg->metric);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, MX_ERR_CONNECTION, "no CUDA device: %s (this library has no CPU path)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(nullptr, MX_ERR_CONNECTION, "device %d out of range [0, %d)", cfg->device, ndev);
+    mx_store *s = new mx_store();
+    s->magic = kStoreMagic;
+    s->cfg = *cfg;
+    if (s->cfg.id_stride == 0) s->cfg.id_stride = 1;
+    s->elem = cfg->dtype == MX_DTYPE_F32 ? 4 : 2;
+    const uint32_t per16 = (uint32_t)(16 / s->elem);
+    s->ld = ceil_div<uint32_t>(cfg->dim, per16) * per16;
+    s->ldq = ceil_div<uint32_t>(cfg->dim, 8) * 8;
+    auto bail = [&](int32_t code, const char *what, cudaError_t ce) {
+        int32_t r = fail(nullptr, code, "%s: %s", what, cudaGetErrorString(ce));
+        mx_store_destroy(s);
+        return r;
+    };
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return bail(MX_ERR_CONNECTION, "cudaSetDevice", e);
+    cudaDeviceProp prop{};
+    if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess)
+        return bail(MX_ERR_CONNECTION, "cudaGetDeviceProperties", e);
+    if (prop.major != 10)
+        {
+            int32_t r = fail(nullptr, MX_ERR_CONNECTION, "device %d is sm_%d%d; this library ships sm_100a code only",
+                             cfg->device, prop.major, prop.minor);
+            mx_store_destroy(s);
+            return r;
+        }
+    s->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(MX_ERR_CONNECTION, "cudaStreamCreate", e);
+    if ((e = cudaMalloc(&s->zero_rows, sizeof(uint32_t) * MX_MAX_K)) != cudaSuccess ||
+        (e = cudaMalloc(&s->n_zero, 4)) != cudaSuccess || (e = cudaMalloc(&s->flags, 4)) != cudaSuccess)
+        return bail(MX_ERR_CONNECTION, "cudaMalloc", e);
+    cudaMemsetAsync(s->n_zero, 0, 4, s->stream);
+    cudaMemsetAsync(s->flags, 0, 4, s->stream);
+    if (cfg->dtype == MX_DTYPE_F16) s->tc = tc_scan_create(s->sm_count, s->ld, cfg->dim);
+    int32_t rc = reserve(s, cfg->capacity ? cfg->capacity : 1024, MX_ERR_CONNECTION);
+    if (rc != MX_OK) {
+        g_last_error = s->last_error;
+        mx_store_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return MX_OK;
+}
+
+void mx_store_destroy(mx_store *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->cfg.device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->tc) tc_scan_destroy(s->tc);
+    cudaFree(s->rows);
+    cudaFree(s->inv_norm);
+    cudaFree(s->zero_rows);
+    cudaFree(s->n_zero);
+    cudaFree(s->flags);
+    cudaFree(s->q_stage);
+    cudaFree(s->cand_s);
+    cudaFree(s->cand_r);
+    cudaFree(s->dev_io);
+    if (s->pinned) cudaFreeHost(s->pinned);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    s->magic = 0;
+    delete s;
+}
+
+int32_t mx_store_add(mx_store *s, const float *vecs, uint64_t n, uint64_t *first_id_out)
+{
+    if (!s) return MX_ERR_INVALID;
+    if (n == 0) {
+        if (first_id_out) *first_id_out = s->cfg.id_offset + s->n * s->cfg.id_stride + 1;
+        return MX_OK;
+    }
+    if (!vecs) return fail(s, MX_ERR_INVALID, "null vectors");
+    int32_t rc;
+    if ((rc = set_device(s)) != MX_OK) return rc;
+    if ((rc = reserve(s, s->n + n, MX_ERR_INSERTION)) != MX_OK) return rc;
+    // stream the batch through a pinned + device staging buffer in chunks
+    const size_t row_bytes = (size_t)s->cfg.dim * sizeof(float);
+    const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(n, (64ull << 20) / row_bytes));
+    if ((rc = ensure_pinned(s, chunk_rows * row_bytes)) != MX_OK) return rc;
+    if ((rc = ensure_dev_io(s, chunk_rows * row_bytes)) != MX_OK) return rc;
+    const uint64_t n_before = s->n;
+    uint64_t done = 0;
+    while (done < n) {
+        const uint64_t c = std::min(chunk_rows, n - done);
+        memcpy(s->pinned, vecs + done * s->cfg.dim, c * row_bytes);
+        MX_CUDA(s, MX_ERR_INSERTION,
+                cudaMemcpyAsync(s->dev_io, s->pinned, c * row_bytes, cudaMemcpyHostToDevice, s->stream));
+        s->n = n_before + done;  // ingest appends at s->n
+        rc = ingest_device(s, (const float *)s->dev_io, c, s->stream);
+        if (rc != MX_OK) {
+            s->n = n_before;
+            return rc;
+        }
+        MX_CUDA(s, MX_ERR_INSERTION, cudaStreamSynchronize(s->stream));  // pinned buffer is reused
+        done += c;
+    }
+    s->n = n_before;
+    return finish_add(s, n, s->stream, first_id_out);
+}
+
+int32_t mx_store_add_device(mx_store *s, const float *vecs_dev, uint64_t n, uint64_t *first_id_out)
+{
+    if (!s) return MX_ERR_INVALID;
+    if (n == 0) {
+        if (first_id_out) *first_id_out = s->cfg.id_offset + s->n * s->cfg.id_stride + 1;
+        return MX_OK;
+    }
+    if (!vecs_dev) return fail(s, MX_ERR_INVALID, "null vectors");
+    int32_t rc;
+    if ((rc = set_device(s)) != MX_OK) return rc;
+    if ((rc = reserve(s, s->n + n, MX_ERR_INSERTION)) != MX_OK) return rc;
+    // the caller's producer may run on another stream: order after everything issued so far
+    MX_CUDA(s, MX_ERR_INSERTION, cudaDeviceSynchronize());
+    if ((rc = ingest_device(s, vecs_dev, n, s->stream)) != MX_OK) return rc;
+    return finish_add(s, n, s->stream, first_id_out);
+}
+
+int32_t mx_store_search_device(mx_store *s, const float *queries_dev, uint32_t nq, uint32_t k, uint64_t *ids_dev,
+                               float *scores_dev, float *dists_dev, uint32_t *counts_dev, void *cuda_stream)
+{
+    if (!s) return MX_ERR_INVALID;
+    int32_t rc;
+    if ((rc = set_device(s)) != MX_OK) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
+    return search_device_impl(s, queries_dev, nq, k, ids_dev, scores_dev, dists_dev, counts_dev, st);
+}
+
+int32_t mx_store_search(mx_store *s, const float *queries, uint32_t nq, uint32_t k, uint64_t *ids_out,
+                        float *scores_out, uint32_t *counts_out)
+{
+    if (!s) return MX_ERR_INVALID;
+    if (!queries || !ids_out || !scores_out || !counts_out) return fail(s, MX_ERR_INVALID, "null buffer");
+    if (k == 0 || k > MX_MAX_K) return fail(s, MX_ERR_INVALID, "k must be in [1, %u]", MX_MAX_K);
+    if (nq == 0) return MX_OK;
+    for (size_t i = 0; i < (size_t)nq * s->cfg.dim; ++i)
+        if (!std::isfinite(queries[i])) return fail(s, MX_ERR_SEARCH, "non-finite value in query %zu", i / s->cfg.dim);
+    int32_t rc;
+    if ((rc = set_device(s)) != MX_OK) return rc;
+    const size_t qb = (size_t)nq * s->cfg.dim * sizeof(float);
+    const size_t ib = (size_t)nq * k * sizeof(uint64_t), sb = (size_t)nq * k * sizeof(float), cb = (size_t)nq * 4;
+    const size_t off_i = (qb + 255) & ~(size_t)255, off_s = off_i + ((ib + 255) & ~(size_t)255),
+                 off_c = off_s + ((sb + 255) & ~(size_t)255), total = off_c + ((cb + 255) & ~(size_t)255);
+    if ((rc = ensure_pinned(s, total)) != MX_OK) return rc;
+    if ((rc = ensure_dev_io(s, total)) != MX_OK) return rc;
+    char *hp = (char *)s->pinned, *dp = (char *)s->dev_io;
+    memcpy(hp, queries, qb);
+    MX_CUDA(s, MX_ERR_SEARCH, cudaMemcpyAsync(dp, hp, qb, cudaMemcpyHostToDevice, s->stream));
+    rc = search_device_impl(s, (const float *)dp, nq, k, (uint64_t *)(dp + off_i), (float *)(dp + off_s), nullptr,
+                            (uint32_t *)(dp + off_c), s->stream);
+    if (rc != MX_OK) return rc;
+    MX_CUDA(s, MX_ERR_SEARCH,
+            cudaMemcpyAsync(hp + off_i, dp + off_i, total - off_i, cudaMemcpyDeviceToHost, s->stream));
+    MX_CUDA(s, MX_ERR_SEARCH, cudaStreamSynchronize(s->stream));
+    memcpy(ids_out, hp + off_i, ib);
+    memcpy(scores_out, hp + off_s, sb);
+    memcpy(counts_out, hp + off_c, cb);
+    return MX_OK;
+}
+
+int32_t mx_merge_topk_device(const uint64_t *ids_dev, const float *dists_dev, const uint32_t *counts_dev,
+                             uint32_t n_shards, uint32_t nq, uint32_t k, uint32_t metric, uint64_t *ids_out_dev,
+                             float *scores_out_dev, uint32_t *counts_out_dev, int32_t device, void *cuda_stream)
+{
+    if (!ids_dev || !dists_dev || !counts_dev || !ids_out_dev || !scores_out_dev || !counts_out_dev)
+        return fail(nullptr, MX_ERR_INVALID, "null buffer");
+    if (k == 0 || k > MX_MAX_K || n_shards == 0 || metric > MX_METRIC_DOT)
+        return fail(nullptr, MX_ERR_INVALID, "bad merge shape");
+    if (nq == 0) return MX_OK;
+    MX_CUDA(nullptr, MX_ERR_CONNECTION, cudaSetDevice(device));
+    MergeParams mp{ids_dev, dists_dev, counts_dev, ids_out_dev, scores_out_dev, counts_out_dev, n_shards, nq, k, metric};
+    MX_CUDA(nullptr, MX_ERR_SEARCH, launch_merge(mp, (cudaStream_t)cuda_stream));
+    return MX_OK;
+}
+
+int32_t mx_store_len(mx_store *s, uint64_t *n_out)
+{
+    if (!s || !n_out) return MX_ERR_INVALID;
+    *n_out = s->n;
+    return MX_OK;
+}
+
+int32_t mx_store_clear(mx_store *s)
+{
+    if (!s) return MX_ERR_INVALID;
+    int32_t rc;
+    if ((rc = set_device(s)) != MX_OK) return rc;
+    MX_CUDA(s, MX_ERR_DELETE, cudaStreamSynchronize(s->stream));
+    s->n = 0;
+    s->zero_dirty = false;
+    MX_CUDA(s, MX_ERR_DELETE, cudaMemsetAsync(s->n_zero, 0, 4, s->stream));
+    return MX_OK;
+}
+
+int32_t mx_store_delete(mx_store *s, uint64_t id)
+{
+    // reference local.rs:29-32 is `unimplemented!()` (a panic); across the C ABI it is a status
+    return fail(s, MX_ERR_UNSUPPORTED, "removing a single point (id %llu) is not supported by the file store",
+                (unsigned long long)id);
+}
+
+int32_t mx_store_sync(mx_store *s)
+{
+    if (!s) return MX_ERR_INVALID;
+    int32_t rc;
+    if ((rc = set_device(s)) != MX_OK) return rc;
+    MX_CUDA(s, MX_ERR_CONNECTION, cudaStreamSynchronize(s->stream));
+    return MX_OK;
+}
+
+int32_t mx_store_info(mx_store *s, uint32_t *dim, uint32_t *dtype, uint32_t *metric, uint64_t *capacity)
+{
+    if (!s) return MX_ERR_INVALID;
+    if (dim) *dim = s->cfg.dim;
+    if (dtype) *dtype = s->cfg.dtype;
+    if (metric) *metric = s->cfg.metric;
+    if (capacity) *capacity = s->capacity;
+    return MX_OK;
+}
+
+int32_t mx_store_scan_path(mx_store *s, uint32_t nq, uint32_t k, int32_t force)
+{
+    if (!s) return MX_ERR_INVALID;
+    if (force >= -1 && force <= 2) s->force_path = force;
+    return (int32_t)pick_path(s, nq, k);
+}
+
+int32_t mx_store_set_timing(mx_store *s, int32_t on)
+{
+    if (!s) return MX_ERR_INVALID;
+    cudaSetDevice(s->cfg.device);
+    s->timer.reset();
+    s->timer.on = on != 0;
+    return MX_OK;
+}
+
+int32_t mx_store_get_timing(mx_store *s, double *scan_ms_total, uint64_t *scan_launches, double *other_ms_total,
+                            uint64_t *other_launches)
+{
+    if (!s) return MX_ERR_INVALID;
+    cudaSetDevice(s->cfg.device);
+    s->timer.collect();
+    if (scan_ms_total) *scan_ms_total = s->timer.total_ms[0];
+    if (scan_launches) *scan_launches = s->timer.launches[0];
+    if (other_ms_total) *other_ms_total = s->timer.total_ms[1];
+    if (other_launches) *other_launches = s->timer.launches[1];
+    return MX_OK;
+}
+
+int32_t mx_store_get_rows(mx_store *s, uint64_t first_row, uint64_t n, float *out)
+{
+    if (!s || !out) return MX_ERR_INVALID;
+    if (first_row + n > s->n) return fail(s, MX_ERR_INVALID, "row range [%llu, %llu) exceeds len %llu",
+                                          (unsigned long long)first_row, (unsigned long long)(first_row + n),
+                                          (unsigned long long)s->n);
+    int32_t rc;
+    if ((rc = set_device(s)) != MX_OK) return rc;
+    const size_t row_bytes = (size_t)s->cfg.dim * sizeof(float);
+    const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(n ? n : 1, (64ull << 20) / row_bytes));
+    if ((rc = ensure_pinned(s, chunk_rows * row_bytes)) != MX_OK) return rc;
+    if ((rc = ensure_dev_io(s, chunk_rows * row_bytes)) != MX_OK) return rc;
+    for (uint64_t done = 0; done < n;) {
+        const uint64_t c = std::min(chunk_rows, n - done);
+        MX_CUDA(s, MX_ERR_FILE_IO, launch_export_rows(s->rows, s->cfg.dtype, s->ld, s->cfg.dim, first_row + done, c,
+                                                      (float *)s->dev_io, s->stream));
+        MX_CUDA(s, MX_ERR_FILE_IO,
+                cudaMemcpyAsync(s->pinned, s->dev_io, c * row_bytes, cudaMemcpyDeviceToHost, s->stream));
+        MX_CUDA(s, MX_ERR_FILE_IO, cudaStreamSynchronize(s->stream));
+        memcpy(out + done * s->cfg.dim, s->pinned, c * row_bytes);
+        done += c;
+    }
+    return MX_OK;
+}
+
+int32_t mx_store_has_file(const char *dir)
+{
+    std::string path;
+    if (!dir_join(dir, path)) return 0;
+    struct stat st;
+    return stat(path.c_str(), &st) == 0 ? 1 : 0;
+}
+
+int32_t mx_store_remove_file(const char *dir)
+{
+    std::string path;
+    if (!dir_join(dir, path)) return MX_ERR_INVALID;
+    if (unlink(path.c_str()) != 0 && errno != ENOENT)
+        return fail(nullptr, MX_ERR_FILE_IO, "unlink %s: %s", path.c_str(), strerror(errno));
+    return MX_OK;
+}
+
+int32_t mx_store_save(mx_store *s, const char *dir)
+{
+    if (!s) return MX_ERR_INVALID;
+    std::string path;
+    if (!dir_join(dir, path)) return fail(s, MX_ERR_INVALID, "null dir");
+    int32_t rc;
+    if ((rc = set_device(s)) != MX_OK) return rc;
+    std::string tmp = path + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(s, MX_ERR_SAVE, "open %s: %s", tmp.c_str(), strerror(errno));
+    FileHeader h{};
+    memcpy(h.magic, kFileMagic, 8);
+    h.dim = s->cfg.dim;
+    h.dtype = s->cfg.dtype;
+    h.metric = s->cfg.metric;
+    h.ld = s->ld;
+    h.n = s->n;
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    const size_t row_bytes = (size_t)s->ld * s->elem;
+    const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / row_bytes);
+    if (ok && (rc = ensure_pinned(s, chunk_rows * row_bytes)) != MX_OK) {
+        fclose(f);
+        return rc;
+    }
+    for (uint64_t done = 0; ok && done < s->n;) {
+        const uint64_t c = std::min(chunk_rows, s->n - done);
+        cudaError_t e = cudaMemcpyAsync(s->pinned, (const char *)s->rows + done * row_bytes, c * row_bytes,
+                                        cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) {
+            fclose(f);
+            unlink(tmp.c_str());
+            return fail(s, MX_ERR_SAVE, "device read failed: %s", cudaGetErrorString(e));
+        }
+        ok = fwrite(s->pinned, row_bytes, c, f) == c;
+        done += c;
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) {
+        unlink(tmp.c_str());
+        return fail(s, MX_ERR_SAVE, "write %s: %s", path.c_str(), strerror(errno));
+    }
+    return MX_OK;
+}
+
+int32_t mx_store_load(const char *dir, int32_t device, mx_store **out)
+{
+    if (!out) return fail(nullptr, MX_ERR_INVALID, "null argument");
+    *out = nullptr;
+    std::string path;
+    if (!dir_join(dir, path)) return fail(nullptr, MX_ERR_INVALID, "null dir");
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return fail(nullptr, MX_ERR_FILE_IO, "open %s: %s", path.c_str(), strerror(errno));
+    FileHeader h{};
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kFileMagic, 8) != 0) {
+        fclose(f);
+        return fail(nullptr, MX_ERR_SERDE, "%s: bad header", path.c_str());
+    }
+    mx_store_cfg cfg{};
+    cfg.dim = h.dim;
+    cfg.dtype = h.dtype;
+    cfg.metric = h.metric;
+    cfg.device = device;
+    cfg.capacity = h.n + h.n / 8 + 1024;
+    mx_store *s = nullptr;
+    int32_t rc = mx_store_create(&cfg, &s);
+    if (rc != MX_OK) {
+        fclose(f);
+        return rc;
+    }
+    auto bail = [&](int32_t code, const char *msg) {
+        int32_t r = fail(nullptr, code, "%s: %s", path.c_str(), msg);
+        fclose(f);
+        mx_store_destroy(s);
+        return r;
+    };
+    if (h.ld != s->ld) return bail(MX_ERR_SERDE, "row stride mismatch");
+    // raw stored rows -> widen to f32 on the device -> normal ingest (rounding is idempotent)
+    const size_t row_bytes = (size_t)s->ld * s->elem;
+    const uint64_t chunk_rows = std::max<uint64_t>(1, (32ull << 20) / row_bytes);
+    void *raw_dev = nullptr;
+    float *f32_dev = nullptr;
+    if (cudaMalloc(&raw_dev, chunk_rows * row_bytes) != cudaSuccess ||
+        cudaMalloc(&f32_dev, chunk_rows * (size_t)h.dim * 4) != cudaSuccess) {
+        cudaFree(raw_dev);
+        return bail(MX_ERR_CONNECTION, "cudaMalloc failed");
+    }
+    rc = ensure_pinned(s, chunk_rows * row_bytes);
+    for (uint64_t done = 0; rc == MX_OK && done < h.n;) {
+        const uint64_t c = std::min(chunk_rows, h.n - done);
+        if (fread(s->pinned, row_bytes, c, f) != c) {
+            rc = fail(nullptr, MX_ERR_SERDE, "%s: truncated file", path.c_str());
+            break;
+        }
+        cudaMemcpyAsync(raw_dev, s->pinned, c * row_bytes, cudaMemcpyHostToDevice, s->stream);
+        launch_export_rows(raw_dev, s->cfg.dtype, s->ld, s->cfg.dim, 0, c, f32_dev, s->stream);
+        rc = ingest_device(s, f32_dev, c, s->stream);
+        if (rc == MX_OK) rc = finish_add(s, c, s->stream, nullptr);
+        if (rc != MX_OK) g_last_error = s->last_error;
+        done += c;
+    }
+    cudaFree(raw_dev);
+    cudaFree(f32_dev);
+    fclose(f);
+    if (rc != MX_OK) {
+        mx_store_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return MX_OK;
+}
+
+}  // extern "C"
