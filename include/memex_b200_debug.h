@@ -1,0 +1,26 @@
+/*
+ * memex_b200_debug.h -- test-only entry points of libmemex_b200.so.
+ *
+ * NOT part of the drop-in boundary (that is memex_b200.h): these expose single kernels so that
+ * tests/ can check them in isolation against a plain reference.  All pointers are DEVICE pointers.
+ */
+#ifndef MEMEX_B200_DEBUG_H
+#define MEMEX_B200_DEBUG_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* out[M,N] = epi(A[M,K] . W[N,K]^T) on the tcgen05 path.
+ *   fmt 1 = bf16, 0 = f16 (A, W, residual, out);  bias/gamma/beta f32
+ *   epi 0 = +bias, 1 = +bias, erf-GELU, 2 = LayerNorm(+bias +residual) (N must be 384)
+ * returns 0 or a negative MX_ERR_* code; synchronous. */
+int32_t mx_debug_gemm(const void *A, const void *W, const float *bias, const void *residual, const float *gamma,
+                      const float *beta, void *out, uint32_t M, uint32_t N, uint32_t K, uint32_t fmt, uint32_t epi,
+                      float ln_eps, int32_t device);
+const char *mx_debug_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

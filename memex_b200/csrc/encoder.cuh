@@ -1,0 +1,33 @@
+// encoder.cuh -- launchers of the encoder's non-GEMM kernels (encoder_kernels.cu) and of the
+// attention kernels.  ACT selects the activation storage type: 0 = f32 (validation path),
+// 1 = bf16, 2 = f16 (tensor-core paths).
+#pragma once
+#include "common.cuh"
+
+namespace mx {
+
+enum ActType { ACT_F32 = 0, ACT_BF16 = 1, ACT_F16 = 2 };
+inline size_t act_size(int act) { return act == ACT_F32 ? 4 : 2; }
+
+// K4: x[t, :] = LayerNorm(word[ids[t]] + pos[t % S] + type[0])
+cudaError_t launch_embed_ln(const int32_t *ids, const float *word, const float *pos, const float *type0,
+                            const float *gamma, const float *beta, float eps, void *x, int act, uint32_t n_tokens,
+                            uint32_t S, uint32_t H, uint32_t vocab, cudaStream_t st);
+
+// K6 (CUDA-core version): ctx = softmax(q k^T / sqrt(dh) + mask(lens)) v, from the fused qkv buffer
+// [T, 3H] (q | k | v, heads contiguous inside each).  Rows at or beyond lens[b] are written as zero.
+cudaError_t launch_attention_simt(const void *qkv, const int32_t *lens_dev, void *ctx, int act, uint32_t B, uint32_t S,
+                                  uint32_t H, uint32_t heads, cudaStream_t st);
+
+// fp32 path only: x = LayerNorm(y + residual) (the GEMM already added the bias)
+cudaError_t launch_add_ln_f32(const float *y, const float *residual, const float *gamma, const float *beta, float eps,
+                              float *out, uint32_t rows, uint32_t H, cudaStream_t st);
+
+// K10: masked mean-pool over the first lens[b] tokens, optional L2 normalise -> out [B, H] f32
+cudaError_t launch_pool_normalize(const void *x, int act, const int32_t *lens_dev, float *out, uint32_t B, uint32_t S,
+                                  uint32_t H, uint32_t normalize, cudaStream_t st);
+
+// f32 -> 16-bit weight conversion (rows of `cols`, written at out + row * ldo)
+cudaError_t launch_convert_weight(const float *src, void *dst, int act, uint64_t numel, cudaStream_t st);
+
+}  // namespace mx

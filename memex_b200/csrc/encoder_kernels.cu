@@ -1,0 +1,441 @@
+// encoder_kernels.cu -- the encoder's non-GEMM stages and the fp32 validation GEMM.
+//
+// Restates, op for op, what rust-bert's BertForSentenceEmbeddings + Pooling + Normalize run on
+// libtorch for `model.encode(&segments)` (reference lib/libmemex/src/llm/embedding.rs:109):
+//   BertEmbeddings : word + position + token_type(0) -> LayerNorm(eps)              (K4)
+//   BertSelfAttention: softmax(q k^T / sqrt(dh) + padding mask) v                    (K6, SIMT form)
+//   BertSelfOutput / BertOutput: LayerNorm(dense(x) + residual)                      (fp32 path)
+//   Pooling(mean over attention_mask) -> Normalize(p=2)                              (K10)
+// All statistics, softmax and pooling arithmetic is f32 regardless of the activation type.
+#include "common.cuh"
+#include "encoder.cuh"
+#include "gemm.cuh"
+
+namespace mx {
+
+template <int ACT>
+struct Act;
+template <>
+struct Act<ACT_F32> {
+    using T = float;
+    __device__ static __forceinline__ float ld(const T *p) { return *p; }
+    __device__ static __forceinline__ void st(T *p, float v) { *p = v; }
+};
+template <>
+struct Act<ACT_BF16> {
+    using T = __nv_bfloat16;
+    __device__ static __forceinline__ float ld(const T *p) { return __bfloat162float(*p); }
+    __device__ static __forceinline__ void st(T *p, float v) { *p = __float2bfloat16_rn(v); }
+};
+template <>
+struct Act<ACT_F16> {
+    using T = __half;
+    __device__ static __forceinline__ float ld(const T *p) { return __half2float(*p); }
+    __device__ static __forceinline__ void st(T *p, float v) { *p = __float2half_rn(v); }
+};
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+constexpr int kMaxHPerLane = 32;  // H <= 1024
+
+// two-pass LayerNorm of a row held as vals[i] = row[lane + 32 i]
+__device__ __forceinline__ void row_layer_norm(float (&vals)[kMaxHPerLane], uint32_t H, float eps, float &mean,
+                                               float &rstd)
+{
+    const uint32_t lane = lane_id();
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxHPerLane; ++i)
+        if (lane + 32 * i < H) s += vals[i];
+    mean = warp_sum(s) / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxHPerLane; ++i)
+        if (lane + 32 * i < H) {
+            const float d = vals[i] - mean;
+            q = fmaf(d, d, q);
+        }
+    rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: embedding gather + LayerNorm, one warp per token
+// ---------------------------------------------------------------------------------------------
+template <int ACT>
+__global__ void __launch_bounds__(256) embed_ln_kernel(const int32_t *__restrict__ ids, const float *__restrict__ word,
+                                                       const float *__restrict__ pos, const float *__restrict__ type0,
+                                                       const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                       float eps, typename Act<ACT>::T *__restrict__ x, uint32_t n_tokens,
+                                                       uint32_t S, uint32_t H, uint32_t vocab)
+{
+    const uint32_t t = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (t >= n_tokens) return;
+    const uint32_t lane = lane_id();
+    uint32_t id = (uint32_t)ids[t];
+    if (id >= vocab) id = 0;  // out-of-vocabulary ids read the [PAD] row instead of faulting
+    const float *wr = word + (size_t)id * H;
+    const float *pr = pos + (size_t)(t % S) * H;
+    float vals[kMaxHPerLane];
+#pragma unroll
+    for (int i = 0; i < kMaxHPerLane; ++i) {
+        const uint32_t c = lane + 32 * i;
+        vals[i] = c < H ? (wr[c] + type0[c]) + pr[c] : 0.f;   // HF: (inputs_embeds + token_type) + position
+    }
+    float mean, rstd;
+    row_layer_norm(vals, H, eps, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < kMaxHPerLane; ++i) {
+        const uint32_t c = lane + 32 * i;
+        if (c < H) Act<ACT>::st(x + (size_t)t * H + c, (vals[i] - mean) * rstd * gamma[c] + beta[c]);
+    }
+}
+
+cudaError_t launch_embed_ln(const int32_t *ids, const float *word, const float *pos, const float *type0,
+                            const float *gamma, const float *beta, float eps, void *x, int act, uint32_t n_tokens,
+                            uint32_t S, uint32_t H, uint32_t vocab, cudaStream_t st)
+{
+    if (H > 32 * kMaxHPerLane) return cudaErrorInvalidValue;
+    const unsigned grid = ceil_div<uint32_t>(n_tokens, 8);
+#define MX_L(A)                                                                                              \
+    embed_ln_kernel<A><<<grid, 256, 0, st>>>(ids, word, pos, type0, gamma, beta, eps, (typename Act<A>::T *)x, \
+                                             n_tokens, S, H, vocab)
+    if (act == ACT_F32) MX_L(ACT_F32);
+    else if (act == ACT_BF16) MX_L(ACT_BF16);
+    else MX_L(ACT_F16);
+#undef MX_L
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6, SIMT form: one CTA per (sequence, head, 64-query chunk); keys staged through shared memory in
+// blocks of 128 with an online softmax; one warp works on 8 queries.
+// ---------------------------------------------------------------------------------------------
+constexpr int kAttQ = 64;      // queries per CTA
+constexpr int kAttKB = 128;    // keys per staged block
+constexpr int kAttWarps = 8;
+constexpr int kAttQPW = kAttQ / kAttWarps;
+
+template <int ACT, int DH>
+__global__ void __launch_bounds__(kAttWarps * 32) attention_simt_kernel(const typename Act<ACT>::T *__restrict__ qkv,
+                                                                       const int32_t *__restrict__ lens,
+                                                                       typename Act<ACT>::T *__restrict__ ctx, uint32_t S,
+                                                                       uint32_t H, uint32_t heads, float scale)
+{
+    using T = typename Act<ACT>::T;
+    constexpr int DPL = DH / 32;  // output dims per lane
+    extern __shared__ __align__(16) float att_smem[];
+    float *qs = att_smem;                        // [kAttQ][DH]
+    float *ks = qs + kAttQ * DH;                 // [kAttKB][DH + 1]
+    float *vs = ks + kAttKB * (DH + 1);          // [kAttKB][DH]
+
+    const uint32_t b = blockIdx.x / heads, h = blockIdx.x % heads;
+    const uint32_t q0 = blockIdx.y * kAttQ;
+    const uint32_t len = min((uint32_t)max(lens[b], 0), S);
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const size_t ld = 3 * (size_t)H;
+    const T *base = qkv + (size_t)b * S * ld + (size_t)h * DH;
+
+    if (q0 >= len) {
+        // whole chunk is padding: zero rows keep the following GEMMs finite
+        for (uint32_t i = threadIdx.x; i < kAttQ * DH; i += blockDim.x) {
+            const uint32_t qi = q0 + i / DH;
+            if (qi < S) Act<ACT>::st(ctx + ((size_t)b * S + qi) * H + h * DH + i % DH, 0.f);
+        }
+        return;
+    }
+    for (uint32_t i = threadIdx.x; i < kAttQ * DH; i += blockDim.x) {
+        const uint32_t qi = q0 + i / DH;
+        qs[i] = qi < S ? Act<ACT>::ld(base + (size_t)qi * ld + i % DH) * scale : 0.f;
+    }
+
+    float m[kAttQPW], l[kAttQPW], acc[kAttQPW][DPL];
+#pragma unroll
+    for (int i = 0; i < kAttQPW; ++i) {
+        m[i] = kNegInf;
+        l[i] = 0.f;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) acc[i][d] = 0.f;
+    }
+
+    for (uint32_t k0 = 0; k0 < len; k0 += kAttKB) {
+        const uint32_t kn = min((uint32_t)kAttKB, len - k0);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < kAttKB * DH; i += blockDim.x) {
+            const uint32_t kj = i / DH, d = i % DH;
+            float kv = 0.f, vv = 0.f;
+            if (kj < kn) {
+                kv = Act<ACT>::ld(base + (size_t)(k0 + kj) * ld + H + d);
+                vv = Act<ACT>::ld(base + (size_t)(k0 + kj) * ld + 2 * H + d);
+            }
+            ks[kj * (DH + 1) + d] = kv;
+            vs[kj * DH + d] = vv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kAttQPW; ++i) {
+            const float *q = qs + (warp * kAttQPW + i) * DH;
+            float sc[kAttKB / 32];
+            float bmax = kNegInf;
+#pragma unroll
+            for (int j = 0; j < kAttKB / 32; ++j) {
+                const uint32_t kj = lane + 32 * j;
+                float s = 0.f;
+#pragma unroll 8
+                for (int d = 0; d < DH; ++d) s = fmaf(q[d], ks[kj * (DH + 1) + d], s);
+                sc[j] = kj < kn ? s : kNegInf;
+                bmax = fmaxf(bmax, sc[j]);
+            }
+            bmax = warp_max(bmax);
+            const float mnew = fmaxf(m[i], bmax);
+            const float corr = __expf(m[i] - mnew);   // m = -inf on the first block -> 0
+            float psum = 0.f;
+#pragma unroll
+            for (int j = 0; j < kAttKB / 32; ++j) {
+                sc[j] = __expf(sc[j] - mnew);
+                psum += sc[j];
+            }
+            l[i] = l[i] * corr + warp_sum(psum);
+            m[i] = mnew;
+#pragma unroll
+            for (int d = 0; d < DPL; ++d) acc[i][d] *= corr;
+#pragma unroll
+            for (int j = 0; j < kAttKB / 32; ++j) {
+                for (int src = 0; src < 32; ++src) {
+                    const float pj = __shfl_sync(0xffffffffu, sc[j], src);
+                    const uint32_t kj = src + 32 * j;
+#pragma unroll
+                    for (int d = 0; d < DPL; ++d) acc[i][d] = fmaf(pj, vs[kj * DH + lane + 32 * d], acc[i][d]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kAttQPW; ++i) {
+        const uint32_t qi = q0 + warp * kAttQPW + i;
+        if (qi >= S) continue;
+        const bool valid = qi < len;
+        const float inv = valid ? 1.0f / l[i] : 0.f;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d)
+            Act<ACT>::st(ctx + ((size_t)b * S + qi) * H + h * DH + lane + 32 * d, valid ? acc[i][d] * inv : 0.f);
+    }
+}
+
+template <int ACT, int DH>
+static cudaError_t launch_att(const void *qkv, const int32_t *lens, void *ctx, uint32_t B, uint32_t S, uint32_t H,
+                              uint32_t heads, cudaStream_t st)
+{
+    using T = typename Act<ACT>::T;
+    auto kern = attention_simt_kernel<ACT, DH>;
+    const size_t smem = sizeof(float) * (kAttQ * DH + kAttKB * (DH + 1) + kAttKB * DH);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid(B * heads, ceil_div<uint32_t>(S, kAttQ));
+    kern<<<grid, kAttWarps * 32, smem, st>>>((const T *)qkv, lens, (T *)ctx, S, H, heads, 1.0f / sqrtf((float)DH));
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_attention_simt(const void *qkv, const int32_t *lens_dev, void *ctx, int act, uint32_t B, uint32_t S,
+                                  uint32_t H, uint32_t heads, cudaStream_t st)
+{
+    const uint32_t dh = H / heads;
+#define MX_A(A)                                                                       \
+    switch (dh) {                                                                     \
+        case 32: return launch_att<A, 32>(qkv, lens_dev, ctx, B, S, H, heads, st);    \
+        case 64: return launch_att<A, 64>(qkv, lens_dev, ctx, B, S, H, heads, st);    \
+        case 128: return launch_att<A, 128>(qkv, lens_dev, ctx, B, S, H, heads, st);  \
+        default: return cudaErrorInvalidValue;                                        \
+    }
+    if (act == ACT_F32) { MX_A(ACT_F32) }
+    if (act == ACT_BF16) { MX_A(ACT_BF16) }
+    MX_A(ACT_F16)
+#undef MX_A
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 path: out = LayerNorm(y + residual), one warp per row
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add_ln_f32_kernel(const float *__restrict__ y, const float *__restrict__ residual,
+                                                         const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                         float eps, float *__restrict__ out, uint32_t rows, uint32_t H)
+{
+    const uint32_t r = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const uint32_t lane = lane_id();
+    float vals[kMaxHPerLane];
+#pragma unroll
+    for (int i = 0; i < kMaxHPerLane; ++i) {
+        const uint32_t c = lane + 32 * i;
+        vals[i] = c < H ? y[(size_t)r * H + c] + residual[(size_t)r * H + c] : 0.f;
+    }
+    float mean, rstd;
+    row_layer_norm(vals, H, eps, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < kMaxHPerLane; ++i) {
+        const uint32_t c = lane + 32 * i;
+        if (c < H) out[(size_t)r * H + c] = (vals[i] - mean) * rstd * gamma[c] + beta[c];
+    }
+}
+
+cudaError_t launch_add_ln_f32(const float *y, const float *residual, const float *gamma, const float *beta, float eps,
+                              float *out, uint32_t rows, uint32_t H, cudaStream_t st)
+{
+    if (H > 32 * kMaxHPerLane) return cudaErrorInvalidValue;
+    add_ln_f32_kernel<<<ceil_div<uint32_t>(rows, 8), 256, 0, st>>>(y, residual, gamma, beta, eps, out, rows, H);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K10: masked mean-pool + L2 normalise, one CTA per sequence
+// ---------------------------------------------------------------------------------------------
+template <int ACT>
+__global__ void __launch_bounds__(256) pool_normalize_kernel(const typename Act<ACT>::T *__restrict__ x,
+                                                             const int32_t *__restrict__ lens, float *__restrict__ out,
+                                                             uint32_t S, uint32_t H, uint32_t normalize)
+{
+    __shared__ float red[8];
+    __shared__ float inv_s;
+    const uint32_t b = blockIdx.x;
+    const uint32_t len = min((uint32_t)max(lens[b], 0), S);
+    const float denom = fmaxf((float)len, 1e-9f);   // sentence-transformers Pooling: clamp(sum_mask, 1e-9)
+    float sq = 0.f;
+    float pooled[4];                                 // H <= 1024 with 256 threads
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t c = threadIdx.x + 256 * i;
+        float s = 0.f;
+        if (c < H)
+            for (uint32_t t = 0; t < len; ++t) s += Act<ACT>::ld(x + ((size_t)b * S + t) * H + c);
+        pooled[i] = s / denom;
+        sq = fmaf(pooled[i], pooled[i], sq);
+    }
+    sq = warp_sum(sq);
+    if (lane_id() == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        inv_s = normalize ? 1.0f / fmaxf(sqrtf(t), 1e-12f) : 1.0f;   // F.normalize(p=2, eps=1e-12)
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t c = threadIdx.x + 256 * i;
+        if (c < H) out[(size_t)b * H + c] = pooled[i] * inv_s;
+    }
+}
+
+cudaError_t launch_pool_normalize(const void *x, int act, const int32_t *lens_dev, float *out, uint32_t B, uint32_t S,
+                                  uint32_t H, uint32_t normalize, cudaStream_t st)
+{
+    if (H > 1024) return cudaErrorInvalidValue;
+    if (act == ACT_F32)
+        pool_normalize_kernel<ACT_F32><<<B, 256, 0, st>>>((const float *)x, lens_dev, out, S, H, normalize);
+    else if (act == ACT_BF16)
+        pool_normalize_kernel<ACT_BF16><<<B, 256, 0, st>>>((const __nv_bfloat16 *)x, lens_dev, out, S, H, normalize);
+    else
+        pool_normalize_kernel<ACT_F16><<<B, 256, 0, st>>>((const __half *)x, lens_dev, out, S, H, normalize);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int ACT>
+__global__ void convert_weight_kernel(const float *__restrict__ src, typename Act<ACT>::T *__restrict__ dst, uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) Act<ACT>::st(dst + i, src[i]);
+}
+
+cudaError_t launch_convert_weight(const float *src, void *dst, int act, uint64_t numel, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)ceil_div<uint64_t>(numel, 256);
+    if (act == ACT_F32)
+        convert_weight_kernel<ACT_F32><<<grid, 256, 0, st>>>(src, (float *)dst, numel);
+    else if (act == ACT_BF16)
+        convert_weight_kernel<ACT_BF16><<<grid, 256, 0, st>>>(src, (__nv_bfloat16 *)dst, numel);
+    else
+        convert_weight_kernel<ACT_F16><<<grid, 256, 0, st>>>(src, (__half *)dst, numel);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 validation GEMM: out = epi(A . W^T), 64x64 tile, 256 threads x (4x4), K step 16
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(256) gemm_ref_kernel(GemmRefParams p)
+{
+    __shared__ float As[16][64 + 4];
+    __shared__ float Ws[16][64 + 4];
+    const uint32_t tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    const uint32_t m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (uint32_t k0 = 0; k0 < p.K; k0 += 16) {
+        for (uint32_t i = threadIdx.x; i < 64 * 16; i += 256) {
+            const uint32_t r = i / 16, c = i % 16;
+            As[c][r] = (m0 + r < p.M && k0 + c < p.K) ? p.A[(size_t)(m0 + r) * p.K + k0 + c] : 0.f;
+            Ws[c][r] = (n0 + r < p.N && k0 + c < p.K) ? p.W[(size_t)(n0 + r) * p.K + k0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i] = As[kk][ty * 4 + i];
+                w[i] = Ws[kk][tx * 4 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+            if (m < p.M && n < p.N) {
+                float v = acc[i][j] + p.bias[n];
+                if (EPI == EPI_BIAS_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+                p.out[(size_t)m * p.N + n] = v;
+            }
+        }
+}
+
+cudaError_t launch_gemm_ref(const GemmRefParams &p, int epi, cudaStream_t st)
+{
+    dim3 grid(ceil_div<uint32_t>(p.N, 64), ceil_div<uint32_t>(p.M, 64));
+    if (epi == EPI_BIAS_GELU)
+        gemm_ref_kernel<EPI_BIAS_GELU><<<grid, 256, 0, st>>>(p);
+    else
+        gemm_ref_kernel<EPI_BIAS><<<grid, 256, 0, st>>>(p);
+    count_launch();
+    if (epi == EPI_BIAS_RES_LN) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        return launch_add_ln_f32(p.out, p.residual, p.gamma, p.beta, p.ln_eps, p.out, p.M, p.N, st);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace mx

@@ -1,0 +1,317 @@
+// gemm_tc.cu -- K5/K7/K8/K9: the encoder's dense layers on tcgen05 tensor cores.
+//
+//   out[M, N] = epilogue( A[M, K] . W[N, K]^T )          A, W bf16 K-major; f32 accumulate in TMEM
+//
+// replaces the nn.Linear GEMMs libtorch executes for rust-bert's BertEncoder under
+// `model.encode(&segments)` (reference lib/libmemex/src/llm/embedding.rs:109), with the
+// element-wise work that follows each of them fused into the epilogue:
+//   EPI_BIAS       + bias                                   (fused Q|K|V projection)
+//   EPI_BIAS_GELU  + bias, erf-GELU                         (intermediate.dense)
+//   EPI_BIAS_RES_LN+ bias, + residual, LayerNorm(gamma,beta)(attention.output / output; BN == N)
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected
+// lane; also owns the TMEM allocation), warps 2..5 = epilogue (TMEM -> registers -> global).
+// Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two
+// accumulator stages when 2 * BN <= 512 columns), and the static tile schedule
+// tile = blockIdx.x + i * gridDim.x with the N index fastest (concurrent CTAs share A rows in L2).
+#include "common.cuh"
+#include "gemm.cuh"
+#include "tc.cuh"
+
+namespace mx {
+
+using namespace tc;
+
+constexpr int kGemmThreads = 192;
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // 128 bytes of bf16: one swizzle atom
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kChunks = BN > 256 ? 2 : 1;          // one tcgen05.mma covers N <= 256
+    static constexpr int kChunkN = BN / kChunks;
+    static constexpr int kAccStages = (2 * BN <= 512) ? 2 : 1;
+    static constexpr int kTmemCols = (kAccStages * BN <= 128) ? 128 : (kAccStages * BN <= 256 ? 256 : 512);
+    static constexpr int kStageBytes = kBM * kBK * 2 + BN * kBK * 2;
+    static constexpr int kStages = (200 * 1024) / kStageBytes < 8 ? (200 * 1024) / kStageBytes : 8;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(kChunkN % 16 == 0 && kChunkN <= 256, "invalid UMMA N");
+    static_assert((BN * kBK * 2 / kChunks) % 1024 == 0, "B chunks must stay 1024-byte aligned");
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int FMT>
+__device__ __forceinline__ uint32_t pack16(float a, float b)
+{
+    if constexpr (FMT == 1) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t *>(&h);
+    } else {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t *>(&h);
+    }
+}
+template <int FMT>
+__device__ __forceinline__ float2 unpack16(uint32_t u)
+{
+    if constexpr (FMT == 1)
+        return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&u));
+    else
+        return __half22float2(*reinterpret_cast<__half2 *>(&u));
+}
+
+template <int BN, int EPI, int FMT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p)
+{
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t *empty = full + Cfg::kStages;
+    uint64_t *tmem_full = empty + Cfg::kStages;
+    uint64_t *tmem_empty = tmem_full + Cfg::kAccStages;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + Cfg::kAccStages);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tiles_n = p.N / BN;
+    const uint32_t tiles_m = (p.M + kBM - 1) / kBM;
+    const uint32_t n_tiles = tiles_m * tiles_n;
+    const uint32_t k_blocks = (p.K + kBK - 1) / kBK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < Cfg::kStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < Cfg::kAccStages; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const uint32_t m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+                for (uint32_t kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char *sa = smem + stage * Cfg::kStageBytes;
+                    unsigned char *sb = sa + kBM * kBK * 2;
+                    mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+                    tma_load_2d(sa, &tmA, &full[stage], kb * kBK, m_blk * kBM, kEvictFirst);
+#pragma unroll
+                    for (int c = 0; c < Cfg::kChunks; ++c)
+                        tma_load_2d(sb + c * (Cfg::kChunkN * kBK * 2), &tmB, &full[stage], kb * kBK,
+                                    n_blk * BN + c * Cfg::kChunkN, kEvictLast);
+                    if (++stage == Cfg::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(kBM, Cfg::kChunkN, FMT);
+            uint32_t stage = 0, phase = 0, local = 0;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+                const uint32_t as = local % Cfg::kAccStages, aphase = (local / Cfg::kAccStages) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                for (uint32_t kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t sb = sa + kBM * kBK * 2;
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        const uint64_t adesc = make_smem_desc(sa + k * 32);
+#pragma unroll
+                        for (int c = 0; c < Cfg::kChunks; ++c) {
+                            const uint64_t bdesc = make_smem_desc(sb + c * (Cfg::kChunkN * kBK * 2) + k * 32);
+                            umma(tmem_base + as * BN + c * Cfg::kChunkN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == Cfg::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full[as]);
+            }
+        }
+    } else {
+        // ================= epilogue: 4 warps, warp % 4 selects the TMEM lane quarter =================
+        const uint32_t quarter = warp & 3;
+        uint32_t local = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+            const uint32_t m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+            const uint32_t as = local % Cfg::kAccStages, aphase = (local / Cfg::kAccStages) & 1;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const uint32_t row = m_blk * kBM + quarter * 32 + lane;
+            const bool row_ok = row < p.M;
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * BN;
+            const uint32_t col0 = n_blk * BN;
+            uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + (size_t)row * p.ldo + col0;
+
+            if constexpr (EPI == EPI_BIAS_RES_LN) {
+                // pass 1: x = acc + bias + residual, kept in TMEM; row sums
+                const uint16_t *rrow = reinterpret_cast<const uint16_t *>(p.residual) + (size_t)row * p.ldr + col0;
+                float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    uint4 rr[4];
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4 *>(rrow + c * 32 + j * 8);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rr[j] = make_uint4(0, 0, 0, 0);
+                    }
+                    const uint32_t *rh = reinterpret_cast<const uint32_t *>(rr);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 r2 = unpack16<FMT>(rh[j]);
+                        const float x0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + col0 + c * 32 + 2 * j) + r2.x;
+                        const float x1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + col0 + c * 32 + 2 * j + 1) + r2.y;
+                        sum += x0 + x1;
+                        sq = fmaf(x0, x0, fmaf(x1, x1, sq));
+                        v[2 * j] = __float_as_uint(x0);
+                        v[2 * j + 1] = __float_as_uint(x1);
+                    }
+                    tmem_st32(taddr + c * 32, v);
+                }
+                tmem_st_wait();
+                const float mean = sum * (1.0f / BN);
+                const float var = fmaxf(sq * (1.0f / BN) - mean * mean, 0.f);
+                const float rstd = rsqrtf(var + p.ln_eps);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    uint32_t o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n0 = col0 + c * 32 + 2 * j;
+                        const float y0 = (__uint_as_float(v[2 * j]) - mean) * rstd * __ldg(p.gamma + n0) + __ldg(p.beta + n0);
+                        const float y1 =
+                            (__uint_as_float(v[2 * j + 1]) - mean) * rstd * __ldg(p.gamma + n0 + 1) + __ldg(p.beta + n0 + 1);
+                        o[j] = pack16<FMT>(y0, y1);
+                    }
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4 *>(orow + c * 32 + j * 8) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    uint32_t o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float x0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + col0 + c * 32 + 2 * j);
+                        float x1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + col0 + c * 32 + 2 * j + 1);
+                        if constexpr (EPI == EPI_BIAS_GELU) {
+                            x0 = gelu_erf(x0);
+                            x1 = gelu_erf(x1);
+                        }
+                        o[j] = pack16<FMT>(x0, x1);
+                    }
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4 *>(orow + c * 32 + j * 8) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+template <int BN, int EPI, int FMT>
+static cudaError_t launch_cfg(const GemmParams &p, const CUtensorMap &tmA, const CUtensorMap &tmB, int sm_count,
+                              cudaStream_t st)
+{
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm_tc_kernel<BN, EPI, FMT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    const uint32_t n_tiles = ceil_div<uint32_t>(p.M, kBM) * (p.N / BN);
+    const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+int gemm_tc_block_n(uint32_t N, int epi)
+{
+    if (epi == EPI_BIAS_RES_LN) return N == 384 ? 384 : 0;   // the row statistic needs the whole row in one CTA
+    if (N % 256 == 0) return 256;
+    if (N % 192 == 0) return 192;
+    if (N % 128 == 0) return 128;
+    return 0;
+}
+
+cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStream_t st, const char **why)
+{
+    const int bn = gemm_tc_block_n(p.N, epi);
+    if (bn == 0 || p.K % 8 != 0 || p.lda % 8 != 0 || p.ldw % 8 != 0 || p.ldo % 8 != 0) {
+        if (why) *why = "unsupported GEMM shape for the tcgen05 path";
+        return cudaErrorInvalidValue;
+    }
+    CUtensorMap tmA, tmB;
+    const uint32_t chunk_rows = bn > 256 ? bn / 2 : bn;
+    if (!make_tmap_k_major_16bit(&tmA, p.A, p.M, p.K, p.lda, kBM, p.fmt == 1) ||
+        !make_tmap_k_major_16bit(&tmB, p.W, p.N, p.K, p.ldw, chunk_rows, p.fmt == 1)) {
+        if (why) *why = "cuTensorMapEncodeTiled failed";
+        return cudaErrorInvalidValue;
+    }
+#define MX_GEMM(BN_, EPI_)                                                      \
+    return p.fmt == 1 ? launch_cfg<BN_, EPI_, 1>(p, tmA, tmB, sm_count, st)     \
+                      : launch_cfg<BN_, EPI_, 0>(p, tmA, tmB, sm_count, st)
+    if (epi == EPI_BIAS_RES_LN) MX_GEMM(384, EPI_BIAS_RES_LN);
+    if (epi == EPI_BIAS_GELU) {
+        if (bn == 256) MX_GEMM(256, EPI_BIAS_GELU);
+        if (bn == 192) MX_GEMM(192, EPI_BIAS_GELU);
+        MX_GEMM(128, EPI_BIAS_GELU);
+    }
+    if (bn == 256) MX_GEMM(256, EPI_BIAS);
+    if (bn == 192) MX_GEMM(192, EPI_BIAS);
+    MX_GEMM(128, EPI_BIAS);
+#undef MX_GEMM
+}
+
+}  // namespace mx

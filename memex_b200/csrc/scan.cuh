@@ -73,4 +73,16 @@ cudaError_t launch_export_rows(const void *rows, uint32_t dtype, uint32_t ld, ui
 cudaError_t launch_stage_queries(const float *q, uint32_t nq, uint32_t dim, uint32_t ldq, float *out,
                                  cudaStream_t st);
 
+// K2: fp16 batched scan on tcgen05 (scan_tc.cu).  Same candidate-list contract as the stream scan.
+struct TcScanState;
+TcScanState *tc_scan_create(int sm_count, uint32_t ld, uint32_t dim);  // nullptr if shape unsupported
+void tc_scan_destroy(TcScanState *t);
+void tc_scan_invalidate(TcScanState *t);  // the row matrix moved: tensor maps must be rebuilt
+bool tc_scan_supports(const TcScanState *t, uint32_t k);
+uint32_t tc_scan_max_k();
+uint32_t tc_scan_lists(const TcScanState *t, uint64_t n_rows);
+uint32_t tc_scan_lcap(uint32_t k);
+cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacity, uint32_t k, KernelTimer *timer,
+                           cudaStream_t st, const char **why);
+
 }  // namespace mx

@@ -1,0 +1,228 @@
+"""Host-side mirror of memex's sentence embedder over the C ABI (Python face).
+
+Mirrors reference lib/libmemex/src/llm/embedding.rs: EmbeddingError (:10-16), EmbeddingResult
+(:18-22), EmbeddingsModelType (:24-55), ModelConfig (:57-73, default AllMiniLmL12V2 / 256 / 86),
+SentenceEmbedder::{spawn, encode, encode_single} (:77-152: a dedicated thread owns the model,
+requests arrive over a bounded channel of 100) and segment_text (:155-198).
+
+The one line that changes is `model.encode(&segments)` (:109): instead of rust-bert -> libtorch
+CPU, the segments are tokenised on the host and the padded ids go to mx_embedder_encode, which
+runs the whole BERT forward + mean-pool + L2-normalise on the GPU.  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import queue
+import threading
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+
+
+class EmbeddingError(Exception):
+    pass
+
+
+class EncodingFailure(EmbeddingError):       # embedding.rs:12-13
+    pass
+
+
+class SetupError(EmbeddingError):            # embedding.rs:14-15
+    pass
+
+
+@dataclass
+class EmbeddingResult:                       # embedding.rs:18-22
+    content: str
+    vector: list
+
+
+class EmbeddingsModelType(enum.Enum):        # embedding.rs:24-33
+    DistiluseBaseMultilingualCased = "distiluse-base-multilingual-cased"
+    BertBaseNliMeanTokens = "bert-base-nli-mean-tokens"
+    AllMiniLmL12V2 = "all-MiniLM-L12-v2"
+    AllMiniLmL6V2 = "all-MiniLM-L6-v2"
+    AllDistilrobertaV1 = "all-distilroberta-v1"
+    ParaphraseAlbertSmallV2 = "paraphrase-albert-small-v2"
+    SentenceT5Base = "sentence-t5-base"
+
+
+@dataclass(frozen=True)
+class Architecture:
+    layers: int
+    hidden: int
+    heads: int
+    ffn: int
+    vocab: int = 30522
+    max_pos: int = 512
+    type_vocab: int = 2
+    ln_eps: float = 1e-12
+    normalize: bool = True
+    max_seq_length: int = 256    # sentence_bert_config.json of the model (what rust-bert truncates to)
+
+
+# BERT-family models of the enum (the others are DistilBERT / RoBERTa / ALBERT / T5 stacks that the
+# reference can only segment for L12 / L6 / distilroberta anyway, embedding.rs:156-161)
+ARCHITECTURES = {
+    EmbeddingsModelType.AllMiniLmL6V2: Architecture(6, 384, 12, 1536, max_seq_length=256),
+    EmbeddingsModelType.AllMiniLmL12V2: Architecture(12, 384, 12, 1536, max_seq_length=128),
+    EmbeddingsModelType.BertBaseNliMeanTokens: Architecture(12, 768, 12, 3072, normalize=False, max_seq_length=128),
+}
+
+
+@dataclass(frozen=True)
+class ModelConfig:                           # embedding.rs:57-73
+    model: EmbeddingsModelType = EmbeddingsModelType.AllMiniLmL12V2
+    max_length: int = 256
+    stride: int = 86                         # overlap roughly a third of the previous text
+
+
+PRECISION = {"bf16": 0, "f32": 1, "f16": 2}
+
+
+class B200Encoder:
+    """Owns an mx_embedder handle: ids [B,S] + lens [B] -> unit-norm f32 [B,H]."""
+
+    def __init__(self, arch: Architecture, weights: dict, precision: str = "bf16", device: int = 0,
+                 max_tokens: int = 0):
+        self.arch = arch
+        names, tensors, keep = [], [], []
+        for name, arr in weights.items():
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            keep.append(a)
+            names.append(name.encode())
+            tensors.append((names[-1], a.ctypes.data_as(C.POINTER(C.c_float)), a.size))
+        arr_t = (capi.Tensor * len(tensors))(*[capi.Tensor(n, d, s) for n, d, s in tensors])
+        cfg = capi.ModelCfg(layers=arch.layers, hidden=arch.hidden, heads=arch.heads, ffn=arch.ffn,
+                            vocab=arch.vocab, max_pos=arch.max_pos, type_vocab=arch.type_vocab,
+                            ln_eps=arch.ln_eps, normalize=1 if arch.normalize else 0,
+                            precision=PRECISION[precision], max_tokens=max_tokens)
+        h = C.c_void_p()
+        rc = capi.lib().mx_embedder_create(C.byref(cfg), arr_t, len(tensors), device, C.byref(h))
+        if rc != capi.OK:
+            msg = capi.lib().mx_last_error(None)
+            raise SetupError(msg.decode(errors="replace") if msg else f"status {rc}")
+        self._h = h
+        self.precision = precision
+
+    @property
+    def handle(self):
+        return self._h
+
+    def encode_ids(self, ids: np.ndarray, lens: np.ndarray) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        B, S = ids.shape
+        out = np.zeros((B, self.arch.hidden), dtype=np.float32)
+        rc = capi.lib().mx_embedder_encode(self._h, ids.ctypes.data, lens.ctypes.data, B, S, out.ctypes.data)
+        if rc != capi.OK:
+            msg = capi.lib().mx_last_error(self._h)
+            raise EncodingFailure(msg.decode(errors="replace") if msg else f"status {rc}")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            capi.lib().mx_embedder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def segment_text(model_config: ModelConfig, text: str, tokenizer) -> list[str]:
+    """embedding.rs:155-198 with the tokenizer passed in (the reference re-loads it per call, :163).
+
+    `tokenizer` is a `tokenizers.Tokenizer`; windows of `max_length` tokens overlapping by `stride`,
+    each decoded back to text (the first one also gets `.replace(" ' ", "'")`, :183).
+    """
+    if model_config.model not in (EmbeddingsModelType.AllMiniLmL12V2, EmbeddingsModelType.AllMiniLmL6V2,
+                                  EmbeddingsModelType.AllDistilrobertaV1):
+        raise SetupError("Model not supported yet")
+    tokenizer.enable_truncation(max_length=model_config.max_length, stride=model_config.stride)
+    try:
+        encoding = tokenizer.encode(text, add_special_tokens=False)
+        segments = [tokenizer.decode(encoding.ids, skip_special_tokens=True).replace(" ' ", "'")]
+        for over in encoding.overflowing:
+            segments.append(tokenizer.decode(over.ids, skip_special_tokens=True))
+    except Exception:
+        raise EncodingFailure(text)
+    finally:
+        tokenizer.no_truncation()
+    return segments
+
+
+def tokenize_batch(tokenizer, segments: list[str], max_seq_length: int, pad_id: int = 0):
+    """What rust-bert's SentenceEmbeddingsModel::tokenize does before the forward pass: add
+    [CLS]/[SEP], truncate to the model's max_seq_length, pad to the longest of the batch."""
+    tokenizer.enable_truncation(max_length=max_seq_length)
+    try:
+        encs = tokenizer.encode_batch(segments, add_special_tokens=True)
+    finally:
+        tokenizer.no_truncation()
+    S = max(1, max(len(e.ids) for e in encs))
+    ids = np.full((len(encs), S), pad_id, dtype=np.int32)
+    lens = np.zeros(len(encs), dtype=np.int32)
+    for i, e in enumerate(encs):
+        ids[i, :len(e.ids)] = e.ids
+        lens[i] = len(e.ids)
+    return ids, lens
+
+
+class SentenceEmbedder:
+    """embedding.rs:77-152: `spawn` starts the runner thread that owns the model."""
+
+    def __init__(self, sender: "queue.Queue"):
+        self.sender = sender
+
+    @classmethod
+    def spawn(cls, model_config: ModelConfig, encoder: B200Encoder, tokenizer):
+        """-> (thread handle, SentenceEmbedder).  `encoder` / `tokenizer` are the already-loaded
+        model and tokenizer (the reference loads both inside the runner, :99-100,163 -- per task;
+        SURVEY.md F9 -- here they are process-wide and handed in)."""
+        q: queue.Queue = queue.Queue(maxsize=100)                 # mpsc::sync_channel(100), :87
+        handle = threading.Thread(target=cls._runner, args=(q, model_config, encoder, tokenizer), daemon=True)
+        handle.start()
+        return handle, cls(q)
+
+    @staticmethod
+    def _runner(receiver, model_config, encoder, tokenizer):
+        while True:
+            msg = receiver.get()
+            if msg is None:
+                return
+            text, segment, reply = msg
+            try:
+                segments = segment_text(model_config, text, tokenizer) if segment else [text]
+                ids, lens = tokenize_batch(tokenizer, segments, encoder.arch.max_seq_length)
+                embeddings = encoder.encode_ids(ids, lens)        # <- model.encode(&segments), :109
+                if len(segments) != len(embeddings):
+                    raise EncodingFailure("# of embeddings doesn't match # of segments")
+                reply.put([EmbeddingResult(content=s, vector=v.tolist()) for s, v in zip(segments, embeddings)])
+            except Exception as e:  # the reference's runner dies; here the caller gets the error
+                reply.put(e)
+
+    def _call(self, text: str, segment: bool):
+        reply: queue.Queue = queue.Queue(maxsize=1)               # oneshot::channel
+        self.sender.put((text, segment, reply))
+        res = reply.get()
+        if isinstance(res, Exception):
+            raise res
+        return res
+
+    def encode(self, text: str) -> list[EmbeddingResult]:
+        """segment the text into windows and embed each (embedding.rs:138-142)"""
+        return self._call(text, True)
+
+    def encode_single(self, text: str):
+        """single shot, no segmentation; long text is truncated by the model (embedding.rs:146-151)"""
+        res = self._call(text, False)
+        return res.pop() if res else None
+
+    def shutdown(self):
+        self.sender.put(None)

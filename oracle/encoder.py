@@ -48,7 +48,7 @@ class EncoderConfig:
 MINILM_L6 = EncoderConfig(layers=6)
 MINILM_L12 = EncoderConfig(layers=12)              # memex default, embedding.rs:64-73
 BERT_BASE = EncoderConfig(layers=12, hidden=768, heads=12, ffn=3072)  # BertBaseNliMeanTokens / e5-base
-TINY = EncoderConfig(layers=2, hidden=64, heads=4, ffn=128, vocab=200, max_pos=64)
+TINY = EncoderConfig(layers=2, hidden=64, heads=2, ffn=128, vocab=200, max_pos=64)
 
 
 def weight_names(cfg: EncoderConfig):

@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/*.h declares; without a
+GPU every computing entry point fails loudly (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from memex_b200 import capi, storage, embedding
+
+
+def test_exports_every_declared_symbol():
+    L = capi.lib()
+    names = capi.declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), f"{n} is declared in memex_b200.h but not exported"
+    dbg = open(os.path.join(os.path.dirname(capi.HEADER), "memex_b200_debug.h")).read()
+    dbg = re.sub(r"/\*.*?\*/", "", dbg, flags=re.S)
+    for n in set(re.findall(r"\b(mx_debug_[a-z0-9_]+)\s*\(", dbg)):
+        assert hasattr(L, n)
+
+
+def test_abi_version_and_launch_counter():
+    L = capi.lib()
+    assert L.mx_abi_version() == 1
+    assert L.mx_launch_count() >= 0
+
+
+def test_sass_is_sm100a_only_and_has_tcgen05_tma():
+    """cuobjdump evidence that the tensor-core kernels are tcgen05 + TMA (B200_PROFILING.md table)."""
+    import shutil
+    import subprocess
+    from memex_b200 import build
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "-lelf", build.LIB], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run(["cuobjdump", "-sass", build.LIB], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass          # tcgen05.mma kind::f16
+    assert "UTMALDG" in sass          # cp.async.bulk.tensor
+    assert "LDTM" in sass             # tcgen05.ld
+    assert "HMMA." not in sass.replace("UTCHMMA", "")   # no legacy mma.sync path
+
+
+@pytest.mark.skipif(capi.lib().mx_device_count() > 0, reason="box has a GPU")
+def test_no_cpu_fallback_store():
+    cfg = capi.StoreCfg(dim=8, dtype=0, metric=0, device=0, capacity=0, id_offset=0, id_stride=1)
+    h = C.c_void_p()
+    rc = capi.lib().mx_store_create(C.byref(cfg), C.byref(h))
+    assert rc == capi.ERR_CONNECTION and not h.value
+    assert b"no CPU path" in capi.lib().mx_last_error(None)
+    with pytest.raises(storage.VectorStoreError) as ei:
+        storage.B200Store.new("/tmp/mx-nogpu", dim=8)
+    assert ei.value.variant == "ConnectionError"
+
+
+@pytest.mark.skipif(capi.lib().mx_device_count() > 0, reason="box has a GPU")
+def test_no_cpu_fallback_embedder():
+    import numpy as np
+    arch = embedding.Architecture(1, 64, 2, 128, vocab=50, max_pos=16)
+    with pytest.raises(embedding.SetupError) as ei:
+        embedding.B200Encoder(arch, {"x": np.zeros(1, np.float32)}, precision="f32")
+    assert "no CPU path" in str(ei.value)
+
+
+def test_argument_validation_needs_no_device():
+    L = capi.lib()
+    h = C.c_void_p()
+    assert L.mx_store_create(None, C.byref(h)) == capi.ERR_INVALID
+    bad = capi.StoreCfg(dim=0, dtype=0, metric=0, device=0, capacity=0, id_offset=0, id_stride=1)
+    assert L.mx_store_create(C.byref(bad), C.byref(h)) == capi.ERR_INVALID
+    bad = capi.StoreCfg(dim=4, dtype=7, metric=0, device=0, capacity=0, id_offset=0, id_stride=1)
+    assert L.mx_store_create(C.byref(bad), C.byref(h)) == capi.ERR_UNSUPPORTED
+    assert L.mx_store_delete(None, 1) == capi.ERR_UNSUPPORTED      # local.rs:29-32, as a status
+    assert L.mx_store_has_file(b"/nonexistent-dir") == 0
+
+
+def test_factory_rejects_unknown_schemes():
+    # storage/mod.rs:104-136: unknown scheme -> Unsupported(uri)
+    for uri in ("qdrant://x", "hnsw://tmp", "nonsense"):
+        with pytest.raises(storage.VectorStoreError) as ei:
+            storage.get_vector_storage(uri, "c")
+        assert ei.value.variant == "Unsupported"

@@ -1,0 +1,291 @@
+"""GPU parity tests of the vector store (through the C ABI) against the CPU oracle.
+
+First block re-expresses the reference's own tests, lib/libmemex/src/storage/local.rs:175-242.
+Bar: ids identical to the exact (distance asc, id asc) ranking, scores BIT-identical to the
+oracle's DistCosine + local.rs:86 arithmetic evaluated on the stored rows.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from memex_b200 import capi
+from memex_b200.storage import B200Store, VectorData, VectorStoreError, get_vector_storage
+from oracle import cosine
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_data():
+    """local.rs:175-199"""
+    return [
+        VectorData(_id="test-one", document_id="test-one", text="", segment_id=0, vector=[0.0, 0.1, 0.2]),
+        VectorData(_id="test-two", document_id="test-two", text="", segment_id=0, vector=[0.1, 0.1, 0.1]),
+        VectorData(_id="test-three", document_id="test-three", text="", segment_id=0, vector=[0.3, 0.2, 0.1]),
+    ]
+
+
+# ---- the reference's tests, re-expressed --------------------------------------------------------
+
+def test_hnsw(tmp_path):
+    """local.rs:201-214"""
+    store = B200Store.new(tmp_path)
+    store.bulk_insert(test_data())
+    results = store.search([0.1, 0.1, 0.1], 3)
+    assert len(results) == 3
+    doc_id, _ = results[0]
+    assert doc_id == "test-two"
+    # beyond what the reference asserts: full order and scores of the golden fixture
+    fx = json.load(open(os.path.join(GOLD, "search_ref_fixture.json")))
+    assert [r[0] for r in results] == fx["expected_ids"]
+    assert [int(np.float32(r[1]).view(np.uint32)) for r in results] == fx["expected_score_bits"]
+    store.delete_all()
+
+
+def test_save_load(tmp_path):
+    """local.rs:216-227"""
+    path = tmp_path / "vectortest"
+    store = B200Store.new(path)
+    store.bulk_insert(test_data())
+    store.save(path)
+    loaded = B200Store.load(path)
+    assert len(loaded._id_map) == len(store._id_map)
+    assert loaded.get_nb_point() == 3
+    assert loaded.search([0.1, 0.1, 0.1], 3) == store.search([0.1, 0.1, 0.1], 3)
+    # vectors.meta.json stays byte-compatible with serde_json's HashMap<usize, String> dump
+    meta = json.load(open(path / "vectors.meta.json"))
+    assert meta == {"1": "test-one", "2": "test-two", "3": "test-three"}
+    store.delete_all()
+
+
+def test_delete_all(tmp_path):
+    """local.rs:229-242"""
+    store = B200Store.new(tmp_path)
+    store.bulk_insert(test_data())
+    store.save(tmp_path)
+    store.delete_all()
+    assert len(store._id_map) == 0
+    assert store.get_nb_point() == 0
+    with pytest.raises(VectorStoreError):
+        B200Store.load(tmp_path)
+
+
+def test_delete_single_is_unsupported_not_a_panic(tmp_path):
+    """local.rs:29-32 is unimplemented!(); the ABI returns Unsupported"""
+    store = B200Store.new(tmp_path)
+    store.bulk_insert(test_data())
+    with pytest.raises(VectorStoreError) as ei:
+        store.delete("test-one")
+    assert ei.value.variant == "Unsupported"
+    assert len(store.search([0.1, 0.1, 0.1], 3)) == 3     # handle still usable
+
+
+def test_factory_new_then_load(tmp_path):
+    """storage/mod.rs:107-121 with the b200:// scheme"""
+    vs = get_vector_storage(f"b200://{tmp_path}", "coll")
+    vs.add_vectors(test_data())
+    assert vs.search([0.1, 0.1, 0.1], 2)[0][0] == "test-two"
+    vs2 = get_vector_storage(f"b200://{tmp_path}", "coll")     # meta exists -> load
+    assert [r[0] for r in vs2.search([0.1, 0.1, 0.1], 3)] == ["test-two", "test-three", "test-one"]
+    vs2.delete_collection()
+    assert vs2.search([0.1, 0.1, 0.1], 3) == []
+
+
+# ---- parity against the oracle -------------------------------------------------------------------
+
+def unit_rows(n, d, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return x
+
+
+def check_parity(store, corpus_as_stored, queries, k, metric="cosine"):
+    ids, scores, counts = store.search_matrix(queries, k)
+    oi, os_, oc = cosine.exact_topk(corpus_as_stored, queries, k, metric=metric)
+    np.testing.assert_array_equal(counts, oc)
+    np.testing.assert_array_equal(ids, oi)
+    np.testing.assert_array_equal(scores.view(np.uint32), os_.view(np.uint32))
+
+
+def test_golden_small(tmp_path):
+    g = np.load(os.path.join(GOLD, "search_small.npz"))
+    store = B200Store.new(tmp_path, dim=24)
+    store.add_matrix(g["corpus"])
+    ids, scores, counts = store.search_matrix(g["queries"], 7)
+    np.testing.assert_array_equal(ids, g["ids"])
+    np.testing.assert_array_equal(scores.view(np.uint32), g["score_bits"])
+
+
+@pytest.mark.parametrize("n,d,nq,k", [
+    (1, 3, 1, 1), (5, 3, 2, 10), (1000, 384, 1, 10), (1000, 384, 7, 10), (20000, 384, 1, 10),
+    (20000, 384, 64, 10), (3001, 17, 3, 5), (4096, 768, 2, 32), (777, 100, 5, 64), (5000, 384, 2, 256),
+    (300, 1, 1, 3), (70000, 64, 9, 10),
+])
+def test_parity_f32(tmp_path, n, d, nq, k):
+    corpus = unit_rows(n, d, 1234)
+    queries = unit_rows(nq, d, 4321)
+    store = B200Store.new(tmp_path, dim=d)
+    store.add_matrix(corpus)
+    check_parity(store, corpus, queries, k)
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(1000, 384, 1, 10), (20000, 384, 64, 10), (9000, 768, 3, 10), (513, 40, 2, 7)])
+def test_parity_f16_store(tmp_path, n, d, nq, k):
+    """fp16 corpus: ids / scores are exact w.r.t. the oracle fed the SAME fp16-rounded rows, and
+    within 1e-4 of the fp32-corpus oracle (BASELINE.md parity gates)."""
+    corpus = unit_rows(n, d, 1234)
+    queries = unit_rows(nq, d, 4321)
+    store = B200Store.new(tmp_path, dim=d, dtype="f16")
+    store.add_matrix(corpus)
+    stored = corpus.astype(np.float16).astype(np.float32)
+    check_parity(store, stored, queries, k)
+    ids, scores, _ = store.search_matrix(queries, k)
+    for i in range(nq):
+        ref = cosine.scores_of(corpus, queries[i], ids[i])
+        assert np.abs(ref - scores[i]).max() <= 1e-4
+    back = np.zeros((min(n, 100), d), dtype=np.float32)
+    assert capi.lib().mx_store_get_rows(store.handle, 0, back.shape[0], back.ctypes.data) == 0
+    np.testing.assert_array_equal(back, stored[:back.shape[0]])
+
+
+def test_unnormalised_rows_duplicates_and_zero_rows(tmp_path):
+    rng = np.random.default_rng(5)
+    corpus = (rng.standard_normal((4000, 48)) * rng.uniform(0.01, 50, (4000, 1))).astype(np.float32)
+    corpus[100] = corpus[7]              # duplicates: tie -> lower id first
+    corpus[2500] = corpus[7]
+    corpus[33] = 0.0                     # zero-norm rows have distance 0 -> score 1.0 (DistCosine)
+    corpus[3999] = 0.0
+    queries = np.stack([corpus[7] * 0.5, rng.standard_normal(48).astype(np.float32), corpus[1234]])
+    store = B200Store.new(tmp_path, dim=48)
+    store.add_matrix(corpus)
+    check_parity(store, corpus, queries, 10)
+    ids, scores, _ = store.search_matrix(queries[:1], 10)
+    assert list(ids[0][:2]) == [34, 4000] and scores[0][0] == 1.0     # the zero rows, by id
+
+
+def test_zero_query_returns_first_rows(tmp_path):
+    corpus = unit_rows(500, 16, 1)
+    store = B200Store.new(tmp_path, dim=16)
+    store.add_matrix(corpus)
+    check_parity(store, corpus, np.zeros((1, 16), np.float32), 5)
+
+
+def test_dot_metric(tmp_path):
+    rng = np.random.default_rng(6)
+    corpus = rng.standard_normal((3000, 96)).astype(np.float32)
+    queries = rng.standard_normal((4, 96)).astype(np.float32)
+    store = B200Store.new(tmp_path, dim=96, metric="dot")
+    store.add_matrix(corpus)
+    check_parity(store, corpus, queries, 10, metric="dot")
+
+
+def test_incremental_inserts_match_bulk(tmp_path):
+    corpus = unit_rows(300, 32, 2)
+    q = unit_rows(2, 32, 3)
+    a = B200Store.new(tmp_path / "a", dim=32, capacity=4)          # forces several regrowths
+    for i in range(0, 300, 7):
+        first = a.add_matrix(corpus[i:i + 7])
+        assert first == i + 1                                      # next_id = len + 1 (local.rs:63)
+    check_parity(a, corpus, q, 10)
+
+
+def test_empty_store_and_bad_arguments(tmp_path):
+    store = B200Store.new(tmp_path, dim=8)
+    ids, scores, counts = store.search_matrix(np.ones((2, 8), np.float32), 4)
+    assert (counts == 0).all() and (ids == 0).all()
+    assert store.search([1.0] * 8, 4) == []
+    L = capi.lib()
+    assert L.mx_store_search(store.handle, None, 1, 1, None, None, None) == capi.ERR_INVALID
+    q = np.ones((1, 8), np.float32)
+    i = np.zeros((1, 300), np.uint64); s = np.zeros((1, 300), np.float32); c = np.zeros(1, np.uint32)
+    assert L.mx_store_search(store.handle, q.ctypes.data, 1, 300, i.ctypes.data, s.ctypes.data, c.ctypes.data) == capi.ERR_INVALID
+    assert L.mx_store_search(store.handle, q.ctypes.data, 1, 0, i.ctypes.data, s.ctypes.data, c.ctypes.data) == capi.ERR_INVALID
+    with pytest.raises(VectorStoreError) as ei:
+        store.add_matrix(np.ones((2, 9), np.float32))
+    assert ei.value.variant == "InsertionError"
+    bad = np.ones((3, 8), np.float32); bad[1, 2] = np.nan
+    with pytest.raises(VectorStoreError) as ei:
+        store.add_matrix(bad)
+    assert ei.value.variant == "InsertionError" and store.get_nb_point() == 0
+    qn = np.ones((1, 8), np.float32); qn[0, 0] = np.inf
+    store.add_matrix(np.ones((2, 8), np.float32))
+    with pytest.raises(VectorStoreError) as ei:
+        store.search_matrix(qn, 1)
+    assert ei.value.variant == "SearchError"
+
+
+def test_sharded_ids_and_device_merge(tmp_path):
+    """row sharding: two stores with id_offset / id_stride + mx_merge_topk_device == one store"""
+    import torch
+    corpus = unit_rows(6000, 64, 8)
+    queries = unit_rows(5, 64, 9)
+    k = 10
+    whole = B200Store.new(tmp_path / "w", dim=64)
+    whole.add_matrix(corpus)
+    wi, ws, wc = whole.search_matrix(queries, k)
+    for mode in ("contiguous", "round_robin"):
+        if mode == "contiguous":
+            shards = [B200Store.new(tmp_path / f"c{r}", dim=64, id_offset=3000 * r) for r in range(2)]
+            parts = [corpus[:3000], corpus[3000:]]
+        else:
+            shards = [B200Store.new(tmp_path / f"r{r}", dim=64, id_offset=r, id_stride=2) for r in range(2)]
+            parts = [corpus[0::2], corpus[1::2]]
+        qd = torch.from_numpy(queries).cuda()
+        ids = torch.zeros((2, 5, k), dtype=torch.int64, device="cuda")
+        dists = torch.zeros((2, 5, k), dtype=torch.float32, device="cuda")
+        scores = torch.zeros((2, 5, k), dtype=torch.float32, device="cuda")
+        counts = torch.zeros((2, 5), dtype=torch.int32, device="cuda")
+        L = capi.lib()
+        for r in range(2):
+            shards[r].add_matrix(parts[r])
+            rc = L.mx_store_search_device(shards[r].handle, qd.data_ptr(), 5, k, ids[r].data_ptr(), scores[r].data_ptr(),
+                                          dists[r].data_ptr(), counts[r].data_ptr(), None)
+            assert rc == 0
+            assert L.mx_store_sync(shards[r].handle) == 0
+        oi = torch.zeros((5, k), dtype=torch.int64, device="cuda")
+        os_ = torch.zeros((5, k), dtype=torch.float32, device="cuda")
+        oc = torch.zeros(5, dtype=torch.int32, device="cuda")
+        rc = L.mx_merge_topk_device(ids.data_ptr(), dists.data_ptr(), counts.data_ptr(), 2, 5, k, capi.METRIC_COSINE,
+                                    oi.data_ptr(), os_.data_ptr(), oc.data_ptr(), 0, None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(oi.cpu().numpy().astype(np.uint64), wi)
+        np.testing.assert_array_equal(os_.cpu().numpy().view(np.uint32), ws.view(np.uint32))
+        np.testing.assert_array_equal(oc.cpu().numpy().astype(np.uint32), wc)
+
+
+def test_full_size_properties_1m(tmp_path):
+    """BASELINE config 2 size (1M x 384 f32): size-independent properties + spot-checked scores."""
+    n, d, k = 1_000_000, 384, 10
+    rng = np.random.default_rng(1234)
+    corpus = rng.standard_normal((n, d), dtype=np.float32)
+    corpus /= np.linalg.norm(corpus, axis=1, keepdims=True)
+    store = B200Store.new(tmp_path, dim=d, capacity=n)
+    for i in range(0, n, 250_000):
+        store.add_matrix(corpus[i:i + 250_000])
+    assert store.get_nb_point() == n
+    rows = np.array([0, 17, 499_999, 999_999])
+    queries = corpus[rows] + 0.05 * rng.standard_normal((4, d)).astype(np.float32)
+    ids, scores, counts = store.search_matrix(queries, k)
+    assert (counts == k).all()
+    np.testing.assert_array_equal(ids[:, 0], rows + 1)                       # planted neighbour found
+    assert (np.diff(scores, axis=1) <= 0).all()                              # sorted best first
+    for i in range(4):
+        assert len(set(ids[i])) == k
+        np.testing.assert_array_equal(cosine.scores_of(corpus, queries[i], ids[i]).view(np.uint32),
+                                      scores[i].view(np.uint32))             # bit-exact scores
+    # exactness of the k-th boundary, checked with the full oracle for one query
+    oi, os_, _ = cosine.exact_topk(corpus, queries[:1], k)
+    np.testing.assert_array_equal(ids[:1], oi)
+    np.testing.assert_array_equal(scores[:1].view(np.uint32), os_.view(np.uint32))
+    # idempotence + batch == singles
+    ids2, scores2, _ = store.search_matrix(queries, k)
+    np.testing.assert_array_equal(ids, ids2)
+    for i in range(4):
+        si, ss, _ = store.search_matrix(queries[i:i + 1], k)
+        np.testing.assert_array_equal(si[0], ids[i])
+        np.testing.assert_array_equal(ss[0].view(np.uint32), scores[i].view(np.uint32))
