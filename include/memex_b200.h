@@ -104,6 +104,17 @@ int32_t mx_merge_topk_device(const uint64_t *ids_dev, const float *dists_dev,
                              uint32_t metric, uint64_t *ids_out_dev, float *scores_out_dev,
                              uint32_t *counts_out_dev, int32_t device, void *cuda_stream);
 
+/* The same two steps with ONE buffer per shard, so that a single all-gather moves a shard's whole
+ * answer: blob = { ids u64 [nq,k] | keys f32 [nq,k] | counts u32 [nq] }, mx_topk_blob_bytes(nq,k)
+ * bytes (16-byte multiple).  blobs_dev holds n_shards blobs blob_stride_bytes apart. */
+uint64_t mx_topk_blob_bytes(uint32_t nq, uint32_t k);
+int32_t mx_store_search_blob_device(mx_store *s, const float *queries_dev, uint32_t nq, uint32_t k,
+                                    void *blob_dev, void *cuda_stream);
+int32_t mx_merge_topk_blobs_device(const void *blobs_dev, uint64_t blob_stride_bytes, uint32_t n_shards,
+                                   uint32_t nq, uint32_t k, uint32_t metric, uint64_t *ids_out_dev,
+                                   float *scores_out_dev, uint32_t *counts_out_dev, int32_t device,
+                                   void *cuda_stream);
+
 int32_t mx_store_len(mx_store *s, uint64_t *n_out); /* hnsw.get_nb_point(), local.rs:238 */
 int32_t mx_store_clear(mx_store *s);                /* delete_all's index reset, local.rs:48-50 */
 int32_t mx_store_delete(mx_store *s, uint64_t id);  /* local.rs:29-32: always MX_ERR_UNSUPPORTED */

@@ -82,6 +82,10 @@ def lib() -> C.CDLL:
     sig("mx_store_search_device", C.c_int32, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp)
     sig("mx_merge_topk_device", C.c_int32, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32,
         C.c_uint32, vp, vp, vp, C.c_int32, vp)
+    sig("mx_topk_blob_bytes", C.c_uint64, C.c_uint32, C.c_uint32)
+    sig("mx_store_search_blob_device", C.c_int32, vp, vp, C.c_uint32, C.c_uint32, vp, vp)
+    sig("mx_merge_topk_blobs_device", C.c_int32, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+        C.c_uint32, vp, vp, vp, C.c_int32, vp)
     sig("mx_store_len", C.c_int32, vp, u64p)
     sig("mx_store_clear", C.c_int32, vp)
     sig("mx_store_delete", C.c_int32, vp, C.c_uint64)

@@ -236,10 +236,12 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeParams p)
     __syncthreads();
     for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
         const uint32_t g = j / p.k, e = j - g * p.k;
-        const uint32_t c = p.counts[(size_t)g * p.nq + q];
-        const bool ok = e < c;
-        key[j] = ok ? p.dists[((size_t)g * p.nq + q) * p.k + e] : 0.f;
-        id[j] = ok ? p.ids[((size_t)g * p.nq + q) * p.k + e] : 0;
+        const uint32_t *cg = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(p.counts) + g * p.stride_counts);
+        const float *dg = reinterpret_cast<const float *>(reinterpret_cast<const char *>(p.dists) + g * p.stride_dists);
+        const uint64_t *ig = reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(p.ids) + g * p.stride_ids);
+        const bool ok = e < cg[q];
+        key[j] = ok ? dg[(size_t)q * p.k + e] : 0.f;
+        id[j] = ok ? ig[(size_t)q * p.k + e] : 0;
         if (ok) atomicAdd(&total_s, 1u);
     }
     __syncthreads();

@@ -46,9 +46,10 @@ struct RerankParams {
 cudaError_t launch_rerank(const RerankParams &p, cudaStream_t st);
 
 struct MergeParams {
-    const uint64_t *ids;     // [G, nq, k]
-    const float *dists;      // [G, nq, k]
-    const uint32_t *counts;  // [G, nq]
+    const uint64_t *ids;     // shard g: [nq, k] at (char *)ids + g * stride_ids
+    const float *dists;      // shard g: [nq, k] at (char *)dists + g * stride_dists
+    const uint32_t *counts;  // shard g: [nq]    at (char *)counts + g * stride_counts
+    uint64_t stride_ids, stride_dists, stride_counts;  // bytes between consecutive shards
     uint64_t *ids_out;
     float *scores_out;
     uint32_t *counts_out;

@@ -66,6 +66,8 @@ struct mx_store : HandleBase {
     void *dev_io = nullptr;
     size_t dev_io_cap = 0;
     TcScanState *tc = nullptr;
+    float *blob_scores = nullptr;  // scratch of mx_store_search_blob_device
+    size_t blob_scores_cap = 0;
     KernelTimer timer;
 };
 
@@ -387,6 +389,7 @@ void mx_store_destroy(mx_store *s)
     cudaFree(s->cand_s);
     cudaFree(s->cand_r);
     cudaFree(s->dev_io);
+    cudaFree(s->blob_scores);
     if (s->pinned) cudaFreeHost(s->pinned);
     if (s->stream) cudaStreamDestroy(s->stream);
     s->magic = 0;
@@ -488,19 +491,65 @@ int32_t mx_store_search(mx_store *s, const float *queries, uint32_t nq, uint32_t
     return MX_OK;
 }
 
+static int32_t merge_impl(const MergeParams &mp, int32_t device, void *cuda_stream)
+{
+    if (!mp.ids || !mp.dists || !mp.counts || !mp.ids_out || !mp.scores_out || !mp.counts_out)
+        return fail(nullptr, MX_ERR_INVALID, "null buffer");
+    if (mp.k == 0 || mp.k > MX_MAX_K || mp.n_shards == 0 || mp.metric > MX_METRIC_DOT)
+        return fail(nullptr, MX_ERR_INVALID, "bad merge shape");
+    if (mp.nq == 0) return MX_OK;
+    MX_CUDA(nullptr, MX_ERR_CONNECTION, cudaSetDevice(device));
+    MX_CUDA(nullptr, MX_ERR_SEARCH, launch_merge(mp, (cudaStream_t)cuda_stream));
+    return MX_OK;
+}
+
 int32_t mx_merge_topk_device(const uint64_t *ids_dev, const float *dists_dev, const uint32_t *counts_dev,
                              uint32_t n_shards, uint32_t nq, uint32_t k, uint32_t metric, uint64_t *ids_out_dev,
                              float *scores_out_dev, uint32_t *counts_out_dev, int32_t device, void *cuda_stream)
 {
-    if (!ids_dev || !dists_dev || !counts_dev || !ids_out_dev || !scores_out_dev || !counts_out_dev)
-        return fail(nullptr, MX_ERR_INVALID, "null buffer");
-    if (k == 0 || k > MX_MAX_K || n_shards == 0 || metric > MX_METRIC_DOT)
-        return fail(nullptr, MX_ERR_INVALID, "bad merge shape");
-    if (nq == 0) return MX_OK;
-    MX_CUDA(nullptr, MX_ERR_CONNECTION, cudaSetDevice(device));
-    MergeParams mp{ids_dev, dists_dev, counts_dev, ids_out_dev, scores_out_dev, counts_out_dev, n_shards, nq, k, metric};
-    MX_CUDA(nullptr, MX_ERR_SEARCH, launch_merge(mp, (cudaStream_t)cuda_stream));
-    return MX_OK;
+    MergeParams mp{ids_dev, dists_dev, counts_dev, (uint64_t)nq * k * 8, (uint64_t)nq * k * 4, (uint64_t)nq * 4,
+                   ids_out_dev, scores_out_dev, counts_out_dev, n_shards, nq, k, metric};
+    return merge_impl(mp, device, cuda_stream);
+}
+
+uint64_t mx_topk_blob_bytes(uint32_t nq, uint32_t k) { return (((uint64_t)nq * k * 12 + (uint64_t)nq * 4) + 15) & ~15ull; }
+
+int32_t mx_store_search_blob_device(mx_store *s, const float *queries_dev, uint32_t nq, uint32_t k, void *blob_dev,
+                                    void *cuda_stream)
+{
+    if (!blob_dev) return fail(s, MX_ERR_INVALID, "null buffer");
+    char *b = static_cast<char *>(blob_dev);
+    // scores are not part of the blob (the merge recomputes them from the keys): park them behind the keys' slot
+    // of a scratch area the store owns
+    if (!s) return MX_ERR_INVALID;
+    int32_t rc;
+    if ((rc = set_device(s)) != MX_OK) return rc;
+    const size_t sb = (size_t)nq * k * sizeof(float);
+    if (sb > s->blob_scores_cap) {
+        if (s->blob_scores) cudaFree(s->blob_scores);
+        s->blob_scores = nullptr;
+        s->blob_scores_cap = 0;
+        MX_CUDA(s, MX_ERR_SEARCH, cudaMalloc(&s->blob_scores, sb));
+        s->blob_scores_cap = sb;
+    }
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
+    return search_device_impl(s, queries_dev, nq, k, reinterpret_cast<uint64_t *>(b), s->blob_scores,
+                              reinterpret_cast<float *>(b + (size_t)nq * k * 8),
+                              reinterpret_cast<uint32_t *>(b + (size_t)nq * k * 12), st);
+}
+
+int32_t mx_merge_topk_blobs_device(const void *blobs_dev, uint64_t blob_stride_bytes, uint32_t n_shards, uint32_t nq,
+                                   uint32_t k, uint32_t metric, uint64_t *ids_out_dev, float *scores_out_dev,
+                                   uint32_t *counts_out_dev, int32_t device, void *cuda_stream)
+{
+    if (!blobs_dev) return fail(nullptr, MX_ERR_INVALID, "null buffer");
+    if (blob_stride_bytes < mx_topk_blob_bytes(nq, k) || blob_stride_bytes % 8 != 0)
+        return fail(nullptr, MX_ERR_INVALID, "blob stride too small or not 8-byte aligned");
+    const char *b = static_cast<const char *>(blobs_dev);
+    MergeParams mp{reinterpret_cast<const uint64_t *>(b), reinterpret_cast<const float *>(b + (size_t)nq * k * 8),
+                   reinterpret_cast<const uint32_t *>(b + (size_t)nq * k * 12), blob_stride_bytes, blob_stride_bytes,
+                   blob_stride_bytes, ids_out_dev, scores_out_dev, counts_out_dev, n_shards, nq, k, metric};
+    return merge_impl(mp, device, cuda_stream);
 }
 
 int32_t mx_store_len(mx_store *s, uint64_t *n_out)
