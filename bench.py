@@ -1,0 +1,550 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the memex embedding + vector-search hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): queries/sec over a 10 M x 384 corpus, top-10.  One STEP = one batch of 64
+queries scanned against the whole corpus (fp16 rows, cosine, exact top-10).  At N GPUs the 10 M
+rows are dealt contiguously over the ranks (row sharding): every rank scans
+its shard, ONE all-gather moves the per-shard top-k, every rank merges -> "scaling": "strong".
+
+The JSON line also carries, as sub-objects, the two other configurations BASELINE.json names for
+one GPU (they do not shard, so they are reported at N = 1 by rank 0 only):
+  "single_query": config 2, 1 M x 384 fp32, one query per call, top-10
+  "embed":        config 3, segments embedded / sec, MiniLM-L6, B = 256, S = 256, bf16
+
+`--impl reference` times the CPU restatement of the reference's own search path (HNSW, M = 16,
+ef_construction = 200, ef = 32; oracle/hnsw_oracle.cpp) on the host cores: the reference is Rust
+over un-vendored crates and cannot be built here (DESIGN.md "Oracle").
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DIM = 384
+TOPK = 10
+NQ = 64
+CORPUS_SEED, QUERY_SEED = 1234, 4321
+CHUNK_ROWS = 250_000           # generator granularity: chunk c is torch.Generator(seed = CORPUS_SEED + c)
+HNSW_SAMPLE_ROWS = 6_000       # bounded sample the CPU HNSW restatement is built over
+EXACT_SAMPLE_ROWS = 500_000    # bounded sample for the all-core exact brute force
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                    tf_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def ncu_traffic(kernel_key: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture"""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel_key)
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if not (t0 - 0.15 <= t <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            # region shorter than the sampling period: take whatever was seen
+            for t, line in self.rows[-3:]:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0]))
+                    mx = max(mx, float(f[1]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic corpus / queries (N(0,1) rows, L2-normalised; queries = rows + noise)
+# ------------------------------------------------------------------------------------------------
+def corpus_chunk_device(chunk: int, rows: int, device):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(CORPUS_SEED + chunk)
+    x = torch.randn((rows, DIM), generator=g, device=device, dtype=torch.float32)
+    return torch.nn.functional.normalize(x, dim=1)
+
+
+def queries_device(nq: int, device):
+    """rows 0, 97, 194, ... of chunk 0 plus N(0, 0.1^2) noise, renormalised -- identical on every rank"""
+    import torch
+    base = corpus_chunk_device(0, CHUNK_ROWS, device)[torch.arange(nq, device=device) * 97 % CHUNK_ROWS]
+    g = torch.Generator(device=device)
+    g.manual_seed(QUERY_SEED)
+    q = base + 0.1 * torch.randn((nq, DIM), generator=g, device=device, dtype=torch.float32)
+    return torch.nn.functional.normalize(q, dim=1).contiguous()
+
+
+def fill_shard(store, start: int, count: int, device):
+    """rows [start, start + count) of the global corpus -> the local shard, generated on the device"""
+    import torch
+    done = 0
+    while done < count:
+        g_row = start + done
+        chunk, off = divmod(g_row, CHUNK_ROWS)
+        take = min(CHUNK_ROWS - off, count - done)
+        x = corpus_chunk_device(chunk, CHUNK_ROWS, device)[off:off + take].contiguous()
+        torch.cuda.synchronize(device)
+        store.add_local_device(x.data_ptr(), take)
+        done += take
+        del x
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle/ is test infrastructure: only these baseline legs may execute it)
+# ------------------------------------------------------------------------------------------------
+def corpus_rows_host(n: int) -> np.ndarray:
+    rng = np.random.default_rng(CORPUS_SEED)
+    x = rng.standard_normal((n, DIM), dtype=np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return x
+
+
+def queries_host(x: np.ndarray, nq: int) -> np.ndarray:
+    rng = np.random.default_rng(QUERY_SEED)
+    q = x[(np.arange(nq) * 97) % len(x)] + 0.1 * rng.standard_normal((nq, DIM), dtype=np.float32)
+    return (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+
+
+def cpu_hnsw_baseline(steps: int, warmup: int, threads: int):
+    """The reference's search as shipped (local.rs:48,76): HNSW M=16 efC=200, ef=32, cosine.
+    Built over a bounded sample (build is the reference's O(N log N) insert path and is not timed);
+    each step = one 64-query batch.  Returns (queries/sec, info)."""
+    from oracle import cosine
+    x = corpus_rows_host(HNSW_SAMPLE_ROWS)
+    h = cosine.HnswOracle(DIM, seed=1)
+    t0 = time.perf_counter()
+    h.insert(x)
+    build_s = time.perf_counter() - t0
+    q = queries_host(x, NQ)
+    for _ in range(max(1, warmup)):
+        h.search(q, TOPK, 32, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ids, _, _ = h.search(q, TOPK, 32, threads)
+    dt = time.perf_counter() - t0
+    e_ids, _, _ = cosine.exact_topk(x, q, TOPK)
+    recall = float(np.mean([len(set(ids[i]) & set(e_ids[i])) / TOPK for i in range(NQ)]))
+    return NQ * steps / dt, dict(build_s=round(build_s, 1), recall_at_10=round(recall, 3), ms_per_step=dt / steps * 1e3)
+
+
+def cpu_exact_baseline():
+    """all-core exact brute force with the reference's distance arithmetic (oracle/cosine_oracle.c)
+    over a bounded sample of the rows; a scan is linear in rows, so q/s at 10 M = q/s(sample) * sample / 10 M"""
+    from oracle import cosine
+    x = corpus_rows_host(EXACT_SAMPLE_ROWS)
+    q = queries_host(x, NQ)
+    cosine.exact_topk(x[:10000], q, TOPK)
+    t0 = time.perf_counter()
+    cosine.exact_topk(x, q, TOPK)
+    dt = time.perf_counter() - t0
+    return NQ / dt, cosine.num_threads()
+
+
+def cpu_embed_baseline(batch: int = 16, seq: int = 256):
+    """HF BertModel fp32 on torch-CPU (the libtorch kernels tch dispatches to), all host threads"""
+    import torch
+    from oracle import encoder as enc_oracle
+    cfg = enc_oracle.MINILM_L6
+    w = enc_oracle.make_weights(cfg, seed=3)
+    ids, lens = enc_oracle.make_inputs(cfg, batch, seq, seed=7)
+    enc_oracle.hf_encode(cfg, w, ids[:2], lens[:2])
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < 8.0 or reps < 2:
+        enc_oracle.hf_encode(cfg, w, ids, lens)
+        reps += 1
+    dt = time.perf_counter() - t0
+    return batch * reps / dt, torch.get_num_threads(), f"{reps} x (B={batch}, S={seq}) MiniLM-L6 fp32, HF BertModel on torch-CPU"
+
+
+# ------------------------------------------------------------------------------------------------
+def workload_config(rows: int, n_gpus: int):
+    return {"workload": f"{rows // 1_000_000}Mx{DIM} fp16 corpus, cosine top-{TOPK}, {NQ}-query batches"
+            if rows % 1_000_000 == 0 else f"{rows}x{DIM} fp16 corpus, cosine top-{TOPK}, {NQ}-query batches",
+            "rows": rows, "dim": DIM, "k": TOPK, "queries_per_step": NQ, "corpus_dtype": "f16",
+            "parallelism": f"row-sharded x{n_gpus}, one all-gather of per-shard top-k" if n_gpus > 1 else "single GPU",
+            "l2": "inputs larger than L2 (shard >= 0.96 GB vs 126 MB L2); no flush needed"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    v, info = cpu_hnsw_baseline(args.steps, args.warmup, threads)
+    sample = (f"HNSW restatement (M=16, efC=200, ef=32) built over a {HNSW_SAMPLE_ROWS}-row sample of the corpus "
+              f"(build {info['build_s']} s, untimed); {args.steps} steps x {NQ} queries on {threads} threads; "
+              f"recall@10 vs exact = {info['recall_at_10']}; HNSW search cost grows ~log N, so this over-states "
+              f"the reference's q/s at 10 M rows")
+    line = {"impl": "reference", "metric": "queries/sec", "value": v, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.rows, args.gpus),
+            "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def bench_single_query(device, steps: int, warmup: int, pk):
+    """config 2: 1 M x 384 fp32, one query per call, top-10"""
+    import torch
+    from memex_b200 import capi
+    from memex_b200.sharded import ShardedStore
+    rows = 1_000_000
+    L = capi.lib()
+    st = ShardedStore("/tmp/mx_bench_single", DIM, rows, dtype="f32", device=device.index)
+    fill_shard(st, 0, rows, device)
+    q = queries_device(64, device)
+    for i in range(warmup):
+        st.search_device(q[i % 64:i % 64 + 1], TOPK)
+    torch.cuda.synchronize(device)
+    L.mx_store_set_timing(st.local.handle, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        st.search_device(q[i % 64:i % 64 + 1], TOPK)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / steps
+    scan_ms, scan_n, oth_ms, oth_n = C.c_double(), C.c_uint64(), C.c_double(), C.c_uint64()
+    L.mx_store_get_timing(st.local.handle, C.byref(scan_ms), C.byref(scan_n), C.byref(oth_ms), C.byref(oth_n))
+    L.mx_store_set_timing(st.local.handle, 0)
+    algo = rows * DIM * 4 + rows * 4
+    per = scan_ms.value / max(1, scan_n.value)
+    ach = algo / (per * 1e-3) / 1e9
+    # end to end with host buffers
+    qh = q.cpu().numpy()
+    st.local.search_matrix(qh[:1], TOPK)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        st.local.search_matrix(qh[i % 64:i % 64 + 1], TOPK)
+    e2e = steps / (time.perf_counter() - t0)
+    st.close()
+    return {"workload": "1Mx384 fp32 corpus, cosine top-10, one query per call", "value": 1e3 / ms, "unit": "queries/s",
+            "ms_per_query": ms, "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": DIM * 4,
+                                        "d2h_bytes_per_step": TOPK * 12 + 4},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                         "traffic": ncu_traffic("scan_stream_f32_q1"), "kernel": "scan_stream_kernel<float>",
+                         "kernel_ms": per, "other_kernels_ms_per_step": oth_ms.value / max(1, steps)}}
+
+
+def bench_embed(device, steps: int, warmup: int, pk, cpu: bool):
+    """config 3: batch-256 segment embedding, MiniLM-L6, S = 256, bf16 activations on tcgen05"""
+    import torch
+    from memex_b200 import capi
+    from memex_b200.embedding import Architecture, B200Encoder
+    # seeded random weights at the true shapes (no checkpoint on the box); generated here, not via oracle/
+    Lyr, H, heads, F, vocab, max_pos = 6, 384, 12, 1536, 30522, 512
+    rng = np.random.default_rng(3)
+    w = {}
+
+    def lin(name, o, i):
+        w[name + ".weight"] = (rng.standard_normal((o, i)) * (1.5 / np.sqrt(i))).astype(np.float32)
+        w[name + ".bias"] = (0.1 * rng.standard_normal(o)).astype(np.float32)
+
+    def ln(name):
+        w[name + ".weight"] = (1 + 0.1 * rng.standard_normal(H)).astype(np.float32)
+        w[name + ".bias"] = (0.1 * rng.standard_normal(H)).astype(np.float32)
+
+    w["embeddings.word_embeddings.weight"] = (0.5 * rng.standard_normal((vocab, H))).astype(np.float32)
+    w["embeddings.position_embeddings.weight"] = (0.5 * rng.standard_normal((max_pos, H))).astype(np.float32)
+    w["embeddings.token_type_embeddings.weight"] = (0.5 * rng.standard_normal((2, H))).astype(np.float32)
+    ln("embeddings.LayerNorm")
+    for i in range(Lyr):
+        p = f"encoder.layer.{i}."
+        for n in ("query", "key", "value"):
+            lin(p + "attention.self." + n, H, H)
+        lin(p + "attention.output.dense", H, H)
+        ln(p + "attention.output.LayerNorm")
+        lin(p + "intermediate.dense", F, H)
+        lin(p + "output.dense", H, F)
+        ln(p + "output.LayerNorm")
+    B, S = 256, 256
+    arch = Architecture(Lyr, H, heads, F, vocab, max_pos)
+    enc = B200Encoder(arch, w, precision="bf16", device=device.index, max_tokens=B * S)
+    L = capi.lib()
+    ids_h = torch.from_numpy(np.random.default_rng(7).integers(1000, 30000, size=(B, S)).astype(np.int32)).pin_memory()
+    lens = np.full(B, S, dtype=np.int32)
+    ids_d = ids_h.to(device)
+    out_d = torch.zeros((B, H), dtype=torch.float32, device=device)
+    st = torch.cuda.current_stream(device).cuda_stream
+
+    def step():
+        rc = L.mx_embedder_encode_device(enc.handle, ids_d.data_ptr(), lens.ctypes.data, B, S, out_d.data_ptr(), st)
+        assert rc == 0, L.mx_last_error(enc.handle)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(device)
+    L.mx_embedder_set_timing(enc.handle, 1)
+    l0 = L.mx_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(device)
+    launches = L.mx_launch_count() - l0
+    ms = e0.elapsed_time(e1) / steps
+    g_ms, g_n, o_ms, o_n = C.c_double(), C.c_uint64(), C.c_double(), C.c_uint64()
+    L.mx_embedder_get_timing(enc.handle, C.byref(g_ms), C.byref(g_n), C.byref(o_ms), C.byref(o_n))
+    L.mx_embedder_set_timing(enc.handle, 0)
+    T = B * S
+    gemm_flops = Lyr * T * 24 * H * H                      # QKV + out + FFN up/down, 2 flop / MAC
+    att_flops = Lyr * T * 4 * S * H
+    gemm_tf = gemm_flops * steps / (g_ms.value * 1e-3) / 1e12 if g_ms.value > 0 else 0.0
+    step_tf = (gemm_flops + att_flops) / (ms * 1e-3) / 1e12
+    # end to end: host ids -> C ABI -> host embeddings
+    ids_np = ids_h.numpy()
+    enc.encode_ids(ids_np, lens)
+    t0 = time.perf_counter()
+    n_e2e = max(3, steps // 2)
+    for _ in range(n_e2e):
+        enc.encode_ids(ids_np, lens)
+    e2e = B * n_e2e / (time.perf_counter() - t0)
+    res = {"workload": "batch-256 segment embedding, MiniLM-L6, seq_len 256, bf16 activations (seeded random weights)",
+           "value": B * 1e3 / ms, "unit": "segments/s", "ms_per_step": ms, "dtype": "bf16",
+           "e2e": {"value": e2e, "unit": "segments/s", "h2d_bytes_per_step": B * S * 4 + B * 4, "d2h_bytes_per_step": B * H * 4},
+           "gpu_launches_per_step": launches // max(1, steps),
+           "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                        "frac": gemm_tf / pk["tf_sustained"], "traffic": ncu_traffic("gemm_tc"),
+                        "kernel": "gemm_tc_kernel (4 launches / layer)", "gemm_ms_per_step": g_ms.value / steps,
+                        "other_ms_per_step": o_ms.value / steps, "whole_step_tflops": step_tf,
+                        "whole_step_frac": step_tf / pk["tf_sustained"], "peak_kind": "sustained bf16, " + pk["src"]}}
+    enc.close()
+    if cpu:
+        v, cores, sample = cpu_embed_baseline()
+        res["cpu_baseline"] = {"value": v, "unit": "segments/s", "cores": cores, "kind": "port", "sample": sample}
+    return res
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from memex_b200 import capi
+    from memex_b200.sharded import ShardedStore
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    L = capi.lib()
+    if L.mx_device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: libmemex_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        group = dist.group.WORLD
+    pk = peaks()
+
+    store = ShardedStore(f"/tmp/mx_bench_{rank}", DIM, args.rows, dtype="f16", device=local, rank=rank, world=world,
+                         group=group)
+    fill_shard(store, store.plan.start(rank), store.plan.count(rank), device)
+    q_dev = queries_device(NQ, device)
+    torch.cuda.synchronize(device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(group=group)
+        torch.cuda.synchronize(device)
+
+    # ---- device-resident: queries already in HBM ----
+    for _ in range(args.warmup):
+        store.search_device(q_dev, TOPK)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    L.mx_store_set_timing(store.local.handle, 1)
+    l0 = L.mx_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin = sampler.mark()
+    e0.record()
+    for _ in range(args.steps):
+        ids_d, scores_d, counts_d = store.search_device(q_dev, TOPK)
+    e1.record()
+    barrier()
+    t_end = sampler.mark()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    launches = torch.tensor([L.mx_launch_count() - l0], dtype=torch.int64, device=device)
+    scan_ms, scan_n, oth_ms, oth_n = C.c_double(), C.c_uint64(), C.c_double(), C.c_uint64()
+    L.mx_store_get_timing(store.local.handle, C.byref(scan_ms), C.byref(scan_n), C.byref(oth_ms), C.byref(oth_n))
+    L.mx_store_set_timing(store.local.handle, 0)
+    scan_per = torch.tensor([scan_ms.value / max(1, scan_n.value)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(launches, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(scan_per, op=dist.ReduceOp.MAX, group=group)
+    ms_step = ms_total.item() / args.steps
+    ids_dev_result = ids_d.cpu().numpy().copy()
+
+    # ---- end to end: host queries in, host results out, through the public API ----
+    q_host = q_dev.cpu().numpy() if rank == 0 else None
+    store.search(q_host, TOPK, nq=NQ)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ids_h, scores_h, counts_h = store.search(q_host, TOPK, nq=NQ)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX, group=group)
+    if rank == 0:
+        sampler.stop()
+    assert (ids_h.astype(np.int64) == ids_dev_result.astype(np.int64)).all(), "host and device paths disagree"
+    assert (counts_h == TOPK).all() and (np.diff(scores_h, axis=1) <= 0).all()
+
+    rows_local = store.plan.count(0)    # the largest shard
+    elem = 2
+    algo_bytes = rows_local * DIM * elem + rows_local * 4
+    ach = algo_bytes / (scan_per.item() * 1e-3) / 1e9
+    path = L.mx_store_scan_path(store.local.handle, NQ, TOPK, -1)
+    kernel = {0: "scan_stream_kernel<float>", 1: "scan_stream_kernel<__half>", 2: "scan_tc_kernel (tcgen05)"}[path]
+    line = {
+        "metric": "queries/sec", "value": NQ * 1e3 / ms_step, "unit": "queries/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": workload_config(args.rows, world),
+        "e2e": {"value": NQ * args.steps / e2e_s.item(), "unit": "queries/s", "h2d_bytes_per_step": NQ * DIM * 4,
+                "d2h_bytes_per_step": NQ * TOPK * 12 + NQ * 4},
+        "gpu_launches": int(launches.item()),
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                     "traffic": ncu_traffic(f"scan_path{path}_nq{NQ}"), "kernel": kernel,
+                     "kernel_ms": scan_per.item(), "algorithmic_bytes_per_launch": algo_bytes,
+                     "other_kernels_ms_per_step": oth_ms.value / args.steps, "peak_kind": "copy bandwidth, " + pk["src"]},
+    }
+    if rank == 0:
+        line["clocks"] = sampler.summary(t_begin, t_end)
+    store.close()
+    del store
+    torch.cuda.empty_cache()
+
+    if rank == 0 and world == 1:
+        if not args.skip_extras:
+            line["single_query"] = bench_single_query(device, max(50, args.steps * 5), max(20, args.warmup), pk)
+            line["embed"] = bench_embed(device, max(5, args.steps // 2), max(3, args.warmup), pk, not args.skip_cpu)
+        if not args.skip_cpu:
+            v, info = cpu_hnsw_baseline(20, 3, 1)
+            line["cpu_baseline"] = {
+                "value": v, "unit": "queries/s", "cores": 1, "kind": "port",
+                "sample": (f"HNSW restatement of the reference's search (M=16, efC=200, ef=32), single thread as the "
+                           f"reference's mutex-serialised search, over a {HNSW_SAMPLE_ROWS}-row sample (build "
+                           f"{info['build_s']} s untimed), 20 x {NQ} queries; recall@10 = {info['recall_at_10']}; "
+                           f"approximate search, cost ~log N")}
+            ev, cores = cpu_exact_baseline()
+            line["cpu_exact"] = {
+                "value": ev * EXACT_SAMPLE_ROWS / args.rows, "unit": "queries/s", "cores": cores, "kind": "port",
+                "sample": (f"exact brute force with DistCosine arithmetic over {EXACT_SAMPLE_ROWS} of the rows x {NQ} "
+                           f"queries = {ev:.1f} q/s, scaled linearly to {args.rows} rows")}
+    if world > 1:
+        dist.barrier(group=group)
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--skip-cpu", action="store_true", help="leave out the CPU baseline legs")
+    ap.add_argument("--skip-extras", action="store_true", help="leave out the single_query / embed sub-benches")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
