@@ -350,7 +350,7 @@ def bench_embed(device, steps: int, warmup: int, pk, cpu: bool):
     lens = np.full(B, S, dtype=np.int32)
     ids_d = ids_h.to(device)
     out_d = torch.zeros((B, H), dtype=torch.float32, device=device)
-    st = torch.cuda.current_stream(device).cuda_stream
+    st = torch.cuda.current_stream(device).cuda_stream or 1   # 0 would mean "the embedder's own stream"; 1 = cudaStreamLegacy
 
     def step():
         rc = L.mx_embedder_encode_device(enc.handle, ids_d.data_ptr(), lens.ctypes.data, B, S, out_d.data_ptr(), st)

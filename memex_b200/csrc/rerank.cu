@@ -84,11 +84,15 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
     // 1. every warp folds a slice of the candidate lists into its own list
     WarpTopK<E> top;
     top.init();
-    for (uint32_t l = warp; l < p.n_lists; l += kRerankWarps) {
-        const size_t o = ((size_t)q * p.n_lists + l) * p.lcap;
-        for (uint32_t e = 0; e < p.lcap / 32; ++e) {
-            const float v = p.cand_s[o + e * 32 + lane];
-            const uint32_t r = p.cand_r[o + e * 32 + lane];
+    {
+        // the (query, list) candidate lists are contiguous: n_lists * lcap entries, 32 at a time
+        const uint32_t total = p.n_lists * p.lcap;
+        const size_t o = (size_t)q * total;
+        for (uint32_t i = warp * 32; i < total; i += kRerankWarps * 32) {
+            const uint32_t idx = i + lane;
+            const bool in = idx < total;
+            const float v = in ? p.cand_s[o + idx] : kNegInf;
+            const uint32_t r = in ? p.cand_r[o + idx] : kNoRow;
             top.offer(r != kNoRow, v, r);
         }
     }
@@ -197,8 +201,10 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
 
 cudaError_t launch_rerank(const RerankParams &p, cudaStream_t st)
 {
-    const uint32_t E = p.lcap / 32;
-    const size_t smem = (size_t)p.ldq * 4 + (size_t)kRerankWarps * p.lcap * 8 + (size_t)(p.lcap + MX_MAX_K) * 8;
+    // the rerank's own list holds the 32 * E best approximate candidates, E chosen from k as the stream scan does
+    const uint32_t lk = scan_stream_lcap(p.k);
+    const uint32_t E = lk / 32;
+    const size_t smem = (size_t)p.ldq * 4 + (size_t)kRerankWarps * lk * 8 + (size_t)(lk + MX_MAX_K) * 8;
 #define MX_RR(EE)                                                                                  \
     {                                                                                              \
         auto kern = rerank_kernel<EE>;                                                             \

@@ -1,21 +1,431 @@
-// scan_tc.cu -- K2 placeholder: the tcgen05 batched scan is not built yet; the store falls back to
-// the CUDA-core stream scan for fp16 stores (still a GPU kernel -- there is no CPU path).
+// scan_tc.cu -- K2: batched cosine / dot-product scan of an fp16 corpus on tcgen05 tensor cores.
+//
+// Replaces, for a BATCH of queries, the per-candidate `DistCosine::eval` calls hnsw_rs makes under
+// `self.hnsw.search(vec, limit, 16 * 2)` (reference lib/libmemex/src/storage/local.rs:76) with one
+// exhaustive pass over the flat [N, d] fp16 row matrix:
+//
+//     S[q, n] = Q16[q, :] . C[n, :]  (* inv_norm[n] for cosine)        q < 128 per pass
+//
+// The scan is HBM-bound only if every corpus byte is read ONCE for all queries of the batch, which
+// at 64-128 queries needs ~400-800 TFLOP/s -- tensor cores -- and the [q, N] score matrix must never
+// leave the SM.  So: the queries sit in shared memory as the M = 128 operand for the whole kernel,
+// 128-row corpus tiles stream through a TMA ring as the N operand, scores accumulate in TMEM
+// (4 accumulator stages of 128 columns), and the epilogue warps (one THREAD per query = one TMEM
+// lane) filter the 128 scores of each tile against a running threshold and keep an L-entry
+// candidate list per (query, CTA) in shared memory.  rerank.cu merges the lists and re-scores the
+// survivors with the reference's exact f64 arithmetic, so this stage only has to deliver a superset.
+//
+// Threshold = max(local list minimum [strict >], global per-query lower bound tau[q] [>=]).
+// tau[q] is published with an atomic max by any CTA whose list for q is full: L rows with
+// score >= tau exist somewhere, so a row scoring below tau cannot be in the top L <= needed k.
+// It keeps the number of list insertions per thread ~L*ln(N/L)/CTAs instead of ~L*ln(N/CTAs/L).
+//
+// Roofline: HBM.  Algorithmic bytes per launch = N * ld * 2 (+ 4 N inv_norm).
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 tcgen05.mma issuer + TMEM owner,
+// warps 2..5 epilogue (warp % 4 = TMEM lane quarter).
 #include "common.cuh"
 #include "scan.cuh"
+#include "tc.cuh"
 
 namespace mx {
-struct TcScanState {};
-TcScanState *tc_scan_create(int, uint32_t, uint32_t) { return nullptr; }
-void tc_scan_destroy(TcScanState *) {}
-void tc_scan_invalidate(TcScanState *) {}
-bool tc_scan_supports(const TcScanState *, uint32_t) { return false; }
-uint32_t tc_scan_max_k() { return 0; }
-uint32_t tc_scan_lists(const TcScanState *, uint64_t) { return 0; }
-uint32_t tc_scan_lcap(uint32_t) { return 0; }
-cudaError_t tc_scan_launch(TcScanState *, const ScanParams &, uint64_t, uint32_t, KernelTimer *, cudaStream_t,
-                           const char **why)
+
+using namespace tc;
+
+namespace {
+
+constexpr int kTcThreads = 192;
+constexpr int kQM = 128;            // queries per pass = UMMA M
+constexpr int kTileN = 128;         // corpus rows per tile = UMMA N
+constexpr int kBK = 64;             // fp16 elements per k-block (one 128-byte swizzle atom)
+constexpr int kMaxKB = 6;           // dim <= 384
+constexpr int kAccStages = 4;       // 4 x 128 TMEM columns
+constexpr int kInvSlots = 8;
+constexpr int kKBBytes = kQM * kBK * 2;  // 16 KB: one k-block of Q, or one k-block of a corpus tile
+
+template <int L>
+struct TcCfg {
+    static constexpr int kStages = L <= 16 ? 6 : 5;
+    static constexpr int kListBytes = L * kQM * 8;
+    static constexpr int kInvBytes = kInvSlots * kTileN * 4;
+    static constexpr int kBarBytes = 512;
+    static constexpr int smem_bytes(int kb) { return kb * kKBBytes + kStages * kKBBytes + kListBytes + kInvBytes + kBarBytes + 1024; }
+};
+
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
 {
-    if (why) *why = "tcgen05 scan not built";
-    return cudaErrorNotSupported;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
+
+__device__ __forceinline__ float ld_relaxed(const float *p)
+{
+    float v;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// monotone max on a float cell initialised to -inf
+__device__ __forceinline__ void atomic_max_float(float *addr, float v)
+{
+    if (v >= 0.f)
+        atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else
+        atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+struct TcParams {
+    const float *inv_norm;  // [>= n_tiles * 128] (cosine) or nullptr (dot)
+    float *tau;             // [nq_pad] global lower bounds, -inf on entry
+    float *cand_s;
+    uint32_t *cand_r;
+    uint32_t n_rows, nq, n_lists, k_blocks;
+};
+
+template <int L, bool USE_INV>
+__global__ void __launch_bounds__(kTcThreads, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, TcParams p)
+{
+    using Cfg = TcCfg<L>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sq = smem;                                          // [k_blocks][128 x 64] fp16, swizzled
+    unsigned char *ring = sq + p.k_blocks * kKBBytes;                  // [kStages][128 x 64]
+    float *list_s = reinterpret_cast<float *>(ring + Cfg::kStages * kKBBytes);  // [L][128]
+    uint32_t *list_r = reinterpret_cast<uint32_t *>(list_s + L * kQM);
+    float *sinv = reinterpret_cast<float *>(list_r + L * kQM);         // [kInvSlots][128]
+    uint64_t *full = reinterpret_cast<uint64_t *>(sinv + kInvSlots * kTileN);
+    uint64_t *empty = full + Cfg::kStages;
+    uint64_t *tmem_full = empty + Cfg::kStages;
+    uint64_t *tmem_empty = tmem_full + kAccStages;
+    uint64_t *inv_full = tmem_empty + kAccStages;
+    uint64_t *q_full = inv_full + kInvSlots;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(q_full + 1);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_tiles = (p.n_rows + kTileN - 1) / kTileN;
+    const uint32_t q0 = blockIdx.y * kQM;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmC);
+        for (int i = 0; i < Cfg::kStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < kAccStages; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);
+        }
+        for (int i = 0; i < kInvSlots; ++i) mbar_init(&inv_full[i], 1);
+        mbar_init(q_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, p.k_blocks * kKBBytes);
+            for (uint32_t kb = 0; kb < p.k_blocks; ++kb)
+                tma_load_2d(sq + kb * kKBBytes, &tmQ, q_full, kb * kBK, q0, kEvictLast);
+            uint32_t stage = 0, phase = 0, local = 0;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+                if (USE_INV) {
+                    const uint32_t slot = local % kInvSlots;
+                    mbar_arrive_expect_tx(&inv_full[slot], kTileN * 4);
+                    bulk_load_1d(sinv + slot * kTileN, p.inv_norm + (size_t)tile * kTileN, kTileN * 4, &inv_full[slot]);
+                }
+                for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], kKBBytes);
+                    tma_load_2d(ring + stage * kKBBytes, &tmC, &full[stage], kb * kBK, tile * kTileN, kEvictFirst);
+                    if (++stage == Cfg::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(kQM, kTileN, 0 /* f16 */);
+            mbar_wait(q_full, 0);
+            tc_fence_after();
+            const uint32_t sq_addr = smem_u32(sq);
+            uint32_t stage = 0, phase = 0, local = 0;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+                const uint32_t as = local % kAccStages, aphase = (local / kAccStages) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = sq_addr + kb * kKBBytes;
+                    const uint32_t sb = smem_u32(ring + stage * kKBBytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k)
+                        umma(tmem_base + as * kTileN, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty[stage]);
+                    if (++stage == Cfg::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full[as]);
+            }
+        }
+    } else {
+        // ================= epilogue: thread = query (TMEM lane), columns = corpus rows =================
+        const uint32_t quarter = warp & 3;
+        const uint32_t t = quarter * 32 + lane;
+        const bool q_ok = q0 + t < p.nq;
+        float *ls = list_s + t;
+        uint32_t *lr = list_r + t;
+#pragma unroll
+        for (int e = 0; e < L; ++e) {
+            ls[e * kQM] = kNegInf;
+            lr[e * kQM] = kNoRow;
+        }
+        float lthr = kNegInf;     // minimum of the local list (-inf until it is full)
+        uint32_t lpos = 0;        // where that minimum sits
+        uint32_t filled = 0;
+        const float *tau = p.tau + q0 + t;
+        const float kPosInf = __int_as_float(0x7f800000);
+        uint32_t local = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+            const uint32_t as = local % kAccStages, aphase = (local / kAccStages) & 1;
+            const uint32_t slot = local % kInvSlots, sphase = (local / kInvSlots) & 1;
+            float g = q_ok ? ld_relaxed(tau) : kPosInf;
+            if (USE_INV) mbar_wait(&inv_full[slot], sphase);
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            // s >= g  <=>  s > gm
+            const float gm = (g == kNegInf) ? kNegInf : nextafterf(g, kNegInf);
+            float thr = fmaxf(lthr, gm);
+            const float *inv = sinv + slot * kTileN;
+            const uint32_t row0 = tile * kTileN;
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * kTileN;
+#pragma unroll 1
+            for (int c = 0; c < kTileN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c * 32, v);
+                tmem_ld_wait();
+                bool any = false;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float4 iv = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (USE_INV) iv = *reinterpret_cast<const float4 *>(inv + c * 32 + j4 * 4);
+                    const float s0 = __uint_as_float(v[4 * j4 + 0]) * iv.x;
+                    const float s1 = __uint_as_float(v[4 * j4 + 1]) * iv.y;
+                    const float s2 = __uint_as_float(v[4 * j4 + 2]) * iv.z;
+                    const float s3 = __uint_as_float(v[4 * j4 + 3]) * iv.w;
+                    v[4 * j4 + 0] = __float_as_uint(s0);
+                    v[4 * j4 + 1] = __float_as_uint(s1);
+                    v[4 * j4 + 2] = __float_as_uint(s2);
+                    v[4 * j4 + 3] = __float_as_uint(s3);
+                    any |= (s0 > thr) | (s1 > thr) | (s2 > thr) | (s3 > thr);
+                }
+                if (any) {
+                    // slow path (rare after warm-up): the scores go to a dynamically indexed local array so
+                    // that the insertion code exists once instead of 32 times
+                    uint32_t m = 0;
+                    float sv[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        sv[j] = __uint_as_float(v[j]);
+                        m |= (sv[j] > thr ? 1u : 0u) << j;
+                    }
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float s = sv[j];
+                        const uint32_t row = row0 + c * 32 + j;
+                        if (s > thr && row < p.n_rows) {
+                            ls[lpos * kQM] = s;
+                            lr[lpos * kQM] = row;
+                            if (filled < L) ++filled;
+                            // new eviction entry: minimal score, ties -> maximal row (empty slots first)
+                            float ms = ls[0];
+                            uint32_t mr = lr[0], mp = 0;
+#pragma unroll
+                            for (int e = 1; e < L; ++e) {
+                                const float se = ls[e * kQM];
+                                const uint32_t re = lr[e * kQM];
+                                if (se < ms || (se == ms && re > mr)) {
+                                    ms = se;
+                                    mr = re;
+                                    mp = e;
+                                }
+                            }
+                            lpos = mp;
+                            lthr = ms;
+                            if (filled == L && lthr > g) {
+                                atomic_max_float(p.tau + q0 + t, lthr);
+                                g = lthr;
+                            }
+                            thr = fmaxf(lthr, gm);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        if (q_ok) {
+            const size_t o = ((size_t)(q0 + t) * p.n_lists + blockIdx.x) * L;
+#pragma unroll
+            for (int e = 0; e < L; ++e) {
+                p.cand_s[o + e] = ls[e * kQM];
+                p.cand_r[o + e] = lr[e * kQM];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// queries f32 [nq, ldq] -> unit-norm fp16 [nq_pad, ld] (zero rows beyond nq), tau[nq_pad] = -inf.
+// Scaling a query by a positive constant changes neither the cosine nor the dot ranking, and keeps
+// every fp16 component in [-1, 1].
+__global__ void __launch_bounds__(128) tc_prepare_queries_kernel(const float *q, uint32_t nq, uint32_t dim, uint32_t ldq,
+                                                                 __half *q16, uint32_t ld, float *tau)
+{
+    const uint32_t row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const uint32_t lane = lane_id();
+    float ss = 0.f;
+    if (row < nq)
+        for (uint32_t c = lane; c < dim; c += 32) {
+            const float v = q[(size_t)row * ldq + c];
+            ss = fmaf(v, v, ss);
+        }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+    for (uint32_t c = lane; c < ld; c += 32)
+        q16[(size_t)row * ld + c] = __float2half_rn((row < nq && c < dim) ? q[(size_t)row * ldq + c] * inv : 0.f);
+    if (lane == 0) tau[row] = kNegInf;
+}
+
+}  // namespace
+
+struct TcScanState {
+    int sm_count;
+    uint32_t ld, dim, k_blocks;
+    __half *q16 = nullptr;
+    float *tau = nullptr;
+    uint32_t q_cap = 0;  // rows
+};
+
+TcScanState *tc_scan_create(int sm_count, uint32_t ld, uint32_t dim)
+{
+    if (dim == 0 || dim > kMaxKB * kBK || ld % 8 != 0) return nullptr;
+    if (!encode_tiled_fn()) return nullptr;
+    TcScanState *t = new TcScanState();
+    t->sm_count = sm_count;
+    t->ld = ld;
+    t->dim = dim;
+    t->k_blocks = ceil_div<uint32_t>(dim, kBK);
+    return t;
+}
+
+void tc_scan_destroy(TcScanState *t)
+{
+    if (!t) return;
+    cudaFree(t->q16);
+    cudaFree(t->tau);
+    delete t;
+}
+
+void tc_scan_invalidate(TcScanState *) {}  // tensor maps are rebuilt on every launch
+
+uint32_t tc_scan_max_k() { return 26; }
+bool tc_scan_supports(const TcScanState *t, uint32_t k) { return t != nullptr && k <= tc_scan_max_k(); }
+uint32_t tc_scan_lcap(uint32_t k) { return k <= 10 ? 16u : 32u; }
+uint32_t tc_scan_lists(const TcScanState *t, uint64_t n_rows)
+{
+    return (uint32_t)std::min<uint64_t>((uint64_t)t->sm_count, ceil_div<uint64_t>(n_rows, kTileN));
+}
+
+template <int L>
+static cudaError_t launch_tc(const CUtensorMap &tmQ, const CUtensorMap &tmC, const TcParams &tp, bool use_inv, dim3 grid,
+                             cudaStream_t st)
+{
+    const int smem = TcCfg<L>::smem_bytes((int)tp.k_blocks);
+    cudaError_t e;
+    if (use_inv) {
+        auto kern = scan_tc_kernel<L, true>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+        kern<<<grid, kTcThreads, smem, st>>>(tmQ, tmC, tp);
+    } else {
+        auto kern = scan_tc_kernel<L, false>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+        kern<<<grid, kTcThreads, smem, st>>>(tmQ, tmC, tp);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacity, uint32_t k, KernelTimer *timer,
+                           cudaStream_t st, const char **why)
+{
+    (void)capacity;
+    const uint32_t nq_pad = ceil_div<uint32_t>(p.nq, kQM) * kQM;
+    if (nq_pad > t->q_cap) {
+        cudaFree(t->q16);
+        cudaFree(t->tau);
+        t->q16 = nullptr;
+        t->tau = nullptr;
+        t->q_cap = 0;
+        cudaError_t e = cudaMalloc(&t->q16, (size_t)nq_pad * t->ld * sizeof(__half));
+        if (e == cudaSuccess) e = cudaMalloc(&t->tau, (size_t)nq_pad * sizeof(float));
+        if (e != cudaSuccess) {
+            if (why) *why = "query staging allocation failed";
+            return e;
+        }
+        t->q_cap = nq_pad;
+    }
+    if (timer) timer->begin(st, 1);
+    tc_prepare_queries_kernel<<<nq_pad / 4, 128, 0, st>>>(p.queries, p.nq, t->dim, p.ldq, t->q16, t->ld, t->tau);
+    count_launch();
+    if (timer) timer->end(st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+
+    CUtensorMap tmQ, tmC;
+    if (!make_tmap_k_major_16bit(&tmQ, t->q16, nq_pad, t->dim, t->ld, kQM, false) ||
+        !make_tmap_k_major_16bit(&tmC, p.rows, p.n_rows, t->dim, p.ld, kTileN, false)) {
+        if (why) *why = "cuTensorMapEncodeTiled failed";
+        return cudaErrorInvalidValue;
+    }
+    TcParams tp{};
+    tp.inv_norm = p.use_inv ? p.inv_norm : nullptr;
+    tp.tau = t->tau;
+    tp.cand_s = p.cand_s;
+    tp.cand_r = p.cand_r;
+    tp.n_rows = p.n_rows;
+    tp.nq = p.nq;
+    tp.n_lists = p.n_lists;
+    tp.k_blocks = t->k_blocks;
+    dim3 grid(p.n_lists, nq_pad / kQM);
+    if (timer) timer->begin(st, 0);
+    e = tc_scan_lcap(k) == 16 ? launch_tc<16>(tmQ, tmC, tp, p.use_inv != 0, grid, st)
+                              : launch_tc<32>(tmQ, tmC, tp, p.use_inv != 0, grid, st);
+    if (timer) timer->end(st);
+    if (e != cudaSuccess && why) *why = "scan_tc_kernel launch failed";
+    return e;
+}
+
 }  // namespace mx

@@ -109,7 +109,7 @@ int32_t reserve(mx_store *s, uint64_t want, int32_t err_code)
     void *nrows = nullptr;
     float *ninv = nullptr;
     MX_CUDA(s, err_code, cudaMalloc(&nrows, cap * s->ld * s->elem));
-    cudaError_t e = cudaMalloc(&ninv, cap * sizeof(float));
+    cudaError_t e = cudaMalloc(&ninv, (cap + 128) * sizeof(float));  // scan_tc reads whole 128-row tiles
     if (e != cudaSuccess) {
         cudaFree(nrows);
         return fail(s, err_code, "cudaMalloc(inv_norm) failed: %s", cudaGetErrorString(e));

@@ -122,7 +122,9 @@ class ShardedStore:
         nq = q_dev.shape[0]
         b = self._buffers(nq, k)
         L = capi.lib()
-        st = torch.cuda.current_stream(self.device).cuda_stream
+        # torch's default stream has handle 0, which the C ABI reads as "the store's own stream": name the
+        # legacy default stream explicitly (cudaStreamLegacy == 0x1) so the work is ordered with torch's
+        st = torch.cuda.current_stream(self.device).cuda_stream or 1
         mine = b["mine"]
         rc = L.mx_store_search_blob_device(self.local.handle, q_dev.data_ptr(), nq, k, mine.data_ptr(), st)
         if rc != capi.OK:

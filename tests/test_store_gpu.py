@@ -292,3 +292,75 @@ def test_full_size_properties_1m(tmp_path):
         si, ss, _ = store.search_matrix(queries[i:i + 1], k)
         np.testing.assert_array_equal(si[0], ids[i])
         np.testing.assert_array_equal(ss[0].view(np.uint32), scores[i].view(np.uint32))
+
+
+# ---- K2: the tcgen05 batched scan (fp16 stores, nq >= 8) ------------------------------------------
+
+@pytest.mark.parametrize("n,d,nq,k,metric", [
+    (20000, 384, 64, 10, "cosine"), (128, 384, 8, 10, "cosine"), (129, 64, 9, 3, "cosine"),
+    (50001, 384, 128, 10, "cosine"), (30000, 384, 200, 10, "cosine"), (7777, 100, 33, 20, "cosine"),
+    (40000, 256, 64, 26, "cosine"), (25000, 384, 64, 10, "dot"), (100, 8, 16, 10, "cosine"),
+])
+def test_parity_tcgen05_scan(tmp_path, n, d, nq, k, metric):
+    """the batched tensor-core path gives the same ids and bit-identical scores as the oracle"""
+    rng = np.random.default_rng(n + d + nq)
+    corpus = (rng.standard_normal((n, d)) * rng.uniform(0.5, 2.0, (n, 1))).astype(np.float32)   # unnormalised rows
+    queries = (corpus[rng.integers(0, n, nq)] + 0.3 * rng.standard_normal((nq, d))).astype(np.float32)
+    store = B200Store.new(tmp_path, dim=d, dtype="f16", metric=metric)
+    store.add_matrix(corpus)
+    assert capi.lib().mx_store_scan_path(store.handle, nq, k, -1) == 2
+    stored = corpus.astype(np.float16).astype(np.float32)
+    check_parity(store, stored, queries, k, metric=metric)
+    # and agrees with the CUDA-core stream path on the same store
+    a = store.search_matrix(queries, k)
+    assert capi.lib().mx_store_scan_path(store.handle, nq, k, 1) == 1
+    b = store.search_matrix(queries, k)
+    capi.lib().mx_store_scan_path(store.handle, nq, k, -1)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+def test_tcgen05_scan_duplicates_and_growth(tmp_path):
+    """many exact duplicates spread over the CTAs' row ranges: ties resolve to the lowest ids; the store
+    regrows between searches (tensor maps are rebuilt per launch)"""
+    rng = np.random.default_rng(77)
+    d, nq, k = 128, 16, 10
+    corpus = rng.standard_normal((60000, d)).astype(np.float32)
+    dup = rng.standard_normal(d).astype(np.float32)
+    dup_rows = rng.choice(60000, 300, replace=False)
+    corpus[dup_rows] = dup
+    queries = np.tile(dup, (nq, 1)) + 0.01 * rng.standard_normal((nq, d)).astype(np.float32)
+    store = B200Store.new(tmp_path, dim=d, dtype="f16", capacity=1000)
+    stored = corpus.astype(np.float16).astype(np.float32)
+    for lo in range(0, 60000, 20000):
+        store.add_matrix(corpus[lo:lo + 20000])
+        check_parity(store, stored[:lo + 20000], queries, k)
+    ids, _, _ = store.search_matrix(queries, k)
+    np.testing.assert_array_equal(ids[0], np.sort(dup_rows)[:k] + 1)
+
+
+def test_full_size_properties_tcgen05_2m(tmp_path):
+    """2 M x 384 fp16, 64 queries: planted neighbours found, scores bit-exact, one query checked in full"""
+    n, d, k, nq = 2_000_000, 384, 10, 64
+    rng = np.random.default_rng(99)
+    store = B200Store.new(tmp_path, dim=d, dtype="f16", capacity=n)
+    keep = []
+    for i in range(0, n, 250_000):
+        part = rng.standard_normal((250_000, d), dtype=np.float32)
+        part /= np.linalg.norm(part, axis=1, keepdims=True)
+        store.add_matrix(part)
+        keep.append(part.astype(np.float16))
+    stored16 = np.concatenate(keep)
+    rows = rng.integers(0, n, nq)
+    queries = stored16[rows].astype(np.float32) + 0.03 * rng.standard_normal((nq, d)).astype(np.float32)
+    assert capi.lib().mx_store_scan_path(store.handle, nq, k, -1) == 2
+    ids, scores, counts = store.search_matrix(queries, k)
+    assert (counts == k).all()
+    np.testing.assert_array_equal(ids[:, 0], rows + 1)
+    assert (np.diff(scores, axis=1) <= 0).all()
+    stored = stored16.astype(np.float32)
+    for i in (0, 31, 63):
+        np.testing.assert_array_equal(cosine.scores_of(stored, queries[i], ids[i]).view(np.uint32), scores[i].view(np.uint32))
+    oi, os_, _ = cosine.exact_topk(stored, queries[:2], k)
+    np.testing.assert_array_equal(ids[:2], oi)
+    np.testing.assert_array_equal(scores[:2].view(np.uint32), os_.view(np.uint32))
