@@ -1,6 +1,7 @@
 // debug.cu -- test-only entry points (include/memex_b200_debug.h): single kernels, device pointers.
 #include "../../include/memex_b200_debug.h"
 #include "common.cuh"
+#include "encoder.cuh"
 #include "gemm.cuh"
 
 using namespace mx;
@@ -44,6 +45,23 @@ int32_t mx_debug_gemm(const void *A, const void *W, const float *bias, const voi
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         g_debug_error = std::string(cudaGetErrorString(e)) + (why ? std::string(" (") + why + ")" : "");
+        return MX_ERR_ENCODE;
+    }
+    return MX_OK;
+}
+
+int32_t mx_debug_attention(const void *qkv, const int32_t *lens_dev, void *ctx, uint32_t B, uint32_t S, uint32_t H,
+                           uint32_t heads, uint32_t fmt, uint32_t impl, int32_t device)
+{
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) {
+        const int act = fmt == 1 ? ACT_BF16 : ACT_F16;
+        e = impl == 0 ? launch_attention_simt(qkv, lens_dev, ctx, act, B, S, H, heads, nullptr)
+                      : launch_attention_mma(qkv, lens_dev, ctx, act, B, S, H, heads, nullptr);
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        g_debug_error = cudaGetErrorString(e);
         return MX_ERR_ENCODE;
     }
     return MX_OK;

@@ -155,7 +155,10 @@ int32_t forward(mx_embedder *e, const int32_t *ids_dev, const int32_t *lens_dev,
         const LayerWeights &w = e->layers[l];
         if ((rc = run_gemm(e, e->x, w.wqkv, w.bqkv, nullptr, nullptr, nullptr, e->qkv, T, 3 * H, H, EPI_BIAS, st)) != MX_OK) return rc;
         e->timer.begin(st, 1);
-        MX_CUDA(e, MX_ERR_ENCODE, launch_attention_simt(e->qkv, lens_dev, e->ctx, e->act, B, S, H, c.heads, st));
+        if (e->act == ACT_F32)
+            MX_CUDA(e, MX_ERR_ENCODE, launch_attention_simt(e->qkv, lens_dev, e->ctx, e->act, B, S, H, c.heads, st));
+        else
+            MX_CUDA(e, MX_ERR_ENCODE, launch_attention_mma(e->qkv, lens_dev, e->ctx, e->act, B, S, H, c.heads, st));
         e->timer.end(st);
         if ((rc = run_gemm(e, e->ctx, w.wo, w.bo, e->x, w.ln1_g, w.ln1_b, e->x1, T, H, H, EPI_BIAS_RES_LN, st)) != MX_OK) return rc;
         if ((rc = run_gemm(e, e->x1, w.w1, w.b1, nullptr, nullptr, nullptr, e->hh, T, F, H, EPI_BIAS_GELU, st)) != MX_OK) return rc;

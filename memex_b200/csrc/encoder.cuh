@@ -19,6 +19,10 @@ cudaError_t launch_embed_ln(const int32_t *ids, const float *word, const float *
 cudaError_t launch_attention_simt(const void *qkv, const int32_t *lens_dev, void *ctx, int act, uint32_t B, uint32_t S,
                                   uint32_t H, uint32_t heads, cudaStream_t st);
 
+// K6 (tensor-core version, attention_mma.cu): same contract, 16-bit activations only
+cudaError_t launch_attention_mma(const void *qkv, const int32_t *lens_dev, void *ctx, int act, uint32_t B, uint32_t S,
+                                 uint32_t H, uint32_t heads, cudaStream_t st);
+
 // fp32 path only: x = LayerNorm(y + residual) (the GEMM already added the bias)
 cudaError_t launch_add_ln_f32(const float *y, const float *residual, const float *gamma, const float *beta, float eps,
                               float *out, uint32_t rows, uint32_t H, cudaStream_t st);

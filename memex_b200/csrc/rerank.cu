@@ -62,24 +62,35 @@ __device__ __forceinline__ float key_to_score(float key, uint32_t metric)
 
 constexpr int kRerankThreads = 512;
 constexpr int kRerankWarps = kRerankThreads / 32;
+constexpr int kFoldChunk = 384;           // elements of a row staged per pass
+constexpr int kFoldPitch = kFoldChunk + 1;  // odd pitch: lane j reading row j is bank-conflict free
+constexpr int kFoldBatches = 2;           // 32-entry batches folded concurrently (one warp each)
 
+// One CTA per query:
+//   1. every warp folds a slice of the scan's candidate lists into a warp-resident top-(32 E) list;
+//   2. the 16 warp lists are merged by counting ranks (one thread per entry) -> the 32 E best rows;
+//   3. the lowest-id zero-norm rows are appended (cosine: d = 0 for them whatever the query);
+//   4. exact keys: candidate rows are staged in shared memory with coalesced loads, then ONE THREAD
+//      per candidate folds its row left to right in f64 -- the reference's order of operations;
+//   5. duplicates dropped, entries rank-sorted by (key asc, id asc), best k written.
 template <int E>
 __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
 {
     constexpr int kList = 32 * E;
     constexpr int kMaxEntries = kList + (int)MX_MAX_K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *qs = reinterpret_cast<float *>(smem_raw);                 // [ldq]
-    float *ws = qs + p.ldq;                                          // [warps][kList] scores
+    float *qs = reinterpret_cast<float *>(smem_raw);                 // [kFoldChunk] query chunk
+    float *ws = qs + kFoldChunk;                                     // [warps][kList] scores
     uint32_t *wr = reinterpret_cast<uint32_t *>(ws + kRerankWarps * kList);
     float *ekey = reinterpret_cast<float *>(wr + kRerankWarps * kList);  // [kMaxEntries]
     uint32_t *erow = reinterpret_cast<uint32_t *>(ekey + kMaxEntries);
+    float *rowbuf = reinterpret_cast<float *>(erow + kMaxEntries);   // [kFoldBatches * 32][kFoldPitch]
     __shared__ uint32_t n_entries_s;
     __shared__ int zero_query_s;
 
     const uint32_t q = blockIdx.x;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < p.ldq; i += blockDim.x) qs[i] = p.queries[(size_t)q * p.ldq + i];
+    const float *qg = p.queries + (size_t)q * p.ldq;
 
     // 1. every warp folds a slice of the candidate lists into its own list
     WarpTopK<E> top;
@@ -101,48 +112,89 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
         ws[warp * kList + e * 32 + lane] = top.s[e];
         wr[warp * kList + e * 32 + lane] = top.r[e];
     }
+    for (uint32_t j = threadIdx.x; j < kMaxEntries; j += blockDim.x) {
+        ekey[j] = 0.f;
+        erow[j] = kNoRow;
+    }
     __syncthreads();
-    // 2. warp 0 folds the warp lists; appends the lowest-id zero-norm rows (cosine: d = 0)
-    if (warp == 0) {
-        for (int w = 1; w < kRerankWarps; ++w)
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const float v = ws[w * kList + e * 32 + lane];
-                const uint32_t r = wr[w * kList + e * 32 + lane];
-                top.offer(r != kNoRow, v, r);
-            }
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            ekey[e * 32 + lane] = 0.f;
-            erow[e * 32 + lane] = top.r[e];
-        }
+    // 2. rank of every entry among all warp lists; rows are unique across lists (a row is scanned by
+    //    one CTA), so ranks of real entries are unique and the kList best land in erow[0 .. kList)
+    for (uint32_t j = threadIdx.x; j < kRerankWarps * kList; j += blockDim.x) {
+        const float v = ws[j];
+        const uint32_t r = wr[j];
+        if (r == kNoRow) continue;
+        uint32_t rank = 0;
+        for (uint32_t i = 0; i < kRerankWarps * kList; ++i) rank += cand_before(ws[i], wr[i], v, r) ? 1u : 0u;
+        if (rank < kList) erow[rank] = r;
+    }
+    // 3. the lowest-id zero-norm rows (cosine: d = 0)
+    if (threadIdx.x == 0) {
         uint32_t n = kList;
-        if (p.metric == MX_METRIC_COSINE) {
-            const uint32_t nz = min(min(*p.n_zero, p.k), (uint32_t)MX_MAX_K);
-            for (uint32_t i = lane; i < nz; i += 32) {
-                ekey[kList + i] = 0.f;
-                erow[kList + i] = p.zero_rows[i];
-            }
-            n += nz;
-        }
-        if (lane == 0) n_entries_s = n;
+        if (p.metric == MX_METRIC_COSINE) n += min(min(*p.n_zero, p.k), (uint32_t)MX_MAX_K);
+        n_entries_s = n;
     }
     __syncthreads();
     const uint32_t n_entries = n_entries_s;
+    for (uint32_t i = threadIdx.x; i + kList < n_entries; i += blockDim.x) erow[kList + i] = p.zero_rows[i];
+    __syncthreads();
 
-    // 3. exact key per entry (one thread each)
-    double aa = 1.0;
-    for (uint32_t j = threadIdx.x; j < n_entries; j += blockDim.x) {
-        const uint32_t row = erow[j];
-        if (row != kNoRow && row < p.n_rows)
-            ekey[j] = exact_key(qs, p.rows, p.dtype, p.metric, (size_t)row * p.ld, p.dim, &aa);
-        else
-            erow[j] = kNoRow;
+    // 4. exact key per entry.  Batches of 32 entries; the rows of kFoldBatches batches are staged per pass
+    //    (chunks of kFoldChunk elements), then lane j of warp b folds entry 32 * (b0 + b) + j.
+    double q_aa = 0.0;
+    const uint32_t n_batches = (n_entries + 31) / 32;
+    for (uint32_t b0 = 0; b0 < n_batches; b0 += kFoldBatches) {
+        const uint32_t first = b0 * 32;
+        const uint32_t n_here = min((uint32_t)kFoldBatches * 32, n_entries - first);
+        double ab = 0.0, aa = 0.0, bb = 0.0;
+        const bool folder = warp < kFoldBatches && warp * 32 + lane < n_here;
+        const uint32_t my_row = folder ? erow[first + warp * 32 + lane] : kNoRow;
+        for (uint32_t c0 = 0; c0 < p.dim; c0 += kFoldChunk) {
+            const uint32_t cn = min((uint32_t)kFoldChunk, p.dim - c0);
+            __syncthreads();   // previous chunk fully consumed
+            for (uint32_t i = threadIdx.x; i < cn; i += blockDim.x) qs[i] = qg[c0 + i];
+            // stage: entry e of this pass, element i -> rowbuf[e][i]; consecutive threads read consecutive elements
+            for (uint32_t e = warp; e < n_here; e += kRerankWarps) {
+                const uint32_t row = erow[first + e];
+                if (row == kNoRow || row >= p.n_rows) continue;
+                const size_t off = (size_t)row * p.ld + c0;
+                for (uint32_t i = lane; i < cn; i += 32) rowbuf[e * kFoldPitch + i] = load_elem(p.rows, p.dtype, off + i);
+            }
+            __syncthreads();
+            if (folder && my_row != kNoRow && my_row < p.n_rows) {
+                const float *rb = rowbuf + (warp * 32 + lane) * kFoldPitch;
+                for (uint32_t i = 0; i < cn; ++i) {
+                    const float a = qs[i], b = rb[i];
+                    ab = __dadd_rn(ab, (double)__fmul_rn(a, b));
+                    aa = __dadd_rn(aa, (double)__fmul_rn(a, a));
+                    bb = __dadd_rn(bb, (double)__fmul_rn(b, b));
+                }
+            }
+        }
+        if (folder) {
+            const uint32_t j = first + warp * 32 + lane;
+            if (my_row != kNoRow && my_row < p.n_rows) {
+                float key;
+                if (p.metric == MX_METRIC_DOT)
+                    key = -(float)ab;
+                else if (aa > 0.0 && bb > 0.0)
+                    key = (float)fmax(__dsub_rn(1.0, __ddiv_rn(ab, __dsqrt_rn(__dmul_rn(aa, bb)))), 0.0);
+                else
+                    key = 0.f;
+                ekey[j] = key;
+                q_aa = aa;
+            } else {
+                erow[j] = kNoRow;
+            }
+        }
     }
     if (threadIdx.x == 0) {
-        // the query's own norm decides the degenerate case (DistCosine: aa == 0 -> d = 0 for all)
-        double a2 = 0.0;
-        for (uint32_t i = 0; i < p.dim; ++i) a2 = __dadd_rn(a2, (double)__fmul_rn(qs[i], qs[i]));
+        // the query's own norm decides the degenerate case (DistCosine: aa == 0 -> d = 0 for all rows).
+        // thread 0 folded entry 0 when that entry was real; otherwise (no candidates at all) fold here.
+        double a2 = q_aa;
+        if (!(erow[0] != kNoRow)) {
+            a2 = 0.0;
+            for (uint32_t i = 0; i < p.dim; ++i) a2 = __dadd_rn(a2, (double)__fmul_rn(qg[i], qg[i]));
+        }
         zero_query_s = (p.metric == MX_METRIC_COSINE && !(a2 > 0.0)) ? 1 : 0;
     }
     __syncthreads();
@@ -160,7 +212,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
         return;
     }
 
-    // 4. drop duplicates (a zero row can also arrive through the scan), then rank-sort
+    // 5. drop duplicates (a zero row can also arrive through the scan), then rank-sort
     for (uint32_t j = threadIdx.x; j < n_entries; j += blockDim.x) {
         const uint32_t row = erow[j];
         bool dup = false;
@@ -204,7 +256,8 @@ cudaError_t launch_rerank(const RerankParams &p, cudaStream_t st)
     // the rerank's own list holds the 32 * E best approximate candidates, E chosen from k as the stream scan does
     const uint32_t lk = scan_stream_lcap(p.k);
     const uint32_t E = lk / 32;
-    const size_t smem = (size_t)p.ldq * 4 + (size_t)kRerankWarps * lk * 8 + (size_t)(lk + MX_MAX_K) * 8;
+    const size_t smem = (size_t)kFoldChunk * 4 + (size_t)kRerankWarps * lk * 8 + (size_t)(lk + MX_MAX_K) * 8 +
+                        (size_t)kFoldBatches * 32 * kFoldPitch * 4;
 #define MX_RR(EE)                                                                                  \
     {                                                                                              \
         auto kern = rerank_kernel<EE>;                                                             \

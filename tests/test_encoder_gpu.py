@@ -84,6 +84,40 @@ capi.lib().mx_debug_gemm.argtypes = [C.c_void_p] * 7 + [C.c_uint32] * 5 + [C.c_f
 capi.lib().mx_debug_last_error.restype = C.c_char_p
 
 
+capi.lib().mx_debug_attention.restype = C.c_int32
+capi.lib().mx_debug_attention.argtypes = [C.c_void_p] * 3 + [C.c_uint32] * 6 + [C.c_int32]
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("fmt,tol", [(1, 2e-2), (0, 3e-3)])
+@pytest.mark.parametrize("B,S,H,heads", [(3, 64, 64, 2), (4, 256, 384, 12), (2, 200, 768, 12), (5, 37, 384, 12),
+                                         (2, 130, 256, 2), (1, 512, 384, 12)])
+def test_attention_kernels_against_torch(B, S, H, heads, fmt, tol, impl):
+    """K6 in isolation: softmax(q k^T / sqrt(dh) + padding mask) v, rows beyond lens[b] are zero"""
+    import torch
+    torch.manual_seed(B * 1000 + S + H)
+    dt = torch.bfloat16 if fmt == 1 else torch.float16
+    dh = H // heads
+    qkv = (torch.randn(B, S, 3 * H, device="cuda") * 1.5).to(dt)
+    lens = torch.randint(1, S + 1, (B,), device="cuda", dtype=torch.int32)
+    lens[0] = S
+    if B > 1:
+        lens[1] = 1
+    if B > 2:
+        lens[2] = 0
+    out = torch.full((B, S, H), float("nan"), device="cuda").to(dt)
+    rc = capi.lib().mx_debug_attention(qkv.data_ptr(), lens.data_ptr(), out.data_ptr(), B, S, H, heads, fmt, impl, 0)
+    assert rc == 0, capi.lib().mx_debug_last_error()
+    q, k, v = [x.float().reshape(B, S, heads, dh).transpose(1, 2) for x in qkv.split(H, dim=2)]
+    mask = torch.arange(S, device="cuda")[None, :] < lens[:, None]
+    sc = q @ k.transpose(-1, -2) / dh ** 0.5
+    sc = sc.masked_fill(~mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(sc, dim=-1).nan_to_num(0.0) @ v).transpose(1, 2).reshape(B, S, H)
+    ref = ref * mask[:, :, None]
+    err = (out.float() - ref).abs().max().item()
+    assert np.isfinite(err) and err <= tol * max(1.0, ref.abs().max().item()), err
+
+
 @pytest.mark.parametrize("precision,min_cos,max_abs", [("bf16", 1 - 2e-4, 2e-3), ("f16", 1 - 1e-5, 5e-4)])
 def test_tensor_core_paths_vs_oracle(precision, min_cos, max_abs):
     cfg = enc_oracle.MINILM_L6
