@@ -160,16 +160,21 @@ __global__ void __launch_bounds__(kAmWarps * 32) attention_mma_kernel(const uint
                 mma16816<BF16>(s[j], qf[2 * kk + 1], kf[2], kf[3]);
             }
         }
-        // scale, mask, block row max
+        // mask (only a block that straddles len has keys to mask), block row max of the raw scores
+        if (k0 + kAmKB > len) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t key = k0 + 8 * j + 2 * t;
+                const bool ok0 = key < len, ok1 = key + 1 < len;
+                s[j][0] = ok0 ? s[j][0] : kNegInf;
+                s[j][1] = ok1 ? s[j][1] : kNegInf;
+                s[j][2] = ok0 ? s[j][2] : kNegInf;
+                s[j][3] = ok1 ? s[j][3] : kNegInf;
+            }
+        }
         float mx_a = kNegInf, mx_b = kNegInf;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const uint32_t key = k0 + 8 * j + 2 * t;
-            const bool ok0 = key < len, ok1 = key + 1 < len;
-            s[j][0] = ok0 ? s[j][0] * scale_log2e : kNegInf;
-            s[j][1] = ok1 ? s[j][1] * scale_log2e : kNegInf;
-            s[j][2] = ok0 ? s[j][2] * scale_log2e : kNegInf;
-            s[j][3] = ok1 ? s[j][3] * scale_log2e : kNegInf;
             mx_a = fmaxf(mx_a, fmaxf(s[j][0], s[j][1]));
             mx_b = fmaxf(mx_b, fmaxf(s[j][2], s[j][3]));
         }
@@ -177,8 +182,9 @@ __global__ void __launch_bounds__(kAmWarps * 32) attention_mma_kernel(const uint
         mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
         mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
         mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+        // running maxima are kept in the exp2 domain (raw score * scale * log2 e; the scale is positive).
         // key k0 < len always holds inside the loop, so the new maxima are finite
-        const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);
+        const float mn_a = fmaxf(m_a, mx_a * scale_log2e), mn_b = fmaxf(m_b, mx_b * scale_log2e);
         const float corr_a = fast_exp2(m_a - mn_a), corr_b = fast_exp2(m_b - mn_b);
         m_a = mn_a;
         m_b = mn_b;
@@ -186,8 +192,8 @@ __global__ void __launch_bounds__(kAmWarps * 32) attention_mma_kernel(const uint
         uint32_t pf[4][4];   // A fragments of P: 4 k-steps of 16 keys
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float p0 = fast_exp2(s[j][0] - mn_a), p1 = fast_exp2(s[j][1] - mn_a);
-            const float p2 = fast_exp2(s[j][2] - mn_b), p3 = fast_exp2(s[j][3] - mn_b);
+            const float p0 = fast_exp2(fmaf(s[j][0], scale_log2e, -mn_a)), p1 = fast_exp2(fmaf(s[j][1], scale_log2e, -mn_a));
+            const float p2 = fast_exp2(fmaf(s[j][2], scale_log2e, -mn_b)), p3 = fast_exp2(fmaf(s[j][3], scale_log2e, -mn_b));
             sum_a += p0 + p1;
             sum_b += p2 + p3;
             pf[j >> 1][(j & 1) * 2 + 0] = pack2<BF16>(p0, p1);

@@ -10,7 +10,7 @@
 //   EPI_BIAS_RES_LN+ bias, + residual, LayerNorm(gamma,beta)(attention.output / output; BN == N)
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected
-// lane; also owns the TMEM allocation), warps 2..5 = epilogue (TMEM -> registers -> global).
+// lane; also owns the TMEM allocation), warps 2.. = epilogue (8 or 16 warps: TMEM -> registers -> global).
 // Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two
 // accumulator stages when 2 * BN <= 512 columns), and the static tile schedule
 // tile = blockIdx.x + i * gridDim.x with the N index fastest (concurrent CTAs share A rows in L2).
@@ -22,7 +22,6 @@ namespace mx {
 
 using namespace tc;
 
-constexpr int kGemmThreads = 192;
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 128 bytes of bf16: one swizzle atom
 
@@ -34,12 +33,38 @@ struct GemmCfg {
     static constexpr int kTmemCols = (kAccStages * BN <= 128) ? 128 : (kAccStages * BN <= 256 ? 256 : 512);
     static constexpr int kStageBytes = kBM * kBK * 2 + BN * kBK * 2;
     static constexpr int kStages = (200 * 1024) / kStageBytes < 8 ? (200 * 1024) / kStageBytes : 8;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    // epilogue: 4 TMEM lane quarters x kColGroups column groups, one warp each -- several warps per SM
+    // sub-partition so that the bias / GELU / LayerNorm arithmetic is issue-bound, not latency-bound
+    static constexpr int kColGroups = (BN % 128 == 0) ? 4 : 2;
+    static constexpr int kColsPerWarp = BN / kColGroups;
+    static constexpr int kEpiWarps = 4 * kColGroups;
+    static constexpr int kThreads = 64 + 32 * kEpiWarps;
+    static constexpr int kStatBytes = 2 * kColGroups * kBM * 8;   // LayerNorm partial (sum, sq), double buffered
+    static constexpr int kVecBytes = 3 * BN * 4;                  // bias tiles (x2) or bias | gamma | beta, staged in smem
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStatBytes + kVecBytes;
+    static_assert(kColsPerWarp % 32 == 0, "an epilogue warp works in 32-column chunks");
     static_assert(kChunkN % 16 == 0 && kChunkN <= 256, "invalid UMMA N");
     static_assert((BN * kBK * 2 / kChunks) % 1024 == 0, "B chunks must stay 1024-byte aligned");
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-GELU for the 16-bit paths.  erf(t) = 1 - 2^(-q(t)) on t in [0, 4] with q a degree-5 polynomial
+// without constant term (least-squares/minimax fit of -log2(erfc(t)); max |error| of erf 6.7e-7 when
+// evaluated in f32, far below the bf16/f16 output resolution); |t| > 4 is clamped (erf(4) = 1 - 1.5e-8).
+// One SFU op (ex2) instead of erff's two polynomial branches.  The fp32 validation path keeps erff.
+__device__ __forceinline__ float gelu_erf(float x)
+{
+    const float t = fminf(fabsf(x) * 0.70710678118654752f, 4.0f);
+    float q = fmaf(t, 0.00294416f, -0.02959005f);
+    q = fmaf(t, q, 0.14866564f);
+    q = fmaf(t, q, 0.91850936f);
+    q = fmaf(t, q, 1.627889f);
+    q *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-q));
+    const float erf_x = copysignf(1.0f - e, x);
+    const float h = 0.5f * x;
+    return fmaf(h, erf_x, h);
+}
 
 template <int FMT>
 __device__ __forceinline__ uint32_t pack16(float a, float b)
@@ -62,7 +87,7 @@ __device__ __forceinline__ float2 unpack16(uint32_t u)
 }
 
 template <int BN, int EPI, int FMT>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(GemmCfg<BN>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p)
 {
     using Cfg = GemmCfg<BN>;
@@ -73,6 +98,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t *tmem_full = empty + Cfg::kStages;
     uint64_t *tmem_empty = tmem_full + Cfg::kAccStages;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + Cfg::kAccStages);
+    float2 *stat = reinterpret_cast<float2 *>(smem + Cfg::kStages * Cfg::kStageBytes + 256);  // [2][kColGroups][kBM]
+    float *svec = reinterpret_cast<float *>(smem + Cfg::kStages * Cfg::kStageBytes + 256 + Cfg::kStatBytes);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_n = p.N / BN;
@@ -89,7 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < Cfg::kAccStages; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);
+            mbar_init(&tmem_empty[i], Cfg::kEpiWarps);
         }
         fence_barrier_init();
     }
@@ -155,29 +182,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ================= epilogue: 4 warps, warp % 4 selects the TMEM lane quarter =================
+        // ================= epilogue: warp % 4 selects the TMEM lane quarter, (warp - 2) / 4 the column group ======
         const uint32_t quarter = warp & 3;
+        const uint32_t cg = (warp - 2) >> 2;
+        constexpr int kCW = Cfg::kColsPerWarp;
+        constexpr uint32_t kEpiThreads = Cfg::kEpiWarps * 32;
+        const uint32_t etid = threadIdx.x - 64;
+        if constexpr (EPI == EPI_BIAS_RES_LN) {
+            // BN == N: one set of per-column vectors for the whole kernel
+            for (uint32_t i = etid; i < BN; i += kEpiThreads) {
+                svec[i] = __ldg(p.bias + i);
+                svec[BN + i] = __ldg(p.gamma + i);
+                svec[2 * BN + i] = __ldg(p.beta + i);
+            }
+            bar_sync(1, kEpiThreads);
+        }
         uint32_t local = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
             const uint32_t m_blk = tile / tiles_n, n_blk = tile % tiles_n;
             const uint32_t as = local % Cfg::kAccStages, aphase = (local / Cfg::kAccStages) & 1;
+            const float *sbias = svec;
+            if constexpr (EPI != EPI_BIAS_RES_LN) {
+                // this tile's bias slice -> smem (double buffered; the barrier of tile i+1 orders reuse)
+                float *bt = svec + (local & 1) * BN;
+                for (uint32_t i = etid; i < BN; i += kEpiThreads) bt[i] = __ldg(p.bias + n_blk * BN + i);
+                bar_sync(1, kEpiThreads);
+                sbias = bt;
+            }
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            const uint32_t row = m_blk * kBM + quarter * 32 + lane;
+            const uint32_t row_in_tile = quarter * 32 + lane;
+            const uint32_t row = m_blk * kBM + row_in_tile;
             const bool row_ok = row < p.M;
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * BN;
-            const uint32_t col0 = n_blk * BN;
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * BN + cg * kCW;
+            const uint32_t col0 = n_blk * BN + cg * kCW;
             uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + (size_t)row * p.ldo + col0;
 
             if constexpr (EPI == EPI_BIAS_RES_LN) {
-                // pass 1: x = acc + bias + residual, kept in TMEM; row sums
+                // pass 1: x = acc + bias + residual, kept in TMEM; partial row sums of this warp's columns
                 const uint16_t *rrow = reinterpret_cast<const uint16_t *>(p.residual) + (size_t)row * p.ldr + col0;
                 float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = 0; c < kCW / 32; ++c) {
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
-                    tmem_ld_wait();
                     uint4 rr[4];
                     if (row_ok) {
 #pragma unroll
@@ -186,12 +234,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 4; ++j) rr[j] = make_uint4(0, 0, 0, 0);
                     }
+                    tmem_ld_wait();
                     const uint32_t *rh = reinterpret_cast<const uint32_t *>(rr);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float2 r2 = unpack16<FMT>(rh[j]);
-                        const float x0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + col0 + c * 32 + 2 * j) + r2.x;
-                        const float x1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + col0 + c * 32 + 2 * j + 1) + r2.y;
+                        const float2 b2 = *reinterpret_cast<const float2 *>(sbias + cg * kCW + c * 32 + 2 * j);
+                        const float x0 = __uint_as_float(v[2 * j]) + b2.x + r2.x;
+                        const float x1 = __uint_as_float(v[2 * j + 1]) + b2.y + r2.y;
                         sum += x0 + x1;
                         sq = fmaf(x0, x0, fmaf(x1, x1, sq));
                         v[2 * j] = __float_as_uint(x0);
@@ -199,22 +249,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     tmem_st32(taddr + c * 32, v);
                 }
+                float2 *st2 = stat + (local & 1) * (Cfg::kColGroups * kBM);
+                st2[cg * kBM + row_in_tile] = make_float2(sum, sq);
                 tmem_st_wait();
+                bar_sync(1, Cfg::kEpiWarps * 32);
+                sum = 0.f;
+                sq = 0.f;
+#pragma unroll
+                for (int i = 0; i < Cfg::kColGroups; ++i) {
+                    const float2 t2 = st2[i * kBM + row_in_tile];
+                    sum += t2.x;
+                    sq += t2.y;
+                }
                 const float mean = sum * (1.0f / BN);
                 const float var = fmaxf(sq * (1.0f / BN) - mean * mean, 0.f);
                 const float rstd = rsqrtf(var + p.ln_eps);
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = 0; c < kCW / 32; ++c) {
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
                     tmem_ld_wait();
                     uint32_t o[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int n0 = col0 + c * 32 + 2 * j;
-                        const float y0 = (__uint_as_float(v[2 * j]) - mean) * rstd * __ldg(p.gamma + n0) + __ldg(p.beta + n0);
-                        const float y1 =
-                            (__uint_as_float(v[2 * j + 1]) - mean) * rstd * __ldg(p.gamma + n0 + 1) + __ldg(p.beta + n0 + 1);
+                        const float2 g2 = *reinterpret_cast<const float2 *>(svec + BN + cg * kCW + c * 32 + 2 * j);
+                        const float2 be2 = *reinterpret_cast<const float2 *>(svec + 2 * BN + cg * kCW + c * 32 + 2 * j);
+                        const float y0 = (__uint_as_float(v[2 * j]) - mean) * rstd * g2.x + be2.x;
+                        const float y1 = (__uint_as_float(v[2 * j + 1]) - mean) * rstd * g2.y + be2.y;
                         o[j] = pack16<FMT>(y0, y1);
                     }
                     if (row_ok) {
@@ -225,15 +286,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             } else {
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = 0; c < kCW / 32; ++c) {
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
                     tmem_ld_wait();
                     uint32_t o[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        float x0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + col0 + c * 32 + 2 * j);
-                        float x1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + col0 + c * 32 + 2 * j + 1);
+                        const float2 b2 = *reinterpret_cast<const float2 *>(sbias + cg * kCW + c * 32 + 2 * j);
+                        float x0 = __uint_as_float(v[2 * j]) + b2.x;
+                        float x1 = __uint_as_float(v[2 * j + 1]) + b2.y;
                         if constexpr (EPI == EPI_BIAS_GELU) {
                             x0 = gelu_erf(x0);
                             x1 = gelu_erf(x1);
@@ -271,7 +333,7 @@ static cudaError_t launch_cfg(const GemmParams &p, const CUtensorMap &tmA, const
     if (e != cudaSuccess) return e;
     const uint32_t n_tiles = ceil_div<uint32_t>(p.M, kBM) * (p.N / BN);
     const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
     count_launch();
     return cudaGetLastError();
 }

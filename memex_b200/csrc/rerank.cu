@@ -60,6 +60,50 @@ __device__ __forceinline__ float key_to_score(float key, uint32_t metric)
     return __fsub_rn(1.0f, __fdiv_rn(1.0f, __fdiv_rn(1.0f, key)));  // local.rs:86
 }
 
+// ---- warp-wide sorted lists of 32 (score, row) pairs, best first (cand_before order) ------------------
+// bitonic sort across the lanes of a warp: lane 0 ends up with the best entry
+__device__ __forceinline__ void warp_sort32(float &v, uint32_t &r)
+{
+    const uint32_t lane = lane_id();
+#pragma unroll
+    for (uint32_t k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, j);
+            const uint32_t orow = __shfl_xor_sync(0xffffffffu, r, j);
+            const bool take_better = ((lane & k) == 0) == ((lane & j) == 0);
+            const bool mine_better = cand_before(v, r, ov, orow);
+            if (take_better != mine_better && !(v == ov && r == orow)) {
+                v = ov;
+                r = orow;
+            }
+        }
+    }
+}
+// (v, r) sorted across lanes and (bv, br) sorted across lanes -> the 32 best of the union, sorted
+__device__ __forceinline__ void warp_merge32(float &v, uint32_t &r, float bv, uint32_t br)
+{
+    const uint32_t lane = lane_id();
+    // best(A[i], B[31 - i]) is the top half of the union as a bitonic sequence
+    const float rv = __shfl_sync(0xffffffffu, bv, 31 - lane);
+    const uint32_t rr = __shfl_sync(0xffffffffu, br, 31 - lane);
+    if (cand_before(rv, rr, v, r)) {
+        v = rv;
+        r = rr;
+    }
+#pragma unroll
+    for (uint32_t j = 16; j > 0; j >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, j);
+        const uint32_t orow = __shfl_xor_sync(0xffffffffu, r, j);
+        const bool take_better = (lane & j) == 0;
+        const bool mine_better = cand_before(v, r, ov, orow);
+        if (take_better != mine_better && !(v == ov && r == orow)) {
+            v = ov;
+            r = orow;
+        }
+    }
+}
+
 constexpr int kRerankThreads = 512;
 constexpr int kRerankWarps = kRerankThreads / 32;
 constexpr int kFoldChunk = 384;           // elements of a row staged per pass
@@ -92,40 +136,64 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const float *qg = p.queries + (size_t)q * p.ldq;
 
-    // 1. every warp folds a slice of the candidate lists into its own list
-    WarpTopK<E> top;
-    top.init();
-    {
-        // the (query, list) candidate lists are contiguous: n_lists * lcap entries, 32 at a time
-        const uint32_t total = p.n_lists * p.lcap;
-        const size_t o = (size_t)q * total;
-        for (uint32_t i = warp * 32; i < total; i += kRerankWarps * 32) {
-            const uint32_t idx = i + lane;
-            const bool in = idx < total;
-            const float v = in ? p.cand_s[o + idx] : kNegInf;
-            const uint32_t r = in ? p.cand_r[o + idx] : kNoRow;
-            top.offer(r != kNoRow, v, r);
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        ws[warp * kList + e * 32 + lane] = top.s[e];
-        wr[warp * kList + e * 32 + lane] = top.r[e];
-    }
     for (uint32_t j = threadIdx.x; j < kMaxEntries; j += blockDim.x) {
         ekey[j] = 0.f;
         erow[j] = kNoRow;
     }
-    __syncthreads();
-    // 2. rank of every entry among all warp lists; rows are unique across lists (a row is scanned by
-    //    one CTA), so ranks of real entries are unique and the kList best land in erow[0 .. kList)
-    for (uint32_t j = threadIdx.x; j < kRerankWarps * kList; j += blockDim.x) {
-        const float v = ws[j];
-        const uint32_t r = wr[j];
-        if (r == kNoRow) continue;
-        uint32_t rank = 0;
-        for (uint32_t i = 0; i < kRerankWarps * kList; ++i) rank += cand_before(ws[i], wr[i], v, r) ? 1u : 0u;
-        if (rank < kList) erow[rank] = r;
+    const uint32_t total = p.n_lists * p.lcap;   // the (query, list) candidate lists are contiguous
+    const size_t cbase = (size_t)q * total;
+    if constexpr (E == 1) {
+        // 1+2 (k <= 24): sorted-list algebra.  Each warp sorts 32 candidates at a time and merges them
+        // into its running sorted top-32; warp 0 then merges the 16 warp lists.
+        float bv = kNegInf;
+        uint32_t br = kNoRow;
+        for (uint32_t i = warp * 32; i < total; i += kRerankWarps * 32) {
+            const uint32_t idx = i + lane;
+            float v = idx < total ? p.cand_s[cbase + idx] : kNegInf;
+            uint32_t r = idx < total ? p.cand_r[cbase + idx] : kNoRow;
+            if (r == kNoRow) v = kNegInf;
+            warp_sort32(v, r);
+            if (i == warp * 32) {
+                bv = v;
+                br = r;
+            } else {
+                warp_merge32(bv, br, v, r);
+            }
+        }
+        ws[warp * 32 + lane] = bv;
+        wr[warp * 32 + lane] = br;
+        __syncthreads();
+        if (warp == 0) {
+            for (int w = 1; w < kRerankWarps; ++w) warp_merge32(bv, br, ws[w * 32 + lane], wr[w * 32 + lane]);
+            erow[lane] = br;
+        }
+    } else {
+        // 1. every warp folds a slice of the candidate lists into its own list
+        WarpTopK<E> top;
+        top.init();
+        for (uint32_t i = warp * 32; i < total; i += kRerankWarps * 32) {
+            const uint32_t idx = i + lane;
+            const bool in = idx < total;
+            const float v = in ? p.cand_s[cbase + idx] : kNegInf;
+            const uint32_t r = in ? p.cand_r[cbase + idx] : kNoRow;
+            top.offer(r != kNoRow, v, r);
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            ws[warp * kList + e * 32 + lane] = top.s[e];
+            wr[warp * kList + e * 32 + lane] = top.r[e];
+        }
+        __syncthreads();
+        // 2. rank of every entry among all warp lists; rows are unique across lists (a row is scanned by
+        //    one CTA), so ranks of real entries are unique and the kList best land in erow[0 .. kList)
+        for (uint32_t j = threadIdx.x; j < kRerankWarps * kList; j += blockDim.x) {
+            const float v = ws[j];
+            const uint32_t r = wr[j];
+            if (r == kNoRow) continue;
+            uint32_t rank = 0;
+            for (uint32_t i = 0; i < kRerankWarps * kList; ++i) rank += cand_before(ws[i], wr[i], v, r) ? 1u : 0u;
+            if (rank < kList) erow[rank] = r;
+        }
     }
     // 3. the lowest-id zero-norm rows (cosine: d = 0)
     if (threadIdx.x == 0) {
@@ -152,16 +220,45 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
             const uint32_t cn = min((uint32_t)kFoldChunk, p.dim - c0);
             __syncthreads();   // previous chunk fully consumed
             for (uint32_t i = threadIdx.x; i < cn; i += blockDim.x) qs[i] = qg[c0 + i];
-            // stage: entry e of this pass, element i -> rowbuf[e][i]; consecutive threads read consecutive elements
-            for (uint32_t e = warp; e < n_here; e += kRerankWarps) {
-                const uint32_t row = erow[first + e];
-                if (row == kNoRow || row >= p.n_rows) continue;
-                const size_t off = (size_t)row * p.ld + c0;
-                for (uint32_t i = lane; i < cn; i += 32) rowbuf[e * kFoldPitch + i] = load_elem(p.rows, p.dtype, off + i);
+            // stage: entry e of this pass -> rowbuf[e][0 .. cn) as f32.  16-byte loads, all of a row's loads issued
+            // before the first use (a warp owns entries e = warp, warp + 16, ...)
+            {
+                const uint32_t per16 = p.dtype == MX_DTYPE_F32 ? 4u : 8u;        // elements per 16-byte chunk
+                const uint32_t n16 = (cn + per16 - 1) / per16;                   // c0 and ld are multiples of per16
+                for (uint32_t e = warp; e < n_here; e += kRerankWarps) {
+                    const uint32_t row = erow[first + e];
+                    if (row == kNoRow || row >= p.n_rows) continue;
+                    const uint4 *src = reinterpret_cast<const uint4 *>(
+                        reinterpret_cast<const char *>(p.rows) + ((size_t)row * p.ld + c0) * (p.dtype == MX_DTYPE_F32 ? 4 : 2));
+                    uint4 buf[3];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const uint32_t ch = lane + 32 * u;
+                        buf[u] = ch < n16 ? src[ch] : make_uint4(0, 0, 0, 0);
+                    }
+                    float *dst = rowbuf + e * kFoldPitch;
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const uint32_t ch = lane + 32 * u;
+                        if (ch >= n16) continue;
+                        if (p.dtype == MX_DTYPE_F32) {
+                            const float *f = reinterpret_cast<const float *>(&buf[u]);
+#pragma unroll
+                            for (int x = 0; x < 4; ++x)
+                                if (ch * 4 + x < cn) dst[ch * 4 + x] = f[x];
+                        } else {
+                            const __half *hh = reinterpret_cast<const __half *>(&buf[u]);
+#pragma unroll
+                            for (int x = 0; x < 8; ++x)
+                                if (ch * 8 + x < cn) dst[ch * 8 + x] = __half2float(hh[x]);
+                        }
+                    }
+                }
             }
             __syncthreads();
             if (folder && my_row != kNoRow && my_row < p.n_rows) {
                 const float *rb = rowbuf + (warp * 32 + lane) * kFoldPitch;
+#pragma unroll 4
                 for (uint32_t i = 0; i < cn; ++i) {
                     const float a = qs[i], b = rb[i];
                     ab = __dadd_rn(ab, (double)__fmul_rn(a, b));

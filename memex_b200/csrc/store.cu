@@ -198,18 +198,23 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
     if ((path == 0) != (s->cfg.dtype == MX_DTYPE_F32))
         return fail(s, MX_ERR_UNSUPPORTED, "scan path %u does not match the store dtype", path);
 
-    // stage queries: [nq, ldq] f32 zero padded
-    const size_t qfloats = (size_t)nq * s->ldq;
-    if (qfloats > s->q_stage_cap) {
-        if (s->q_stage) cudaFree(s->q_stage);
-        s->q_stage = nullptr;
-        s->q_stage_cap = 0;
-        MX_CUDA(s, MX_ERR_SEARCH, cudaMalloc(&s->q_stage, qfloats * sizeof(float)));
-        s->q_stage_cap = qfloats;
+    // queries as [nq, ldq] f32, zero padded to a multiple of 8 floats: when dim already is one (384, 768, ...)
+    // the caller's buffer is used in place, otherwise it is staged once
+    const float *q_use = q_dev;
+    if (s->ldq != s->cfg.dim) {
+        const size_t qfloats = (size_t)nq * s->ldq;
+        if (qfloats > s->q_stage_cap) {
+            if (s->q_stage) cudaFree(s->q_stage);
+            s->q_stage = nullptr;
+            s->q_stage_cap = 0;
+            MX_CUDA(s, MX_ERR_SEARCH, cudaMalloc(&s->q_stage, qfloats * sizeof(float)));
+            s->q_stage_cap = qfloats;
+        }
+        s->timer.begin(st, 1);
+        MX_CUDA(s, MX_ERR_SEARCH, launch_stage_queries(q_dev, nq, s->cfg.dim, s->ldq, s->q_stage, st));
+        s->timer.end(st);
+        q_use = s->q_stage;
     }
-    s->timer.begin(st, 1);
-    MX_CUDA(s, MX_ERR_SEARCH, launch_stage_queries(q_dev, nq, s->cfg.dim, s->ldq, s->q_stage, st));
-    s->timer.end(st);
 
     uint32_t n_lists, lcap;
     if (path == 2) {
@@ -235,7 +240,7 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
     ScanParams sp{};
     sp.rows = s->rows;
     sp.inv_norm = s->inv_norm;
-    sp.queries = s->q_stage;
+    sp.queries = q_use;
     sp.cand_s = s->cand_s;
     sp.cand_r = s->cand_r;
     sp.n_rows = (uint32_t)s->n;
@@ -257,7 +262,7 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
 
     RerankParams rp{};
     rp.rows = s->rows;
-    rp.queries = s->q_stage;
+    rp.queries = q_use;
     rp.cand_s = s->cand_s;
     rp.cand_r = s->cand_r;
     rp.zero_rows = s->zero_rows;
