@@ -538,9 +538,18 @@ def main():
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--skip-cpu", action="store_true", help="leave out the CPU baseline legs")
     ap.add_argument("--skip-extras", action="store_true", help="leave out the single_query / embed sub-benches")
+    ap.add_argument("--only", default="", choices=["", "embed", "single"],
+                    help="profiling aid: run just one sub-bench on one GPU and print its object")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
-    if args.impl == "reference":
+    if args.only:
+        import torch
+        torch.cuda.set_device(0)
+        dev = torch.device("cuda", 0)
+        fn = bench_embed if args.only == "embed" else bench_single_query
+        res = fn(dev, args.steps, args.warmup, peaks(), False) if args.only == "embed" else fn(dev, args.steps, args.warmup, peaks())
+        print(json.dumps(res), flush=True)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -47,6 +47,26 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `pending` of this thread's most recent groups are still in flight (immediate operand)
+__device__ __forceinline__ void cp_async_wait_pending(uint32_t pending)
+{
+    switch (pending) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+}
 __device__ __forceinline__ float fast_exp2(float x)
 {
     float y;
@@ -66,7 +86,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b)
 }
 
 template <bool BF16, int DH>
-__global__ void __launch_bounds__(kAmWarps * 32) attention_mma_kernel(const uint16_t *__restrict__ qkv,
+__global__ void __launch_bounds__(kAmWarps * 32, DH <= 32 ? 3 : 1) attention_mma_kernel(const uint16_t *__restrict__ qkv,
                                                                       const int32_t *__restrict__ lens,
                                                                       uint16_t *__restrict__ ctx, uint32_t S, uint32_t H,
                                                                       uint32_t heads, float scale_log2e)
@@ -98,44 +118,43 @@ __global__ void __launch_bounds__(kAmWarps * 32) attention_mma_kernel(const uint
     uint16_t *Ks = Qs + kAmQ * PITCH;              // [n_keys][PITCH]
     uint16_t *Vs = Ks + (size_t)n_keys * PITCH;    // [n_keys][PITCH]
 
+    // asynchronous staging (cp.async, 16 bytes each): group 0 = Q + keys [0, 64), group g = keys [64 g, 64 g + 64).
+    // Block kb of the main loop only waits for groups 0..kb, so the later loads overlap the first blocks' math.
     for (uint32_t i = threadIdx.x; i < kAmQ * CH; i += blockDim.x) {
         const uint32_t r = i / CH, c = i % CH, qi = q0 + r;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (qi < S) v = *reinterpret_cast<const uint4 *>(base + (size_t)qi * ldq + c * 8);
-        *reinterpret_cast<uint4 *>(Qs + r * PITCH + c * 8) = v;
+        uint16_t *dst = Qs + r * PITCH + c * 8;
+        if (qi < S)
+            cp_async16(dst, base + (size_t)qi * ldq + c * 8);
+        else
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
     }
-    for (uint32_t i = threadIdx.x; i < n_keys * CH; i += blockDim.x) {
-        const uint32_t r = i / CH, c = i % CH;
-        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-        if (r < S) {
-            kv = *reinterpret_cast<const uint4 *>(base + (size_t)r * ldq + H + c * 8);
-            vv = *reinterpret_cast<const uint4 *>(base + (size_t)r * ldq + 2 * H + c * 8);
+    for (uint32_t kb = 0; kb < n_kb; ++kb) {
+        for (uint32_t i = threadIdx.x; i < kAmKB * CH; i += blockDim.x) {
+            const uint32_t r = kb * kAmKB + i / CH, c = i % CH;
+            uint16_t *kd = Ks + r * PITCH + c * 8, *vd = Vs + r * PITCH + c * 8;
+            if (r < S) {
+                cp_async16(kd, base + (size_t)r * ldq + H + c * 8);
+                cp_async16(vd, base + (size_t)r * ldq + 2 * H + c * 8);
+            } else {
+                *reinterpret_cast<uint4 *>(kd) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4 *>(vd) = make_uint4(0, 0, 0, 0);
+            }
         }
-        *reinterpret_cast<uint4 *>(Ks + r * PITCH + c * 8) = kv;
-        *reinterpret_cast<uint4 *>(Vs + r * PITCH + c * 8) = vv;
+        cp_async_commit();
     }
-    __syncthreads();
 
     const uint32_t g = lane >> 2, t = lane & 3;
     const uint32_t row_a = q0 + warp * 16 + g, row_b = row_a + 8;     // the two rows this thread's fragments cover
-    if (q0 + warp * 16 >= len) {
-        // all 16 rows of this warp are padding
+    // a warp whose 16 rows are all padding still takes part in the block barriers below
+    const bool active = q0 + warp * 16 < len;
+    if (!active) {
         for (uint32_t i = lane; i < 16 * CH; i += 32) {
             const uint32_t qi = q0 + warp * 16 + i / CH;
             if (qi < S) *reinterpret_cast<uint4 *>(obase + (size_t)qi * H + (i % CH) * 8) = make_uint4(0, 0, 0, 0);
         }
-        return;
     }
 
-    // Q fragments: KS k-steps x (a0a1, a2a3, a4a5, a6a7)
-    uint32_t qf[KS][4];
-    {
-        const uint32_t mi = lane >> 3;
-        const uint32_t r = warp * 16 + (lane & 7) + (mi & 1) * 8;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks)
-            ldmatrix_x4(qf[ks], (uint32_t)__cvta_generic_to_shared(Qs + r * PITCH + ks * 16 + (mi >> 1) * 8));
-    }
+    uint32_t qf[KS][4];   // Q fragments: KS k-steps x (a0a1, a2a3, a4a5, a6a7), loaded once group 0 has landed
 
     float o[NT][4];
 #pragma unroll
@@ -146,6 +165,16 @@ __global__ void __launch_bounds__(kAmWarps * 32) attention_mma_kernel(const uint
 
     for (uint32_t kb = 0; kb < n_kb; ++kb) {
         const uint32_t k0 = kb * kAmKB;
+        cp_async_wait_pending(n_kb - 1 - kb);
+        __syncthreads();
+        if (!active) continue;
+        if (kb == 0) {
+            const uint32_t mi = lane >> 3;
+            const uint32_t r = warp * 16 + (lane & 7) + (mi & 1) * 8;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+                ldmatrix_x4(qf[ks], (uint32_t)__cvta_generic_to_shared(Qs + r * PITCH + ks * 16 + (mi >> 1) * 8));
+        }
         float s[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -222,6 +251,7 @@ __global__ void __launch_bounds__(kAmWarps * 32) attention_mma_kernel(const uint
             }
         }
     }
+    if (!active) return;
     l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
     l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
     l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);

@@ -25,35 +25,54 @@ using namespace tc;
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 128 bytes of bf16: one swizzle atom
 
-template <int BN>
+constexpr int kResMaxKB = 6;   // resident-weights variant: K <= 384
+
+// RES = the CTA keeps its [BN, K] weight slice resident in shared memory and streams only activations
+// (K <= 384): weights are read from L2 once per CTA instead of once per tile, which takes the K = 384
+// GEMMs off the L2 -> SM bandwidth limit (a 128 x 192 x 384 tile would otherwise pull 240 KB for 2304 MMA cycles).
+template <int BN, bool RES, bool LN>
 struct GemmCfg {
     static constexpr int kChunks = BN > 256 ? 2 : 1;          // one tcgen05.mma covers N <= 256
     static constexpr int kChunkN = BN / kChunks;
     static constexpr int kAccStages = (2 * BN <= 512) ? 2 : 1;
     static constexpr int kTmemCols = (kAccStages * BN <= 128) ? 128 : (kAccStages * BN <= 256 ? 256 : 512);
-    static constexpr int kStageBytes = kBM * kBK * 2 + BN * kBK * 2;
-    static constexpr int kStages = (200 * 1024) / kStageBytes < 8 ? (200 * 1024) / kStageBytes : 8;
+    static constexpr int kABytes = kBM * kBK * 2;             // one k-block of activations
+    static constexpr int kBBytes = BN * kBK * 2;              // one k-block of weights
+    static constexpr int kStageBytes = RES ? kABytes : kABytes + kBBytes;
+    static constexpr int kResBytes = RES ? kResMaxKB * kBBytes : 0;
     // epilogue: 4 TMEM lane quarters x kColGroups column groups, one warp each -- several warps per SM
     // sub-partition so that the bias / GELU / LayerNorm arithmetic is issue-bound, not latency-bound
-    static constexpr int kColGroups = (BN % 128 == 0) ? 4 : 2;
+    static constexpr int kColGroups = (BN % 128 == 0) ? 4 : 3;   // 192 -> 3 x 64 columns
     static constexpr int kColsPerWarp = BN / kColGroups;
     static constexpr int kEpiWarps = 4 * kColGroups;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
-    static constexpr int kStatBytes = 2 * kColGroups * kBM * 8;   // LayerNorm partial (sum, sq), double buffered
-    static constexpr int kVecBytes = 3 * BN * 4;                  // bias tiles (x2) or bias | gamma | beta, staged in smem
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStatBytes + kVecBytes;
-    static_assert(kColsPerWarp % 32 == 0, "an epilogue warp works in 32-column chunks");
+    static constexpr int kStatBytes = LN ? 2 * kColGroups * kBM * 8 : 0;   // LayerNorm partial (sum, sq), double buffered
+    static constexpr int kMaxBiasN = RES ? 2048 : 4096;
+    static constexpr int kVecBytes = LN ? 3 * BN * 4 : kMaxBiasN * 4;      // bias | gamma | beta, or the whole bias vector
+    // output staging for TMA stores: one [32 rows x 32 columns] 16-bit tile (2 KB, 64-byte swizzle) per epilogue warp
+    static constexpr int kOutBytes = LN ? 0 : kEpiWarps * 2048;
+    static constexpr int kTailBytes = ((256 + kStatBytes + kVecBytes + 1023) / 1024) * 1024 + kOutBytes;
+    // the activation (+ weight) ring takes what is left of the 227 KB
+    static constexpr int kRingBudget = 227 * 1024 - 1024 - kTailBytes - kResBytes;
+    static constexpr int kStages = kRingBudget / kStageBytes < 8 ? kRingBudget / kStageBytes : 8;
+    static constexpr int kRingOff = kResBytes;
+    static constexpr int kBarOff = kRingOff + kStages * kStageBytes;
+    static constexpr int kOutOff = kBarOff + kTailBytes - kOutBytes;    // 1024-byte aligned (all parts before it are)
+    static constexpr int kSmemBytes = kBarOff + 1024 /*align*/ + kTailBytes;
     static_assert(kChunkN % 16 == 0 && kChunkN <= 256, "invalid UMMA N");
     static_assert((BN * kBK * 2 / kChunks) % 1024 == 0, "B chunks must stay 1024-byte aligned");
+    static_assert(kColsPerWarp % 32 == 0, "an epilogue warp works in 32-column chunks");
+    static_assert(kStages >= 2, "ring too small");
+    static_assert(!RES || kChunks == 1, "resident variant: BN <= 256");
 };
 
 // erf-GELU for the 16-bit paths.  erf(t) = 1 - 2^(-q(t)) on t in [0, 4] with q a degree-5 polynomial
 // without constant term (least-squares/minimax fit of -log2(erfc(t)); max |error| of erf 6.7e-7 when
-// evaluated in f32, far below the bf16/f16 output resolution); |t| > 4 is clamped (erf(4) = 1 - 1.5e-8).
+// evaluated in f32, far below the bf16/f16 output resolution); beyond t = 4 the polynomial keeps growing.
 // One SFU op (ex2) instead of erff's two polynomial branches.  The fp32 validation path keeps erff.
 __device__ __forceinline__ float gelu_erf(float x)
 {
-    const float t = fminf(fabsf(x) * 0.70710678118654752f, 4.0f);
+    const float t = fabsf(x) * 0.70710678118654752f;   // q is increasing beyond t = 4, so 2^-q just underflows to 0
     float q = fmaf(t, 0.00294416f, -0.02959005f);
     q = fmaf(t, q, 0.14866564f);
     q = fmaf(t, q, 0.91850936f);
@@ -86,26 +105,46 @@ __device__ __forceinline__ float2 unpack16(uint32_t u)
         return __half22float2(*reinterpret_cast<__half2 *>(&u));
 }
 
-template <int BN, int EPI, int FMT>
-__global__ void __launch_bounds__(GemmCfg<BN>::kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p)
+template <int BN, int EPI, int FMT, bool RES>
+__global__ void __launch_bounds__(GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN>::kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, GemmParams p)
 {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN>;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::kStages * Cfg::kStageBytes);
+    // 1024-byte alignment by OFFSET (keeps the pointer in the shared address space: LDS/STS, not generic LD/ST)
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *ring = smem + Cfg::kRingOff;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
     uint64_t *empty = full + Cfg::kStages;
     uint64_t *tmem_full = empty + Cfg::kStages;
     uint64_t *tmem_empty = tmem_full + Cfg::kAccStages;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + Cfg::kAccStages);
-    float2 *stat = reinterpret_cast<float2 *>(smem + Cfg::kStages * Cfg::kStageBytes + 256);  // [2][kColGroups][kBM]
-    float *svec = reinterpret_cast<float *>(smem + Cfg::kStages * Cfg::kStageBytes + 256 + Cfg::kStatBytes);
+    uint64_t *b_full = tmem_empty + Cfg::kAccStages;
+    uint64_t *b_empty = b_full + 1;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(b_empty + 1);
+    float2 *stat = reinterpret_cast<float2 *>(smem + Cfg::kBarOff + 256);  // [2][kColGroups][kBM]
+    float *svec = reinterpret_cast<float *>(smem + Cfg::kBarOff + 256 + Cfg::kStatBytes);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_n = p.N / BN;
     const uint32_t tiles_m = (p.M + kBM - 1) / kBM;
     const uint32_t n_tiles = tiles_m * tiles_n;
     const uint32_t k_blocks = (p.K + kBK - 1) / kBK;
+    // tile schedule.  streaming: tile = blockIdx.x + i * gridDim.x, n fastest (concurrent CTAs share A rows in L2).
+    // resident: a contiguous range of the n-major list, so a CTA changes its weight slice at most a few times.
+    uint32_t t_begin, t_end, t_step;
+    if constexpr (RES) {
+        const uint32_t per = (n_tiles + gridDim.x - 1) / gridDim.x;
+        t_begin = min(n_tiles, blockIdx.x * per);
+        t_end = min(n_tiles, t_begin + per);
+        t_step = 1;
+    } else {
+        t_begin = blockIdx.x;
+        t_end = n_tiles;
+        t_step = gridDim.x;
+    }
+    auto tile_m = [&](uint32_t t) { return RES ? t % tiles_m : t / tiles_n; };
+    auto tile_n = [&](uint32_t t) { return RES ? t / tiles_m : t % tiles_n; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -118,6 +157,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], Cfg::kEpiWarps);
         }
+        mbar_init(b_full, 1);
+        mbar_init(b_empty, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, Cfg::kTmemCols);
@@ -129,19 +170,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const uint32_t m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+            uint32_t stage = 0, phase = 0, seg = 0, cur_n = 0xffffffffu;
+            for (uint32_t tile = t_begin; tile < t_end; tile += t_step) {
+                const uint32_t m_blk = tile_m(tile), n_blk = tile_n(tile);
+                if constexpr (RES) {
+                    if (n_blk != cur_n) {
+                        // new weight slice: wait until every MMA that reads the old one has completed
+                        if (seg > 0) mbar_wait(b_empty, (seg - 1) & 1);
+                        mbar_arrive_expect_tx(b_full, k_blocks * Cfg::kBBytes);
+                        for (uint32_t kb = 0; kb < k_blocks; ++kb)
+                            tma_load_2d(smem + kb * Cfg::kBBytes, &tmB, b_full, kb * kBK, n_blk * BN, kEvictLast);
+                        cur_n = n_blk;
+                        ++seg;
+                    }
+                }
                 for (uint32_t kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    unsigned char *sa = smem + stage * Cfg::kStageBytes;
-                    unsigned char *sb = sa + kBM * kBK * 2;
+                    unsigned char *sa = ring + stage * Cfg::kStageBytes;
                     mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-                    tma_load_2d(sa, &tmA, &full[stage], kb * kBK, m_blk * kBM, kEvictFirst);
+                    tma_load_2d(sa, &tmA, &full[stage], kb * kBK, m_blk * kBM, RES ? kEvictLast : kEvictFirst);
+                    if constexpr (!RES) {
+                        unsigned char *sb = sa + Cfg::kABytes;
 #pragma unroll
-                    for (int c = 0; c < Cfg::kChunks; ++c)
-                        tma_load_2d(sb + c * (Cfg::kChunkN * kBK * 2), &tmB, &full[stage], kb * kBK,
-                                    n_blk * BN + c * Cfg::kChunkN, kEvictLast);
+                        for (int c = 0; c < Cfg::kChunks; ++c)
+                            tma_load_2d(sb + c * (Cfg::kChunkN * kBK * 2), &tmB, &full[stage], kb * kBK,
+                                        n_blk * BN + c * Cfg::kChunkN, kEvictLast);
+                    }
                     if (++stage == Cfg::kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -153,16 +207,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ================= MMA issuer =================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(kBM, Cfg::kChunkN, FMT);
-            uint32_t stage = 0, phase = 0, local = 0;
-            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+            uint32_t stage = 0, phase = 0, local = 0, seg = 0, cur_n = 0xffffffffu;
+            for (uint32_t tile = t_begin; tile < t_end; tile += t_step, ++local) {
                 const uint32_t as = local % Cfg::kAccStages, aphase = (local / Cfg::kAccStages) & 1;
+                if constexpr (RES) {
+                    const uint32_t n_blk = tile_n(tile);
+                    if (n_blk != cur_n) {
+                        mbar_wait(b_full, seg & 1);
+                        tc_fence_after();
+                        cur_n = n_blk;
+                        ++seg;
+                    }
+                }
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
                 for (uint32_t kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                    const uint32_t sb = sa + kBM * kBK * 2;
+                    const uint32_t sa = smem_u32(ring + stage * Cfg::kStageBytes);
+                    const uint32_t sb = RES ? smem_u32(smem + kb * Cfg::kBBytes) : sa + Cfg::kABytes;
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
                         const uint64_t adesc = make_smem_desc(sa + k * 32);
@@ -179,6 +242,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 umma_commit(&tmem_full[as]);
+                if constexpr (RES) {
+                    // last tile that reads this weight slice: its completion frees the resident buffer
+                    const uint32_t next = tile + t_step;
+                    if (next < t_end && tile_n(next) != cur_n) umma_commit(b_empty);
+                }
             }
         }
     } else {
@@ -196,46 +264,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 svec[2 * BN + i] = __ldg(p.beta + i);
             }
             bar_sync(1, kEpiThreads);
+        } else {
+            // the whole bias vector (N <= kMaxBiasN, checked by the launcher): no per-tile global load on the critical path
+            for (uint32_t i = etid; i < p.N; i += kEpiThreads) svec[i] = __ldg(p.bias + i);
+            bar_sync(1, kEpiThreads);
+            if (etid == 0) tma_prefetch_desc(&tmO);
         }
+        unsigned char *obuf = smem + Cfg::kOutOff + (warp - 2) * 2048;
         uint32_t local = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
-            const uint32_t m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+        for (uint32_t tile = t_begin; tile < t_end; tile += t_step, ++local) {
+            const uint32_t m_blk = tile_m(tile), n_blk = tile_n(tile);
             const uint32_t as = local % Cfg::kAccStages, aphase = (local / Cfg::kAccStages) & 1;
-            const float *sbias = svec;
-            if constexpr (EPI != EPI_BIAS_RES_LN) {
-                // this tile's bias slice -> smem (double buffered; the barrier of tile i+1 orders reuse)
-                float *bt = svec + (local & 1) * BN;
-                for (uint32_t i = etid; i < BN; i += kEpiThreads) bt[i] = __ldg(p.bias + n_blk * BN + i);
-                bar_sync(1, kEpiThreads);
-                sbias = bt;
-            }
-            mbar_wait(&tmem_full[as], aphase);
-            tc_fence_after();
+            const float *sbias = EPI == EPI_BIAS_RES_LN ? svec : svec + n_blk * BN;
             const uint32_t row_in_tile = quarter * 32 + lane;
             const uint32_t row = m_blk * kBM + row_in_tile;
             const bool row_ok = row < p.M;
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * BN + cg * kCW;
             const uint32_t col0 = n_blk * BN + cg * kCW;
             uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + (size_t)row * p.ldo + col0;
+            [[maybe_unused]] uint4 rr[EPI == EPI_BIAS_RES_LN ? kCW / 8 : 1];
+            if constexpr (EPI == EPI_BIAS_RES_LN) {
+                // this thread's slice of the residual row, requested while the MMAs of the tile are still running
+                const uint16_t *rrow = reinterpret_cast<const uint16_t *>(p.residual) + (size_t)row * p.ldr + col0;
+#pragma unroll
+                for (int j = 0; j < kCW / 8; ++j)
+                    rr[j] = row_ok ? *reinterpret_cast<const uint4 *>(rrow + j * 8) : make_uint4(0, 0, 0, 0);
+            }
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
 
             if constexpr (EPI == EPI_BIAS_RES_LN) {
                 // pass 1: x = acc + bias + residual, kept in TMEM; partial row sums of this warp's columns
-                const uint16_t *rrow = reinterpret_cast<const uint16_t *>(p.residual) + (size_t)row * p.ldr + col0;
                 float sum = 0.f, sq = 0.f;
-#pragma unroll 1
+#pragma unroll
                 for (int c = 0; c < kCW / 32; ++c) {
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
-                    uint4 rr[4];
-                    if (row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4 *>(rrow + c * 32 + j * 8);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) rr[j] = make_uint4(0, 0, 0, 0);
-                    }
                     tmem_ld_wait();
-                    const uint32_t *rh = reinterpret_cast<const uint32_t *>(rr);
+                    const uint32_t *rh = reinterpret_cast<const uint32_t *>(&rr[c * 4]);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float2 r2 = unpack16<FMT>(rh[j]);
@@ -285,11 +351,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             } else {
-#pragma unroll 1
-                for (int c = 0; c < kCW / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c * 32, v);
+                // two register buffers: the TMEM load of chunk c + 1 is in flight while chunk c is processed
+                constexpr int kNC = kCW / 32;
+                uint32_t vbuf[2][32];
+                tmem_ld32(taddr, vbuf[0]);
+#pragma unroll
+                for (int c = 0; c < kNC; ++c) {
                     tmem_ld_wait();
+                    if (c + 1 < kNC) tmem_ld32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
+                    const uint32_t(&v)[32] = vbuf[c & 1];
                     uint32_t o[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -302,16 +372,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         o[j] = pack16<FMT>(x0, x1);
                     }
-                    if (row_ok) {
+                    // [32 rows x 32 columns] -> this warp's staging tile (64-byte swizzle) -> one TMA store.
+                    // (A direct st.global from the accumulator layout writes 16 bytes to each of 32 rows per
+                    // instruction -- 32 LSU wavefronts for 512 bytes.)
+                    if (lane == 0) bulk_wait_read0();   // the previous store has finished reading the tile
+                    __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4 *>(orow + c * 32 + j * 8) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4 *>(obuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                            make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmO, obuf, (int32_t)(col0 + c * 32), (int32_t)(m_blk * kBM + quarter * 32));
+                        bulk_commit();
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        if constexpr (EPI != EPI_BIAS_RES_LN) {
+            if (lane == 0) bulk_wait_read0();
         }
     }
 
@@ -323,19 +406,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-template <int BN, int EPI, int FMT>
-static cudaError_t launch_cfg(const GemmParams &p, const CUtensorMap &tmA, const CUtensorMap &tmB, int sm_count,
-                              cudaStream_t st)
+template <int BN, int EPI, int FMT, bool RES>
+static cudaError_t launch_cfg(const GemmParams &p, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO,
+                              int sm_count, cudaStream_t st)
 {
-    using Cfg = GemmCfg<BN>;
-    auto kern = gemm_tc_kernel<BN, EPI, FMT>;
+    using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN>;
+    auto kern = gemm_tc_kernel<BN, EPI, FMT, RES>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     const uint32_t n_tiles = ceil_div<uint32_t>(p.M, kBM) * (p.N / BN);
     const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmO, p);
     count_launch();
     return cudaGetLastError();
+}
+
+// resident-weights variant: K <= 384, N a multiple of 192, enough tiles per CTA to amortise the weight load
+static bool use_resident(const GemmParams &p, int epi, int sm_count)
+{
+    if (epi == EPI_BIAS_RES_LN) return false;
+    if (p.K > (uint32_t)(kResMaxKB * kBK) || p.N % 192 != 0 || p.N > 2048) return false;
+    const uint32_t n_tiles = ceil_div<uint32_t>(p.M, kBM) * (p.N / 192);
+    return n_tiles >= 4u * (uint32_t)sm_count;
 }
 
 int gemm_tc_block_n(uint32_t N, int epi)
@@ -349,30 +441,38 @@ int gemm_tc_block_n(uint32_t N, int epi)
 
 cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStream_t st, const char **why)
 {
-    const int bn = gemm_tc_block_n(p.N, epi);
+    const bool res = use_resident(p, epi, sm_count);
+    const int bn = res ? 192 : gemm_tc_block_n(p.N, epi);
     if (bn == 0 || p.K % 8 != 0 || p.lda % 8 != 0 || p.ldw % 8 != 0 || p.ldo % 8 != 0) {
         if (why) *why = "unsupported GEMM shape for the tcgen05 path";
         return cudaErrorInvalidValue;
     }
-    CUtensorMap tmA, tmB;
+    if (epi != EPI_BIAS_RES_LN && p.N > (res ? 2048u : 4096u)) {
+        if (why) *why = "N > 4096 is not supported by the bias staging";
+        return cudaErrorInvalidValue;
+    }
+    CUtensorMap tmA, tmB, tmO;
     const uint32_t chunk_rows = bn > 256 ? bn / 2 : bn;
     if (!make_tmap_k_major_16bit(&tmA, p.A, p.M, p.K, p.lda, kBM, p.fmt == 1) ||
-        !make_tmap_k_major_16bit(&tmB, p.W, p.N, p.K, p.ldw, chunk_rows, p.fmt == 1)) {
+        !make_tmap_k_major_16bit(&tmB, p.W, p.N, p.K, p.ldw, chunk_rows, p.fmt == 1) ||
+        !make_tmap_store_32x32_16bit(&tmO, p.out, p.M, p.N, p.ldo, p.fmt == 1)) {
         if (why) *why = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
     }
-#define MX_GEMM(BN_, EPI_)                                                      \
-    return p.fmt == 1 ? launch_cfg<BN_, EPI_, 1>(p, tmA, tmB, sm_count, st)     \
-                      : launch_cfg<BN_, EPI_, 0>(p, tmA, tmB, sm_count, st)
-    if (epi == EPI_BIAS_RES_LN) MX_GEMM(384, EPI_BIAS_RES_LN);
+#define MX_GEMM(BN_, EPI_, RES_)                                                       \
+    return p.fmt == 1 ? launch_cfg<BN_, EPI_, 1, RES_>(p, tmA, tmB, tmO, sm_count, st)      \
+                      : launch_cfg<BN_, EPI_, 0, RES_>(p, tmA, tmB, tmO, sm_count, st)
+    if (epi == EPI_BIAS_RES_LN) MX_GEMM(384, EPI_BIAS_RES_LN, false);
     if (epi == EPI_BIAS_GELU) {
-        if (bn == 256) MX_GEMM(256, EPI_BIAS_GELU);
-        if (bn == 192) MX_GEMM(192, EPI_BIAS_GELU);
-        MX_GEMM(128, EPI_BIAS_GELU);
+        if (res) MX_GEMM(192, EPI_BIAS_GELU, true);
+        if (bn == 256) MX_GEMM(256, EPI_BIAS_GELU, false);
+        if (bn == 192) MX_GEMM(192, EPI_BIAS_GELU, false);
+        MX_GEMM(128, EPI_BIAS_GELU, false);
     }
-    if (bn == 256) MX_GEMM(256, EPI_BIAS);
-    if (bn == 192) MX_GEMM(192, EPI_BIAS);
-    MX_GEMM(128, EPI_BIAS);
+    if (res) MX_GEMM(192, EPI_BIAS, true);
+    if (bn == 256) MX_GEMM(256, EPI_BIAS, false);
+    if (bn == 192) MX_GEMM(192, EPI_BIAS, false);
+    MX_GEMM(128, EPI_BIAS, false);
 #undef MX_GEMM
 }
 

@@ -88,7 +88,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 {
     using Cfg = TcCfg<L>;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by OFFSET: the pointer stays in the shared address space (LDS/STS, not generic LD/ST)
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sq = smem;                                          // [k_blocks][128 x 64] fp16, swizzled
     unsigned char *ring = sq + p.k_blocks * kKBBytes;                  // [kStages][128 x 64]
     float *list_s = reinterpret_cast<float *>(ring + Cfg::kStages * kKBBytes);  // [L][128]
