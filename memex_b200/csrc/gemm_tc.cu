@@ -14,6 +14,8 @@
 // Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two
 // accumulator stages when 2 * BN <= 512 columns), and the static tile schedule
 // tile = blockIdx.x + i * gridDim.x with the N index fastest (concurrent CTAs share A rows in L2).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm.cuh"
 #include "tc.cuh"
@@ -105,7 +107,10 @@ __device__ __forceinline__ float2 unpack16(uint32_t u)
         return __half22float2(*reinterpret_cast<__half2 *>(&u));
 }
 
-template <int BN, int EPI, int FMT, bool RES>
+// MC = 2-CTA cluster: the two CTAs work on vertically adjacent tiles (same n_blk, m_blk = 2 i + rank), each loads
+// HALF of every weight k-block and multicasts it into both CTAs' rings, which halves the L2 -> SM weight traffic
+// (the streaming GEMMs are otherwise L2-bandwidth-bound: a 128 x 256 x 384 tile pulls 288 KB for 3072 MMA cycles).
+template <int BN, int EPI, int FMT, bool RES, bool MC>
 __global__ void __launch_bounds__(GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, GemmParams p)
@@ -133,7 +138,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // tile schedule.  streaming: tile = blockIdx.x + i * gridDim.x, n fastest (concurrent CTAs share A rows in L2).
     // resident: a contiguous range of the n-major list, so a CTA changes its weight slice at most a few times.
     uint32_t t_begin, t_end, t_step;
-    if constexpr (RES) {
+    uint32_t cta_rank = 0;
+    if constexpr (MC) cta_rank = cluster_ctarank();
+    if constexpr (MC) {
+        // units = (pair of vertically adjacent tiles); a cluster strides over them, n fastest
+        t_begin = blockIdx.x >> 1;
+        t_end = ((tiles_m + 1) / 2) * tiles_n;
+        t_step = gridDim.x >> 1;
+    } else if constexpr (RES) {
         const uint32_t per = (n_tiles + gridDim.x - 1) / gridDim.x;
         t_begin = min(n_tiles, blockIdx.x * per);
         t_end = min(n_tiles, t_begin + per);
@@ -143,7 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         t_end = n_tiles;
         t_step = gridDim.x;
     }
-    auto tile_m = [&](uint32_t t) { return RES ? t % tiles_m : t / tiles_n; };
+    auto tile_m = [&](uint32_t t) { return MC ? 2 * (t / tiles_n) + cta_rank : (RES ? t % tiles_m : t / tiles_n); };
     auto tile_n = [&](uint32_t t) { return RES ? t / tiles_m : t % tiles_n; };
 
     if (warp == 0 && lane == 0) {
@@ -151,7 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < Cfg::kStages; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], MC ? 2 : 1);   // MC: a stage is free once BOTH CTAs' MMAs have read it
         }
         for (int i = 0; i < Cfg::kAccStages; ++i) {
             mbar_init(&tmem_full[i], 1);
@@ -164,6 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) tmem_alloc(tmem_ptr, Cfg::kTmemCols);
     tc_fence_before();
     __syncthreads();
+    if constexpr (MC) cluster_sync_all();   // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -191,10 +204,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tma_load_2d(sa, &tmA, &full[stage], kb * kBK, m_blk * kBM, RES ? kEvictLast : kEvictFirst);
                     if constexpr (!RES) {
                         unsigned char *sb = sa + Cfg::kABytes;
+                        if constexpr (MC) {
+                            // this CTA's half of the weight k-block, delivered to both CTAs (and to both `full` barriers)
+                            constexpr int kHalfRows = BN / 2;
+                            tma_load_2d_multicast(sb + cta_rank * (kHalfRows * kBK * 2), &tmB, &full[stage], kb * kBK,
+                                                  n_blk * BN + cta_rank * kHalfRows, (uint16_t)3, kEvictLast);
+                        } else {
 #pragma unroll
-                        for (int c = 0; c < Cfg::kChunks; ++c)
-                            tma_load_2d(sb + c * (Cfg::kChunkN * kBK * 2), &tmB, &full[stage], kb * kBK,
-                                        n_blk * BN + c * Cfg::kChunkN, kEvictLast);
+                            for (int c = 0; c < Cfg::kChunks; ++c)
+                                tma_load_2d(sb + c * (Cfg::kChunkN * kBK * 2), &tmB, &full[stage], kb * kBK,
+                                            n_blk * BN + c * Cfg::kChunkN, kEvictLast);
+                        }
                     }
                     if (++stage == Cfg::kStages) {
                         stage = 0;
@@ -235,7 +255,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             umma(tmem_base + as * BN + c * Cfg::kChunkN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                     }
-                    umma_commit(&empty[stage]);
+                    if constexpr (MC)
+                        umma_commit_multicast(&empty[stage], (uint16_t)3);
+                    else
+                        umma_commit(&empty[stage]);
                     if (++stage == Cfg::kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -400,31 +423,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (MC) cluster_sync_all();   // no CTA leaves while the peer can still signal its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
-template <int BN, int EPI, int FMT, bool RES>
+template <int BN, int EPI, int FMT, bool RES, bool MC>
 static cudaError_t launch_cfg(const GemmParams &p, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO,
                               int sm_count, cudaStream_t st)
 {
     using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN>;
-    auto kern = gemm_tc_kernel<BN, EPI, FMT, RES>;
+    auto kern = gemm_tc_kernel<BN, EPI, FMT, RES, MC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
-    const uint32_t n_tiles = ceil_div<uint32_t>(p.M, kBM) * (p.N / BN);
-    const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmO, p);
-    count_launch();
-    return cudaGetLastError();
+    const uint32_t tiles_m = ceil_div<uint32_t>(p.M, kBM), tiles_n = p.N / BN;
+    if constexpr (MC) {
+        const uint32_t units = ceil_div<uint32_t>(tiles_m, 2) * tiles_n;
+        const uint32_t clusters = std::min<uint32_t>(units, (uint32_t)sm_count / 2);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(Cfg::kThreads);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, p);
+        count_launch();
+        return e != cudaSuccess ? e : cudaGetLastError();
+    } else {
+        const uint32_t n_tiles = tiles_m * tiles_n;
+        const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
+        kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmO, p);
+        count_launch();
+        return cudaGetLastError();
+    }
 }
 
 // resident-weights variant: K <= 384, N a multiple of 192, enough tiles per CTA to amortise the weight load
 static bool use_resident(const GemmParams &p, int epi, int sm_count)
 {
     if (epi == EPI_BIAS_RES_LN) return false;
+    // measured on B200 (r1): with 144 KB of weights resident only 3 activation stages (48 KB) fit, and the ring then
+    // cannot cover the TMA round trip; the streaming + multicast variant is faster.  Kept as an opt-in experiment.
+    static const bool enabled = getenv("MX_GEMM_RESIDENT") != nullptr;
+    if (!enabled) return false;
     if (p.K > (uint32_t)(kResMaxKB * kBK) || p.N % 192 != 0 || p.N > 2048) return false;
     const uint32_t n_tiles = ceil_div<uint32_t>(p.M, kBM) * (p.N / 192);
     return n_tiles >= 4u * (uint32_t)sm_count;
@@ -451,28 +500,43 @@ cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStrea
         if (why) *why = "N > 4096 is not supported by the bias staging";
         return cudaErrorInvalidValue;
     }
+    // 2-CTA clusters with weight multicast (needs enough tile pairs to fill the chip).  Measured on B200 (r1,
+    // profiles/README.md): it halves the weight traffic from L2 but the kernels are paced by the tensor pipe, not by
+    // L2, and the lock-step of the two CTAs costs 3-6 % -- so it is opt-in (MX_GEMM_MULTICAST=1; the parity tests
+    // run both settings).
+    static const bool mc_on = getenv("MX_GEMM_MULTICAST") != nullptr;
+    const bool mc = !res && mc_on && sm_count >= 2 && ceil_div<uint32_t>(p.M, 2 * kBM) * (p.N / bn) >= (uint32_t)sm_count / 2;
     CUtensorMap tmA, tmB, tmO;
-    const uint32_t chunk_rows = bn > 256 ? bn / 2 : bn;
+    const uint32_t chunk_rows = mc ? bn / 2 : (bn > 256 ? bn / 2 : bn);
     if (!make_tmap_k_major_16bit(&tmA, p.A, p.M, p.K, p.lda, kBM, p.fmt == 1) ||
         !make_tmap_k_major_16bit(&tmB, p.W, p.N, p.K, p.ldw, chunk_rows, p.fmt == 1) ||
         !make_tmap_store_32x32_16bit(&tmO, p.out, p.M, p.N, p.ldo, p.fmt == 1)) {
         if (why) *why = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
     }
-#define MX_GEMM(BN_, EPI_, RES_)                                                       \
-    return p.fmt == 1 ? launch_cfg<BN_, EPI_, 1, RES_>(p, tmA, tmB, tmO, sm_count, st)      \
-                      : launch_cfg<BN_, EPI_, 0, RES_>(p, tmA, tmB, tmO, sm_count, st)
-    if (epi == EPI_BIAS_RES_LN) MX_GEMM(384, EPI_BIAS_RES_LN, false);
+#define MX_GEMM(BN_, EPI_, RES_, MC_)                                                         \
+    return p.fmt == 1 ? launch_cfg<BN_, EPI_, 1, RES_, MC_>(p, tmA, tmB, tmO, sm_count, st)   \
+                      : launch_cfg<BN_, EPI_, 0, RES_, MC_>(p, tmA, tmB, tmO, sm_count, st)
+#define MX_GEMM_MC(BN_, EPI_)                 \
+    do {                                      \
+        if (mc) {                             \
+            MX_GEMM(BN_, EPI_, false, true);  \
+        } else {                              \
+            MX_GEMM(BN_, EPI_, false, false); \
+        }                                     \
+    } while (0)
+    if (epi == EPI_BIAS_RES_LN) MX_GEMM_MC(384, EPI_BIAS_RES_LN);
     if (epi == EPI_BIAS_GELU) {
-        if (res) MX_GEMM(192, EPI_BIAS_GELU, true);
-        if (bn == 256) MX_GEMM(256, EPI_BIAS_GELU, false);
-        if (bn == 192) MX_GEMM(192, EPI_BIAS_GELU, false);
-        MX_GEMM(128, EPI_BIAS_GELU, false);
+        if (res) MX_GEMM(192, EPI_BIAS_GELU, true, false);
+        if (bn == 256) MX_GEMM_MC(256, EPI_BIAS_GELU);
+        if (bn == 192) MX_GEMM_MC(192, EPI_BIAS_GELU);
+        MX_GEMM_MC(128, EPI_BIAS_GELU);
     }
-    if (res) MX_GEMM(192, EPI_BIAS, true);
-    if (bn == 256) MX_GEMM(256, EPI_BIAS, false);
-    if (bn == 192) MX_GEMM(192, EPI_BIAS, false);
-    MX_GEMM(128, EPI_BIAS, false);
+    if (res) MX_GEMM(192, EPI_BIAS, true, false);
+    if (bn == 256) MX_GEMM_MC(256, EPI_BIAS);
+    if (bn == 192) MX_GEMM_MC(192, EPI_BIAS);
+    MX_GEMM_MC(128, EPI_BIAS);
+#undef MX_GEMM_MC
 #undef MX_GEMM
 }
 

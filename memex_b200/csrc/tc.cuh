@@ -152,6 +152,30 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// the same load delivered to the same shared-memory offset (and signalled on the same mbarrier offset) of every
+// CTA of the cluster named in cta_mask
+__device__ __forceinline__ void tma_load_2d_multicast(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int32_t c0,
+                                                      int32_t c1, uint16_t cta_mask, uint64_t hint)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5, %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask),
+          "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()   // every thread of every CTA of the cluster
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // shared -> global tile store (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *smem_src, int32_t c0, int32_t c1)
 {
@@ -207,6 +231,14 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t 
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// the same arrive delivered to the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_multicast(uint64_t *bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
                  : "memory");
 }
 

@@ -55,6 +55,8 @@ def test_f32_path_vs_numpy_oracle_ragged_and_chunked():
 @pytest.mark.parametrize("M,N,K,epi", [
     (128, 128, 64, 0), (128, 1152, 384, 0), (300, 1536, 384, 1), (1000, 384, 384, 2), (257, 384, 1536, 2),
     (40000, 1152, 384, 0), (129, 256, 128, 1),
+    # large enough for the 2-CTA multicast variant (>= 74 tile pairs), incl. an odd number of row tiles
+    (20000, 384, 384, 2), (19100, 384, 1536, 2), (20000, 1536, 384, 1), (19000, 128, 64, 0),
 ])
 def test_tcgen05_gemm_against_torch(M, N, K, epi, fmt, tol):
     import torch
@@ -146,3 +148,19 @@ def test_encode_errors():
     from memex_b200.embedding import SetupError
     with pytest.raises(SetupError):
         B200Encoder(arch_of(cfg), w, precision="f32")
+
+
+@pytest.mark.parametrize("switch", ["MX_GEMM_MULTICAST", "MX_GEMM_RESIDENT"])
+def test_gemm_opt_in_variants_in_a_fresh_process(switch):
+    """the 2-CTA weight-multicast and resident-weight GEMM variants are selected by an environment switch that
+    the library reads once, so they are exercised in a child process: same GEMM parity cases + the end-to-end
+    encoder check"""
+    import subprocess
+    import sys
+    if os.environ.get(switch):
+        pytest.skip("already inside the child process")
+    env = dict(os.environ, **{switch: "1"})
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
+                        "tcgen05_gemm_against_torch or tensor_core_paths_vs_oracle"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
