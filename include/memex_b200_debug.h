@@ -13,7 +13,7 @@ extern "C" {
 
 /* out[M,N] = epi(A[M,K] . W[N,K]^T) on the tcgen05 path.
  *   fmt 1 = bf16, 0 = f16 (A, W, residual, out);  bias/gamma/beta f32
- *   epi 0 = +bias, 1 = +bias, erf-GELU, 2 = LayerNorm(+bias +residual) (N must be 384)
+ *   epi 0 = +bias, 1 = +bias, erf-GELU, 2 = LayerNorm(+bias +residual) (N must be 384 or 768)
  * returns 0 or a negative MX_ERR_* code; synchronous. */
 int32_t mx_debug_gemm(const void *A, const void *W, const float *bias, const void *residual, const float *gamma,
                       const float *beta, void *out, uint32_t M, uint32_t N, uint32_t K, uint32_t fmt, uint32_t epi,

@@ -48,7 +48,8 @@ struct GemmCfg {
     static constexpr int kColsPerWarp = BN / kColGroups;
     static constexpr int kEpiWarps = 4 * kColGroups;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
-    static constexpr int kStatBytes = LN ? 2 * kColGroups * kBM * 8 : 0;   // LayerNorm partial (sum, sq), double buffered
+    // LayerNorm partial (sum, sq) per column group, double buffered, + the peer CTA's row totals (split-N variant)
+    static constexpr int kStatBytes = LN ? 2 * kColGroups * kBM * 8 + 2 * kBM * 8 : 0;
     static constexpr int kMaxBiasN = RES ? 2048 : 4096;
     static constexpr int kVecBytes = LN ? 3 * BN * 4 : kMaxBiasN * 4;      // bias | gamma | beta, or the whole bias vector
     // output staging for TMA stores: one [32 rows x 32 columns] 16-bit tile (2 KB, 64-byte swizzle) per epilogue warp
@@ -110,7 +111,13 @@ __device__ __forceinline__ float2 unpack16(uint32_t u)
 // MC = 2-CTA cluster: the two CTAs work on vertically adjacent tiles (same n_blk, m_blk = 2 i + rank), each loads
 // HALF of every weight k-block and multicasts it into both CTAs' rings, which halves the L2 -> SM weight traffic
 // (the streaming GEMMs are otherwise L2-bandwidth-bound: a 128 x 256 x 384 tile pulls 288 KB for 3072 MMA cycles).
-template <int BN, int EPI, int FMT, bool RES, bool MC>
+//
+// SPLIT (LayerNorm epilogue only) = 2-CTA cluster that splits the ROW: CTA rank r owns columns [r BN, (r + 1) BN) of
+// a 128-row tile (N = 2 BN), the two CTAs exchange their per-row (sum, sum of squares) through distributed shared
+// memory and each normalises its half.  With N = 384 that makes BN = 192: two TMEM accumulator stages fit, so the
+// two-pass LayerNorm epilogue overlaps the next tile's MMAs; with N = 768 (BERT-base) it is what makes the fused
+// epilogue possible at all (768 f32 columns do not fit the 512 TMEM columns of one SM).
+template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT>
 __global__ void __launch_bounds__(GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, GemmParams p)
@@ -126,12 +133,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t *tmem_empty = tmem_full + Cfg::kAccStages;
     uint64_t *b_full = tmem_empty + Cfg::kAccStages;
     uint64_t *b_empty = b_full + 1;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(b_empty + 1);
+    // SPLIT: the peer's row totals have arrived.  Two barriers used by alternate tiles: the peer can only send for
+    // tile i + 2 after every warp here has passed its wait for tile i (it needs this CTA's tile i + 1 totals first,
+    // which are sent after the CTA-wide epilogue barrier of tile i + 1), so a barrier never runs a phase ahead.
+    uint64_t *x_full = b_empty + 1;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(x_full + 2);
     float2 *stat = reinterpret_cast<float2 *>(smem + Cfg::kBarOff + 256);  // [2][kColGroups][kBM]
     float *svec = reinterpret_cast<float *>(smem + Cfg::kBarOff + 256 + Cfg::kStatBytes);
+    float2 *xstat = stat + 2 * Cfg::kColGroups * kBM;   // [2][kBM], written by the peer CTA
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tiles_n = p.N / BN;
+    const uint32_t tiles_n = p.N / BN;   // SPLIT: 2
     const uint32_t tiles_m = (p.M + kBM - 1) / kBM;
     const uint32_t n_tiles = tiles_m * tiles_n;
     const uint32_t k_blocks = (p.K + kBK - 1) / kBK;
@@ -139,8 +151,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // resident: a contiguous range of the n-major list, so a CTA changes its weight slice at most a few times.
     uint32_t t_begin, t_end, t_step;
     uint32_t cta_rank = 0;
-    if constexpr (MC) cta_rank = cluster_ctarank();
-    if constexpr (MC) {
+    if constexpr (MC || SPLIT) cta_rank = cluster_ctarank();
+    if constexpr (SPLIT) {
+        // a cluster strides over the row tiles; the rank picks the column half
+        t_begin = blockIdx.x >> 1;
+        t_end = tiles_m;
+        t_step = gridDim.x >> 1;
+    } else if constexpr (MC) {
         // units = (pair of vertically adjacent tiles); a cluster strides over them, n fastest
         t_begin = blockIdx.x >> 1;
         t_end = ((tiles_m + 1) / 2) * tiles_n;
@@ -155,8 +172,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         t_end = n_tiles;
         t_step = gridDim.x;
     }
-    auto tile_m = [&](uint32_t t) { return MC ? 2 * (t / tiles_n) + cta_rank : (RES ? t % tiles_m : t / tiles_n); };
-    auto tile_n = [&](uint32_t t) { return RES ? t / tiles_m : t % tiles_n; };
+    auto tile_m = [&](uint32_t t) {
+        return SPLIT ? t : (MC ? 2 * (t / tiles_n) + cta_rank : (RES ? t % tiles_m : t / tiles_n));
+    };
+    auto tile_n = [&](uint32_t t) { return SPLIT ? cta_rank : (RES ? t / tiles_m : t % tiles_n); };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -171,12 +190,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         mbar_init(b_full, 1);
         mbar_init(b_empty, 1);
+        mbar_init(&x_full[0], kBM);   // one remote arrive per row
+        mbar_init(&x_full[1], kBM);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, Cfg::kTmemCols);
     tc_fence_before();
     __syncthreads();
-    if constexpr (MC) cluster_sync_all();   // the peer's barriers exist before anything is multicast at them
+    if constexpr (MC || SPLIT) cluster_sync_all();   // the peer's barriers exist before anything is sent at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -280,11 +301,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr uint32_t kEpiThreads = Cfg::kEpiWarps * 32;
         const uint32_t etid = threadIdx.x - 64;
         if constexpr (EPI == EPI_BIAS_RES_LN) {
-            // BN == N: one set of per-column vectors for the whole kernel
+            // one set of per-column vectors for the whole kernel (BN == N, or this CTA's half of the row)
+            const uint32_t cbase = SPLIT ? cta_rank * BN : 0;
             for (uint32_t i = etid; i < BN; i += kEpiThreads) {
-                svec[i] = __ldg(p.bias + i);
-                svec[BN + i] = __ldg(p.gamma + i);
-                svec[2 * BN + i] = __ldg(p.beta + i);
+                svec[i] = __ldg(p.bias + cbase + i);
+                svec[BN + i] = __ldg(p.gamma + cbase + i);
+                svec[2 * BN + i] = __ldg(p.beta + cbase + i);
             }
             bar_sync(1, kEpiThreads);
         } else {
@@ -350,8 +372,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     sum += t2.x;
                     sq += t2.y;
                 }
-                const float mean = sum * (1.0f / BN);
-                const float var = fmaxf(sq * (1.0f / BN) - mean * mean, 0.f);
+                if constexpr (SPLIT) {
+                    // this CTA's row totals -> the peer (one thread per row sends), the peer's -> here
+                    if (cg == 0) {
+                        const uint32_t peer = cta_rank ^ 1u;
+                        st_cluster_f32x2(mapa_shared(smem_u32(xstat + (local & 1) * kBM + row_in_tile), peer), sum, sq);
+                        mbar_arrive_remote_release(mapa_shared(smem_u32(&x_full[local & 1]), peer));
+                    }
+                    mbar_wait_acquire_cluster(&x_full[local & 1], (local >> 1) & 1);
+                    const float2 o2 = xstat[(local & 1) * kBM + row_in_tile];
+                    sum += o2.x;
+                    sq += o2.y;
+                }
+                constexpr float kInvN = 1.0f / (SPLIT ? 2 * BN : BN);
+                const float mean = sum * kInvN;
+                const float var = fmaxf(sq * kInvN - mean * mean, 0.f);
                 const float rstd = rsqrtf(var + p.ln_eps);
 #pragma unroll 1
                 for (int c = 0; c < kCW / 32; ++c) {
@@ -423,24 +458,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
-    if constexpr (MC) cluster_sync_all();   // no CTA leaves while the peer can still signal its barriers
+    if constexpr (MC || SPLIT) cluster_sync_all();   // no CTA leaves while the peer can still signal its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
-template <int BN, int EPI, int FMT, bool RES, bool MC>
+template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT = false>
 static cudaError_t launch_cfg(const GemmParams &p, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO,
                               int sm_count, cudaStream_t st)
 {
     using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN>;
-    auto kern = gemm_tc_kernel<BN, EPI, FMT, RES, MC>;
+    auto kern = gemm_tc_kernel<BN, EPI, FMT, RES, MC, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     const uint32_t tiles_m = ceil_div<uint32_t>(p.M, kBM), tiles_n = p.N / BN;
-    if constexpr (MC) {
-        const uint32_t units = ceil_div<uint32_t>(tiles_m, 2) * tiles_n;
+    if constexpr (MC || SPLIT) {
+        const uint32_t units = SPLIT ? tiles_m : ceil_div<uint32_t>(tiles_m, 2) * tiles_n;
         const uint32_t clusters = std::min<uint32_t>(units, (uint32_t)sm_count / 2);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(2 * clusters);
@@ -481,7 +516,8 @@ static bool use_resident(const GemmParams &p, int epi, int sm_count)
 
 int gemm_tc_block_n(uint32_t N, int epi)
 {
-    if (epi == EPI_BIAS_RES_LN) return N == 384 ? 384 : 0;   // the row statistic needs the whole row in one CTA
+    // LayerNorm epilogue: the row lives in one CTA (N = 384) or in the two CTAs of a cluster (N = 384 or 768)
+    if (epi == EPI_BIAS_RES_LN) return (N == 384 || N == 768) ? 384 : 0;
     if (N % 256 == 0) return 256;
     if (N % 192 == 0) return 192;
     if (N % 128 == 0) return 128;
@@ -507,7 +543,8 @@ cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStrea
     static const bool mc_on = getenv("MX_GEMM_MULTICAST") != nullptr;
     const bool mc = !res && mc_on && sm_count >= 2 && ceil_div<uint32_t>(p.M, 2 * kBM) * (p.N / bn) >= (uint32_t)sm_count / 2;
     CUtensorMap tmA, tmB, tmO;
-    const uint32_t chunk_rows = mc ? bn / 2 : (bn > 256 ? bn / 2 : bn);
+    uint32_t chunk_rows = mc ? bn / 2 : (bn > 256 ? bn / 2 : bn);
+    if (epi == EPI_BIAS_RES_LN && !mc) chunk_rows = 192;   // whole-row 384 (2 chunks), split 2 x 192, split 2 x 384 (2 chunks each)
     if (!make_tmap_k_major_16bit(&tmA, p.A, p.M, p.K, p.lda, kBM, p.fmt == 1) ||
         !make_tmap_k_major_16bit(&tmB, p.W, p.N, p.K, p.ldw, chunk_rows, p.fmt == 1) ||
         !make_tmap_store_32x32_16bit(&tmO, p.out, p.M, p.N, p.ldo, p.fmt == 1)) {
@@ -525,7 +562,24 @@ cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStrea
             MX_GEMM(BN_, EPI_, false, false); \
         }                                     \
     } while (0)
-    if (epi == EPI_BIAS_RES_LN) MX_GEMM_MC(384, EPI_BIAS_RES_LN);
+    if (epi == EPI_BIAS_RES_LN) {
+        // N = 768: split over a 2-CTA cluster (2 x 384).  N = 384: split (2 x 192, two accumulator stages) when there
+        // are enough row tiles for the 74 clusters; MX_GEMM_LN_NO_SPLIT keeps the single-CTA whole-row variant.
+        static const bool no_split = getenv("MX_GEMM_LN_NO_SPLIT") != nullptr;
+        const bool can_split = sm_count >= 2;
+        if (p.N == 768) {
+            if (!can_split) {
+                if (why) *why = "N = 768 LayerNorm epilogue needs a 2-CTA cluster";
+                return cudaErrorInvalidValue;
+            }
+            return p.fmt == 1 ? launch_cfg<384, EPI_BIAS_RES_LN, 1, false, false, true>(p, tmA, tmB, tmO, sm_count, st)
+                              : launch_cfg<384, EPI_BIAS_RES_LN, 0, false, false, true>(p, tmA, tmB, tmO, sm_count, st);
+        }
+        if (can_split && !no_split && !mc)
+            return p.fmt == 1 ? launch_cfg<192, EPI_BIAS_RES_LN, 1, false, false, true>(p, tmA, tmB, tmO, sm_count, st)
+                              : launch_cfg<192, EPI_BIAS_RES_LN, 0, false, false, true>(p, tmA, tmB, tmO, sm_count, st);
+        MX_GEMM_MC(384, EPI_BIAS_RES_LN);
+    }
     if (epi == EPI_BIAS_GELU) {
         if (res) MX_GEMM(192, EPI_BIAS_GELU, true, false);
         if (bn == 256) MX_GEMM_MC(256, EPI_BIAS_GELU);

@@ -176,6 +176,41 @@ __device__ __forceinline__ void cluster_sync_all()   // every thread of every CT
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ---- distributed shared memory (2-CTA cluster) ------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t cta_rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b)
+{
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+// arrive on an mbarrier of another CTA of the cluster; release at cluster scope publishes this thread's earlier
+// st.shared::cluster to whoever acquires the barrier
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t *bar, uint32_t parity)
+{
+    uint32_t spins = 0, ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1u << 26)) {
+            printf("memex_b200: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
 // shared -> global tile store (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *smem_src, int32_t c0, int32_t c1)
 {

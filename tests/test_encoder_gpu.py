@@ -57,6 +57,8 @@ def test_f32_path_vs_numpy_oracle_ragged_and_chunked():
     (40000, 1152, 384, 0), (129, 256, 128, 1),
     # large enough for the 2-CTA multicast variant (>= 74 tile pairs), incl. an odd number of row tiles
     (20000, 384, 384, 2), (19100, 384, 1536, 2), (20000, 1536, 384, 1), (19000, 128, 64, 0),
+    # N = 768 LayerNorm epilogue (BERT-base): the row is split over a 2-CTA cluster
+    (1000, 768, 768, 2), (130, 768, 3072, 2), (20000, 768, 768, 2),
 ])
 def test_tcgen05_gemm_against_torch(M, N, K, epi, fmt, tol):
     import torch
@@ -150,7 +152,23 @@ def test_encode_errors():
         B200Encoder(arch_of(cfg), w, precision="f32")
 
 
-@pytest.mark.parametrize("switch", ["MX_GEMM_MULTICAST", "MX_GEMM_RESIDENT"])
+def test_bert_base_shape_tensor_core_path():
+    """hidden 768 / 12 heads of 64 / ffn 3072 (BertBaseNliMeanTokens, e5-base): split-row LayerNorm GEMMs, dh = 64
+    attention.  Two layers keep the CPU oracle quick; every kernel shape is the 12-layer model's."""
+    cfg = enc_oracle.EncoderConfig(layers=2, hidden=768, heads=12, ffn=3072)
+    w = enc_oracle.make_weights(cfg, seed=31)
+    ids, lens = enc_oracle.make_inputs(cfg, 6, 96, seed=32, ragged=True, min_len=3)
+    ref = enc_oracle.hf_encode(cfg, w, ids, lens)
+    for precision, min_cos in (("bf16", 1 - 2e-4), ("f16", 1 - 1e-5), ("f32", 1 - 1e-6)):
+        e = B200Encoder(arch_of(cfg), w, precision=precision, max_tokens=6 * 96)
+        out = e.encode_ids(ids, lens)
+        cos = (out * ref).sum(1)
+        print(f"bert-base shape {precision}: min cosine {cos.min():.7f}")
+        assert (cos >= min_cos).all(), (precision, cos.min())
+        e.close()
+
+
+@pytest.mark.parametrize("switch", ["MX_GEMM_MULTICAST", "MX_GEMM_RESIDENT", "MX_GEMM_LN_NO_SPLIT"])
 def test_gemm_opt_in_variants_in_a_fresh_process(switch):
     """the 2-CTA weight-multicast and resident-weight GEMM variants are selected by an environment switch that
     the library reads once, so they are exercised in a child process: same GEMM parity cases + the end-to-end
