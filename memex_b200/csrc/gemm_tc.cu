@@ -53,7 +53,11 @@ struct GemmCfg {
     static constexpr int kMaxBiasN = RES ? 2048 : 4096;
     static constexpr int kVecBytes = LN ? 3 * BN * 4 : kMaxBiasN * 4;      // bias | gamma | beta, or the whole bias vector
     // output staging for TMA stores: one [32 rows x 32 columns] 16-bit tile (2 KB, 64-byte swizzle) per epilogue warp
-    static constexpr int kOutBytes = LN ? 0 : kEpiWarps * 2048;
+    // (LayerNorm with 64 columns per warp: a [32 rows x 128 bytes] tile per warp, used to transpose the residual
+    //  in and the result out between the coalesced global pattern and the row-per-thread accumulator pattern)
+    static constexpr bool kLnStaged = LN && kColsPerWarp == 64;
+    static constexpr int kOutWarpBytes = LN ? (kLnStaged ? 4096 : 0) : 2048;
+    static constexpr int kOutBytes = kEpiWarps * kOutWarpBytes;
     static constexpr int kTailBytes = ((256 + kStatBytes + kVecBytes + 1023) / 1024) * 1024 + kOutBytes;
     // the activation (+ weight) ring takes what is left of the 227 KB
     static constexpr int kRingBudget = 227 * 1024 - 1024 - kTailBytes - kResBytes;
@@ -315,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bar_sync(1, kEpiThreads);
             if (etid == 0) tma_prefetch_desc(&tmO);
         }
-        unsigned char *obuf = smem + Cfg::kOutOff + (warp - 2) * 2048;
+        unsigned char *obuf = smem + Cfg::kOutOff + (warp - 2) * Cfg::kOutWarpBytes;
         uint32_t local = 0;
         for (uint32_t tile = t_begin; tile < t_end; tile += t_step, ++local) {
             const uint32_t m_blk = tile_m(tile), n_blk = tile_n(tile);
@@ -328,15 +332,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t col0 = n_blk * BN + cg * kCW;
             uint16_t *orow = reinterpret_cast<uint16_t *>(p.out) + (size_t)row * p.ldo + col0;
             [[maybe_unused]] uint4 rr[EPI == EPI_BIAS_RES_LN ? kCW / 8 : 1];
+            // coalesced mapping of the warp's [32 rows x 64 columns] block: 4 rows x 128 bytes per instruction
+            const uint32_t crow = lane >> 3, cch = lane & 7;
             if constexpr (EPI == EPI_BIAS_RES_LN) {
-                // this thread's slice of the residual row, requested while the MMAs of the tile are still running
-                const uint16_t *rrow = reinterpret_cast<const uint16_t *>(p.residual) + (size_t)row * p.ldr + col0;
+                // the residual block, requested while the MMAs of the tile are still running
+                if constexpr (Cfg::kLnStaged) {
 #pragma unroll
-                for (int j = 0; j < kCW / 8; ++j)
-                    rr[j] = row_ok ? *reinterpret_cast<const uint4 *>(rrow + j * 8) : make_uint4(0, 0, 0, 0);
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t r = m_blk * kBM + quarter * 32 + 4 * i + crow;
+                        rr[i] = r < p.M ? *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(p.residual) +
+                                                                           (size_t)r * p.ldr + col0 + cch * 8)
+                                        : make_uint4(0, 0, 0, 0);
+                    }
+                } else {
+                    const uint16_t *rrow = reinterpret_cast<const uint16_t *>(p.residual) + (size_t)row * p.ldr + col0;
+#pragma unroll
+                    for (int j = 0; j < kCW / 8; ++j)
+                        rr[j] = row_ok ? *reinterpret_cast<const uint4 *>(rrow + j * 8) : make_uint4(0, 0, 0, 0);
+                }
             }
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
+            if constexpr (EPI == EPI_BIAS_RES_LN && Cfg::kLnStaged) {
+                // transpose through the warp's staging tile (16-byte chunk index ^= row & 7): coalesced -> row per thread
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t r = 4 * i + crow;
+                    *reinterpret_cast<uint4 *>(obuf + r * 128 + ((cch ^ (r & 7)) << 4)) = rr[i];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const uint4 *>(obuf + lane * 128 + ((j ^ (lane & 7)) << 4));
+                __syncwarp();
+            }
 
             if constexpr (EPI == EPI_BIAS_RES_LN) {
                 // pass 1: x = acc + bias + residual, kept in TMEM; partial row sums of this warp's columns
@@ -402,11 +430,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const float y1 = (__uint_as_float(v[2 * j + 1]) - mean) * rstd * g2.y + be2.y;
                         o[j] = pack16<FMT>(y0, y1);
                     }
-                    if (row_ok) {
+                    if constexpr (Cfg::kLnStaged) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4 *>(obuf + lane * 128 + (((c * 4 + j) ^ (lane & 7)) << 4)) =
+                                make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    } else if (row_ok) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             *reinterpret_cast<uint4 *>(orow + c * 32 + j * 8) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                     }
+                }
+                if constexpr (Cfg::kLnStaged) {
+                    // row per thread -> coalesced: every store instruction writes 4 rows x 128 contiguous bytes
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t rl = 4 * i + crow, r = m_blk * kBM + quarter * 32 + rl;
+                        const uint4 v4 = *reinterpret_cast<const uint4 *>(obuf + rl * 128 + ((cch ^ (rl & 7)) << 4));
+                        if (r < p.M)
+                            *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(p.out) + (size_t)r * p.ldo + col0 + cch * 8) = v4;
+                    }
+                    __syncwarp();
                 }
             } else {
                 // two register buffers: the TMEM load of chunk c + 1 is in flight while chunk c is processed
