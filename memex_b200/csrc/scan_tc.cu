@@ -34,13 +34,13 @@ using namespace tc;
 namespace {
 
 constexpr int kTcThreads = 192;
-constexpr int kQM = 128;            // queries per pass = UMMA M
+constexpr int kQM = 128;            // list stride; queries per pass = UMMA M = 128 (dim <= 384) or 64 (dim <= 768)
 constexpr int kTileN = 128;         // corpus rows per tile = UMMA N
 constexpr int kBK = 64;             // fp16 elements per k-block (one 128-byte swizzle atom)
-constexpr int kMaxKB = 6;           // dim <= 384
+constexpr int kMaxKB = 12;          // dim <= 768 (with M = 64: the query block must stay within 96 KB of smem)
 constexpr int kAccStages = 4;       // 4 x 128 TMEM columns
 constexpr int kInvSlots = 8;
-constexpr int kKBBytes = kQM * kBK * 2;  // 16 KB: one k-block of Q, or one k-block of a corpus tile
+constexpr int kKBBytes = kTileN * kBK * 2;  // 16 KB: one k-block of a corpus tile (a k-block of Q is QM x 128 bytes)
 
 template <int L>
 struct TcCfg {
@@ -48,7 +48,7 @@ struct TcCfg {
     static constexpr int kListBytes = L * kQM * 8;
     static constexpr int kInvBytes = kInvSlots * kTileN * 4;
     static constexpr int kBarBytes = 512;
-    static constexpr int smem_bytes(int kb) { return kb * kKBBytes + kStages * kKBBytes + kListBytes + kInvBytes + kBarBytes + 1024; }
+    static constexpr int smem_bytes(int kb, int qm) { return kb * qm * kBK * 2 + kStages * kKBBytes + kListBytes + kInvBytes + kBarBytes + 1024; }
 };
 
 __device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
@@ -82,7 +82,9 @@ struct TcParams {
     uint32_t n_rows, nq, n_lists, k_blocks;
 };
 
-template <int L, bool USE_INV>
+// QM = 128: TMEM lane = query.  QM = 64 (cta_group::1, M = 64): accumulator row r sits in TMEM lane
+// 32 * (r / 16) + r % 16, i.e. the first 16 lanes of each 32-lane quarter -- epilogue lanes 16..31 idle.
+template <int L, bool USE_INV, int QM>
 __global__ void __launch_bounds__(kTcThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, TcParams p)
 {
@@ -91,7 +93,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // 1024-byte alignment by OFFSET: the pointer stays in the shared address space (LDS/STS, not generic LD/ST)
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *sq = smem;                                          // [k_blocks][128 x 64] fp16, swizzled
-    unsigned char *ring = sq + p.k_blocks * kKBBytes;                  // [kStages][128 x 64]
+    constexpr uint32_t kQKB = QM * kBK * 2;                            // bytes of one k-block of the query block
+    unsigned char *ring = sq + p.k_blocks * kQKB;                      // [kStages][128 x 64]
     float *list_s = reinterpret_cast<float *>(ring + Cfg::kStages * kKBBytes);  // [L][128]
     uint32_t *list_r = reinterpret_cast<uint32_t *>(list_s + L * kQM);
     float *sinv = reinterpret_cast<float *>(list_r + L * kQM);         // [kInvSlots][128]
@@ -105,7 +108,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_tiles = (p.n_rows + kTileN - 1) / kTileN;
-    const uint32_t q0 = blockIdx.y * kQM;
+    const uint32_t q0 = blockIdx.y * QM;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -131,9 +134,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, p.k_blocks * kKBBytes);
+            mbar_arrive_expect_tx(q_full, p.k_blocks * kQKB);
             for (uint32_t kb = 0; kb < p.k_blocks; ++kb)
-                tma_load_2d(sq + kb * kKBBytes, &tmQ, q_full, kb * kBK, q0, kEvictLast);
+                tma_load_2d(sq + kb * kQKB, &tmQ, q_full, kb * kBK, q0, kEvictLast);
             uint32_t stage = 0, phase = 0, local = 0;
             for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
                 if (USE_INV) {
@@ -155,7 +158,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(kQM, kTileN, 0 /* f16 */);
+            constexpr uint32_t idesc = make_idesc(QM, kTileN, 0 /* f16 */);
             mbar_wait(q_full, 0);
             tc_fence_after();
             const uint32_t sq_addr = smem_u32(sq);
@@ -167,7 +170,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = sq_addr + kb * kKBBytes;
+                    const uint32_t sa = sq_addr + kb * kQKB;
                     const uint32_t sb = smem_u32(ring + stage * kKBBytes);
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k)
@@ -185,10 +188,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     } else {
         // ================= epilogue: thread = query (TMEM lane), columns = corpus rows =================
         const uint32_t quarter = warp & 3;
-        const uint32_t t = quarter * 32 + lane;
-        const bool q_ok = q0 + t < p.nq;
-        float *ls = list_s + t;
-        uint32_t *lr = list_r + t;
+        const uint32_t t = QM == 128 ? quarter * 32 + lane : quarter * 16 + (lane & 15);   // query row of this thread
+        const bool q_ok = (QM == 128 || lane < 16) && q0 + t < p.nq;
+        float *ls = list_s + quarter * 32 + lane;    // one list column per thread (idle lanes own an unused one)
+        uint32_t *lr = list_r + quarter * 32 + lane;
 #pragma unroll
         for (int e = 0; e < L; ++e) {
             ls[e * kQM] = kNegInf;
@@ -233,7 +236,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     v[4 * j4 + 3] = __float_as_uint(s3);
                     any |= (s0 > thr) | (s1 > thr) | (s2 > thr) | (s3 > thr);
                 }
-                if (any) {
+                if (any && q_ok) {   // (idle lanes of the M = 64 layout read unowned TMEM lanes: never act on them)
                     // slow path (rare after warm-up): the scores go to a dynamically indexed local array so
                     // that the insertion code exists once instead of 32 times
                     uint32_t m = 0;
@@ -332,7 +335,7 @@ struct TcScanState {
 
 TcScanState *tc_scan_create(int sm_count, uint32_t ld, uint32_t dim)
 {
-    if (dim == 0 || dim > kMaxKB * kBK || ld % 8 != 0) return nullptr;
+    if (dim == 0 || dim > kMaxKB * kBK || ld % 8 != 0) return nullptr;   // > 768: the stream scan takes over
     if (!encode_tiled_fn()) return nullptr;
     TcScanState *t = new TcScanState();
     t->sm_count = sm_count;
@@ -360,30 +363,33 @@ uint32_t tc_scan_lists(const TcScanState *t, uint64_t n_rows)
     return (uint32_t)std::min<uint64_t>((uint64_t)t->sm_count, ceil_div<uint64_t>(n_rows, kTileN));
 }
 
-template <int L>
-static cudaError_t launch_tc(const CUtensorMap &tmQ, const CUtensorMap &tmC, const TcParams &tp, bool use_inv, dim3 grid,
-                             cudaStream_t st)
+template <int L, bool USE_INV, int QM>
+static cudaError_t launch_tc_one(const CUtensorMap &tmQ, const CUtensorMap &tmC, const TcParams &tp, dim3 grid, cudaStream_t st)
 {
-    const int smem = TcCfg<L>::smem_bytes((int)tp.k_blocks);
-    cudaError_t e;
-    if (use_inv) {
-        auto kern = scan_tc_kernel<L, true>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-        kern<<<grid, kTcThreads, smem, st>>>(tmQ, tmC, tp);
-    } else {
-        auto kern = scan_tc_kernel<L, false>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-        kern<<<grid, kTcThreads, smem, st>>>(tmQ, tmC, tp);
-    }
+    const int smem = TcCfg<L>::smem_bytes((int)tp.k_blocks, QM);
+    auto kern = scan_tc_kernel<L, USE_INV, QM>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kTcThreads, smem, st>>>(tmQ, tmC, tp);
     count_launch();
     return cudaGetLastError();
+}
+
+template <int L>
+static cudaError_t launch_tc(const CUtensorMap &tmQ, const CUtensorMap &tmC, const TcParams &tp, bool use_inv, uint32_t qm,
+                             dim3 grid, cudaStream_t st)
+{
+    if (qm == 128)
+        return use_inv ? launch_tc_one<L, true, 128>(tmQ, tmC, tp, grid, st) : launch_tc_one<L, false, 128>(tmQ, tmC, tp, grid, st);
+    return use_inv ? launch_tc_one<L, true, 64>(tmQ, tmC, tp, grid, st) : launch_tc_one<L, false, 64>(tmQ, tmC, tp, grid, st);
 }
 
 cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacity, uint32_t k, KernelTimer *timer,
                            cudaStream_t st, const char **why)
 {
     (void)capacity;
-    const uint32_t nq_pad = ceil_div<uint32_t>(p.nq, kQM) * kQM;
+    const uint32_t qm = t->k_blocks <= 6 ? 128u : 64u;   // queries per pass: the query block must fit 96 KB
+    const uint32_t nq_pad = ceil_div<uint32_t>(p.nq, qm) * qm;
     if (nq_pad > t->q_cap) {
         cudaFree(t->q16);
         cudaFree(t->tau);
@@ -406,7 +412,7 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
     if (e != cudaSuccess) return e;
 
     CUtensorMap tmQ, tmC;
-    if (!make_tmap_k_major_16bit(&tmQ, t->q16, nq_pad, t->dim, t->ld, kQM, false) ||
+    if (!make_tmap_k_major_16bit(&tmQ, t->q16, nq_pad, t->dim, t->ld, qm, false) ||
         !make_tmap_k_major_16bit(&tmC, p.rows, p.n_rows, t->dim, p.ld, kTileN, false)) {
         if (why) *why = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
@@ -420,10 +426,10 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
     tp.nq = p.nq;
     tp.n_lists = p.n_lists;
     tp.k_blocks = t->k_blocks;
-    dim3 grid(p.n_lists, nq_pad / kQM);
+    dim3 grid(p.n_lists, nq_pad / qm);
     if (timer) timer->begin(st, 0);
-    e = tc_scan_lcap(k) == 16 ? launch_tc<16>(tmQ, tmC, tp, p.use_inv != 0, grid, st)
-                              : launch_tc<32>(tmQ, tmC, tp, p.use_inv != 0, grid, st);
+    e = tc_scan_lcap(k) == 16 ? launch_tc<16>(tmQ, tmC, tp, p.use_inv != 0, qm, grid, st)
+                              : launch_tc<32>(tmQ, tmC, tp, p.use_inv != 0, qm, grid, st);
     if (timer) timer->end(st);
     if (e != cudaSuccess && why) *why = "scan_tc_kernel launch failed";
     return e;

@@ -300,6 +300,8 @@ def test_full_size_properties_1m(tmp_path):
     (20000, 384, 64, 10, "cosine"), (128, 384, 8, 10, "cosine"), (129, 64, 9, 3, "cosine"),
     (50001, 384, 128, 10, "cosine"), (30000, 384, 200, 10, "cosine"), (7777, 100, 33, 20, "cosine"),
     (40000, 256, 64, 26, "cosine"), (25000, 384, 64, 10, "dot"), (100, 8, 16, 10, "cosine"),
+    # dim > 384: the M = 64 form of the kernel (64 queries per pass), e5-base / BERT-base dimension 768
+    (30000, 768, 64, 10, "cosine"), (9001, 768, 100, 10, "cosine"), (5000, 512, 9, 20, "dot"), (700, 448, 130, 10, "cosine"),
 ])
 def test_parity_tcgen05_scan(tmp_path, n, d, nq, k, metric):
     """the batched tensor-core path gives the same ids and bit-identical scores as the oracle"""
