@@ -161,7 +161,14 @@ __global__ void __launch_bounds__(kAmWarps * 32, DH <= 32 ? 3 : 1) attention_mma
     for (int n = 0; n < NT; ++n)
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
-    float m_a = kNegInf, m_b = kNegInf, l_a = 0.f, l_b = 0.f;
+    float m_a = kNegInf, m_b = kNegInf;
+    // row sums of P come out of the tensor pipe too: P times a column of ones (every column of this 16 x 8
+    // accumulator tile holds the row's sum); the SFU/ALU-bound softmax loop loses 32 adds per key block
+    float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr uint32_t kOnes = BF16 ? 0x3f803f80u : 0x3c003c00u;
+    // per-lane shared-memory byte addresses of the ldmatrix rows (advanced by one key block per iteration)
+    const uint32_t k_lane = (uint32_t)__cvta_generic_to_shared(Ks + (lane & 7) * PITCH + (lane >> 3) * 8);
+    const uint32_t v_lane = (uint32_t)__cvta_generic_to_shared(Vs + ((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 8);
 
     for (uint32_t kb = 0; kb < n_kb; ++kb) {
         const uint32_t k0 = kb * kAmKB;
@@ -184,7 +191,7 @@ __global__ void __launch_bounds__(kAmWarps * 32, DH <= 32 ? 3 : 1) attention_mma
 #pragma unroll
             for (int kk = 0; kk < KS / 2; ++kk) {
                 uint32_t kf[4];
-                ldmatrix_x4(kf, (uint32_t)__cvta_generic_to_shared(Ks + (k0 + 8 * j + (lane & 7)) * PITCH + kk * 32 + (lane >> 3) * 8));
+                ldmatrix_x4(kf, k_lane + (k0 + 8 * j) * (PITCH * 2) + kk * 64);
                 mma16816<BF16>(s[j], qf[2 * kk], kf[0], kf[1]);
                 mma16816<BF16>(s[j], qf[2 * kk + 1], kf[2], kf[3]);
             }
@@ -217,19 +224,16 @@ __global__ void __launch_bounds__(kAmWarps * 32, DH <= 32 ? 3 : 1) attention_mma
         const float corr_a = fast_exp2(m_a - mn_a), corr_b = fast_exp2(m_b - mn_b);
         m_a = mn_a;
         m_b = mn_b;
-        float sum_a = 0.f, sum_b = 0.f;
         uint32_t pf[4][4];   // A fragments of P: 4 k-steps of 16 keys
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float p0 = fast_exp2(fmaf(s[j][0], scale_log2e, -mn_a)), p1 = fast_exp2(fmaf(s[j][1], scale_log2e, -mn_a));
             const float p2 = fast_exp2(fmaf(s[j][2], scale_log2e, -mn_b)), p3 = fast_exp2(fmaf(s[j][3], scale_log2e, -mn_b));
-            sum_a += p0 + p1;
-            sum_b += p2 + p3;
             pf[j >> 1][(j & 1) * 2 + 0] = pack2<BF16>(p0, p1);
             pf[j >> 1][(j & 1) * 2 + 1] = pack2<BF16>(p2, p3);
         }
-        l_a = l_a * corr_a + sum_a;
-        l_b = l_b * corr_b + sum_b;
+        lsum[0] *= corr_a;
+        lsum[2] *= corr_b;
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
             o[n][0] *= corr_a;
@@ -243,25 +247,29 @@ __global__ void __launch_bounds__(kAmWarps * 32, DH <= 32 ? 3 : 1) attention_mma
 #pragma unroll
             for (int np = 0; np < NT / 2; ++np) {
                 uint32_t vf[4];
-                const uint32_t mi = lane >> 3;
-                ldmatrix_x4_trans(vf, (uint32_t)__cvta_generic_to_shared(
-                                          Vs + (k0 + kk * 16 + (lane & 7) + (mi & 1) * 8) * PITCH + np * 16 + (mi >> 1) * 8));
+                ldmatrix_x4_trans(vf, v_lane + (k0 + kk * 16) * (PITCH * 2) + np * 32);
                 mma16816<BF16>(o[2 * np], pf[kk], vf[0], vf[1]);
                 mma16816<BF16>(o[2 * np + 1], pf[kk], vf[2], vf[3]);
             }
+            mma16816<BF16>(lsum, pf[kk], kOnes, kOnes);
         }
     }
     if (!active) return;
-    l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
-    l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
-    l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
-    l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
-    const float inv_a = row_a < len ? 1.0f / l_a : 0.f;
-    const float inv_b = row_b < len ? 1.0f / l_b : 0.f;
+    const float inv_a = row_a < len ? 1.0f / lsum[0] : 0.f;
+    const float inv_b = row_b < len ? 1.0f / lsum[2] : 0.f;
+    // the warp's 16 x DH result goes through its own rows of the (now idle) Q tile so that global stores are
+    // 16-byte pieces of contiguous rows instead of 4-byte fragments
+    uint16_t *qrow = Qs + warp * 16 * PITCH;
+    __syncwarp();
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
-        if (row_a < S) *reinterpret_cast<uint32_t *>(obase + (size_t)row_a * H + n * 8 + 2 * t) = pack2<BF16>(o[n][0] * inv_a, o[n][1] * inv_a);
-        if (row_b < S) *reinterpret_cast<uint32_t *>(obase + (size_t)row_b * H + n * 8 + 2 * t) = pack2<BF16>(o[n][2] * inv_b, o[n][3] * inv_b);
+        *reinterpret_cast<uint32_t *>(qrow + g * PITCH + n * 8 + 2 * t) = pack2<BF16>(o[n][0] * inv_a, o[n][1] * inv_a);
+        *reinterpret_cast<uint32_t *>(qrow + (g + 8) * PITCH + n * 8 + 2 * t) = pack2<BF16>(o[n][2] * inv_b, o[n][3] * inv_b);
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < 16 * CH; i += 32) {
+        const uint32_t r = i / CH, c = i % CH, qi = q0 + warp * 16 + r;
+        if (qi < S) *reinterpret_cast<uint4 *>(obase + (size_t)qi * H + c * 8) = *reinterpret_cast<const uint4 *>(qrow + r * PITCH + c * 8);
     }
 }
 

@@ -101,12 +101,74 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int32_t *__restrict
     }
 }
 
+// vectorised form for H = 128 * V (384, 768, ...): a lane owns 4 consecutive columns per 128-column group
+template <int ACT, int V>
+__global__ void __launch_bounds__(256) embed_ln_vec_kernel(const int32_t *__restrict__ ids, const float *__restrict__ word,
+                                                           const float *__restrict__ pos, const float *__restrict__ type0,
+                                                           const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                           float eps, typename Act<ACT>::T *__restrict__ x, uint32_t n_tokens,
+                                                           uint32_t S, uint32_t vocab)
+{
+    constexpr uint32_t H = 128 * V;
+    const uint32_t t = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (t >= n_tokens) return;
+    const uint32_t lane = lane_id();
+    uint32_t id = (uint32_t)ids[t];
+    if (id >= vocab) id = 0;
+    const float4 *wr = reinterpret_cast<const float4 *>(word + (size_t)id * H);
+    const float4 *pr = reinterpret_cast<const float4 *>(pos + (size_t)(t % S) * H);
+    const float4 *ty = reinterpret_cast<const float4 *>(type0);
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float4 a = __ldg(wr + lane + 32 * i), b = __ldg(ty + lane + 32 * i), c = __ldg(pr + lane + 32 * i);
+        v[i] = make_float4((a.x + b.x) + c.x, (a.y + b.y) + c.y, (a.z + b.z) + c.z, (a.w + b.w) + c.w);   // HF order
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+        q = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, q))));
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma) + lane + 32 * i);
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(beta) + lane + 32 * i);
+        typename Act<ACT>::T *o = x + (size_t)t * H + (lane + 32 * i) * 4;
+        const float y0 = (v[i].x - mean) * rstd * g.x + b.x, y1 = (v[i].y - mean) * rstd * g.y + b.y;
+        const float y2 = (v[i].z - mean) * rstd * g.z + b.z, y3 = (v[i].w - mean) * rstd * g.w + b.w;
+        if constexpr (ACT == ACT_F32) {
+            *reinterpret_cast<float4 *>(o) = make_float4(y0, y1, y2, y3);
+        } else {
+            Act<ACT>::st(o, y0);
+            Act<ACT>::st(o + 1, y1);
+            Act<ACT>::st(o + 2, y2);
+            Act<ACT>::st(o + 3, y3);
+        }
+    }
+}
+
 cudaError_t launch_embed_ln(const int32_t *ids, const float *word, const float *pos, const float *type0,
                             const float *gamma, const float *beta, float eps, void *x, int act, uint32_t n_tokens,
                             uint32_t S, uint32_t H, uint32_t vocab, cudaStream_t st)
 {
     if (H > 32 * kMaxHPerLane) return cudaErrorInvalidValue;
     const unsigned grid = ceil_div<uint32_t>(n_tokens, 8);
+#define MX_LV(A, V)                                                                                                     \
+    embed_ln_vec_kernel<A, V><<<grid, 256, 0, st>>>(ids, word, pos, type0, gamma, beta, eps, (typename Act<A>::T *)x, \
+                                                    n_tokens, S, vocab)
+    if (H == 384 || H == 768) {
+        if (act == ACT_F32) { if (H == 384) MX_LV(ACT_F32, 3); else MX_LV(ACT_F32, 6); }
+        else if (act == ACT_BF16) { if (H == 384) MX_LV(ACT_BF16, 3); else MX_LV(ACT_BF16, 6); }
+        else { if (H == 384) MX_LV(ACT_F16, 3); else MX_LV(ACT_F16, 6); }
+        count_launch();
+        return cudaGetLastError();
+    }
+#undef MX_LV
 #define MX_L(A)                                                                                              \
     embed_ln_kernel<A><<<grid, 256, 0, st>>>(ids, word, pos, type0, gamma, beta, eps, (typename Act<A>::T *)x, \
                                              n_tokens, S, H, vocab)
@@ -304,29 +366,82 @@ cudaError_t launch_add_ln_f32(const float *y, const float *residual, const float
 // ---------------------------------------------------------------------------------------------
 // K10: masked mean-pool + L2 normalise, one CTA per sequence
 // ---------------------------------------------------------------------------------------------
+// one CTA per sequence; the 8 warps split the tokens, every lane owns columns lane, lane + 32, ... (coalesced rows),
+// partial sums meet in shared memory
 template <int ACT>
 __global__ void __launch_bounds__(256) pool_normalize_kernel(const typename Act<ACT>::T *__restrict__ x,
                                                              const int32_t *__restrict__ lens, float *__restrict__ out,
                                                              uint32_t S, uint32_t H, uint32_t normalize)
 {
+    __shared__ float part[8][1024];   // H <= 1024
     __shared__ float red[8];
     __shared__ float inv_s;
     const uint32_t b = blockIdx.x;
     const uint32_t len = min((uint32_t)max(lens[b], 0), S);
     const float denom = fmaxf((float)len, 1e-9f);   // sentence-transformers Pooling: clamp(sum_mask, 1e-9)
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    if constexpr (ACT != ACT_F32) {
+        // 16-byte loads: a lane owns 8 consecutive columns per 256-column group (H <= 1024 -> 4 groups)
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+        const uint32_t chunks = H / 8;   // H % 8 == 0 on the 16-bit paths
+        for (uint32_t t = warp; t < len; t += 8) {
+            const uint4 *row = reinterpret_cast<const uint4 *>(x + ((size_t)b * S + t) * H);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t ch = lane + 32 * i;
+                if (ch < chunks) {
+                    const uint4 u = row[ch];
+                    const typename Act<ACT>::T *h8 = reinterpret_cast<const typename Act<ACT>::T *>(&u);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[i][e] += Act<ACT>::ld(h8 + e);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t ch = lane + 32 * i;
+            if (ch < chunks)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) part[warp][ch * 8 + e] = acc[i][e];
+        }
+    } else {
+        float acc[kMaxHPerLane];
+#pragma unroll
+        for (int i = 0; i < kMaxHPerLane; ++i) acc[i] = 0.f;
+        for (uint32_t t = warp; t < len; t += 8) {
+            const typename Act<ACT>::T *row = x + ((size_t)b * S + t) * H;
+#pragma unroll
+            for (int i = 0; i < kMaxHPerLane; ++i) {
+                const uint32_t c = lane + 32 * i;
+                if (c < H) acc[i] += Act<ACT>::ld(row + c);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxHPerLane; ++i) {
+            const uint32_t c = lane + 32 * i;
+            if (c < H) part[warp][c] = acc[i];
+        }
+    }
+    __syncthreads();
     float sq = 0.f;
     float pooled[4];                                 // H <= 1024 with 256 threads
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint32_t c = threadIdx.x + 256 * i;
         float s = 0.f;
-        if (c < H)
-            for (uint32_t t = 0; t < len; ++t) s += Act<ACT>::ld(x + ((size_t)b * S + t) * H + c);
+        if (c < H) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += part[w][c];
+        }
         pooled[i] = s / denom;
         sq = fmaf(pooled[i], pooled[i], sq);
     }
     sq = warp_sum(sq);
-    if (lane_id() == 0) red[threadIdx.x >> 5] = sq;
+    if (lane == 0) red[warp] = sq;
     __syncthreads();
     if (threadIdx.x == 0) {
         float t = 0.f;
