@@ -19,7 +19,8 @@ int32_t mx_debug_gemm(const void *A, const void *W, const float *bias, const voi
                       const float *beta, void *out, uint32_t M, uint32_t N, uint32_t K, uint32_t fmt, uint32_t epi,
                       float ln_eps, int32_t device);
 /* ctx[B*S, H] = attention(qkv[B*S, 3H]) with the padding mask lens_dev[B]; fmt as above;
- * impl 0 = CUDA-core kernel, 1 = tensor-core flash kernel (attention_mma.cu).  synchronous. */
+ * impl 0 = CUDA-core kernel, 1 = mma.sync flash kernel (attention_mma.cu), 2 = tcgen05 kernel
+ * (attention_tc.cu; head_dim 32 / 64 and S <= 256, else MX_ERR_ENCODE).  synchronous. */
 int32_t mx_debug_attention(const void *qkv, const int32_t *lens_dev, void *ctx, uint32_t B, uint32_t S, uint32_t H,
                            uint32_t heads, uint32_t fmt, uint32_t impl, int32_t device);
 const char *mx_debug_last_error(void);
