@@ -23,6 +23,8 @@
 // Roofline: HBM.  Algorithmic bytes per launch = N * ld * 2 (+ 4 N inv_norm).
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 tcgen05.mma issuer + TMEM owner,
 // warps 2..5 epilogue (warp % 4 = TMEM lane quarter).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "scan.cuh"
 #include "tc.cuh"
@@ -42,14 +44,23 @@ constexpr int kAccStages = 4;       // 4 x 128 TMEM columns
 constexpr int kInvSlots = 8;
 constexpr int kKBBytes = kTileN * kBK * 2;  // 16 KB: one k-block of a corpus tile (a k-block of Q is QM x 128 bytes)
 
+constexpr int kMaxStages = 12;      // the corpus ring takes whatever shared memory the query block and the lists leave
+
 template <int L>
 struct TcCfg {
-    static constexpr int kStages = L <= 16 ? 6 : 5;
     static constexpr int kListBytes = L * kQM * 8;
     static constexpr int kInvBytes = kInvSlots * kTileN * 4;
     static constexpr int kBarBytes = 512;
-    static constexpr int smem_bytes(int kb, int qm) { return kb * qm * kBK * 2 + kStages * kKBBytes + kListBytes + kInvBytes + kBarBytes + 1024; }
+    static constexpr int fixed_bytes(int kb, int qm) { return kb * qm * kBK * 2 + kListBytes + kInvBytes + kBarBytes + 1024; }
+    // bytes in flight are what hides the HBM latency: 6 stages (96 KB) next to a 128-query block, 9 (144 KB) next to 64 queries
+    static constexpr int stages(int kb, int qm)
+    {
+        const int s = (227 * 1024 - fixed_bytes(kb, qm)) / kKBBytes;
+        return s > kMaxStages ? kMaxStages : s;
+    }
+    static constexpr int smem_bytes(int kb, int qm, int n_stages) { return fixed_bytes(kb, qm) + n_stages * kKBBytes; }
 };
+static_assert((2 * kMaxStages + 2 * kAccStages + kInvSlots + 1) * 8 + 8 <= 512, "barrier block");
 
 __device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
 {
@@ -80,6 +91,7 @@ struct TcParams {
     float *cand_s;
     uint32_t *cand_r;
     uint32_t n_rows, nq, n_lists, k_blocks;
+    uint32_t stages;        // depth of the corpus ring (<= kMaxStages)
 };
 
 // QM = 128: TMEM lane = query.  QM = 64 (cta_group::1, M = 64): accumulator row r sits in TMEM lane
@@ -95,12 +107,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     unsigned char *sq = smem;                                          // [k_blocks][128 x 64] fp16, swizzled
     constexpr uint32_t kQKB = QM * kBK * 2;                            // bytes of one k-block of the query block
     unsigned char *ring = sq + p.k_blocks * kQKB;                      // [kStages][128 x 64]
-    float *list_s = reinterpret_cast<float *>(ring + Cfg::kStages * kKBBytes);  // [L][128]
+    const uint32_t n_stages = p.stages;
+    float *list_s = reinterpret_cast<float *>(ring + n_stages * kKBBytes);  // [L][128]
     uint32_t *list_r = reinterpret_cast<uint32_t *>(list_s + L * kQM);
     float *sinv = reinterpret_cast<float *>(list_r + L * kQM);         // [kInvSlots][128]
     uint64_t *full = reinterpret_cast<uint64_t *>(sinv + kInvSlots * kTileN);
-    uint64_t *empty = full + Cfg::kStages;
-    uint64_t *tmem_full = empty + Cfg::kStages;
+    uint64_t *empty = full + kMaxStages;
+    uint64_t *tmem_full = empty + kMaxStages;
     uint64_t *tmem_empty = tmem_full + kAccStages;
     uint64_t *inv_full = tmem_empty + kAccStages;
     uint64_t *q_full = inv_full + kInvSlots;
@@ -113,7 +126,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmC);
-        for (int i = 0; i < Cfg::kStages; ++i) {
+        for (uint32_t i = 0; i < n_stages; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
@@ -148,7 +161,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], kKBBytes);
                     tma_load_2d(ring + stage * kKBBytes, &tmC, &full[stage], kb * kBK, tile * kTileN, kEvictFirst);
-                    if (++stage == Cfg::kStages) {
+                    if (++stage == n_stages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -177,7 +190,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         umma(tmem_base + as * kTileN, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc,
                              (kb | k) != 0 ? 1u : 0u);
                     umma_commit(&empty[stage]);
-                    if (++stage == Cfg::kStages) {
+                    if (++stage == n_stages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -364,9 +377,14 @@ uint32_t tc_scan_lists(const TcScanState *t, uint64_t n_rows)
 }
 
 template <int L, bool USE_INV, int QM>
-static cudaError_t launch_tc_one(const CUtensorMap &tmQ, const CUtensorMap &tmC, const TcParams &tp, dim3 grid, cudaStream_t st)
+static cudaError_t launch_tc_one(const CUtensorMap &tmQ, const CUtensorMap &tmC, TcParams tp, dim3 grid, cudaStream_t st)
 {
-    const int smem = TcCfg<L>::smem_bytes((int)tp.k_blocks, QM);
+    int n_stages = TcCfg<L>::stages((int)tp.k_blocks, QM);
+    static const int cap = getenv("MX_SCAN_TC_STAGES") ? atoi(getenv("MX_SCAN_TC_STAGES")) : kMaxStages;   // measurement aid
+    if (cap >= 2 && cap < n_stages) n_stages = cap;
+    if (n_stages < 2) return cudaErrorInvalidValue;
+    tp.stages = (uint32_t)n_stages;
+    const int smem = TcCfg<L>::smem_bytes((int)tp.k_blocks, QM, n_stages);
     auto kern = scan_tc_kernel<L, USE_INV, QM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -388,7 +406,12 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
                            cudaStream_t st, const char **why)
 {
     (void)capacity;
-    const uint32_t qm = t->k_blocks <= 6 ? 128u : 64u;   // queries per pass: the query block must fit 96 KB
+    // queries per pass = UMMA M.  128 needs the query block to fit 96 KB (dim <= 384); batches of up to 64 queries use
+    // M = 64 anyway: half the query block buys three more ring stages (MX_SCAN_TC_QM=128 forces the wide form)
+    static const int qm_force = getenv("MX_SCAN_TC_QM") ? atoi(getenv("MX_SCAN_TC_QM")) : 0;
+    uint32_t qm = (t->k_blocks <= 6 && p.nq > 64) ? 128u : 64u;
+    if (qm_force == 128 && t->k_blocks <= 6) qm = 128u;
+    if (qm_force == 64) qm = 64u;
     const uint32_t nq_pad = ceil_div<uint32_t>(p.nq, qm) * qm;
     if (nq_pad > t->q_cap) {
         cudaFree(t->q16);
