@@ -41,7 +41,8 @@ TOPK = 10
 NQ = 64
 CORPUS_SEED, QUERY_SEED = 1234, 4321
 CHUNK_ROWS = 250_000           # generator granularity: chunk c is torch.Generator(seed = CORPUS_SEED + c)
-HNSW_SAMPLE_ROWS = 6_000       # bounded sample the CPU HNSW restatement is built over
+HNSW_SAMPLE_ROWS = 50_000      # bounded sample the CPU HNSW restatement is built over (--impl reference)
+HNSW_LEG_ROWS = 20_000         # ... and for the cpu_baseline leg of the GPU arm
 EXACT_SAMPLE_ROWS = 500_000    # bounded sample for the all-core exact brute force
 
 
@@ -187,15 +188,15 @@ def queries_host(x: np.ndarray, nq: int) -> np.ndarray:
     return (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
 
 
-def cpu_hnsw_baseline(steps: int, warmup: int, threads: int):
+def cpu_hnsw_baseline(steps: int, warmup: int, threads: int, rows: int = HNSW_SAMPLE_ROWS):
     """The reference's search as shipped (local.rs:48,76): HNSW M=16 efC=200, ef=32, cosine.
-    Built over a bounded sample (build is the reference's O(N log N) insert path and is not timed);
-    each step = one 64-query batch.  Returns (queries/sec, info)."""
+    Built over a bounded sample with all host threads (the build -- 2-7 ms per insert on one thread -- is not
+    timed); each step = one 64-query batch on `threads` threads.  Returns (queries/sec, info)."""
     from oracle import cosine
-    x = corpus_rows_host(HNSW_SAMPLE_ROWS)
+    x = corpus_rows_host(rows)
     h = cosine.HnswOracle(DIM, seed=1)
     t0 = time.perf_counter()
-    h.insert(x)
+    h.insert(x, threads=os.cpu_count() or 1)
     build_s = time.perf_counter() - t0
     q = queries_host(x, NQ)
     for _ in range(max(1, warmup)):
@@ -206,7 +207,7 @@ def cpu_hnsw_baseline(steps: int, warmup: int, threads: int):
     dt = time.perf_counter() - t0
     e_ids, _, _ = cosine.exact_topk(x, q, TOPK)
     recall = float(np.mean([len(set(ids[i]) & set(e_ids[i])) / TOPK for i in range(NQ)]))
-    return NQ * steps / dt, dict(build_s=round(build_s, 1), recall_at_10=round(recall, 3), ms_per_step=dt / steps * 1e3)
+    return NQ * steps / dt, dict(build_s=round(build_s, 1), recall_at_10=round(recall, 3), ms_per_step=dt / steps * 1e3, rows=rows)
 
 
 def cpu_exact_baseline():
@@ -256,8 +257,9 @@ def run_reference(args):
     v, info = cpu_hnsw_baseline(args.steps, args.warmup, threads)
     sample = (f"HNSW restatement (M=16, efC=200, ef=32) built over a {HNSW_SAMPLE_ROWS}-row sample of the corpus "
               f"(build {info['build_s']} s, untimed); {args.steps} steps x {NQ} queries on {threads} threads; "
-              f"recall@10 vs exact = {info['recall_at_10']}; HNSW search cost grows ~log N, so this over-states "
-              f"the reference's q/s at 10 M rows")
+              f"recall@10 vs exact = {info['recall_at_10']} (the GPU arm is exact: 1.0); HNSW search cost grows "
+              f"with log N, so this over-states the reference's q/s at 10 M rows, and memex serialises searches behind "
+              f"one mutex (storage/mod.rs:85-92), which this arm does not")
     line = {"impl": "reference", "metric": "queries/sec", "value": v, "unit": "queries/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -510,11 +512,11 @@ def run_ours(args):
             line["single_query"] = bench_single_query(device, max(50, args.steps * 5), max(20, args.warmup), pk)
             line["embed"] = bench_embed(device, max(5, args.steps // 2), max(3, args.warmup), pk, not args.skip_cpu)
         if not args.skip_cpu:
-            v, info = cpu_hnsw_baseline(20, 3, 1)
+            v, info = cpu_hnsw_baseline(20, 3, 1, HNSW_LEG_ROWS)
             line["cpu_baseline"] = {
                 "value": v, "unit": "queries/s", "cores": 1, "kind": "port",
                 "sample": (f"HNSW restatement of the reference's search (M=16, efC=200, ef=32), single thread as the "
-                           f"reference's mutex-serialised search, over a {HNSW_SAMPLE_ROWS}-row sample (build "
+                           f"reference's mutex-serialised search, over a {HNSW_LEG_ROWS}-row sample (build "
                            f"{info['build_s']} s untimed), 20 x {NQ} queries; recall@10 = {info['recall_at_10']}; "
                            f"approximate search, cost ~log N")}
             ev, cores = cpu_exact_baseline()

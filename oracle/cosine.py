@@ -57,6 +57,7 @@ def lib() -> ctypes.CDLL:
         L.mxo_hnsw_new.argtypes = [ctypes.c_uint32, ctypes.c_uint64]
         L.mxo_hnsw_free.argtypes = [ctypes.c_void_p]
         L.mxo_hnsw_insert.argtypes = [ctypes.c_void_p, f32p, ctypes.c_uint64]
+        L.mxo_hnsw_insert_parallel.argtypes = [ctypes.c_void_p, f32p, ctypes.c_uint64, ctypes.c_int]
         L.mxo_hnsw_len.restype = ctypes.c_uint64
         L.mxo_hnsw_len.argtypes = [ctypes.c_void_p]
         L.mxo_hnsw_search.argtypes = [ctypes.c_void_p, f32p, ctypes.c_uint32, ctypes.c_uint32,
@@ -122,10 +123,15 @@ class HnswOracle:
         self._h = lib().mxo_hnsw_new(dim, seed)
         self.dim = dim
 
-    def insert(self, vecs):
+    def insert(self, vecs, threads: int = 1):
+        """threads = 1: one point at a time as local.rs:62-69; > 1: the crate's parallel_insert scheme
+        (bench samples only -- the build is never the timed part)"""
         vecs, pv = _f32(np.atleast_2d(vecs))
         assert vecs.shape[1] == self.dim
-        lib().mxo_hnsw_insert(self._h, pv, vecs.shape[0])
+        if threads > 1:
+            lib().mxo_hnsw_insert_parallel(self._h, pv, vecs.shape[0], threads)
+        else:
+            lib().mxo_hnsw_insert(self._h, pv, vecs.shape[0])
 
     def __len__(self):
         return int(lib().mxo_hnsw_len(self._h))

@@ -21,11 +21,18 @@
  * reporting its recall against the exact ranking.
  *
  * Distance arithmetic is DistCosine's (see cosine_oracle.c).
+ *
+ * Building: memex inserts one point at a time (insert_one below).  For the bench sample the
+ * build is not what is timed, so mxo_hnsw_insert_parallel inserts from several threads with a
+ * lock per point's link lists and one for the entry point -- the scheme of the crate's own
+ * `parallel_insert` -- which makes a 100 k-row sample affordable (2-4 ms per insert otherwise).
  */
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <queue>
 #include <random>
 #include <vector>
@@ -43,9 +50,12 @@ struct Hnsw {
     int64_t entry = -1;
     uint32_t top_level = 0;
     std::mt19937_64 rng;
-    /* visited stamps */
+    /* visited stamps of the serial path */
     std::vector<uint32_t> stamp;
     uint32_t cur_stamp = 0;
+    /* parallel build: one lock per point's link lists, one for (entry, top_level); null when serial */
+    std::unique_ptr<std::mutex[]> node_mu;
+    std::mutex entry_mu;
 
     const float *row(uint32_t i) const { return data.data() + (size_t)i * dim; }
     float dist(const float *q, uint32_t i) const { return mxo_dist_cosine(q, row(i), dim); }
@@ -71,7 +81,14 @@ struct Hnsw {
             Cand c = cand.top();
             cand.pop();
             if (c.first > best.top().first && best.size() >= ef) break;
-            for (uint32_t nb : links[c.second][layer]) {
+            std::vector<uint32_t> nbs_copy;
+            const std::vector<uint32_t> *nbs = &links[c.second][layer];
+            if (node_mu) {   /* another thread may be re-linking this point */
+                std::lock_guard<std::mutex> g(node_mu[c.second]);
+                nbs_copy = *nbs;
+                nbs = &nbs_copy;
+            }
+            for (uint32_t nb : *nbs) {
                 if (st[nb] == cs) continue;
                 st[nb] = cs;
                 float d = dist(q, nb);
@@ -112,32 +129,41 @@ struct Hnsw {
         return out;
     }
 
-    void insert(const float *v)
+    uint32_t draw_level()
     {
-        uint32_t id = (uint32_t)level.size();
-        data.insert(data.end(), v, v + dim);
         std::uniform_real_distribution<double> U(0.0, 1.0);
         double u = U(rng);
         if (u <= 0.0) u = 1e-300;
         uint32_t l = (uint32_t)std::floor(-std::log(u) / std::log((double)M));
-        if (l >= max_layer) l = max_layer - 1;
-        level.push_back(l);
-        links.emplace_back(l + 1);
-        stamp.push_back(0);
-        if (entry < 0) {
-            entry = id;
-            top_level = l;
-            return;
+        return l >= max_layer ? max_layer - 1 : l;
+    }
+
+    /* Alg. 1 for point `id`, whose row, level and (empty) link lists already exist */
+    void link_point(uint32_t id, std::vector<uint32_t> &st, uint32_t &cs)
+    {
+        const uint32_t l = level[id];
+        int64_t ent;
+        uint32_t top;
+        {
+            std::unique_lock<std::mutex> g(entry_mu, std::defer_lock);
+            if (node_mu) g.lock();
+            ent = entry;
+            top = top_level;
+            if (ent < 0) {
+                entry = id;
+                top_level = l;
+                return;
+            }
         }
         const float *q = row(id);
-        std::vector<Cand> ep{{dist(q, (uint32_t)entry), (uint32_t)entry}};
-        for (int64_t lc = top_level; lc > (int64_t)l; --lc) {
-            auto best = search_layer(q, ep, 1, (uint32_t)lc, stamp, cur_stamp);
+        std::vector<Cand> ep{{dist(q, (uint32_t)ent), (uint32_t)ent}};
+        for (int64_t lc = top; lc > (int64_t)l; --lc) {
+            auto best = search_layer(q, ep, 1, (uint32_t)lc, st, cs);
             while (best.size() > 1) best.pop();
             ep = {best.top()};
         }
-        for (int64_t lc = std::min(top_level, l); lc >= 0; --lc) {
-            auto best = search_layer(q, ep, efc, (uint32_t)lc, stamp, cur_stamp);
+        for (int64_t lc = std::min(top, l); lc >= 0; --lc) {
+            auto best = search_layer(q, ep, efc, (uint32_t)lc, st, cs);
             std::vector<Cand> w;
             w.reserve(best.size());
             while (!best.empty()) {
@@ -146,8 +172,14 @@ struct Hnsw {
             }
             uint32_t mmax = lc == 0 ? M0 : M;
             std::vector<uint32_t> nbrs = select_heuristic(w, M);
-            links[id][lc] = nbrs;
+            {
+                std::unique_lock<std::mutex> g;
+                if (node_mu) g = std::unique_lock<std::mutex>(node_mu[id]);
+                links[id][lc] = nbrs;
+            }
             for (uint32_t nb : nbrs) {
+                std::unique_lock<std::mutex> g;
+                if (node_mu) g = std::unique_lock<std::mutex>(node_mu[nb]);
                 auto &ln = links[nb][lc];
                 ln.push_back(id);
                 if (ln.size() > mmax) {
@@ -159,10 +191,34 @@ struct Hnsw {
             }
             ep = w;
         }
-        if (l > top_level) {
-            top_level = l;
-            entry = id;
+        if (l > top) {
+            std::unique_lock<std::mutex> g(entry_mu, std::defer_lock);
+            if (node_mu) g.lock();
+            if (l > top_level) {
+                top_level = l;
+                entry = id;
+            }
         }
+    }
+
+    /* rows, levels and empty link lists for n more points; returns the id of the first */
+    uint32_t append_rows(const float *v, uint64_t n)
+    {
+        const uint32_t first = (uint32_t)level.size();
+        data.insert(data.end(), v, v + (size_t)n * dim);
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint32_t l = draw_level();
+            level.push_back(l);
+            links.emplace_back(l + 1);
+        }
+        stamp.resize(level.size(), 0u);
+        return first;
+    }
+
+    void insert_one(const float *v)
+    {
+        const uint32_t id = append_rows(v, 1);
+        link_point(id, stamp, cur_stamp);
     }
 
     /* Alg. 5; thread-safe for concurrent readers given caller-owned stamps */
@@ -205,7 +261,31 @@ void mxo_hnsw_free(void *p) { delete (Hnsw *)p; }
 void mxo_hnsw_insert(void *p, const float *vecs, uint64_t n)
 {
     Hnsw *h = (Hnsw *)p;
-    for (uint64_t i = 0; i < n; ++i) h->insert(vecs + (size_t)i * h->dim);
+    for (uint64_t i = 0; i < n; ++i) h->insert_one(vecs + (size_t)i * h->dim);
+}
+
+/* same graph family, built by `threads` OpenMP threads (not the timed part of any measurement) */
+void mxo_hnsw_insert_parallel(void *p, const float *vecs, uint64_t n, int threads)
+{
+    Hnsw *h = (Hnsw *)p;
+    if (threads <= 1 || n < 2048) {
+        for (uint64_t i = 0; i < n; ++i) h->insert_one(vecs + (size_t)i * h->dim);
+        return;
+    }
+    /* a serial prefix gives the upper layers some shape before the threads start */
+    const uint64_t serial = 1024;
+    for (uint64_t i = 0; i < serial; ++i) h->insert_one(vecs + (size_t)i * h->dim);
+    const uint32_t first = h->append_rows(vecs + (size_t)serial * h->dim, n - serial);
+    const size_t total = h->level.size();
+    h->node_mu.reset(new std::mutex[total]);
+#pragma omp parallel num_threads(threads)
+    {
+        std::vector<uint32_t> st(total, 0u);
+        uint32_t cs = 0;
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t i = 0; i < (int64_t)(n - serial); ++i) h->link_point(first + (uint32_t)i, st, cs);
+    }
+    h->node_mu.reset();
 }
 
 uint64_t mxo_hnsw_len(void *p) { return ((Hnsw *)p)->level.size(); }

@@ -91,6 +91,24 @@ def test_hnsw_restatement_recall(oracle_lib):
     assert scores_h[0, 0] == oracle_lib.scores_of(c, q[0], [i0])[0]
 
 
+def test_hnsw_parallel_build_matches_serial_quality(oracle_lib):
+    """bench.py builds its HNSW sample with several threads (the build is not timed): the graph must be as good"""
+    rng = np.random.default_rng(7)
+    c = rng.standard_normal((3000, 16)).astype(np.float32)
+    c /= np.linalg.norm(c, axis=1, keepdims=True)
+    q = c[:64] + 0.05 * rng.standard_normal((64, 16)).astype(np.float32)
+    ids_e, _, _ = oracle_lib.exact_topk(c, q, 10)
+    recalls = []
+    for threads in (1, 4):
+        h = oracle_lib.HnswOracle(16, seed=3)
+        h.insert(c, threads=threads)
+        assert len(h) == 3000
+        ids_h, _, counts = h.search(q, 10, ef=32, threads=2)
+        assert (counts == 10).all()
+        recalls.append(np.mean([len(set(ids_h[i]) & set(ids_e[i])) / 10 for i in range(64)]))
+    assert recalls[0] > 0.9 and recalls[1] > 0.9, recalls
+
+
 @pytest.mark.parametrize("name,cfg", [("encoder_tiny", encoder.TINY), ("encoder_l6", encoder.MINILM_L6)])
 def test_encoder_restatements_agree_with_golden(name, cfg):
     g = np.load(os.path.join(GOLD, name + ".npz"))
