@@ -1,0 +1,230 @@
+// embedder.cpp -- B200Encoder, SentenceEmbedder (the actor of reference llm/embedding.rs:77-152), model table and
+// the .safetensors reader.  See memex_host.hpp.
+#include <cstring>
+#include <fstream>
+
+#include "../../include/memex_b200.h"
+#include "json.hpp"
+#include "memex_host.hpp"
+
+namespace memex {
+
+EmbeddingError::EmbeddingError(EmbeddingErrorKind k, const std::string &msg)
+    : std::runtime_error(std::string(k == EmbeddingErrorKind::EncodingFailure ? "Failed to encode string: " : "Unable to load model: ") + msg),
+      kind(k)
+{
+}
+
+std::optional<Architecture> architecture_of(EmbeddingsModelType model)
+{
+    // the others are DistilBERT / RoBERTa / ALBERT / T5 stacks, which the reference can only segment for
+    // L12 / L6 / distilroberta anyway (embedding.rs:156-161)
+    switch (model) {
+        case EmbeddingsModelType::AllMiniLmL6V2: return Architecture{6, 384, 12, 1536, 30522, 512, 2, 1e-12f, true, 256};
+        case EmbeddingsModelType::AllMiniLmL12V2: return Architecture{12, 384, 12, 1536, 30522, 512, 2, 1e-12f, true, 128};
+        case EmbeddingsModelType::BertBaseNliMeanTokens: return Architecture{12, 768, 12, 3072, 30522, 512, 2, 1e-12f, false, 128};
+        default: return std::nullopt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// safetensors: u64 header length | JSON header {name: {dtype, shape, data_offsets}} | raw little-endian data
+// ------------------------------------------------------------------------------------------------
+namespace {
+float half_to_float(uint16_t h)
+{
+    const uint32_t sign = (uint32_t)(h & 0x8000) << 16;
+    uint32_t exp = (h >> 10) & 0x1F, man = h & 0x3FF, bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else {
+            exp = 127 - 15 + 1;
+            while (!(man & 0x400)) { man <<= 1; --exp; }
+            bits = sign | (exp << 23) | ((man & 0x3FF) << 13);
+        }
+    } else if (exp == 31) bits = sign | 0x7F800000u | (man << 13);
+    else bits = sign | ((exp + 112) << 23) | (man << 13);
+    float f;
+    std::memcpy(&f, &bits, 4);
+    return f;
+}
+}  // namespace
+
+Weights Weights::from_safetensors(const std::string &path)
+{
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw EmbeddingError(EmbeddingErrorKind::SetupError, path + ": cannot open");
+    uint64_t hlen = 0;
+    f.read(reinterpret_cast<char *>(&hlen), 8);
+    if (!f || hlen == 0 || hlen > (1ull << 28)) throw EmbeddingError(EmbeddingErrorKind::SetupError, path + ": bad safetensors header");
+    std::string header(hlen, '\0');
+    f.read(&header[0], (std::streamsize)hlen);
+    if (!f) throw EmbeddingError(EmbeddingErrorKind::SetupError, path + ": truncated header");
+    json::Value root;
+    try {
+        root = json::parse(header);
+    } catch (const std::runtime_error &e) {
+        throw EmbeddingError(EmbeddingErrorKind::SetupError, path + ": " + e.what());
+    }
+    Weights w;
+    for (const auto &kv : root.obj) {
+        if (kv.first == "__metadata__") continue;
+        const json::Value *dt = kv.second.get("dtype"), *off = kv.second.get("data_offsets");
+        if (!dt || !off || off->arr.size() != 2) throw EmbeddingError(EmbeddingErrorKind::SetupError, kv.first + ": malformed entry");
+        const uint64_t a = (uint64_t)off->arr[0].num, b = (uint64_t)off->arr[1].num;
+        std::vector<char> raw(b - a);
+        f.seekg((std::streamoff)(8 + hlen + a));
+        f.read(raw.data(), (std::streamsize)raw.size());
+        if (!f) throw EmbeddingError(EmbeddingErrorKind::SetupError, kv.first + ": truncated data");
+        std::vector<float> vals;
+        if (dt->str == "F32") {
+            vals.resize(raw.size() / 4);
+            std::memcpy(vals.data(), raw.data(), vals.size() * 4);
+        } else if (dt->str == "F16" || dt->str == "BF16") {
+            vals.resize(raw.size() / 2);
+            const uint16_t *h = reinterpret_cast<const uint16_t *>(raw.data());
+            for (size_t i = 0; i < vals.size(); ++i) {
+                if (dt->str == "F16") vals[i] = half_to_float(h[i]);
+                else {
+                    const uint32_t bits = (uint32_t)h[i] << 16;
+                    std::memcpy(&vals[i], &bits, 4);
+                }
+            }
+        } else {
+            continue;   // integer buffers (position_ids) are not weights
+        }
+        // sentence-transformers checkpoints carry the names with or without a "bert." prefix
+        std::string name = kv.first;
+        if (name.rfind("bert.", 0) == 0) name = name.substr(5);
+        w.names.push_back(name);
+        w.data.push_back(std::move(vals));
+    }
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// B200Encoder
+// ------------------------------------------------------------------------------------------------
+B200Encoder::B200Encoder(const Architecture &arch, const Weights &weights, Precision precision, int device, uint32_t max_tokens)
+    : arch_(arch)
+{
+    std::vector<mx_tensor> ts(weights.names.size());
+    for (size_t i = 0; i < ts.size(); ++i) {
+        ts[i].name = weights.names[i].c_str();
+        ts[i].data = weights.data[i].data();
+        ts[i].numel = weights.data[i].size();
+    }
+    mx_model_cfg cfg{};
+    cfg.layers = arch.layers;
+    cfg.hidden = arch.hidden;
+    cfg.heads = arch.heads;
+    cfg.ffn = arch.ffn;
+    cfg.vocab = arch.vocab;
+    cfg.max_pos = arch.max_pos;
+    cfg.type_vocab = arch.type_vocab;
+    cfg.ln_eps = arch.ln_eps;
+    cfg.normalize = arch.normalize ? 1 : 0;
+    cfg.precision = (uint32_t)precision;
+    cfg.max_tokens = max_tokens;
+    int32_t rc = mx_embedder_create(&cfg, ts.data(), (uint32_t)ts.size(), device, &handle_);
+    if (rc != MX_OK) {
+        const char *m = mx_last_error(nullptr);
+        throw EmbeddingError(EmbeddingErrorKind::SetupError, m && *m ? m : ("status " + std::to_string(rc)));
+    }
+}
+
+B200Encoder::~B200Encoder()
+{
+    if (handle_) mx_embedder_destroy(handle_);
+}
+
+std::vector<float> B200Encoder::encode_ids(const TokenBatch &b)
+{
+    std::vector<float> out((size_t)b.B * arch_.hidden);
+    if (b.B == 0) return out;
+    int32_t rc = mx_embedder_encode(handle_, b.ids.data(), b.lens.data(), b.B, b.S, out.data());
+    if (rc != MX_OK) {
+        const char *m = mx_last_error(handle_);
+        throw EmbeddingError(EmbeddingErrorKind::EncodingFailure, m && *m ? m : ("status " + std::to_string(rc)));
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SentenceEmbedder
+// ------------------------------------------------------------------------------------------------
+std::shared_ptr<SentenceEmbedder> SentenceEmbedder::spawn(const ModelConfig &model_config, std::shared_ptr<Encoder> encoder,
+                                                          std::shared_ptr<BertTokenizer> tokenizer)
+{
+    std::shared_ptr<SentenceEmbedder> e(new SentenceEmbedder());
+    e->handle_ = std::thread([p = e.get(), model_config, encoder, tokenizer] { p->runner(model_config, encoder, tokenizer); });
+    return e;
+}
+
+SentenceEmbedder::~SentenceEmbedder()
+{
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        closed_ = true;   // dropping the sender ends `while let Ok(..) = receiver.recv()` (embedding.rs:102)
+    }
+    not_empty_.notify_all();
+    not_full_.notify_all();
+    if (handle_.joinable()) handle_.join();
+}
+
+void SentenceEmbedder::runner(ModelConfig model_config, std::shared_ptr<Encoder> encoder, std::shared_ptr<BertTokenizer> tokenizer)
+{
+    while (true) {
+        Message msg;
+        {
+            std::unique_lock<std::mutex> g(mu_);
+            not_empty_.wait(g, [this] { return closed_ || !channel_.empty(); });
+            if (channel_.empty()) return;
+            msg = std::move(channel_.front());
+            channel_.pop_front();
+        }
+        not_full_.notify_one();
+        try {
+            std::vector<std::string> segments =
+                msg.segment ? segment_text(model_config, msg.text, *tokenizer) : std::vector<std::string>{msg.text};
+            const TokenBatch batch = tokenize_batch(*tokenizer, segments, encoder->max_seq_length());
+            const std::vector<float> embeddings = encoder->encode_ids(batch);   // <- model.encode(&segments), embedding.rs:109
+            const uint32_t H = encoder->hidden();
+            if (embeddings.size() != segments.size() * H)   // embedding.rs:110-115
+                throw EmbeddingError(EmbeddingErrorKind::EncodingFailure, "# of embeddings doesn't match # of segments");
+            std::vector<EmbeddingResult> results;
+            results.reserve(segments.size());
+            for (size_t i = 0; i < segments.size(); ++i)
+                results.push_back({segments[i], std::vector<float>(embeddings.begin() + i * H, embeddings.begin() + (i + 1) * H)});
+            msg.sender.set_value(std::move(results));
+        } catch (...) {
+            // the reference's runner returns Err and dies; here the caller gets the error and the actor lives on
+            msg.sender.set_exception(std::current_exception());
+        }
+    }
+}
+
+std::future<std::vector<EmbeddingResult>> SentenceEmbedder::encode_async(std::string text, bool segment)
+{
+    Message m{std::move(text), segment, {}};
+    auto fut = m.sender.get_future();
+    {
+        std::unique_lock<std::mutex> g(mu_);
+        not_full_.wait(g, [this] { return closed_ || channel_.size() < kChannel; });   // sync_channel(100) blocks the sender
+        if (closed_) throw EmbeddingError(EmbeddingErrorKind::EncodingFailure, "embedder has shut down");
+        channel_.push_back(std::move(m));
+    }
+    not_empty_.notify_one();
+    return fut;
+}
+
+std::vector<EmbeddingResult> SentenceEmbedder::encode(const std::string &text) { return encode_async(text, true).get(); }
+
+std::optional<EmbeddingResult> SentenceEmbedder::encode_single(const std::string &text)
+{
+    std::vector<EmbeddingResult> v = encode_async(text, false).get();
+    if (v.empty()) return std::nullopt;
+    return std::move(v.back());   // value.pop(), embedding.rs:150
+}
+
+}  // namespace memex

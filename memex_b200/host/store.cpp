@@ -1,0 +1,408 @@
+// store.cpp -- B200Store / VectorStorage / get_vector_storage / SearchBatcher over the C ABI.
+// Mirrors reference lib/libmemex/src/storage/{mod.rs,local.rs}; see memex_host.hpp.
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "../../include/memex_b200.h"
+#include "json.hpp"
+#include "memex_host.hpp"
+
+namespace memex {
+
+namespace {
+
+const char *kMetaFile = "vectors.meta.json";   // local.rs:19, byte-compatible: {"<usize>":"<id>",...}
+
+StoreErrorKind kind_of(int32_t code, StoreErrorKind fallback)
+{
+    switch (code) {
+        case MX_ERR_CONNECTION: return StoreErrorKind::ConnectionError;
+        case MX_ERR_DELETE: return StoreErrorKind::DeleteError;
+        case MX_ERR_FILE_IO: return StoreErrorKind::FileIOError;
+        case MX_ERR_INSERTION: return StoreErrorKind::InsertionError;
+        case MX_ERR_SEARCH: return StoreErrorKind::SearchError;
+        case MX_ERR_SERDE: return StoreErrorKind::SerdeError;
+        case MX_ERR_SAVE: return StoreErrorKind::SaveError;
+        case MX_ERR_UNSUPPORTED: return StoreErrorKind::Unsupported;
+        default: return fallback;
+    }
+}
+
+[[noreturn]] void raise(int32_t code, const void *handle, StoreErrorKind fallback)
+{
+    const char *m = mx_last_error(handle);
+    throw VectorStoreError(kind_of(code, fallback), m && *m ? m : ("status " + std::to_string(code)));
+}
+
+bool exists(const std::string &p)
+{
+    struct stat st;
+    return ::stat(p.c_str(), &st) == 0;
+}
+
+void make_dirs(const std::string &path)
+{
+    std::string cur;
+    for (size_t i = 0; i <= path.size(); ++i) {
+        if (i == path.size() || path[i] == '/') {
+            if (!cur.empty() && !exists(cur) && ::mkdir(cur.c_str(), 0777) != 0 && errno != EEXIST)
+                throw VectorStoreError(StoreErrorKind::FileIOError, cur + ": " + std::strerror(errno));
+        }
+        if (i < path.size()) cur += path[i];
+    }
+}
+
+std::string join(const std::string &a, const std::string &b)
+{
+    if (a.empty()) return b;
+    return a.back() == '/' ? a + b : a + "/" + b;
+}
+
+}  // namespace
+
+const char *to_string(StoreErrorKind k)
+{
+    switch (k) {
+        case StoreErrorKind::ConnectionError: return "Unable to connect";
+        case StoreErrorKind::DeleteError: return "DeleteError";
+        case StoreErrorKind::FileIOError: return "File IO error";
+        case StoreErrorKind::InsertionError: return "Unable to insert vector";
+        case StoreErrorKind::SearchError: return "Unable to search";
+        case StoreErrorKind::SerdeError: return "Unable to deserialize";
+        case StoreErrorKind::SaveError: return "Unable to save db file";
+        case StoreErrorKind::Unsupported: return "Unsupported vector db";
+    }
+    return "?";
+}
+
+VectorStoreError::VectorStoreError(StoreErrorKind k, const std::string &msg)
+    : std::runtime_error(std::string(to_string(k)) + ": " + msg), kind(k)
+{
+}
+
+std::vector<std::vector<VectorSearchResult>> VectorStore::search_batch(const std::vector<std::vector<float>> &vecs, size_t limit) const
+{
+    std::vector<std::vector<VectorSearchResult>> out;
+    out.reserve(vecs.size());
+    for (const auto &v : vecs) out.push_back(search(v, limit));
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// B200Store
+// ------------------------------------------------------------------------------------------------
+std::unique_ptr<B200Store> B200Store::new_(const std::string &storage_path, const Options &opt)
+{
+    std::unique_ptr<B200Store> s(new B200Store());
+    s->storage_path = storage_path;
+    s->options = opt;
+    mx_store_cfg cfg{};
+    cfg.dim = opt.dim;
+    cfg.dtype = opt.fp16 ? MX_DTYPE_F16 : MX_DTYPE_F32;
+    cfg.metric = opt.dot ? MX_METRIC_DOT : MX_METRIC_COSINE;
+    cfg.device = opt.device;
+    cfg.capacity = opt.capacity;
+    cfg.id_offset = 0;
+    cfg.id_stride = 1;
+    int32_t rc = mx_store_create(&cfg, &s->handle_);
+    if (rc != MX_OK) raise(rc, nullptr, StoreErrorKind::ConnectionError);
+    return s;
+}
+
+bool B200Store::has_store(const std::string &store_path) { return exists(join(store_path, kMetaFile)); }
+
+std::unique_ptr<B200Store> B200Store::load(const std::string &store_path, int device)
+{
+    if (!mx_store_has_file(store_path.c_str()))
+        throw VectorStoreError(StoreErrorKind::FileIOError, join(store_path, "vectors.b200.bin") + ": No such file or directory");
+    std::unique_ptr<B200Store> s(new B200Store());
+    s->storage_path = store_path;
+    int32_t rc = mx_store_load(store_path.c_str(), device, &s->handle_);
+    if (rc != MX_OK) raise(rc, nullptr, StoreErrorKind::FileIOError);
+    std::ifstream f(join(store_path, kMetaFile), std::ios::binary);
+    if (!f) throw VectorStoreError(StoreErrorKind::FileIOError, join(store_path, kMetaFile) + ": " + std::strerror(errno));
+    std::stringstream ss;
+    ss << f.rdbuf();
+    try {
+        json::Value v = json::parse(ss.str());
+        if (v.kind != json::Value::Object) throw std::runtime_error("expected an object");
+        for (const auto &kv : v.obj) {
+            if (kv.second.kind != json::Value::String) throw std::runtime_error("expected string values");
+            char *end = nullptr;
+            unsigned long long id = std::strtoull(kv.first.c_str(), &end, 10);
+            if (end == kv.first.c_str() || *end) throw std::runtime_error("key is not an integer: " + kv.first);
+            s->_id_map[(size_t)id] = kv.second.str;
+        }
+    } catch (const std::runtime_error &e) {
+        throw VectorStoreError(StoreErrorKind::SerdeError, e.what());
+    }
+    uint32_t dim = 0, dtype = 0, metric = 0;
+    uint64_t cap = 0;
+    mx_store_info(s->handle_, &dim, &dtype, &metric, &cap);
+    s->options.dim = dim;
+    s->options.fp16 = dtype == MX_DTYPE_F16;
+    s->options.dot = metric == MX_METRIC_DOT;
+    s->options.device = device;
+    return s;
+}
+
+void B200Store::save(const std::string &store_path) const
+{
+    make_dirs(store_path);
+    int32_t rc = mx_store_save(handle_, store_path.c_str());
+    if (rc != MX_OK) raise(rc, handle_, StoreErrorKind::SaveError);
+    // the id map as serde_json::to_string(&HashMap<usize, String>) renders it (local.rs:155-161)
+    std::string out = "{";
+    bool first = true;
+    for (const auto &kv : _id_map) {
+        if (!first) out += ',';
+        first = false;
+        out += '"' + std::to_string(kv.first) + "\":";
+        json::escape_into(kv.second, out);
+    }
+    out += '}';
+    const std::string tmp = join(store_path, std::string(kMetaFile) + ".tmp");
+    {
+        std::ofstream f(tmp, std::ios::binary | std::ios::trunc);
+        if (!f) throw VectorStoreError(StoreErrorKind::FileIOError, tmp + ": " + std::strerror(errno));
+        f << out;
+        f.flush();
+        if (!f) throw VectorStoreError(StoreErrorKind::FileIOError, tmp + ": write failed");
+    }
+    if (std::rename(tmp.c_str(), join(store_path, kMetaFile).c_str()) != 0)
+        throw VectorStoreError(StoreErrorKind::FileIOError, std::string("rename: ") + std::strerror(errno));
+}
+
+B200Store::~B200Store()
+{
+    if (handle_) mx_store_destroy(handle_);
+}
+
+void B200Store::delete_(const std::string &)
+{
+    // local.rs:29-32 is `unimplemented!()`: a panic.  The ABI reports it instead.
+    raise(mx_store_delete(handle_, 0), handle_, StoreErrorKind::Unsupported);
+}
+
+void B200Store::delete_all()
+{
+    mx_store_remove_file(storage_path.c_str());                 // the data file ...
+    std::remove(join(storage_path, kMetaFile).c_str());         // ... and the id map (local.rs:36-46)
+    int32_t rc = mx_store_clear(handle_);
+    if (rc != MX_OK) raise(rc, handle_, StoreErrorKind::DeleteError);
+    _id_map.clear();
+}
+
+void B200Store::bulk_insert(const std::vector<VectorData> &data)
+{
+    if (data.empty()) return;
+    const size_t dim = options.dim;
+    std::vector<float> rows(data.size() * dim);
+    for (size_t i = 0; i < data.size(); ++i) {
+        if (data[i].vector.size() != dim)
+            throw VectorStoreError(StoreErrorKind::InsertionError, "vector has dimension " + std::to_string(data[i].vector.size()) +
+                                                                       ", store has " + std::to_string(dim));
+        std::copy(data[i].vector.begin(), data[i].vector.end(), rows.begin() + i * dim);
+    }
+    uint64_t first = 0;
+    int32_t rc = mx_store_add(handle_, rows.data(), data.size(), &first);
+    if (rc != MX_OK) raise(rc, handle_, StoreErrorKind::InsertionError);
+    // next_id = _id_map.len() + 1 (local.rs:63): the device's row ids and the map stay in lockstep
+    for (size_t i = 0; i < data.size(); ++i) _id_map[(size_t)first + i] = data[i]._id;
+    if (options.save_on_insert) {
+        try {
+            save(storage_path);   // `let _ = self.save(..)`: errors are ignored there too (local.rs:66-67)
+        } catch (const VectorStoreError &) {
+        }
+    }
+}
+
+void B200Store::insert(const VectorData &data) { bulk_insert({data}); }
+
+std::vector<std::vector<VectorSearchResult>> B200Store::search_batch(const std::vector<std::vector<float>> &vecs, size_t limit) const
+{
+    std::vector<std::vector<VectorSearchResult>> out(vecs.size());
+    if (vecs.empty() || limit == 0 || _id_map.empty()) return out;
+    const size_t dim = options.dim, nq = vecs.size();
+    const uint32_t k = (uint32_t)std::min<size_t>(limit, MX_MAX_K);
+    std::vector<float> q(nq * dim);
+    for (size_t i = 0; i < nq; ++i) {
+        if (vecs[i].size() != dim)
+            throw VectorStoreError(StoreErrorKind::SearchError, "query has dimension " + std::to_string(vecs[i].size()) +
+                                                                    ", store has " + std::to_string(dim));
+        std::copy(vecs[i].begin(), vecs[i].end(), q.begin() + i * dim);
+    }
+    std::vector<uint64_t> ids(nq * k);
+    std::vector<float> scores(nq * k);
+    std::vector<uint32_t> counts(nq);
+    int32_t rc = mx_store_search(handle_, q.data(), (uint32_t)nq, k, ids.data(), scores.data(), counts.data());
+    if (rc != MX_OK) raise(rc, handle_, StoreErrorKind::SearchError);
+    for (size_t i = 0; i < nq; ++i) {
+        out[i].reserve(counts[i]);
+        for (uint32_t j = 0; j < counts[i]; ++j) {
+            auto it = _id_map.find((size_t)ids[i * k + j]);
+            if (it == _id_map.end())   // local.rs:80-83 panics here
+                throw VectorStoreError(StoreErrorKind::SearchError, "Internal inconsistency. Id from vector store not mapped.");
+            out[i].emplace_back(it->second, scores[i * k + j]);
+        }
+    }
+    return out;
+}
+
+std::vector<VectorSearchResult> B200Store::search(const std::vector<float> &vec, size_t limit) const
+{
+    return search_batch({vec}, limit)[0];
+}
+
+uint64_t B200Store::len() const
+{
+    uint64_t n = 0;
+    mx_store_len(handle_, &n);
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// VectorStorage / factory / registry
+// ------------------------------------------------------------------------------------------------
+VectorStorage::VectorStorage(std::shared_ptr<VectorStore> c) : client(std::move(c)), lock_(std::make_shared<std::mutex>()) {}
+
+void VectorStorage::add_vectors(const std::vector<VectorData> &points)
+{
+    std::lock_guard<std::mutex> g(*lock_);
+    client->bulk_insert(points);
+}
+void VectorStorage::delete_collection()
+{
+    std::lock_guard<std::mutex> g(*lock_);
+    client->delete_all();
+}
+std::vector<VectorSearchResult> VectorStorage::search(const std::vector<float> &query, size_t limit) const
+{
+    std::lock_guard<std::mutex> g(*lock_);
+    return client->search(query, limit);
+}
+std::vector<std::vector<VectorSearchResult>> VectorStorage::search_batch(const std::vector<std::vector<float>> &queries, size_t limit) const
+{
+    std::lock_guard<std::mutex> g(*lock_);
+    return client->search_batch(queries, limit);
+}
+
+namespace {
+std::mutex g_registry_mu;
+std::unordered_map<std::string, VectorStorage> &registry()
+{
+    static std::unordered_map<std::string, VectorStorage> r;
+    return r;
+}
+}  // namespace
+
+void drop_vector_storage_registry()
+{
+    std::lock_guard<std::mutex> g(g_registry_mu);
+    registry().clear();
+}
+
+VectorStorage get_vector_storage(const std::string &uri, const std::string &collection)
+{
+    // mod.rs:99-102: anything that does not parse as scheme://rest is Unsupported
+    const size_t sep = uri.find("://");
+    if (sep == std::string::npos || sep == 0) throw VectorStoreError(StoreErrorKind::Unsupported, uri);
+    const std::string scheme = uri.substr(0, sep);
+    if (scheme != "b200" && scheme != "b200+f16" && scheme != "b200+f32") throw VectorStoreError(StoreErrorKind::Unsupported, uri);
+    const std::string key = uri + "\n" + collection;
+    std::lock_guard<std::mutex> g(g_registry_mu);
+    auto it = registry().find(key);
+    if (it != registry().end()) return it->second;
+    // collections are stored as folders (mod.rs:109-113)
+    const std::string storage = join(uri.substr(sep + 3), collection);
+    make_dirs(storage);
+    std::shared_ptr<VectorStore> store;
+    if (B200Store::has_store(storage)) {
+        store = B200Store::load(storage);
+    } else {
+        B200Store::Options opt;
+        opt.fp16 = scheme == "b200+f16";
+        store = B200Store::new_(storage, opt);
+    }
+    VectorStorage vs(store);
+    registry().emplace(key, vs);
+    return vs;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SearchBatcher
+// ------------------------------------------------------------------------------------------------
+SearchBatcher::SearchBatcher(VectorStorage storage, size_t max_batch, uint32_t max_wait_us)
+    : storage_(std::move(storage)), max_batch_(std::max<size_t>(1, max_batch)), max_wait_us_(max_wait_us)
+{
+    worker_ = std::thread([this] { run(); });
+}
+
+SearchBatcher::~SearchBatcher()
+{
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    if (worker_.joinable()) worker_.join();
+}
+
+std::future<std::vector<VectorSearchResult>> SearchBatcher::submit(std::vector<float> query, size_t limit)
+{
+    Req r{std::move(query), limit, {}};
+    auto fut = r.done.get_future();
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        queue_.push_back(std::move(r));
+    }
+    cv_.notify_one();
+    return fut;
+}
+
+void SearchBatcher::run()
+{
+    while (true) {
+        std::vector<Req> batch;
+        {
+            std::unique_lock<std::mutex> g(mu_);
+            cv_.wait(g, [this] { return stop_ || !queue_.empty(); });
+            if (queue_.empty()) return;   // stop requested and nothing left
+            // the first request opens a window of max_wait_us for others to join
+            const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(max_wait_us_);
+            while (queue_.size() < max_batch_ && !stop_) {
+                if (cv_.wait_until(g, deadline) == std::cv_status::timeout) break;
+            }
+            // one scan serves one `limit`: take the head's and everyone who asked for the same
+            const size_t limit = queue_.front().limit;
+            for (auto it = queue_.begin(); it != queue_.end() && batch.size() < max_batch_;) {
+                if (it->limit == limit) {
+                    batch.push_back(std::move(*it));
+                    it = queue_.erase(it);
+                } else {
+                    ++it;
+                }
+            }
+        }
+        std::vector<std::vector<float>> qs;
+        qs.reserve(batch.size());
+        for (auto &r : batch) qs.push_back(std::move(r.q));
+        try {
+            auto res = storage_.search_batch(qs, batch[0].limit);
+            for (size_t i = 0; i < batch.size(); ++i) batch[i].done.set_value(std::move(res[i]));
+        } catch (...) {
+            for (auto &r : batch) r.done.set_exception(std::current_exception());
+        }
+        ++batches_;
+    }
+}
+
+}  // namespace memex
