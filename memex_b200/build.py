@@ -82,5 +82,33 @@ def build(verbose: bool = False, force: bool = False) -> str:
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+HOST_TEST = os.path.join(OUT, "test_host")
+
+
+def build_host() -> str:
+    """C++ host layer (memex_b200/host/) -> _lib/libmemex_host.so + _lib/test_host, linked against libmemex_b200.so"""
+    if not os.path.exists(LIB):
+        build()
+    gxx = shutil.which("g++") or "/usr/bin/g++"
+    srcs = [os.path.join(HOST, f) for f in ("store.cpp", "tokenizer.cpp", "embedder.cpp")]
+    deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".hpp", ".cpp"))] + [
+        os.path.join(HERE, "..", "include", "memex_b200.h"), LIB]
+    newest = max(os.path.getmtime(d) for d in deps)
+    common = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra", "-pthread"]
+    link = ["-L" + OUT, "-lmemex_b200", "-Wl,-rpath,$ORIGIN"]
+    if not os.path.exists(HOST_LIB) or os.path.getmtime(HOST_LIB) < newest:
+        r = subprocess.run([gxx, *common, "-shared", "-o", HOST_LIB, *srcs, *link], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"host library build failed:\n{r.stdout}\n{r.stderr}")
+    if not os.path.exists(HOST_TEST) or os.path.getmtime(HOST_TEST) < max(newest, os.path.getmtime(HOST_LIB)):
+        r = subprocess.run([gxx, *common, "-o", HOST_TEST, os.path.join(HOST, "test_host.cpp"), "-L" + OUT, "-lmemex_host",
+                            "-lmemex_b200", "-Wl,-rpath,$ORIGIN"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"host test build failed:\n{r.stdout}\n{r.stderr}")
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    print(build_host())

@@ -1,0 +1,382 @@
+// test_host.cpp -- tests of the C++ host layer; driven by tests/test_host_cpp.py.
+//   test_host tokenizer <golden.json>     WordPiece / decode / windows / segment_text against the `tokenizers` package
+//   test_host cpu                         host logic that needs no GPU (actor, batcher, factory errors, JSON)
+//   test_host gpu <tmpdir>                the reference's own store tests (local.rs:175-242) + registry + batcher on the GPU
+//   test_host encode <model.safetensors> <ids.bin> <out.bin> L H heads F vocab max_pos precision
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "json.hpp"
+#include "memex_host.hpp"
+
+using namespace memex;
+
+static int g_checks = 0;
+#define CHECK(cond)                                                                      \
+    do {                                                                                 \
+        ++g_checks;                                                                      \
+        if (!(cond)) {                                                                   \
+            std::fprintf(stderr, "CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); \
+            std::exit(1);                                                                \
+        }                                                                                \
+    } while (0)
+
+static std::string slurp(const std::string &p)
+{
+    std::ifstream f(p, std::ios::binary);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
+static std::vector<int32_t> ints(const json::Value &a)
+{
+    std::vector<int32_t> v;
+    for (const auto &x : a.arr) v.push_back((int32_t)x.num);
+    return v;
+}
+
+static int run_tokenizer(const std::string &golden)
+{
+    json::Value g = json::parse(slurp(golden));
+    std::vector<std::string> vocab;
+    for (const auto &t : g.get("vocab")->arr) vocab.push_back(t.str);
+    auto tok = BertTokenizer::from_vocab(vocab);
+    int n = 0;
+    for (const auto &c : g.get("cases")->arr) {
+        const std::string text = c.get("text")->str;
+        const auto ids = tok->encode(text, false);
+        if (ids != ints(*c.get("ids"))) {
+            std::fprintf(stderr, "ids differ for case %d: %s\n got:", n, text.c_str());
+            for (auto i : ids) std::fprintf(stderr, " %d", i);
+            std::fprintf(stderr, "\n");
+            return 1;
+        }
+        CHECK(tok->encode(text, true) == ints(*c.get("ids_special")));
+        const std::string dec = tok->decode(ids, true);
+        if (dec != c.get("decoded")->str) {
+            std::fprintf(stderr, "decode differs for case %d:\n got  %s\n want %s\n", n, dec.c_str(), c.get("decoded")->str.c_str());
+            return 1;
+        }
+        const size_t max_length = (size_t)c.get("max_length")->num, stride = (size_t)c.get("stride")->num;
+        const auto windows = tok->encode_windows(text, max_length, stride);
+        const auto &gw = c.get("windows")->arr;
+        CHECK(windows.size() == gw.size());
+        for (size_t i = 0; i < gw.size(); ++i) CHECK(windows[i] == ints(gw[i]));
+        ModelConfig cfg;
+        cfg.model = EmbeddingsModelType::AllMiniLmL6V2;
+        cfg.max_length = max_length;
+        cfg.stride = stride;
+        const auto segs = segment_text(cfg, text, *tok);
+        const auto &gs = c.get("segments")->arr;
+        CHECK(segs.size() == gs.size());
+        for (size_t i = 0; i < gs.size(); ++i) {
+            if (segs[i] != gs[i].str) {
+                std::fprintf(stderr, "segment %zu differs for case %d:\n got  %s\n want %s\n", i, n, segs[i].c_str(), gs[i].str.c_str());
+                return 1;
+            }
+        }
+        ++n;
+    }
+    // models the reference cannot segment (embedding.rs:156-161)
+    ModelConfig bad;
+    bad.model = EmbeddingsModelType::SentenceT5Base;
+    try {
+        segment_text(bad, "x", *tok);
+        CHECK(false);
+    } catch (const EmbeddingError &e) {
+        CHECK(e.kind == EmbeddingErrorKind::SetupError);
+    }
+    std::printf("tokenizer ok: %d cases, %d checks\n", n, g_checks);
+    return 0;
+}
+
+// ---- fakes for the CPU tests --------------------------------------------------------------------
+struct FakeEncoder : Encoder {
+    std::atomic<int> calls{0};
+    uint32_t hidden() const override { return 4; }
+    uint32_t max_seq_length() const override { return 16; }
+    std::vector<float> encode_ids(const TokenBatch &b) override
+    {
+        ++calls;
+        std::vector<float> out((size_t)b.B * 4);
+        for (uint32_t i = 0; i < b.B; ++i) {
+            out[i * 4 + 0] = (float)b.lens[i];
+            out[i * 4 + 1] = (float)b.ids[(size_t)i * b.S];          // [CLS]
+            out[i * 4 + 2] = (float)b.ids[(size_t)i * b.S + 1];      // first token
+            out[i * 4 + 3] = (float)b.S;
+        }
+        return out;
+    }
+};
+
+struct FakeStore : VectorStore {
+    mutable std::atomic<int> batch_calls{0};
+    mutable std::atomic<int> queries{0};
+    void delete_(const std::string &) override { throw VectorStoreError(StoreErrorKind::Unsupported, "x"); }
+    void delete_all() override {}
+    void bulk_insert(const std::vector<VectorData> &) override {}
+    void insert(const VectorData &) override {}
+    std::vector<VectorSearchResult> search(const std::vector<float> &v, size_t limit) const override
+    {
+        return search_batch({v}, limit)[0];
+    }
+    std::vector<std::vector<VectorSearchResult>> search_batch(const std::vector<std::vector<float>> &vs, size_t limit) const override
+    {
+        ++batch_calls;
+        queries += (int)vs.size();
+        std::this_thread::sleep_for(std::chrono::milliseconds(2));   // a "scan"
+        std::vector<std::vector<VectorSearchResult>> out;
+        for (const auto &v : vs) out.push_back({{"doc-" + std::to_string((int)v[0]), (float)limit}});
+        return out;
+    }
+};
+
+static std::shared_ptr<BertTokenizer> tiny_tokenizer()
+{
+    std::vector<std::string> vocab = {"[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"};
+    for (const char *w : {"a", "b", "c", "d", "e", "f", "g", "h", "the", "fox", "##s", ".", ",", "'"}) vocab.push_back(w);
+    return BertTokenizer::from_vocab(vocab);
+}
+
+static int run_cpu()
+{
+    // ---- JSON: serde_json-style id map round trip
+    {
+        std::string s;
+        json::escape_into("a\"b\\c\n\x01", s);
+        CHECK(s == "\"a\\\"b\\\\c\\n\\u0001\"");
+        json::Value v = json::parse("{\"1\":\"uuid-1\",\"22\":\"x\\ty\\u00e9\",\"n\":[1,2.5,true,null,{\"k\":\"v\"}]}");
+        CHECK(v.get("1")->str == "uuid-1");
+        CHECK(v.get("22")->str == "x\ty\xc3\xa9");
+        CHECK(v.get("n")->arr.size() == 5 && v.get("n")->arr[1].num == 2.5 && v.get("n")->arr[4].get("k")->str == "v");
+        bool threw = false;
+        try { json::parse("{\"a\":}"); } catch (const std::runtime_error &) { threw = true; }
+        CHECK(threw);
+    }
+    // ---- factory errors (mod.rs:99-102,136)
+    for (const char *uri : {"not a uri", "hnsw:///tmp/x", "qdrant://host", "://x"}) {
+        try {
+            get_vector_storage(uri, "c");
+            CHECK(false);
+        } catch (const VectorStoreError &e) {
+            CHECK(e.kind == StoreErrorKind::Unsupported);
+        }
+    }
+    // ---- SentenceEmbedder actor over a fake encoder
+    {
+        auto enc = std::make_shared<FakeEncoder>();
+        auto tok = tiny_tokenizer();
+        ModelConfig cfg;
+        cfg.model = EmbeddingsModelType::AllMiniLmL6V2;
+        cfg.max_length = 4;
+        cfg.stride = 1;
+        auto emb = SentenceEmbedder::spawn(cfg, enc, tok);
+        // 9 tokens, windows of 4 stepping by 3: [0:4] [3:7] [6:9]
+        auto res = emb->encode("a b c d e f g h the");
+        CHECK(res.size() == 3);
+        CHECK(res[0].content == "a b c d" && res[1].content == "d e f g" && res[2].content == "g h the");
+        CHECK(res[0].vector.size() == 4 && res[0].vector[0] == 6.f /* 4 tokens + [CLS] + [SEP] */ && res[0].vector[1] == 2.f);
+        CHECK(res[2].vector[0] == 5.f);
+        CHECK(enc->calls == 1);   // one forward pass per document
+        auto one = emb->encode_single("the fox");
+        CHECK(one.has_value() && one->content == "the fox" && one->vector[0] == 4.f);
+        // single shot longer than the model's window is truncated by the model (embedding.rs:144-151): 16 = max_seq_length
+        auto longer = emb->encode_single("a a a a a a a a a a a a a a a a a a a a a a a a");
+        CHECK(longer->vector[0] == 16.f);
+        // many concurrent callers go through the bounded channel
+        std::vector<std::future<std::vector<EmbeddingResult>>> futs;
+        for (int i = 0; i < 300; ++i) futs.push_back(emb->encode_async("a b", false));
+        for (auto &f : futs) CHECK(f.get().size() == 1);
+        // an unsupported model surfaces as SetupError to the caller and the actor survives
+        ModelConfig bad;
+        bad.model = EmbeddingsModelType::SentenceT5Base;
+        auto emb2 = SentenceEmbedder::spawn(bad, enc, tok);
+        bool threw = false;
+        try { emb2->encode("a"); } catch (const EmbeddingError &e) { threw = e.kind == EmbeddingErrorKind::SetupError; }
+        CHECK(threw);
+        CHECK(emb2->encode_single("a").has_value());
+    }
+    // ---- SearchBatcher: concurrent single queries become few batched scans
+    {
+        auto fake = std::make_shared<FakeStore>();
+        VectorStorage vs(fake);
+        SearchBatcher batcher(vs, 16, 20000);
+        std::vector<std::future<std::vector<VectorSearchResult>>> futs;
+        for (int i = 0; i < 64; ++i) futs.push_back(batcher.submit({(float)i, 0.f}, 10));
+        for (int i = 0; i < 64; ++i) {
+            auto r = futs[i].get();
+            CHECK(r.size() == 1 && r[0].first == "doc-" + std::to_string(i) && r[0].second == 10.f);
+        }
+        CHECK(fake->queries == 64);
+        CHECK(fake->batch_calls <= 8 && batcher.batches_issued() == (uint64_t)fake->batch_calls);   // 64 / 16 = 4 when all queue up in time
+        // different limits are never mixed into one scan
+        auto f1 = batcher.submit({1.f, 0.f}, 3);
+        auto f2 = batcher.submit({2.f, 0.f}, 7);
+        CHECK(f1.get()[0].second == 3.f && f2.get()[0].second == 7.f);
+    }
+    // ---- architecture table
+    CHECK(architecture_of(EmbeddingsModelType::AllMiniLmL6V2)->layers == 6);
+    CHECK(architecture_of(EmbeddingsModelType::AllMiniLmL12V2)->max_seq_length == 128);
+    CHECK(!architecture_of(EmbeddingsModelType::SentenceT5Base).has_value());
+    // ---- no CPU path: creating a store without a CUDA device is a ConnectionError
+    try {
+        auto s = B200Store::new_("/tmp/mx_host_cpu_probe");
+        std::printf("cpu ok (a CUDA device is present): %d checks\n", g_checks);
+    } catch (const VectorStoreError &e) {
+        CHECK(e.kind == StoreErrorKind::ConnectionError);
+        std::printf("cpu ok (no CUDA device: ConnectionError as required): %d checks\n", g_checks);
+    }
+    return 0;
+}
+
+static std::vector<VectorData> test_data()   // local.rs:175-199
+{
+    return {{"test-one", "test-one", "", {0.0f, 0.1f, 0.2f}, 0},
+            {"test-two", "test-two", "", {0.1f, 0.1f, 0.1f}, 0},
+            {"test-three", "test-three", "", {0.3f, 0.2f, 0.1f}, 0}};
+}
+
+static int run_gpu(const std::string &tmp)
+{
+    B200Store::Options o3;
+    o3.dim = 3;
+    // test_hnsw (local.rs:201-214)
+    {
+        auto store = B200Store::new_(tmp + "/t1", o3);
+        store->bulk_insert(test_data());
+        auto results = store->search({0.1f, 0.1f, 0.1f}, 3);
+        CHECK(results.size() == 3);
+        CHECK(results[0].first == "test-two");
+        CHECK(results[1].first == "test-three" && results[2].first == "test-one");
+        CHECK(std::fabs(results[0].second - 1.0f) < 1e-6f && std::fabs(results[1].second - 0.9258201f) < 1e-6f &&
+              std::fabs(results[2].second - 0.7745967f) < 1e-6f);
+        CHECK(store->search({0.1f, 0.1f, 0.1f}, 2).size() == 2);   // clippy asks for 2 (examples/clippy/src/main.rs:209)
+        try {
+            store->delete_("test-one");
+            CHECK(false);
+        } catch (const VectorStoreError &e) {
+            CHECK(e.kind == StoreErrorKind::Unsupported);   // the reference panics here (local.rs:29-32)
+        }
+        try {
+            store->search({0.1f, 0.1f}, 3);
+            CHECK(false);
+        } catch (const VectorStoreError &e) {
+            CHECK(e.kind == StoreErrorKind::SearchError);
+        }
+        store->delete_all();
+    }
+    // test_save_load (local.rs:216-227)
+    {
+        auto store = B200Store::new_(tmp + "/vectortest", o3);
+        store->bulk_insert(test_data());
+        store->save(tmp + "/vectortest");
+        auto loaded = B200Store::load(tmp + "/vectortest");
+        CHECK(loaded->_id_map.size() == store->_id_map.size());
+        CHECK(loaded->len() == 3 && loaded->options.dim == 3);
+        auto r = loaded->search({0.1f, 0.1f, 0.1f}, 3);
+        CHECK(r.size() == 3 && r[0].first == "test-two");
+        // the id map file is what serde_json writes for HashMap<usize, String>: a flat object, string keys
+        json::Value meta = json::parse(slurp(tmp + "/vectortest/vectors.meta.json"));
+        CHECK(meta.kind == json::Value::Object && meta.obj.size() == 3 && meta.get("2")->str == "test-two");
+        store->delete_all();
+    }
+    // test_delete_all (local.rs:229-242)
+    {
+        auto store = B200Store::new_(tmp + "/t3", o3);
+        store->bulk_insert(test_data());
+        store->save(tmp + "/t3");
+        store->delete_all();
+        CHECK(store->_id_map.empty());
+        CHECK(store->len() == 0);
+        CHECK(!B200Store::has_store(tmp + "/t3"));
+        try {
+            B200Store::load(tmp + "/t3");
+            CHECK(false);
+        } catch (const VectorStoreError &) {
+        }
+    }
+    // factory + registry (N1): the same handle comes back; a fresh process-state re-loads from disk
+    {
+        const std::string uri = "b200://" + tmp + "/collections";
+        VectorStorage a = get_vector_storage(uri, "docs");
+        std::vector<VectorData> pts;
+        for (int i = 0; i < 500; ++i) {
+            VectorData d;
+            d._id = "seg-" + std::to_string(i);
+            d.vector.assign(384, 0.f);
+            d.vector[i % 384] = 1.f;
+            d.vector[(i * 7 + 1) % 384] += 0.25f + 0.001f * i;
+            pts.push_back(d);
+        }
+        a.add_vectors(pts);
+        VectorStorage b = get_vector_storage(uri, "docs");
+        CHECK(a.client.get() == b.client.get());
+        auto r1 = b.search(pts[123].vector, 10);
+        CHECK(r1.size() == 10 && r1[0].first == "seg-123" && std::fabs(r1[0].second - 1.0f) < 1e-6f);
+        for (size_t i = 1; i < r1.size(); ++i) CHECK(r1[i - 1].second >= r1[i].second);
+        drop_vector_storage_registry();
+        VectorStorage c = get_vector_storage(uri, "docs");   // vectors.meta.json exists -> load (mod.rs:115-119)
+        CHECK(c.client.get() != a.client.get());
+        auto r2 = c.search(pts[123].vector, 10);
+        CHECK(r2 == r1);
+        // N4: the batcher's answers are the direct answers
+        SearchBatcher batcher(c, 64, 2000);
+        std::vector<std::future<std::vector<VectorSearchResult>>> futs;
+        for (int i = 0; i < 200; ++i) futs.push_back(batcher.submit(pts[i].vector, 5));
+        for (int i = 0; i < 200; ++i) {
+            auto r = futs[i].get();
+            CHECK(r.size() == 5 && r[0].first == "seg-" + std::to_string(i));
+            if (i % 50 == 0) CHECK(r == c.search(pts[i].vector, 5));
+        }
+        CHECK(batcher.batches_issued() < 200);
+        c.delete_collection();
+        CHECK(c.search(pts[0].vector, 3).empty());
+        drop_vector_storage_registry();
+    }
+    std::printf("gpu ok: %d checks\n", g_checks);
+    return 0;
+}
+
+static int run_encode(int argc, char **argv)
+{
+    if (argc < 12) return 2;
+    Architecture arch{(uint32_t)atoi(argv[5]), (uint32_t)atoi(argv[6]), (uint32_t)atoi(argv[7]), (uint32_t)atoi(argv[8]),
+                      (uint32_t)atoi(argv[9]), (uint32_t)atoi(argv[10]), 2, 1e-12f, true, 256};
+    Weights w = Weights::from_safetensors(argv[2]);
+    // ids.bin: u32 B, u32 S, then B*S i32 ids, then B i32 lens
+    std::ifstream f(argv[3], std::ios::binary);
+    TokenBatch tb;
+    f.read(reinterpret_cast<char *>(&tb.B), 4);
+    f.read(reinterpret_cast<char *>(&tb.S), 4);
+    tb.ids.resize((size_t)tb.B * tb.S);
+    tb.lens.resize(tb.B);
+    f.read(reinterpret_cast<char *>(tb.ids.data()), (std::streamsize)tb.ids.size() * 4);
+    f.read(reinterpret_cast<char *>(tb.lens.data()), (std::streamsize)tb.lens.size() * 4);
+    B200Encoder enc(arch, w, (B200Encoder::Precision)atoi(argv[11]), 0, tb.B * tb.S);
+    std::vector<float> out = enc.encode_ids(tb);
+    std::ofstream o(argv[4], std::ios::binary);
+    o.write(reinterpret_cast<const char *>(out.data()), (std::streamsize)out.size() * 4);
+    std::printf("encode ok: %u x %u -> %zu floats\n", tb.B, tb.S, out.size());
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    try {
+        if (argc >= 3 && !std::strcmp(argv[1], "tokenizer")) return run_tokenizer(argv[2]);
+        if (argc >= 2 && !std::strcmp(argv[1], "cpu")) return run_cpu();
+        if (argc >= 3 && !std::strcmp(argv[1], "gpu")) return run_gpu(argv[2]);
+        if (argc >= 2 && !std::strcmp(argv[1], "encode")) return run_encode(argc, argv);
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "uncaught: %s\n", e.what());
+        return 1;
+    }
+    std::fprintf(stderr, "usage: test_host tokenizer <golden.json> | cpu | gpu <tmpdir> | encode ...\n");
+    return 2;
+}
