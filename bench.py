@@ -313,14 +313,9 @@ def bench_single_query(device, steps: int, warmup: int, pk):
                          "kernel_ms": per, "other_kernels_ms_per_step": oth_ms.value / max(1, steps)}}
 
 
-def bench_embed(device, steps: int, warmup: int, pk, cpu: bool):
-    """config 3: batch-256 segment embedding, MiniLM-L6, S = 256, bf16 activations on tcgen05"""
-    import torch
-    from memex_b200 import capi
-    from memex_b200.embedding import Architecture, B200Encoder
-    # seeded random weights at the true shapes (no checkpoint on the box, SURVEY.md F5); generated here, not via oracle/
-    Lyr, H, heads, F, vocab, max_pos = 6, 384, 12, 1536, 30522, 512
-    rng = np.random.default_rng(3)
+def random_bert_weights(Lyr, H, F, vocab, max_pos, seed=3):
+    """seeded random weights at the true shapes (no checkpoint on the box); generated here, not via oracle/"""
+    rng = np.random.default_rng(seed)
     w = {}
 
     def lin(name, o, i):
@@ -344,6 +339,16 @@ def bench_embed(device, steps: int, warmup: int, pk, cpu: bool):
         lin(p + "intermediate.dense", F, H)
         lin(p + "output.dense", H, F)
         ln(p + "output.LayerNorm")
+    return w
+
+
+def bench_embed(device, steps: int, warmup: int, pk, cpu: bool):
+    """config 3: batch-256 segment embedding, MiniLM-L6, S = 256, bf16 activations on tcgen05"""
+    import torch
+    from memex_b200 import capi
+    from memex_b200.embedding import Architecture, B200Encoder
+    Lyr, H, heads, F, vocab, max_pos = 6, 384, 12, 1536, 30522, 512
+    w = random_bert_weights(Lyr, H, F, vocab, max_pos)
     B, S = 256, 256
     arch = Architecture(Lyr, H, heads, F, vocab, max_pos)
     enc = B200Encoder(arch, w, precision="bf16", device=device.index, max_tokens=B * S)
@@ -400,6 +405,126 @@ def bench_embed(device, steps: int, warmup: int, pk, cpu: bool):
     if cpu:
         v, cores, sample = cpu_embed_baseline()
         res["cpu_baseline"] = {"value": v, "unit": "segments/s", "cores": cores, "kind": "port", "sample": sample}
+    return res
+
+
+def bench_ingest(device, pk, rows: int, seconds: float):
+    """config 5 at one GPU's share: a 768-d fp16 shard (50 M x 768 over 8 GPUs = 6.25 M rows, 9.6 GB) searched with
+    64-query batches WHILE segments are embedded (BERT-base shape, S = 512) and appended to the same shard.
+    Two host threads, searcher and ingester, take turns behind one FIFO lock (the store is behind one lock in the
+    reference too, storage/mod.rs:70-92): one 64-query scan, one embedded + appended batch, and so on.  Reports each role
+    alone, then both.  (True overlap of the HBM-bound scan with the tensor-bound forward pass needs the SMs partitioned
+    between the two persistent kernels -- green contexts -- and is not built yet.)"""
+    import torch
+    from memex_b200 import capi
+    from memex_b200.embedding import Architecture, B200Encoder
+    from memex_b200.sharded import ShardedStore
+    L = capi.lib()
+    dim, Lyr, heads, F, vocab, max_pos = 768, 12, 12, 3072, 30522, 512
+    B, S = 16, 512
+    st = ShardedStore("/tmp/mx_bench_ingest", dim, rows + 400_000, dtype="f16", device=device.index)
+    g = torch.Generator(device=device)
+    done = 0
+    while done < rows:
+        take = min(250_000, rows - done)
+        g.manual_seed(CORPUS_SEED + done // 250_000)
+        x = torch.nn.functional.normalize(torch.randn((take, dim), generator=g, device=device), dim=1).contiguous()
+        torch.cuda.synchronize(device)
+        st.add_local_device(x.data_ptr(), take)
+        done += take
+        del x
+    g.manual_seed(QUERY_SEED)
+    q = torch.nn.functional.normalize(torch.randn((NQ, dim), generator=g, device=device), dim=1).contiguous()
+    enc = B200Encoder(Architecture(Lyr, dim, heads, F, vocab, max_pos), random_bert_weights(Lyr, dim, F, vocab, max_pos),
+                      precision="bf16", device=device.index, max_tokens=B * S)
+    ids_d = torch.from_numpy(np.random.default_rng(7).integers(1000, 30000, size=(B, S)).astype(np.int32)).to(device)
+    lens = np.full(B, S, dtype=np.int32)
+    class TicketLock:
+        """FIFO hand-over: threading.Lock lets the releasing thread win the lock again and starves the other role"""
+
+        def __init__(self):
+            self.cv = threading.Condition()
+            self.next_ticket = 0
+            self.serving = 0
+
+        def __enter__(self):
+            with self.cv:
+                t = self.next_ticket
+                self.next_ticket += 1
+                while self.serving != t:
+                    self.cv.wait()
+
+        def __exit__(self, *a):
+            with self.cv:
+                self.serving += 1
+                self.cv.notify_all()
+
+    lock = TicketLock()
+    s_search, s_ingest = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    out_d = torch.zeros((B, dim), dtype=torch.float32, device=device)
+    stop = threading.Event()
+    counts = {"queries": 0, "segments": 0, "rows_scanned": 0}
+
+    def searcher():
+        torch.cuda.set_device(device)
+        with torch.cuda.stream(s_search):
+            while not stop.is_set():
+                with lock:
+                    n_now = len(st)
+                    st.search_device(q, TOPK)
+                    s_search.synchronize()
+                counts["queries"] += NQ
+                counts["rows_scanned"] += n_now
+
+    def ingester():
+        torch.cuda.set_device(device)
+        first = C.c_uint64()
+        while not stop.is_set():
+            # the forward pass runs under the lock too: the scan is a persistent kernel that fills every SM, so kernels of
+            # another stream only get in at its boundaries -- the two roles take turns on the GPU, batch by batch
+            with lock:
+                rc = L.mx_embedder_encode_device(enc.handle, ids_d.data_ptr(), lens.ctypes.data, B, S, out_d.data_ptr(),
+                                                 s_ingest.cuda_stream)
+                assert rc == 0, L.mx_last_error(enc.handle)
+                s_ingest.synchronize()
+                rc = L.mx_store_add_device(st.local.handle, out_d.data_ptr(), B, C.byref(first))
+                assert rc == 0, L.mx_last_error(st.local.handle)
+            counts["segments"] += B
+
+    def window(fns):
+        for k in counts:
+            counts[k] = 0
+        stop.clear()
+        ths = [threading.Thread(target=f) for f in fns]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        time.sleep(seconds)
+        stop.set()
+        for t in ths:
+            t.join()
+        torch.cuda.synchronize(device)
+        dt = time.perf_counter() - t0
+        return {k: v / dt for k, v in counts.items()}
+
+    for _ in range(3):
+        st.search_device(q, TOPK)
+    torch.cuda.synchronize(device)
+    alone_s = window([searcher])
+    alone_i = window([ingester])
+    both = window([searcher, ingester])
+    seg_flops = Lyr * S * (24 * dim * dim + 4 * S * dim)
+    res = {"workload": f"{rows}x{dim} fp16 shard (50Mx768 / 8), 64-query batches, while embedding BERT-base-shape segments "
+                       f"(L=12, H=768, S=512, B={B}) and appending them to the shard",
+           "rows_at_end": len(st),
+           "search_alone": {"queries_per_s": alone_s["queries"], "hbm_gbs": alone_s["rows_scanned"] * (dim * 2 + 4) / 1e9},
+           "ingest_alone": {"segments_per_s": alone_i["segments"], "tflops": alone_i["segments"] * seg_flops / 1e12},
+           "concurrent": {"queries_per_s": both["queries"], "segments_per_s": both["segments"],
+                          "hbm_gbs": both["rows_scanned"] * (dim * 2 + 4) / 1e9, "tflops": both["segments"] * seg_flops / 1e12},
+           "peaks": {"hbm_gbs": pk["hbm"], "tflops_sustained": pk["tf_sustained"]},
+           "timing": f"wall clock over {seconds} s windows, one host thread per role (a throughput figure, not a kernel time)"}
+    enc.close()
+    st.close()
     return res
 
 
@@ -538,9 +663,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--ingest-rows", type=int, default=6_250_000, help="--only ingest: rows of the 768-d shard (50 M / 8)")
+    ap.add_argument("--ingest-seconds", type=float, default=3.0, help="--only ingest: length of each timed window")
     ap.add_argument("--skip-cpu", action="store_true", help="leave out the CPU baseline legs")
     ap.add_argument("--skip-extras", action="store_true", help="leave out the single_query / embed sub-benches")
-    ap.add_argument("--only", default="", choices=["", "embed", "single"],
+    ap.add_argument("--only", default="", choices=["", "embed", "single", "ingest"],
                     help="profiling aid: run just one sub-bench on one GPU and print its object")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
@@ -548,8 +675,12 @@ def main():
         import torch
         torch.cuda.set_device(0)
         dev = torch.device("cuda", 0)
-        fn = bench_embed if args.only == "embed" else bench_single_query
-        res = fn(dev, args.steps, args.warmup, peaks(), False) if args.only == "embed" else fn(dev, args.steps, args.warmup, peaks())
+        if args.only == "ingest":
+            res = bench_ingest(dev, peaks(), args.ingest_rows, args.ingest_seconds)
+        elif args.only == "embed":
+            res = bench_embed(dev, args.steps, args.warmup, peaks(), False)
+        else:
+            res = bench_single_query(dev, args.steps, args.warmup, peaks())
         print(json.dumps(res), flush=True)
     elif args.impl == "reference":
         run_reference(args)
