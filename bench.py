@@ -84,7 +84,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
@@ -401,7 +401,52 @@ def bench_embed(device, steps: int, warmup: int, pk, cpu: bool):
                         "kernel": "gemm_tc_kernel (4 launches / layer)", "gemm_ms_per_step": g_ms.value / steps,
                         "other_ms_per_step": o_ms.value / steps, "whole_step_tflops": step_tf,
                         "whole_step_frac": step_tf / pk["tf_sustained"], "peak_kind": "sustained bf16, " + pk["src"]}}
+    # the same batch with ragged lengths ~ U[16, 256]: the GEMMs still run over all B * S token
+    # slots (no unpadding yet), attention and pooling skip the padding -- flops are counted on REAL tokens
+    lens_r = np.random.default_rng(8).integers(16, S + 1, size=B).astype(np.int32)
+
+    def step_ragged():
+        rc = L.mx_embedder_encode_device(enc.handle, ids_d.data_ptr(), lens_r.ctypes.data, B, S, out_d.data_ptr(), st)
+        assert rc == 0, L.mx_last_error(enc.handle)
+
+    for _ in range(3):
+        step_ragged()
+    torch.cuda.synchronize(device)
+    e0.record()
+    for _ in range(steps):
+        step_ragged()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms_r = e0.elapsed_time(e1) / steps
+    real = int(lens_r.sum())
+    flops_r = Lyr * (real * 24 * H * H + 4 * H * int((lens_r.astype(np.int64) ** 2).sum()))
+    res["ragged"] = {"workload": "same batch, lengths ~ U[16, 256]", "value": B * 1e3 / ms_r, "unit": "segments/s",
+                     "ms_per_step": ms_r, "real_tokens": real, "token_slots": T,
+                     "real_token_tflops": flops_r / (ms_r * 1e-3) / 1e12}
     enc.close()
+    # memex's DEFAULT model (embedding.rs:64-72): all-MiniLM-L12-v2, whose sentence_bert_config truncates to 128 tokens
+    enc12 = B200Encoder(Architecture(12, H, heads, F, vocab, max_pos), random_bert_weights(12, H, F, vocab, max_pos, seed=4),
+                        precision="bf16", device=device.index, max_tokens=B * 128)
+    ids12 = ids_d[:, :128].contiguous()
+    lens12 = np.full(B, 128, dtype=np.int32)
+
+    def step12():
+        rc = L.mx_embedder_encode_device(enc12.handle, ids12.data_ptr(), lens12.ctypes.data, B, 128, out_d.data_ptr(), st)
+        assert rc == 0, L.mx_last_error(enc12.handle)
+
+    for _ in range(3):
+        step12()
+    torch.cuda.synchronize(device)
+    e0.record()
+    for _ in range(steps):
+        step12()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms12 = e0.elapsed_time(e1) / steps
+    f12 = 12 * B * 128 * (24 * H * H + 4 * 128 * H)
+    res["default_model"] = {"workload": "all-MiniLM-L12-v2 shape (memex's default), B = 256, S = 128, bf16", "value": B * 1e3 / ms12,
+                            "unit": "segments/s", "ms_per_step": ms12, "tflops": f12 / (ms12 * 1e-3) / 1e12}
+    enc12.close()
     if cpu:
         v, cores, sample = cpu_embed_baseline()
         res["cpu_baseline"] = {"value": v, "unit": "segments/s", "cores": cores, "kind": "port", "sample": sample}
