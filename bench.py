@@ -41,7 +41,8 @@ TOPK = 10
 NQ = 64
 CORPUS_SEED, QUERY_SEED = 1234, 4321
 CHUNK_ROWS = 250_000           # generator granularity: chunk c is torch.Generator(seed = CORPUS_SEED + c)
-HNSW_SAMPLE_ROWS = 200_000     # bounded sample the CPU HNSW restatement is built over (--impl reference)
+# bounded sample the CPU HNSW restatement is built over (--impl reference); MX_BENCH_HNSW_ROWS shrinks it for the contract test
+HNSW_SAMPLE_ROWS = int(os.environ.get("MX_BENCH_HNSW_ROWS", "200000"))
 HNSW_LEG_ROWS = 20_000         # ... and for the cpu_baseline leg of the GPU arm
 EXACT_SAMPLE_ROWS = 500_000    # bounded sample for the all-core exact brute force
 
