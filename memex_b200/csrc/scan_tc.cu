@@ -20,6 +20,14 @@
 // score >= tau exist somewhere, so a row scoring below tau cannot be in the top L <= needed k.
 // It keeps the number of list insertions per thread ~L*ln(N/L)/CTAs instead of ~L*ln(N/CTAs/L).
 //
+// Threshold seeding.  An insertion is the slow path (the warp diverges and rescans an L-entry list), and a cold list
+// takes ~L ln(n / L) of them per thread: ~100 us per launch at L = 16 whatever the shard size, 330 us at L = 32
+// (measured, scripts/diag_scan_fixed.py).  So every CTA first scans its first P tiles keeping only the two best scores
+// per query (no list), publishes the second best, and after ONE grid-wide barrier (cooperative launch) every thread
+// takes tau0 = the (L/2)-th largest of the published values: L/2 CTAs hold two rows each scoring >= tau0, so tau0 is a
+// valid lower bound for the top L, and it sits at the ~0.07 % quantile instead of -inf.  The P tiles are then scanned
+// again, normally, at the end of the CTA's range.
+//
 // Roofline: HBM.  Algorithmic bytes per launch = N * ld * 2 (+ 4 N inv_norm).
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 tcgen05.mma issuer + TMEM owner,
 // warps 2..5 epilogue (warp % 4 = TMEM lane quarter).
@@ -92,6 +100,11 @@ struct TcParams {
     uint32_t *cand_r;
     uint32_t n_rows, nq, n_lists, k_blocks;
     uint32_t stages;        // depth of the corpus ring (<= kMaxStages)
+    // threshold seeding (see the kernel): the first `sample_tiles` tiles of every CTA are scanned for their two best
+    // scores only; samp [n_lists][nq_pad] collects the second best, sync is the grid-wide arrival counter
+    uint32_t sample_tiles, nq_pad;
+    float *samp;
+    uint32_t *sync;
 };
 
 // QM = 128: TMEM lane = query.  QM = 64 (cta_group::1, M = 64): accumulator row r sits in TMEM lane
@@ -122,6 +135,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_tiles = (p.n_rows + kTileN - 1) / kTileN;
     const uint32_t q0 = blockIdx.y * QM;
+    // this CTA's tiles: blockIdx.x + i * gridDim.x, i < n_local; with seeding the first P of them come twice:
+    // position i of the sequence -> tile index (i < n_local ? i : i - n_local), positions < P are the sampling pass
+    const uint32_t n_local = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t n_sample = p.sample_tiles;
+    const uint32_t n_seq = n_local + n_sample;
+    auto tile_of = [&](uint32_t i) { return blockIdx.x + (i < n_local ? i : i - n_local) * gridDim.x; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -150,8 +169,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_arrive_expect_tx(q_full, p.k_blocks * kQKB);
             for (uint32_t kb = 0; kb < p.k_blocks; ++kb)
                 tma_load_2d(sq + kb * kQKB, &tmQ, q_full, kb * kBK, q0, kEvictLast);
-            uint32_t stage = 0, phase = 0, local = 0;
-            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t local = 0; local < n_seq; ++local) {
+                const uint32_t tile = tile_of(local);
                 if (USE_INV) {
                     const uint32_t slot = local % kInvSlots;
                     mbar_arrive_expect_tx(&inv_full[slot], kTileN * 4);
@@ -175,8 +195,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_wait(q_full, 0);
             tc_fence_after();
             const uint32_t sq_addr = smem_u32(sq);
-            uint32_t stage = 0, phase = 0, local = 0;
-            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t local = 0; local < n_seq; ++local) {
                 const uint32_t as = local % kAccStages, aphase = (local / kAccStages) & 1;
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
@@ -215,11 +235,75 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         uint32_t filled = 0;
         const float *tau = p.tau + q0 + t;
         const float kPosInf = __int_as_float(0x7f800000);
-        uint32_t local = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+        float g_floor = kNegInf;          // tau0 from the sampling pass
+        float b1 = kNegInf, b2 = kNegInf; // two best scores of the sampling pass
+        for (uint32_t local = 0; local < n_seq; ++local) {
+            const uint32_t tile = tile_of(local);
             const uint32_t as = local % kAccStages, aphase = (local / kAccStages) & 1;
             const uint32_t slot = local % kInvSlots, sphase = (local / kInvSlots) & 1;
-            float g = q_ok ? ld_relaxed(tau) : kPosInf;
+            if (local < n_sample) {
+                // ---- sampling pass: the two best scores of this query over the tile, nothing else ----
+                if (USE_INV) mbar_wait(&inv_full[slot], sphase);
+                mbar_wait(&tmem_full[as], aphase);
+                tc_fence_after();
+                const float *inv = sinv + slot * kTileN;
+                const uint32_t row0 = tile * kTileN;
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * kTileN;
+#pragma unroll 1
+                for (int c = 0; c < kTileN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float s = __uint_as_float(v[j]);
+                        if (USE_INV) s *= inv[c * 32 + j];
+                        if (row0 + c * 32 + j >= p.n_rows) s = kNegInf;
+                        b2 = fmaxf(b2, fminf(b1, s));
+                        b1 = fmaxf(b1, s);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                if (local + 1 == n_sample) {
+                    // ---- publish, ONE grid-wide barrier (all CTAs are co-resident: cooperative launch), take tau0 ----
+                    if (q_ok) p.samp[(size_t)blockIdx.x * p.nq_pad + q0 + t] = b2;
+                    __threadfence();
+                    bar_sync(1, 128);
+                    if (threadIdx.x == 64) {
+                        atomicAdd(p.sync, 1u);
+                        uint32_t spins = 0, seen = 0;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync) : "memory");
+                            if (++spins > (1u << 26)) {
+                                printf("memex_b200: scan_tc grid barrier timed out (block %d, %u of %u)\n", blockIdx.x, seen, gridDim.x);
+                                __trap();
+                            }
+                        } while (seen < gridDim.x);
+                    }
+                    bar_sync(1, 128);
+                    if (q_ok && gridDim.x >= (uint32_t)(L / 2)) {
+                        float top[L / 2];
+#pragma unroll
+                        for (int e = 0; e < L / 2; ++e) top[e] = kNegInf;
+                        for (uint32_t c = 0; c < gridDim.x; ++c) {
+                            float v = __ldcg(p.samp + (size_t)c * p.nq_pad + q0 + t);
+                            if (v > top[L / 2 - 1]) {
+#pragma unroll
+                                for (int e = 0; e < L / 2; ++e) {   // sorted insertion, best first
+                                    const float hi = fmaxf(top[e], v);
+                                    v = fminf(top[e], v);
+                                    top[e] = hi;
+                                }
+                            }
+                        }
+                        g_floor = top[L / 2 - 1];
+                    }
+                }
+                continue;
+            }
+            float g = q_ok ? fmaxf(ld_relaxed(tau), g_floor) : kPosInf;
             if (USE_INV) mbar_wait(&inv_full[slot], sphase);
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
@@ -318,8 +402,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // Scaling a query by a positive constant changes neither the cosine nor the dot ranking, and keeps
 // every fp16 component in [-1, 1].
 __global__ void __launch_bounds__(128) tc_prepare_queries_kernel(const float *q, uint32_t nq, uint32_t dim, uint32_t ldq,
-                                                                 __half *q16, uint32_t ld, float *tau)
+                                                                 __half *q16, uint32_t ld, float *tau, uint32_t *sync)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *sync = 0;
     const uint32_t row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const uint32_t lane = lane_id();
     float ss = 0.f;
@@ -343,6 +428,8 @@ struct TcScanState {
     uint32_t ld, dim, k_blocks;
     __half *q16 = nullptr;
     float *tau = nullptr;
+    float *samp = nullptr;      // [sm_count][q_cap]
+    uint32_t *sync = nullptr;
     uint32_t q_cap = 0;  // rows
 };
 
@@ -363,6 +450,8 @@ void tc_scan_destroy(TcScanState *t)
     if (!t) return;
     cudaFree(t->q16);
     cudaFree(t->tau);
+    cudaFree(t->samp);
+    cudaFree(t->sync);
     delete t;
 }
 
@@ -388,6 +477,26 @@ static cudaError_t launch_tc_one(const CUtensorMap &tmQ, const CUtensorMap &tmC,
     auto kern = scan_tc_kernel<L, USE_INV, QM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
+    if (tp.sample_tiles > 0) {
+        // the grid barrier needs every CTA resident at once: cooperative launch (the driver refuses rather than deadlocks)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kTcThreads);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, tmQ, tmC, tp);
+        if (e == cudaSuccess) {
+            count_launch();
+            return cudaGetLastError();
+        }
+        cudaGetLastError();   // not launchable cooperatively here: plain launch without seeding
+        tp.sample_tiles = 0;
+    }
     kern<<<grid, kTcThreads, smem, st>>>(tmQ, tmC, tp);
     count_launch();
     return cudaGetLastError();
@@ -416,11 +525,17 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
     if (nq_pad > t->q_cap) {
         cudaFree(t->q16);
         cudaFree(t->tau);
+        cudaFree(t->samp);
+        cudaFree(t->sync);
         t->q16 = nullptr;
         t->tau = nullptr;
+        t->samp = nullptr;
+        t->sync = nullptr;
         t->q_cap = 0;
         cudaError_t e = cudaMalloc(&t->q16, (size_t)nq_pad * t->ld * sizeof(__half));
         if (e == cudaSuccess) e = cudaMalloc(&t->tau, (size_t)nq_pad * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&t->samp, (size_t)t->sm_count * nq_pad * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&t->sync, 256);
         if (e != cudaSuccess) {
             if (why) *why = "query staging allocation failed";
             return e;
@@ -428,7 +543,7 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
         t->q_cap = nq_pad;
     }
     if (timer) timer->begin(st, 1);
-    tc_prepare_queries_kernel<<<nq_pad / 4, 128, 0, st>>>(p.queries, p.nq, t->dim, p.ldq, t->q16, t->ld, t->tau);
+    tc_prepare_queries_kernel<<<nq_pad / 4, 128, 0, st>>>(p.queries, p.nq, t->dim, p.ldq, t->q16, t->ld, t->tau, t->sync);
     count_launch();
     if (timer) timer->end(st);
     cudaError_t e = cudaGetLastError();
@@ -449,7 +564,17 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
     tp.nq = p.nq;
     tp.n_lists = p.n_lists;
     tp.k_blocks = t->k_blocks;
+    tp.nq_pad = nq_pad;
+    tp.samp = t->samp;
+    tp.sync = t->sync;
     dim3 grid(p.n_lists, nq_pad / qm);
+    // threshold seeding needs every CTA at the barrier: one query pass (grid.y == 1), a full grid, enough tiles per CTA
+    // that scanning P of them twice is cheap; MX_SCAN_TC_SAMPLE=0 turns it off (A/B measurements)
+    static const int sample_cap = getenv("MX_SCAN_TC_SAMPLE") ? atoi(getenv("MX_SCAN_TC_SAMPLE")) : 4;
+    const uint32_t tiles_per_cta = ceil_div<uint32_t>(p.n_rows, kTileN) / std::max<uint32_t>(1u, p.n_lists);
+    tp.sample_tiles = (grid.y == 1 && p.n_lists == (uint32_t)t->sm_count && sample_cap > 0)
+                          ? std::min<uint32_t>((uint32_t)sample_cap, tiles_per_cta / 16)
+                          : 0u;
     if (timer) timer->begin(st, 0);
     e = tc_scan_lcap(k) == 16 ? launch_tc<16>(tmQ, tmC, tp, p.use_inv != 0, qm, grid, st)
                               : launch_tc<32>(tmQ, tmC, tp, p.use_inv != 0, qm, grid, st);
