@@ -343,7 +343,7 @@ def random_bert_weights(Lyr, H, F, vocab, max_pos, seed=3):
     return w
 
 
-def bench_embed(device, steps: int, warmup: int, pk, cpu: bool):
+def bench_embed(device, steps: int, warmup: int, pk, cpu: bool, extras: bool = True):
     """config 3: batch-256 segment embedding, MiniLM-L6, S = 256, bf16 activations on tcgen05"""
     import torch
     from memex_b200 import capi
@@ -402,6 +402,9 @@ def bench_embed(device, steps: int, warmup: int, pk, cpu: bool):
                         "kernel": "gemm_tc_kernel (4 launches / layer)", "gemm_ms_per_step": g_ms.value / steps,
                         "other_ms_per_step": o_ms.value / steps, "whole_step_tflops": step_tf,
                         "whole_step_frac": step_tf / pk["tf_sustained"], "peak_kind": "sustained bf16, " + pk["src"]}}
+    if not extras:
+        enc.close()
+        return res
     # the same batch with ragged lengths ~ U[16, 256]: the GEMMs still run over all B * S token
     # slots (no unpadding yet), attention and pooling skip the padding -- flops are counted on REAL tokens
     lens_r = np.random.default_rng(8).integers(16, S + 1, size=B).astype(np.int32)
@@ -678,6 +681,17 @@ def run_ours(args):
     del store
     torch.cuda.empty_cache()
 
+    if world > 1 and not args.skip_extras:
+        # the embedder does not shard: every GPU runs its own replica on its own batches, no collective.
+        # All ranks run the same timed batches between two barriers; the aggregate is the sum of segments over the
+        # slowest rank's time
+        barrier()
+        emb = bench_embed(device, max(5, args.steps // 2), max(3, args.warmup), pk, False, extras=False)
+        ms = torch.tensor([emb["ms_per_step"]], dtype=torch.float64, device=device)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=group)
+        line["embed"] = {"workload": emb["workload"] + f", one replica per GPU x{world}", "value": world * 256 * 1e3 / ms.item(),
+                         "unit": "segments/s", "ms_per_step": ms.item(), "dtype": "bf16", "scaling": "weak (replicas, no collective)",
+                         "per_gpu_roofline": emb["roofline"]}
     if rank == 0 and world == 1:
         if not args.skip_extras:
             line["single_query"] = bench_single_query(device, max(50, args.steps * 5), max(20, args.warmup), pk)
