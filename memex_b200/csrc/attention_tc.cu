@@ -10,14 +10,16 @@
 //     O[128, dh]   = P V       per 64-key chunk of P; V is the MN-major B operand exactly as it lies in qkv
 // and the softmax in between is one THREAD PER QUERY ROW (thread = TMEM lane): the row max is thread-local, no
 // shuffles; the row sum comes out of the tensor pipe as well (P times a tile of ones, into 16 more TMEM columns).
-// P goes to shared memory as the K-major A operand (bf16, 128-byte swizzle); the score tile never reaches shared or
-// global memory in f32.
+// P never leaves TMEM: it is written back (tcgen05.st, packed 16-bit pairs) over the score columns it came from and
+// read by the tensor pipe as the A operand of P V and P 1 (the `.ts` MMA form) -- no shared-memory round trip and no
+// generic -> async proxy fence (measured: the st.shared + fence.proxy.async version cost 25 us of 128 per layer).
 //
 // The op is bound by the exponentials (S x S x heads per sequence on 16 MUFU lanes per SM against 4 S^2 dh flops at
 // 8192 flop/clk), so a CTA keeps TWO independent units in flight -- group g owns TMEM columns [256 g, 256 g + 256),
 // its own Q / K / V / P buffers, four softmax warps, one TMA producer warp and one MMA issuer warp -- and the
-// tensor pipe and the TMA loads of one group run under the other group's exponentials.  O aliases the first dh
-// columns of the group's S tile (they are dead once chunk 0 of P has been written).
+// tensor pipe and the TMA loads of one group run under the other group's exponentials.  Slot layout: S f32 in columns
+// [0, 256); P overlays [0, 128); O and l use [128, 128 + dh + 16), dead once the scores of those keys have been
+// consumed (the products of the first chunks are held back until then).
 //
 // Persistent: grid = #SMs, units dealt round-robin (the two units of one (sequence, head) land in one CTA).
 //
@@ -29,6 +31,8 @@
 // (148-177 us), single group with ping-pong score slots + P kept in TMEM as the A operand + auxiliary max / drain
 // warps (140-165 us; kept as experiments/attention_tc_pingpong.cu.txt), a rolled 8-key software pipeline (184 us).
 // Next step: 128-key sub-units (four score tiles in TMEM -> four independent streams per sub-partition).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "encoder.cuh"
 #include "tc.cuh"
@@ -51,13 +55,15 @@ struct AttCfg {
     static constexpr int kRowBytes = DH * 2;                    // 64 (SWIZZLE_64B) or 128 (SWIZZLE_128B)
     static constexpr int kQBytes = kQT * kRowBytes;
     static constexpr int kKBytes = kMaxKeys * kRowBytes;
-    static constexpr int kVBufs = DH <= 32 ? 2 : 1;             // the next unit's V lands while this unit's P V runs
-    static constexpr int kPChunkBytes = kQT * 128;              // [128 rows][64 keys] 16-bit
+    static constexpr int kVBufs = 2;                            // the next unit's V lands while this unit's P V runs
+    static constexpr int kOCol = 128;                           // O inside the slot (P occupies [0, 128))
+    static constexpr int kLCol = kOCol + DH;                    // row sums
+    // O and l sit on the score columns [128, 128 + DH + 16): the products wait until those have been consumed
+    static constexpr int kHoldChunk = (kOCol + DH + 16 - 1) / kKC;
     static constexpr int kQOff = 0;
     static constexpr int kKOff = kQBytes;
     static constexpr int kVOff = kKOff + kKBytes;
-    static constexpr int kPOff = kVOff + kVBufs * kKBytes;
-    static constexpr int kGroupBytes = kPOff + 2 * kPChunkBytes;
+    static constexpr int kGroupBytes = kVOff + kVBufs * kKBytes;
     static constexpr int kOnesOff = kGroups * kGroupBytes;      // [16 rows][64 keys] of 1.0, K-major: B operand of the row sums
     static constexpr int kOnesBytes = 16 * 128;
     static constexpr int kBarOff = kOnesOff + kOnesBytes;
@@ -72,8 +78,10 @@ struct AttCfg {
 };
 
 // per-group barrier slots
-enum { B_QK_FULL = 0, B_V_FULL = 1 /* 2 */, B_S_FULL = 3, B_P_READY = 4 /* 2 */, B_P_FREE = 6 /* 2 */, B_O_FULL = 8,
-       B_S_EMPTY = 9, B_PER_GROUP = 10 };
+constexpr int kPRing = 8;   // "P chunk written" barriers: two units' worth, so a phase is always observed before its reuse
+enum { B_QK_FULL = 0, B_V_FULL = 1 /* 2 */, B_S_FULL = 3, B_P_READY = 4 /* kPRing */, B_O_FULL = B_P_READY + kPRing,
+       B_S_EMPTY, B_PER_GROUP };
+static_assert(kGroups * B_PER_GROUP * 8 + 8 <= 256, "barrier block");
 
 __device__ __forceinline__ uint64_t att_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout)
 {
@@ -151,10 +159,16 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32], uint32_t key0, u
 }
 
 // exponentials of 32 scores of this thread's row -> 16 packed 16-bit pairs (keys >= len give 0)
-template <bool BF16>
+template <bool BF16, bool NOEXP = false>
 __device__ __forceinline__ void softmax32(const uint32_t (&v)[32], float sc, float msc, uint32_t key0, uint32_t len,
                                           uint32_t (&o)[16])
 {
+    if constexpr (NOEXP) {   // timing diagnostic only: everything but the MUFU
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            o[j] = pk2<BF16>(fmaf(__uint_as_float(v[2 * j]), sc, -msc), fmaf(__uint_as_float(v[2 * j + 1]), sc, -msc));
+        return;
+    }
     if (key0 + 32 <= len) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -169,7 +183,9 @@ __device__ __forceinline__ void softmax32(const uint32_t (&v)[32], float sc, flo
     }
 }
 
-template <bool BF16, int DH>
+// DIAG != 0 builds are TIMING DIAGNOSTICS with wrong results (MX_ATTN_DIAG, scripts/diag_attention.py):
+//   1 no MUFU, 2 no max pass, 4 no P stores / proxy fence, 8 no pass-2 work at all, 16 no O read-out / store
+template <bool BF16, int DH, int DIAG = 0>
 __global__ void __launch_bounds__(AttCfg<DH>::kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__restrict__ lens, uint16_t *__restrict__ ctx,
                     uint32_t B, uint32_t S, uint32_t H, uint32_t heads, float scale_log2e)
@@ -194,10 +210,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__
             mbar_init(bg + B_V_FULL, 1);
             mbar_init(bg + B_V_FULL + 1, 1);
             mbar_init(bg + B_S_FULL, 1);
-            mbar_init(bg + B_P_READY, 4);       // one arrive per softmax warp
-            mbar_init(bg + B_P_READY + 1, 4);
-            mbar_init(bg + B_P_FREE, 1);
-            mbar_init(bg + B_P_FREE + 1, 1);
+            for (int i = 0; i < kPRing; ++i) mbar_init(bg + B_P_READY + i, 4);   // one arrive per softmax warp
             mbar_init(bg + B_O_FULL, 1);
             mbar_init(bg + B_S_EMPTY, 4);
         }
@@ -217,7 +230,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__
         // ================= softmax: thread = query row = TMEM lane =================
         const uint32_t g = warp >> 2, quarter = warp & 3;
         uint64_t *bg = bars + g * B_PER_GROUP;
-        unsigned char *pbuf = smem + g * Cfg::kGroupBytes + Cfg::kPOff;
         const uint32_t row = quarter * 32 + lane;
         const uint32_t t_s = tmem_base + ((quarter * 32u) << 16) + g * kMaxKeys;
         uint32_t it = 0, cc = 0;
@@ -243,57 +255,54 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__
             uint32_t va[32], vb[32];
             // ---- pass 1: row maximum over the valid keys (the load of step t + 1 is in flight during step t) ----
             float m = kNegInf;
-            tmem_ld32(t_s, va);
-            for (uint32_t t = 0; t < nsteps; t += 2) {
-                tmem_ld_wait();
-                tmem_ld32(t_s + (t + 1) * 32, vb);
-                m = fmaxf(m, max32(va, t * 32, len));
-                tmem_ld_wait();
-                if (t + 2 < nsteps) tmem_ld32(t_s + (t + 2) * 32, va);
-                m = fmaxf(m, max32(vb, (t + 1) * 32, len));
+            if constexpr (DIAG & 2) {
+                m = 0.f;
+            } else {
+                tmem_ld32(t_s, va);
+                for (uint32_t t = 0; t < nsteps; t += 2) {
+                    tmem_ld_wait();
+                    tmem_ld32(t_s + (t + 1) * 32, vb);
+                    m = fmaxf(m, max32(va, t * 32, len));
+                    tmem_ld_wait();
+                    if (t + 2 < nsteps) tmem_ld32(t_s + (t + 2) * 32, va);
+                    m = fmaxf(m, max32(vb, (t + 1) * 32, len));
+                }
             }
-            tmem_ld32(t_s, va);   // first load of pass 2
+            if constexpr (!(DIAG & 8)) tmem_ld32(t_s, va);   // first load of pass 2
             // key 0 < len always holds for a unit that is not skipped, so m is finite
             const float msc = m * scale_log2e;
-            // ---- pass 2: p = 2^(s scale log2e - max), P chunk -> shared memory (K-major, 128-byte swizzle) ----
+            // ---- pass 2: p = 2^(s scale log2e - max) -> packed 16-bit pairs written back over the score columns (key k ->
+            //      column k / 2, always behind this thread's read position); the tensor pipe reads them as the A operand ----
             for (uint32_t c = 0; c < nch; ++c, ++cc) {
-                const uint32_t bsel = cc & 1, use = cc >> 1;
-                unsigned char *prow = pbuf + bsel * Cfg::kPChunkBytes + row * 128;
                 uint32_t o[16];
-                tmem_ld_wait();
-                tmem_ld32(t_s + c * kKC + 32, vb);
-                softmax32<BF16>(va, scale_log2e, msc, c * kKC, len, o);
-                // the P V product that last read this chunk buffer has completed
-                if (use >= 1) mbar_wait(bg + B_P_FREE + bsel, (use - 1) & 1);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<uint4 *>(prow + (((uint32_t)j ^ (row & 7u)) << 4)) =
-                        make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                tmem_ld_wait();
-                if (c + 1 < nch) tmem_ld32(t_s + (c + 1) * kKC, va);
-                softmax32<BF16>(vb, scale_log2e, msc, c * kKC + 32, len, o);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<uint4 *>(prow + (((uint32_t)(4 + j) ^ (row & 7u)) << 4)) =
-                        make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor pipe (async proxy)
+                if constexpr (!(DIAG & 8)) {
+                    tmem_ld_wait();
+                    tmem_ld32(t_s + c * kKC + 32, vb);
+                    softmax32<BF16, (DIAG & 1) != 0>(va, scale_log2e, msc, c * kKC, len, o);
+                    if constexpr (!(DIAG & 4)) tmem_st16(t_s + c * (kKC / 2), o);
+                    tmem_ld_wait();
+                    if (c + 1 < nch) tmem_ld32(t_s + (c + 1) * kKC, va);
+                    softmax32<BF16, (DIAG & 1) != 0>(vb, scale_log2e, msc, c * kKC + 32, len, o);
+                    if constexpr (!(DIAG & 4)) tmem_st16(t_s + c * (kKC / 2) + 16, o);
+                    tmem_st_wait();
+                }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bg + B_P_READY + bsel);
+                if (lane == 0) mbar_arrive(bg + B_P_READY + cc % kPRing);
             }
-            // ---- O = P V in the first DH columns of the tile, the row sums of P (P times ones) in column DH ----
+            // ---- O = P V in columns [128, 128 + DH) of the tile, the row sums of P (P times ones) next to it ----
             mbar_wait(bg + B_O_FULL, it & 1);
             tc_fence_after();
             uint32_t ov[DH], sv[1];
 #pragma unroll
-            for (int c = 0; c < DH / 32; ++c) tmem_ld32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&ov[c * 32]));
-            tmem_ld1(t_s + DH, sv);
+            for (int c = 0; c < DH / 32; ++c) tmem_ld32(t_s + Cfg::kOCol + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&ov[c * 32]));
+            tmem_ld1(t_s + Cfg::kLCol, sv);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bg + B_S_EMPTY);   // the tile may be overwritten by the next unit's Q K^T
             const float inv = q < len ? 1.0f / __uint_as_float(sv[0]) : 0.f;
-            if (q < S) {
+            if (q < S && !(DIAG & 16)) {
 #pragma unroll
                 for (int j = 0; j < DH / 8; ++j) {
                     uint4 w;
@@ -370,21 +379,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__
                          att_desc(grp + Cfg::kKOff + k * 32, Cfg::kSbo, Cfg::kLayout), idesc_s, k != 0 ? 1u : 0u);
                 umma_commit(bg + B_S_FULL);
                 const uint32_t vb = it % Cfg::kVBufs;
+                const uint32_t va0 = grp + Cfg::kVOff + vb * Cfg::kKBytes;
+                const uint32_t hold = nch >= 3 ? min(nch - 1, (uint32_t)Cfg::kHoldChunk) : 0u;
+                uint32_t issued = 0;
                 for (uint32_t c = 0; c < nch; ++c, ++cc) {
-                    const uint32_t bsel = cc & 1, use = cc >> 1;
-                    mbar_wait(bg + B_P_READY + bsel, use & 1);
+                    mbar_wait(bg + B_P_READY + cc % kPRing, (cc / kPRing) & 1);
                     if (c == 0) mbar_wait(bg + B_V_FULL + vb, (it / Cfg::kVBufs) & 1);
+                    if (c < hold) continue;
                     tc_fence_after();
-                    const uint32_t pa = grp + Cfg::kPOff + bsel * Cfg::kPChunkBytes;
-                    const uint32_t va = grp + Cfg::kVOff + vb * Cfg::kKBytes + c * kKC * Cfg::kRowBytes;
+                    for (; issued <= c; ++issued) {
 #pragma unroll
-                    for (int k = 0; k < kKC / 16; ++k) {
-                        umma(t_s, make_smem_desc(pa + k * 32), att_desc(va + k * 16 * Cfg::kRowBytes, Cfg::kSbo, Cfg::kLayout),
-                             idesc_pv, (c | (uint32_t)k) != 0 ? 1u : 0u);
-                        umma(t_s + DH, make_smem_desc(pa + k * 32), make_smem_desc(ones + k * 32), idesc_sum,
-                             (c | (uint32_t)k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kKC / 16; ++k) {
+                            const uint32_t pa = t_s + issued * (kKC / 2) + k * 8;
+                            umma_ts(t_s + Cfg::kOCol, pa, att_desc(va0 + (issued * kKC + k * 16) * Cfg::kRowBytes, Cfg::kSbo, Cfg::kLayout),
+                                    idesc_pv, (issued | (uint32_t)k) != 0 ? 1u : 0u);
+                            umma_ts(t_s + Cfg::kLCol, pa, make_smem_desc(ones + k * 32), idesc_sum, (issued | (uint32_t)k) != 0 ? 1u : 0u);
+                        }
                     }
-                    umma_commit(bg + B_P_FREE + bsel);
                 }
                 umma_commit(bg + B_O_FULL);
                 ++it;
@@ -422,6 +433,19 @@ cudaError_t launch_at(const void *qkv, const int32_t *lens, void *ctx, uint32_t 
 {
     using Cfg = AttCfg<DH>;
     auto kern = attention_tc_kernel<BF16, DH>;
+    if constexpr (BF16 && DH == 32) {
+        static const int diag = getenv("MX_ATTN_DIAG") ? atoi(getenv("MX_ATTN_DIAG")) : 0;
+        switch (diag) {
+            case 1: kern = attention_tc_kernel<BF16, DH, 1>; break;
+            case 2: kern = attention_tc_kernel<BF16, DH, 2>; break;
+            case 3: kern = attention_tc_kernel<BF16, DH, 3>; break;
+            case 4: kern = attention_tc_kernel<BF16, DH, 4>; break;
+            case 7: kern = attention_tc_kernel<BF16, DH, 7>; break;
+            case 10: kern = attention_tc_kernel<BF16, DH, 10>; break;
+            case 26: kern = attention_tc_kernel<BF16, DH, 26>; break;
+            default: break;
+        }
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     CUtensorMap tm;
