@@ -162,11 +162,18 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
         }
         ws[warp * 32 + lane] = bv;
         wr[warp * 32 + lane] = br;
-        __syncthreads();
-        if (warp == 0) {
-            for (int w = 1; w < kRerankWarps; ++w) warp_merge32(bv, br, ws[w * 32 + lane], wr[w * 32 + lane]);
-            erow[lane] = br;
+        // tree merge of the 16 warp lists (the top 32 of a union does not depend on the merge order)
+        for (int half = kRerankWarps / 2; half >= 1; half >>= 1) {
+            __syncthreads();
+            if ((int)warp < half) {
+                warp_merge32(bv, br, ws[(warp + half) * 32 + lane], wr[(warp + half) * 32 + lane]);
+                if (half > 1) {
+                    ws[warp * 32 + lane] = bv;
+                    wr[warp * 32 + lane] = br;
+                }
+            }
         }
+        if (warp == 0) erow[lane] = br;
     } else {
         // 1. every warp folds a slice of the candidate lists into its own list
         WarpTopK<E> top;
@@ -207,15 +214,22 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
     __syncthreads();
 
     // 4. exact key per entry.  Batches of 32 entries; the rows of kFoldBatches batches are staged per pass
-    //    (chunks of kFoldChunk elements), then lane j of warp b folds entry 32 * (b0 + b) + j.
-    double q_aa = 0.0;
+    //    (chunks of kFoldChunk elements), then lane j folds entry 32 * (b0 + b) + j left to right in f64.  The three
+    //    sums of DistCosine are independent chains, so they go to different warps (a f32 -> f64 conversion is an XU op
+    //    and a dependent DADD is ~10 cycles: one thread running all three took 12 of the kernel's 28 us):
+    //    warps [0, F) fold a.b, warps [F, 2F) the row's b.b, warp 2F the query's a.a (once).  Same order of
+    //    operations per sum as the reference, hence the same bits.
+    __shared__ double bb_s[kFoldBatches * 32];
+    __shared__ double aa_s;
     const uint32_t n_batches = (n_entries + 31) / 32;
+    const uint32_t frole = warp / kFoldBatches, fb = warp % kFoldBatches;   // role 0: a.b, 1: b.b, warp 2F: a.a
     for (uint32_t b0 = 0; b0 < n_batches; b0 += kFoldBatches) {
         const uint32_t first = b0 * 32;
         const uint32_t n_here = min((uint32_t)kFoldBatches * 32, n_entries - first);
-        double ab = 0.0, aa = 0.0, bb = 0.0;
-        const bool folder = warp < kFoldBatches && warp * 32 + lane < n_here;
-        const uint32_t my_row = folder ? erow[first + warp * 32 + lane] : kNoRow;
+        double acc = 0.0;
+        const bool folder = frole < 2 && fb * 32 + lane < n_here;
+        const bool q_folder = warp == 2 * kFoldBatches && b0 == 0;
+        const uint32_t my_row = folder ? erow[first + fb * 32 + lane] : kNoRow;
         for (uint32_t c0 = 0; c0 < p.dim; c0 += kFoldChunk) {
             const uint32_t cn = min((uint32_t)kFoldChunk, p.dim - c0);
             __syncthreads();   // previous chunk fully consumed
@@ -257,19 +271,26 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
             }
             __syncthreads();
             if (folder && my_row != kNoRow && my_row < p.n_rows) {
-                const float *rb = rowbuf + (warp * 32 + lane) * kFoldPitch;
+                const float *rb = rowbuf + (fb * 32 + lane) * kFoldPitch;
+                if (frole == 0) {
 #pragma unroll 4
-                for (uint32_t i = 0; i < cn; ++i) {
-                    const float a = qs[i], b = rb[i];
-                    ab = __dadd_rn(ab, (double)__fmul_rn(a, b));
-                    aa = __dadd_rn(aa, (double)__fmul_rn(a, a));
-                    bb = __dadd_rn(bb, (double)__fmul_rn(b, b));
+                    for (uint32_t i = 0; i < cn; ++i) acc = __dadd_rn(acc, (double)__fmul_rn(qs[i], rb[i]));
+                } else {
+#pragma unroll 4
+                    for (uint32_t i = 0; i < cn; ++i) acc = __dadd_rn(acc, (double)__fmul_rn(rb[i], rb[i]));
                 }
+            } else if (q_folder) {
+#pragma unroll 4
+                for (uint32_t i = 0; i < cn; ++i) acc = __dadd_rn(acc, (double)__fmul_rn(qs[i], qs[i]));
             }
         }
-        if (folder) {
-            const uint32_t j = first + warp * 32 + lane;
+        if (frole == 1 && folder) bb_s[fb * 32 + lane] = acc;
+        if (q_folder && lane == 0) aa_s = acc;
+        __syncthreads();
+        if (frole == 0 && folder) {
+            const uint32_t j = first + fb * 32 + lane;
             if (my_row != kNoRow && my_row < p.n_rows) {
+                const double ab = acc, aa = aa_s, bb = bb_s[fb * 32 + lane];
                 float key;
                 if (p.metric == MX_METRIC_DOT)
                     key = -(float)ab;
@@ -278,7 +299,6 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
                 else
                     key = 0.f;
                 ekey[j] = key;
-                q_aa = aa;
             } else {
                 erow[j] = kNoRow;
             }
@@ -287,9 +307,8 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
     if (threadIdx.x == 0) {
         // the query's own norm decides the degenerate case (DistCosine: aa == 0 -> d = 0 for all rows).
         // thread 0 folded entry 0 when that entry was real; otherwise (no candidates at all) fold here.
-        double a2 = q_aa;
-        if (!(erow[0] != kNoRow)) {
-            a2 = 0.0;
+        double a2 = n_batches > 0 ? aa_s : 0.0;   // folded by warp 2F during the first pass
+        if (n_batches == 0) {
             for (uint32_t i = 0; i < p.dim; ++i) a2 = __dadd_rn(a2, (double)__fmul_rn(qg[i], qg[i]));
         }
         zero_query_s = (p.metric == MX_METRIC_COSINE && !(a2 > 0.0)) ? 1 : 0;
