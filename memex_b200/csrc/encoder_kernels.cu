@@ -144,10 +144,13 @@ __global__ void __launch_bounds__(256) embed_ln_vec_kernel(const int32_t *__rest
         if constexpr (ACT == ACT_F32) {
             *reinterpret_cast<float4 *>(o) = make_float4(y0, y1, y2, y3);
         } else {
-            Act<ACT>::st(o, y0);
-            Act<ACT>::st(o + 1, y1);
-            Act<ACT>::st(o + 2, y2);
-            Act<ACT>::st(o + 3, y3);
+            // one 8-byte store per lane instead of four 2-byte ones
+            typename Act<ACT>::T tmp[4];
+            Act<ACT>::st(tmp, y0);
+            Act<ACT>::st(tmp + 1, y1);
+            Act<ACT>::st(tmp + 2, y2);
+            Act<ACT>::st(tmp + 3, y3);
+            *reinterpret_cast<uint2 *>(o) = *reinterpret_cast<const uint2 *>(tmp);
         }
     }
 }
@@ -388,18 +391,27 @@ __global__ void __launch_bounds__(256) pool_normalize_kernel(const typename Act<
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
         const uint32_t chunks = H / 8;   // H % 8 == 0 on the 16-bit paths
-        for (uint32_t t = warp; t < len; t += 8) {
-            const uint4 *row = reinterpret_cast<const uint4 *>(x + ((size_t)b * S + t) * H);
+        // four tokens per trip: all their loads are issued before the first add (the loop is latency-bound otherwise)
+        for (uint32_t t0 = warp; t0 < len; t0 += 32) {
+            uint4 u[4][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t ch = lane + 32 * i;
-                if (ch < chunks) {
-                    const uint4 u = row[ch];
-                    const typename Act<ACT>::T *h8 = reinterpret_cast<const typename Act<ACT>::T *>(&u);
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t t = t0 + 8 * k;
+                const uint4 *row = reinterpret_cast<const uint4 *>(x + ((size_t)b * S + min(t, len - 1)) * H);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t ch = lane + 32 * i;
+                    u[k][i] = (ch < chunks && t < len) ? row[ch] : make_uint4(0, 0, 0, 0);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const typename Act<ACT>::T *h8 = reinterpret_cast<const typename Act<ACT>::T *>(&u[k][i]);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) acc[i][e] += Act<ACT>::ld(h8 + e);
                 }
-            }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
