@@ -49,7 +49,7 @@ constexpr int kTileN = 128;         // corpus rows per tile = UMMA N
 constexpr int kBK = 64;             // fp16 elements per k-block (one 128-byte swizzle atom)
 constexpr int kMaxKB = 12;          // dim <= 768 (with M = 64: the query block must stay within 96 KB of smem)
 constexpr int kAccStages = 4;       // 4 x 128 TMEM columns
-constexpr int kInvSlots = 8;
+constexpr int kInvSlots = 24;        // inverse-norm tiles in flight: the producer runs up to kMaxStages + kAccStages tiles ahead (k_blocks = 1)
 constexpr int kKBBytes = kTileN * kBK * 2;  // 16 KB: one k-block of a corpus tile (a k-block of Q is QM x 128 bytes)
 
 constexpr int kMaxStages = 12;      // the corpus ring takes whatever shared memory the query block and the lists leave

@@ -302,6 +302,8 @@ def test_full_size_properties_1m(tmp_path):
     (40000, 256, 64, 26, "cosine"), (25000, 384, 64, 10, "dot"), (100, 8, 16, 10, "cosine"),
     # dim > 384: the M = 64 form of the kernel (64 queries per pass), e5-base / BERT-base dimension 768
     (30000, 768, 64, 10, "cosine"), (9001, 768, 100, 10, "cosine"), (5000, 512, 9, 20, "dot"), (700, 448, 130, 10, "cosine"),
+    # one k-block per tile: the TMA producer runs a dozen tiles ahead of the epilogue (inverse-norm slot depth), M = 128 form
+    (300000, 32, 100, 10, "cosine"),
 ])
 def test_parity_tcgen05_scan(tmp_path, n, d, nq, k, metric):
     """the batched tensor-core path gives the same ids and bit-identical scores as the oracle"""
@@ -339,6 +341,38 @@ def test_tcgen05_scan_duplicates_and_growth(tmp_path):
         check_parity(store, stored[:lo + 20000], queries, k)
     ids, _, _ = store.search_matrix(queries, k)
     np.testing.assert_array_equal(ids[0], np.sort(dup_rows)[:k] + 1)
+
+
+@pytest.mark.parametrize("n,d,nq,k,metric", [
+    (400_000, 64, 64, 10, "cosine"),    # 21 tiles per CTA -> 1 sample tile
+    (700_000, 64, 16, 26, "cosine"),    # 37 tiles per CTA -> 2 sample tiles, L = 32 lists (tau0 = 16th of the second bests)
+    (1_300_001, 32, 64, 10, "dot"),     # 68 tiles per CTA -> 4 sample tiles, ragged last tile, dot metric
+])
+def test_tcgen05_scan_threshold_seeding(tmp_path, n, d, nq, k, metric):
+    """shards large enough for the seeded scan (two-best sampling pass + grid barrier + tau0): full oracle parity with
+    exact ties planted at the top -- duplicates of the query rows inside and outside the sampled tiles -- and with
+    near-duplicates crowding the threshold"""
+    rng = np.random.default_rng(n % 1000 + d + k)
+    corpus = rng.standard_normal((n, d)).astype(np.float32)
+    picks = rng.integers(0, n, nq)
+    queries = corpus[picks].copy()
+    # exact duplicates of the first 8 query rows: some in the very first tiles (the sampled ones), some anywhere
+    for j in range(8):
+        where = np.concatenate([rng.integers(0, 148 * 128, 3), rng.integers(0, n, 5)])
+        corpus[where] = corpus[picks[j]]
+    # a crowd of near-ties for query 8: 15 rows that differ only by fp16 rounding (fewer than the 22 spare places the
+    # rerank list has beyond k = 10 -- the documented limit of the approximate stage, DESIGN.md section 5)
+    crowd = rng.integers(0, n, 15)
+    corpus[crowd] = corpus[picks[8]] * (1 + 1e-3 * rng.standard_normal((15, 1)).astype(np.float32))
+    queries = corpus[picks].copy()
+    store = B200Store.new(tmp_path, dim=d, dtype="f16", metric=metric, capacity=n)
+    store.add_matrix(corpus)
+    assert capi.lib().mx_store_scan_path(store.handle, nq, k, -1) == 2
+    stored = corpus.astype(np.float16).astype(np.float32)
+    check_parity(store, stored, queries, k, metric=metric)
+    # a second, unrelated batch on the same store (the barrier counter and tau are reset per launch)
+    q2 = rng.standard_normal((nq, d)).astype(np.float32)
+    check_parity(store, stored, q2, k, metric=metric)
 
 
 def test_full_size_properties_tcgen05_2m(tmp_path):
