@@ -666,7 +666,10 @@ def run_ours(args):
         "metric": "queries/sec", "value": NQ * 1e3 / ms_step, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": workload_config(args.rows, world),
+        "config": dict(workload_config(args.rows, world),
+                       **({"exchange": ("peer-memory push + flag wait inside the merge kernel (NVLink P2P stores, no collective call)"
+                                        if store.exchange == "p2p" else "one NCCL all_gather_into_tensor of the per-shard blobs")}
+                          if world > 1 else {})),
         "e2e": {"value": NQ * args.steps / e2e_s.item(), "unit": "queries/s", "h2d_bytes_per_step": NQ * DIM * 4,
                 "d2h_bytes_per_step": NQ * TOPK * 12 + NQ * 4},
         "gpu_launches": int(launches.item()),

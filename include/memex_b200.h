@@ -115,6 +115,21 @@ int32_t mx_merge_topk_blobs_device(const void *blobs_dev, uint64_t blob_stride_b
                                    float *scores_out_dev, uint32_t *counts_out_dev, int32_t device,
                                    void *cuda_stream);
 
+/* Peer-memory form of the exchange step (instead of the all-gather): every rank owns an exchange buffer that all
+ * peers can address (CUDA IPC / symmetric memory, set up by the host side): [2][world] blob slots of
+ * blob_stride bytes, then `world` u32 flags (zero-initialised).  mx_exchange_push_device stores this rank's blob into
+ * slot_offset_bytes of EVERY peer's buffer (peer_bases: HOST array of `world` device-visible base addresses, this
+ * rank's own included) over NVLink and then release-stores `epoch` into that peer's flag [rank];
+ * mx_merge_topk_blobs_wait_device waits (bounded) until its `world` flags have reached `epoch`, then merges.  The
+ * host alternates the two slot sets and increments the epoch per batch. */
+int32_t mx_exchange_push_device(const void *blob_dev, uint64_t blob_bytes, const uint64_t *peer_bases, uint32_t world,
+                                uint32_t rank, uint64_t slot_offset_bytes, uint64_t flag_offset_bytes, uint32_t epoch,
+                                int32_t device, void *cuda_stream);
+int32_t mx_merge_topk_blobs_wait_device(const void *blobs_dev, uint64_t blob_stride_bytes, uint32_t n_shards,
+                                        uint32_t nq, uint32_t k, uint32_t metric, uint64_t *ids_out_dev,
+                                        float *scores_out_dev, uint32_t *counts_out_dev, const uint32_t *flags_dev,
+                                        uint32_t epoch, int32_t device, void *cuda_stream);
+
 int32_t mx_store_len(mx_store *s, uint64_t *n_out); /* hnsw.get_nb_point(), local.rs:238 */
 int32_t mx_store_clear(mx_store *s);                /* delete_all's index reset, local.rs:48-50 */
 int32_t mx_store_delete(mx_store *s, uint64_t id);  /* local.rs:29-32: always MX_ERR_UNSUPPORTED */

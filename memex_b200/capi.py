@@ -86,6 +86,10 @@ def lib() -> C.CDLL:
     sig("mx_store_search_blob_device", C.c_int32, vp, vp, C.c_uint32, C.c_uint32, vp, vp)
     sig("mx_merge_topk_blobs_device", C.c_int32, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
         C.c_uint32, vp, vp, vp, C.c_int32, vp)
+    sig("mx_exchange_push_device", C.c_int32, vp, C.c_uint64, u64p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32,
+        C.c_int32, vp)
+    sig("mx_merge_topk_blobs_wait_device", C.c_int32, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp,
+        vp, C.c_uint32, C.c_int32, vp)
     sig("mx_store_len", C.c_int32, vp, u64p)
     sig("mx_store_clear", C.c_int32, vp)
     sig("mx_store_delete", C.c_int32, vp, C.c_uint64)

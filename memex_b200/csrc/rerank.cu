@@ -408,15 +408,28 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeParams p)
     __shared__ uint32_t total_s;
     const uint32_t q = blockIdx.x;
     if (threadIdx.x == 0) total_s = 0;
+    if (p.wait_flags != nullptr && threadIdx.x < p.n_shards) {
+        // peer-memory exchange: shard g's answer was stored into this GPU's memory by rank g, followed by a release store of
+        // the epoch into flag g.  Bounded wait: a lost peer must surface as a launch failure, not as a hung GPU.
+        uint32_t seen, spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.wait_flags + threadIdx.x) : "memory");
+            if (++spins > (1u << 27)) {
+                printf("memex_b200: merge wait for shard %u timed out (flag %u, epoch %u)\n", threadIdx.x, seen, p.wait_epoch);
+                __trap();
+            }
+        } while ((int32_t)(seen - p.wait_epoch) < 0);
+    }
     __syncthreads();
     for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
         const uint32_t g = j / p.k, e = j - g * p.k;
         const uint32_t *cg = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(p.counts) + g * p.stride_counts);
         const float *dg = reinterpret_cast<const float *>(reinterpret_cast<const char *>(p.dists) + g * p.stride_dists);
         const uint64_t *ig = reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(p.ids) + g * p.stride_ids);
-        const bool ok = e < cg[q];
-        key[j] = ok ? dg[(size_t)q * p.k + e] : 0.f;
-        id[j] = ok ? ig[(size_t)q * p.k + e] : 0;
+        // .cg loads: the blobs may have been written by another GPU since this SM last read these addresses
+        const bool ok = e < __ldcg(cg + q);
+        key[j] = ok ? __ldcg(dg + (size_t)q * p.k + e) : 0.f;
+        id[j] = ok ? __ldcg(reinterpret_cast<const unsigned long long *>(ig) + (size_t)q * p.k + e) : 0;
         if (ok) atomicAdd(&total_s, 1u);
     }
     __syncthreads();
@@ -443,6 +456,29 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeParams p)
         }
     }
     if (threadIdx.x == 0) p.counts_out[q] = count;
+}
+
+// One CTA per peer: 16-byte stores of this rank's blob into the peer's slot, a system-scope fence, then the flag.
+__global__ void __launch_bounds__(256) exchange_push_kernel(PushParams p)
+{
+    const uint32_t peer = blockIdx.x;
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.blob);
+    uint4 *dst = reinterpret_cast<uint4 *>(p.peer_base[peer] + p.slot_offset);
+    for (uint64_t i = threadIdx.x; i < p.blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t *flag = reinterpret_cast<uint32_t *>(p.peer_base[peer] + p.flag_offset) + p.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(p.epoch) : "memory");
+    }
+}
+
+cudaError_t launch_exchange_push(const PushParams &p, cudaStream_t st)
+{
+    if (p.world == 0 || p.world > (uint32_t)kMaxPeers || p.blob_bytes % 16 != 0) return cudaErrorInvalidValue;
+    exchange_push_kernel<<<p.world, 256, 0, st>>>(p);
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_merge(const MergeParams &p, cudaStream_t st)

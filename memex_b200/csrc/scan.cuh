@@ -54,8 +54,23 @@ struct MergeParams {
     float *scores_out;
     uint32_t *counts_out;
     uint32_t n_shards, nq, k, metric;
+    // peer-memory exchange: when set, shard g's blob is only read once wait_flags[g] has reached wait_epoch
+    // (release-stored by the peer that pushed it, launch_exchange_push)
+    const uint32_t *wait_flags = nullptr;
+    uint32_t wait_epoch = 0;
 };
 cudaError_t launch_merge(const MergeParams &p, cudaStream_t st);
+
+// this rank's blob -> slot of every peer's gathered buffer (P2P stores over NVLink), then flag[rank] = epoch on that peer
+constexpr int kMaxPeers = 16;
+struct PushParams {
+    const void *blob;
+    uint64_t blob_bytes;             // multiple of 16
+    uint64_t peer_base[kMaxPeers];   // device-visible base address of every peer's exchange buffer (this rank's included)
+    uint64_t slot_offset, flag_offset;
+    uint32_t world, rank, epoch;
+};
+cudaError_t launch_exchange_push(const PushParams &p, cudaStream_t st);
 
 // ingest: f32 rows -> stored dtype (+ inv_norm, zero-row list, non-finite flag)
 struct IngestParams {

@@ -557,6 +557,49 @@ int32_t mx_merge_topk_blobs_device(const void *blobs_dev, uint64_t blob_stride_b
     return merge_impl(mp, device, cuda_stream);
 }
 
+int32_t mx_merge_topk_blobs_wait_device(const void *blobs_dev, uint64_t blob_stride_bytes, uint32_t n_shards, uint32_t nq,
+                                        uint32_t k, uint32_t metric, uint64_t *ids_out_dev, float *scores_out_dev,
+                                        uint32_t *counts_out_dev, const uint32_t *flags_dev, uint32_t epoch, int32_t device,
+                                        void *cuda_stream)
+{
+    if (!blobs_dev || !flags_dev) return fail(nullptr, MX_ERR_INVALID, "null buffer");
+    if (blob_stride_bytes < mx_topk_blob_bytes(nq, k) || blob_stride_bytes % 8 != 0)
+        return fail(nullptr, MX_ERR_INVALID, "blob stride too small or not 8-byte aligned");
+    if (n_shards > (uint32_t)kMaxPeers) return fail(nullptr, MX_ERR_INVALID, "more than %d shards", kMaxPeers);
+    const char *b = static_cast<const char *>(blobs_dev);
+    MergeParams mp{reinterpret_cast<const uint64_t *>(b), reinterpret_cast<const float *>(b + (size_t)nq * k * 8),
+                   reinterpret_cast<const uint32_t *>(b + (size_t)nq * k * 12), blob_stride_bytes, blob_stride_bytes,
+                   blob_stride_bytes, ids_out_dev, scores_out_dev, counts_out_dev, n_shards, nq, k, metric};
+    mp.wait_flags = flags_dev;
+    mp.wait_epoch = epoch;
+    return merge_impl(mp, device, cuda_stream);
+}
+
+int32_t mx_exchange_push_device(const void *blob_dev, uint64_t blob_bytes, const uint64_t *peer_bases, uint32_t world,
+                                uint32_t rank, uint64_t slot_offset_bytes, uint64_t flag_offset_bytes, uint32_t epoch,
+                                int32_t device, void *cuda_stream)
+{
+    if (!blob_dev || !peer_bases) return fail(nullptr, MX_ERR_INVALID, "null buffer");
+    if (world == 0 || world > (uint32_t)kMaxPeers || rank >= world || blob_bytes % 16 != 0 || slot_offset_bytes % 16 != 0 ||
+        flag_offset_bytes % 4 != 0)
+        return fail(nullptr, MX_ERR_INVALID, "bad exchange shape");
+    PushParams pp{};
+    pp.blob = blob_dev;
+    pp.blob_bytes = blob_bytes;
+    for (uint32_t i = 0; i < world; ++i) {
+        if (!peer_bases[i]) return fail(nullptr, MX_ERR_INVALID, "null peer buffer");
+        pp.peer_base[i] = peer_bases[i];
+    }
+    pp.slot_offset = slot_offset_bytes;
+    pp.flag_offset = flag_offset_bytes;
+    pp.world = world;
+    pp.rank = rank;
+    pp.epoch = epoch;
+    MX_CUDA(nullptr, MX_ERR_CONNECTION, cudaSetDevice(device));
+    MX_CUDA(nullptr, MX_ERR_SEARCH, launch_exchange_push(pp, (cudaStream_t)cuda_stream));
+    return MX_OK;
+}
+
 int32_t mx_store_len(mx_store *s, uint64_t *n_out)
 {
     if (!s || !n_out) return MX_ERR_INVALID;

@@ -8,12 +8,19 @@ its own shard with the same C-ABI call the single-GPU store uses and reports GLO
 (mx_topk_blob_bytes) and every rank merges the G * k candidates per query on its device with
 `mx_merge_topk_blobs_device` -- ordering (key asc, id asc), exactly the single-store ordering.
 
+The exchange step has two forms.  Default: peer memory -- every rank owns an exchange buffer its peers can address
+(torch symmetric memory: CUDA IPC / fabric handles over NVLink), `mx_exchange_push_device` stores the rank's blob into
+all peers' buffers and release-stores an epoch flag, and `mx_merge_topk_blobs_wait_device` waits for its flags inside
+the merge kernel: two of this library's own kernels, no collective library call on the query path.  Fallback (when
+the symmetric-memory rendezvous is not available, or MX_EXCHANGE=nccl): one NCCL all_gather_into_tensor.
+
 torch is used for device buffers, the stream and the collective only; all arithmetic is in
 libmemex_b200.so.  There is no CPU path.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -77,6 +84,41 @@ class ShardedStore:
         self.local = B200Store.new(storage_path, dim=dim, dtype=dtype, metric=metric, device=device,
                                    capacity=self.plan.count(rank), id_offset=self.plan.start(rank), id_stride=1)
         self._bufs = {}
+        self.exchange = "none" if world == 1 else "nccl"
+        self._want_p2p = world > 1 and os.environ.get("MX_EXCHANGE", "p2p") != "nccl"
+
+    def _setup_p2p(self, b, blob: int):
+        """exchange buffer addressable by every peer: [2][world] blob slots + world u32 flags; all ranks or none"""
+        import torch
+        import torch.distributed as dist
+        ok, peers, buf = 1, None, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            stride = (blob + 15) & ~15
+            nbytes = 2 * self.world * stride + 64
+            dev = torch.device("cuda", self.device)
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+            buf.zero_()
+            torch.cuda.synchronize(dev)
+            name = getattr(self.group, "group_name", None) or dist.group.WORLD.group_name
+            try:
+                hdl = symm_mem.rendezvous(buf, name)
+            except TypeError:
+                hdl = symm_mem.rendezvous(buf, group=name)
+            peers = [int(p) for p in hdl.buffer_ptrs]
+            if len(peers) != self.world or not all(peers):
+                ok = 0
+        except Exception as e:  # noqa: BLE001 -- any failure means "use the collective"
+            b["p2p_error"] = repr(e)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", self.device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) != 1:
+            return False
+        b["xbuf"], b["xstride"] = buf, stride
+        b["peers"] = (C.c_uint64 * self.world)(*peers)
+        dist.barrier(group=self.group)   # every rank's flags are zero before anyone pushes
+        return True
 
     # ---- ingest: rows already on this rank's device (f32 [n, dim]); ids follow the plan ----
     def add_local_device(self, rows_dev_ptr: int, n: int) -> int:
@@ -129,14 +171,33 @@ class ShardedStore:
         rc = L.mx_store_search_blob_device(self.local.handle, q_dev.data_ptr(), nq, k, mine.data_ptr(), st)
         if rc != capi.OK:
             _raise(rc, self.local.handle, SearchError)
+        metric = capi.METRIC_DOT if self.metric == "dot" else capi.METRIC_COSINE
+        if self.world > 1 and self._want_p2p and "p2p" not in b:
+            b["p2p"] = self._setup_p2p(b, b["blob_bytes"])
+            if b["p2p"]:
+                self.exchange = "p2p"
+        if self.world > 1 and b.get("p2p"):
+            # the one exchange step, peer-memory form: push to every peer's slot [epoch parity][rank], wait inside the merge
+            b["epoch"] = epoch = b.get("epoch", 0) + 1
+            stride, base = b["xstride"], b["xbuf"].data_ptr()
+            half = (epoch & 1) * self.world * stride
+            rc = L.mx_exchange_push_device(mine.data_ptr(), stride, b["peers"], self.world, self.rank, half + self.rank * stride,
+                                           2 * self.world * stride, epoch, self.device, st)
+            if rc != capi.OK:
+                _raise(rc, None, SearchError)
+            rc = L.mx_merge_topk_blobs_wait_device(base + half, stride, self.world, nq, k, metric, b["ids"].data_ptr(),
+                                                   b["scores"].data_ptr(), b["counts"].data_ptr(),
+                                                   base + 2 * self.world * stride, epoch, self.device, st)
+            if rc != capi.OK:
+                _raise(rc, None, SearchError)
+            return b["ids"], b["scores"], b["counts"]
         if self.world > 1:
-            # the one exchange step: each rank contributes blob_bytes
+            # the one exchange step, collective form: each rank contributes blob_bytes
             dist.all_gather_into_tensor(b["gathered"].view(-1), mine, group=self.group)
             blobs, n_shards = b["gathered"], self.world
         else:
             blobs, n_shards = mine, 1
-        rc = L.mx_merge_topk_blobs_device(blobs.data_ptr(), b["blob_bytes"], n_shards, nq, k,
-                                          capi.METRIC_DOT if self.metric == "dot" else capi.METRIC_COSINE,
+        rc = L.mx_merge_topk_blobs_device(blobs.data_ptr(), b["blob_bytes"], n_shards, nq, k, metric,
                                           b["ids"].data_ptr(), b["scores"].data_ptr(), b["counts"].data_ptr(),
                                           self.device, st)
         if rc != capi.OK:

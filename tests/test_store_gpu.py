@@ -261,6 +261,55 @@ def test_sharded_ids_and_device_merge(tmp_path):
         np.testing.assert_array_equal(oc.cpu().numpy().astype(np.uint32), wc)
 
 
+def test_peer_memory_exchange_kernels(tmp_path):
+    """the peer-memory form of the exchange step (mx_exchange_push_device + mx_merge_topk_blobs_wait_device) with three
+    "ranks" living on one GPU: every rank's exchange buffer ends up with all blobs, flags carry the epoch, and the merged
+    answer equals the single-store answer over several epochs (both slot sets)"""
+    import torch
+    world, nq, k, d = 3, 7, 10, 48
+    corpus = unit_rows(9000, d, 21)
+    L = capi.lib()
+    whole = B200Store.new(tmp_path / "w", dim=d)
+    whole.add_matrix(corpus)
+    shards = []
+    for r in range(world):
+        st = B200Store.new(tmp_path / f"s{r}", dim=d, id_offset=3000 * r)
+        st.add_matrix(corpus[3000 * r:3000 * (r + 1)])
+        shards.append(st)
+    blob = int(L.mx_topk_blob_bytes(nq, k))
+    stride = (blob + 15) & ~15
+    xbufs = [torch.zeros(2 * world * stride + 64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    peers = (C.c_uint64 * world)(*[x.data_ptr() for x in xbufs])
+    mine = [torch.zeros(stride, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    oi = torch.zeros((nq, k), dtype=torch.int64, device="cuda")
+    os_ = torch.zeros((nq, k), dtype=torch.float32, device="cuda")
+    oc = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    for epoch in range(1, 5):
+        queries = unit_rows(nq, d, 100 + epoch)
+        qd = torch.from_numpy(queries).cuda()
+        wi, ws, wc = whole.search_matrix(queries, k)
+        half = (epoch & 1) * world * stride
+        for r in range(world):
+            assert L.mx_store_search_blob_device(shards[r].handle, qd.data_ptr(), nq, k, mine[r].data_ptr(), None) == 0
+            assert L.mx_store_sync(shards[r].handle) == 0
+            assert L.mx_exchange_push_device(mine[r].data_ptr(), stride, peers, world, r, half + r * stride, 2 * world * stride,
+                                             epoch, 0, None) == 0
+        for r in range(world):
+            base = xbufs[r].data_ptr()
+            rc = L.mx_merge_topk_blobs_wait_device(base + half, stride, world, nq, k, capi.METRIC_COSINE, oi.data_ptr(),
+                                                   os_.data_ptr(), oc.data_ptr(), base + 2 * world * stride, epoch, 0, None)
+            assert rc == 0
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(oi.cpu().numpy().astype(np.uint64), wi)
+            np.testing.assert_array_equal(os_.cpu().numpy().view(np.uint32), ws.view(np.uint32))
+            np.testing.assert_array_equal(oc.cpu().numpy().astype(np.uint32), wc)
+            flags = xbufs[r][2 * world * stride:2 * world * stride + 4 * world].view(torch.int32).cpu().numpy()
+            assert (flags == epoch).all()
+    # bad shapes are status codes, not crashes
+    assert L.mx_exchange_push_device(mine[0].data_ptr(), stride + 1, peers, world, 0, 0, 0, 1, 0, None) == capi.ERR_INVALID
+    assert L.mx_exchange_push_device(mine[0].data_ptr(), stride, peers, world, world, 0, 0, 1, 0, None) == capi.ERR_INVALID
+
+
 def test_full_size_properties_1m(tmp_path):
     """BASELINE config 2 size (1M x 384 f32): size-independent properties + spot-checked scores."""
     n, d, k = 1_000_000, 384, 10
