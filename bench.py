@@ -593,6 +593,7 @@ def run_ours(args):
     device = torch.device("cuda", local)
     group = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=device)
         group = dist.group.WORLD
     pk = peaks()
