@@ -592,8 +592,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     group = None
+    saved_stdout = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
+        # stdout carries exactly one JSON line: NCCL prints its version banner to fd 1 when the first communicator comes up
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=device)
         group = dist.group.WORLD
     pk = peaks()
@@ -716,6 +720,10 @@ def run_ours(args):
     if world > 1:
         dist.barrier(group=group)
         dist.destroy_process_group()
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
         print(json.dumps(line), flush=True)
 

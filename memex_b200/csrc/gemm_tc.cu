@@ -92,6 +92,49 @@ __device__ __forceinline__ float gelu_erf(float x)
     return fmaf(h, erf_x, h);
 }
 
+// The same polynomial for two values at once with the packed f32x2 instructions of sm_100 (FFMA2 / FMUL2: one issue
+// slot for two FMAs -- the epilogue of the intermediate GEMM is bound by instruction issue, not by the FMA pipe).
+__device__ __forceinline__ uint64_t pk_f32x2(float lo, float hi)
+{
+    return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+{
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// x0, x1 <- gelu_erf(x0 + b0), gelu_erf(x1 + b1)
+__device__ __forceinline__ void bias_gelu_erf2(float &x0, float &x1, float b0, float b1)
+{
+    constexpr float kC5 = 0.00294416f, kC4 = -0.02959005f, kC3 = 0.14866564f, kC2 = 0.91850936f, kC1 = 1.627889f;
+    uint64_t x;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(pk_f32x2(x0, x1)), "l"(pk_f32x2(b0, b1)));
+    const uint64_t t = mul2(x & 0x7fffffff7fffffffull, pk_f32x2(0.70710678118654752f, 0.70710678118654752f));   // |x| / sqrt 2
+    uint64_t q = fma2(t, pk_f32x2(kC5, kC5), pk_f32x2(kC4, kC4));
+    q = fma2(t, q, pk_f32x2(kC3, kC3));
+    q = fma2(t, q, pk_f32x2(kC2, kC2));
+    q = fma2(t, q, pk_f32x2(kC1, kC1));
+    q = mul2(q, t ^ 0x8000000080000000ull);   // -q(t): 2^(-q) needs no separate negation
+    float e0, e1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(__uint_as_float((uint32_t)q)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(__uint_as_float((uint32_t)(q >> 32))));
+    // erf(|x| / sqrt 2) = 1 - e, with the sign of x; gelu = h + h * erf, h = x / 2
+    const uint64_t one = pk_f32x2(1.0f, 1.0f), m_one = pk_f32x2(-1.0f, -1.0f);
+    uint64_t erf_abs = fma2(pk_f32x2(e0, e1), m_one, one);
+    const uint64_t erf_x = erf_abs | (x & 0x8000000080000000ull);
+    const uint64_t h = mul2(x, pk_f32x2(0.5f, 0.5f));
+    const uint64_t g = fma2(h, erf_x, h);
+    x0 = __uint_as_float((uint32_t)g);
+    x1 = __uint_as_float((uint32_t)(g >> 32));
+}
+
 template <int FMT>
 __device__ __forceinline__ uint32_t pack16(float a, float b)
 {
@@ -467,11 +510,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float2 b2 = *reinterpret_cast<const float2 *>(sbias + cg * kCW + c * 32 + 2 * j);
-                        float x0 = __uint_as_float(v[2 * j]) + b2.x;
-                        float x1 = __uint_as_float(v[2 * j + 1]) + b2.y;
+                        float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
                         if constexpr (EPI == EPI_BIAS_GELU) {
-                            x0 = gelu_erf(x0);
-                            x1 = gelu_erf(x1);
+                            bias_gelu_erf2(x0, x1, b2.x, b2.y);
+                        } else {
+                            x0 += b2.x;
+                            x1 += b2.y;
                         }
                         o[j] = pack16<FMT>(x0, x1);
                     }
