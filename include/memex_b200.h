@@ -175,8 +175,35 @@ typedef struct mx_tensor {
 
 int32_t mx_embedder_create(const mx_model_cfg *cfg, const mx_tensor *weights, uint32_t n_weights,
                            int32_t device, mx_embedder **out);
+
+/* The other encoder stacks of memex's EmbeddingsModelType (embedding.rs:24-55) that share BERT's
+ * post-LayerNorm layer: RoBERTa (AllDistilrobertaV1 -- one of the three models segment_text
+ * accepts, embedding.rs:156-161), DistilBERT + Dense (DistiluseBaseMultilingualCased) and ALBERT
+ * (ParaphraseAlbertSmallV2).  Weights keep the BERT names above; the host side renames
+ * DistilBERT / ALBERT checkpoints (memex_b200/embedding.py::canonical_weights).  Extra tensors:
+ *   "dense.linear.weight" [dense_out, hidden], "dense.linear.bias" [dense_out]   (2_Dense module)
+ *   "embeddings.projection.weight" [hidden, embed_dim], "embeddings.projection.bias" [hidden]
+ * All-zero ext == mx_embedder_create. */
+#define MX_ACT_IDENTITY 0u
+#define MX_ACT_TANH 1u
+#define MX_FFN_GELU_ERF 0u  /* BERT / RoBERTa / DistilBERT "gelu" */
+#define MX_FFN_GELU_TANH 1u /* ALBERT "gelu_new" */
+typedef struct mx_model_ext {
+    uint32_t pos_offset;    /* row of the position table used by token 0 (RoBERTa: padding_idx + 1 = 2) */
+    uint32_t no_token_type; /* 1: the stack has no token-type table (DistilBERT) */
+    uint32_t dense_out;     /* > 0: sentence-transformers Dense module after pooling, this many outputs */
+    uint32_t dense_act;     /* MX_ACT_* */
+    uint32_t dense_bias;    /* 1: "dense.linear.bias" is present */
+    uint32_t ffn_act;       /* MX_FFN_* */
+    uint32_t embed_dim;     /* > 0 and != hidden: factorised embeddings (ALBERT), projected to hidden */
+    uint32_t share_layers;  /* 1: every layer uses the weights of "encoder.layer.0." (ALBERT) */
+} mx_model_ext;
+int32_t mx_embedder_create_ex(const mx_model_cfg *cfg, const mx_model_ext *ext, const mx_tensor *weights,
+                              uint32_t n_weights, int32_t device, mx_embedder **out);
+/* width of one output row: dense_out when a Dense module is present, else hidden */
+int32_t mx_embedder_out_dim(mx_embedder *e, uint32_t *dim);
 void mx_embedder_destroy(mx_embedder *e);
-/* ids [B, S] int32 padded, lens [B] (tokens beyond lens[b] are ignored), out [B, hidden] f32;
+/* ids [B, S] int32 padded, lens [B] (tokens beyond lens[b] are ignored), out [B, out_dim] f32;
  * HOST buffers. */
 int32_t mx_embedder_encode(mx_embedder *e, const int32_t *ids, const int32_t *lens, uint32_t B,
                            uint32_t S, float *out);

@@ -43,6 +43,12 @@ class ModelCfg(C.Structure):
                 ("precision", C.c_uint32), ("max_tokens", C.c_uint32)]
 
 
+class ModelExt(C.Structure):
+    _fields_ = [("pos_offset", C.c_uint32), ("no_token_type", C.c_uint32), ("dense_out", C.c_uint32),
+                ("dense_act", C.c_uint32), ("dense_bias", C.c_uint32), ("ffn_act", C.c_uint32),
+                ("embed_dim", C.c_uint32), ("share_layers", C.c_uint32)]
+
+
 class Tensor(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_float)), ("numel", C.c_uint64)]
 
@@ -105,6 +111,9 @@ def lib() -> C.CDLL:
     sig("mx_store_get_timing", C.c_int32, vp, f64p, u64p, f64p, u64p)
     sig("mx_embedder_create", C.c_int32, C.POINTER(ModelCfg), C.POINTER(Tensor), C.c_uint32,
         C.c_int32, C.POINTER(vp))
+    sig("mx_embedder_create_ex", C.c_int32, C.POINTER(ModelCfg), C.POINTER(ModelExt), C.POINTER(Tensor), C.c_uint32,
+        C.c_int32, C.POINTER(vp))
+    sig("mx_embedder_out_dim", C.c_int32, vp, u32p)
     sig("mx_embedder_destroy", None, vp)
     sig("mx_embedder_encode", C.c_int32, vp, vp, vp, C.c_uint32, C.c_uint32, vp)
     sig("mx_embedder_encode_device", C.c_int32, vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp)

@@ -37,6 +37,8 @@ struct LayerWeights {
 
 struct mx_embedder : HandleBase {
     mx_model_cfg cfg{};
+    mx_model_ext ext{};
+    uint32_t out_dim = 0;       // dense_out when the Dense module is present, else hidden
     int device = 0;
     int sm_count = kNumSMsDefault;
     int act = ACT_BF16;
@@ -45,6 +47,9 @@ struct mx_embedder : HandleBase {
     cudaStream_t stream = nullptr;
     std::vector<void *> allocs;
     float *word = nullptr, *pos = nullptr, *type0 = nullptr, *emb_g = nullptr, *emb_b = nullptr;
+    void *proj_w = nullptr;     // ALBERT: [hidden, embed_dim] in the activation dtype
+    float *proj_b = nullptr;
+    float *dense_w = nullptr, *dense_b = nullptr, *pooled_dev = nullptr;   // Dense module (f32)
     std::vector<LayerWeights> layers;
     // workspaces sized for cfg.max_tokens
     void *x = nullptr, *x1 = nullptr, *qkv = nullptr, *ctx = nullptr, *hh = nullptr;
@@ -150,13 +155,21 @@ int32_t forward(mx_embedder *e, const int32_t *ids_dev, const int32_t *lens_dev,
 {
     const mx_model_cfg &c = e->cfg;
     const uint32_t T = B * S, H = c.hidden, F = c.ffn;
+    const uint32_t E = e->ext.embed_dim ? e->ext.embed_dim : H;
+    const int epi_ffn = e->ext.ffn_act == MX_FFN_GELU_TANH ? EPI_BIAS_GELU_TANH : EPI_BIAS_GELU;
+    // RoBERTa numbers its positions from padding_idx + 1: token i of a right-padded row reads row i + pos_offset
+    const float *pos = e->pos + (size_t)e->ext.pos_offset * E;
+    int32_t rc;
     e->timer.begin(st, 1);
     MX_CUDA(e, MX_ERR_ENCODE,
-            launch_embed_ln(ids_dev, e->word, e->pos, e->type0, e->emb_g, e->emb_b, c.ln_eps, e->x, e->act, T, S, H, c.vocab, st));
+            launch_embed_ln(ids_dev, e->word, pos, e->type0, e->emb_g, e->emb_b, c.ln_eps, E == H ? e->x : e->ctx, e->act, T, S, E,
+                            c.vocab, st));
     e->timer.end(st);
-    int32_t rc;
+    // ALBERT: factorised embeddings, projected to the hidden width
+    if (E != H && (rc = run_gemm(e, e->ctx, e->proj_w, e->proj_b, nullptr, nullptr, nullptr, e->x, T, H, E, EPI_BIAS, st)) != MX_OK)
+        return rc;
     for (uint32_t l = 0; l < c.layers; ++l) {
-        const LayerWeights &w = e->layers[l];
+        const LayerWeights &w = e->layers[e->ext.share_layers ? 0 : l];
         if ((rc = run_gemm(e, e->x, w.wqkv, w.bqkv, nullptr, nullptr, nullptr, e->qkv, T, 3 * H, H, EPI_BIAS, st)) != MX_OK) return rc;
         e->timer.begin(st, 1);
         if (e->act == ACT_F32)
@@ -169,11 +182,19 @@ int32_t forward(mx_embedder *e, const int32_t *ids_dev, const int32_t *lens_dev,
             MX_CUDA(e, MX_ERR_ENCODE, launch_attention_mma(e->qkv, lens_dev, e->ctx, e->act, B, S, H, c.heads, st));
         e->timer.end(st);
         if ((rc = run_gemm(e, e->ctx, w.wo, w.bo, e->x, w.ln1_g, w.ln1_b, e->x1, T, H, H, EPI_BIAS_RES_LN, st)) != MX_OK) return rc;
-        if ((rc = run_gemm(e, e->x1, w.w1, w.b1, nullptr, nullptr, nullptr, e->hh, T, F, H, EPI_BIAS_GELU, st)) != MX_OK) return rc;
+        if ((rc = run_gemm(e, e->x1, w.w1, w.b1, nullptr, nullptr, nullptr, e->hh, T, F, H, epi_ffn, st)) != MX_OK) return rc;
         if ((rc = run_gemm(e, e->hh, w.w2, w.b2, e->x1, w.ln2_g, w.ln2_b, e->x, T, H, F, EPI_BIAS_RES_LN, st)) != MX_OK) return rc;
     }
     e->timer.begin(st, 1);
-    MX_CUDA(e, MX_ERR_ENCODE, launch_pool_normalize(e->x, e->act, lens_dev, out_dev, B, S, H, c.normalize, st));
+    if (e->ext.dense_out) {
+        // Pooling -> Dense -> (Normalize): the order of the sentence-transformers module list
+        MX_CUDA(e, MX_ERR_ENCODE, launch_pool_normalize(e->x, e->act, lens_dev, e->pooled_dev, B, S, H, 0, st));
+        MX_CUDA(e, MX_ERR_ENCODE,
+                launch_dense_tail(e->pooled_dev, e->dense_w, e->dense_b, out_dev, B, H, e->ext.dense_out, e->ext.dense_act,
+                                  c.normalize, st));
+    } else {
+        MX_CUDA(e, MX_ERR_ENCODE, launch_pool_normalize(e->x, e->act, lens_dev, out_dev, B, S, H, c.normalize, st));
+    }
     e->timer.end(st);
     return MX_OK;
 }
@@ -185,8 +206,30 @@ extern "C" {
 int32_t mx_embedder_create(const mx_model_cfg *cfg, const mx_tensor *weights, uint32_t n_weights, int32_t device,
                            mx_embedder **out)
 {
+    return mx_embedder_create_ex(cfg, nullptr, weights, n_weights, device, out);
+}
+
+int32_t mx_embedder_out_dim(mx_embedder *e, uint32_t *dim)
+{
+    if (!e || !dim) return MX_ERR_INVALID;
+    *dim = e->out_dim;
+    return MX_OK;
+}
+
+int32_t mx_embedder_create_ex(const mx_model_cfg *cfg, const mx_model_ext *ext_in, const mx_tensor *weights, uint32_t n_weights,
+                              int32_t device, mx_embedder **out)
+{
     if (!cfg || !out || (!weights && n_weights)) return fail(nullptr, MX_ERR_INVALID, "null argument");
     *out = nullptr;
+    mx_model_ext ext{};
+    if (ext_in) ext = *ext_in;
+    if (ext.embed_dim == cfg->hidden) ext.embed_dim = 0;
+    if (ext.pos_offset >= cfg->max_pos) return fail(nullptr, MX_ERR_SETUP, "pos_offset %u >= max_pos %u", ext.pos_offset, cfg->max_pos);
+    if (ext.dense_out > 1024) return fail(nullptr, MX_ERR_SETUP, "dense_out %u > 1024", ext.dense_out);
+    if (ext.dense_act > MX_ACT_TANH || ext.ffn_act > MX_FFN_GELU_TANH)
+        return fail(nullptr, MX_ERR_SETUP, "unknown activation code (dense_act %u, ffn_act %u)", ext.dense_act, ext.ffn_act);
+    if (ext.embed_dim && (ext.embed_dim > cfg->hidden || ext.embed_dim % 64 != 0))
+        return fail(nullptr, MX_ERR_SETUP, "embed_dim %u must be a multiple of 64 and <= hidden", ext.embed_dim);
     if (cfg->layers == 0 || cfg->hidden == 0 || cfg->heads == 0 || cfg->ffn == 0 || cfg->vocab == 0 || cfg->max_pos == 0)
         return fail(nullptr, MX_ERR_SETUP, "model config has a zero dimension");
     if (cfg->hidden % cfg->heads != 0) return fail(nullptr, MX_ERR_SETUP, "hidden %% heads != 0");
@@ -198,7 +241,7 @@ int32_t mx_embedder_create(const mx_model_cfg *cfg, const mx_tensor *weights, ui
     const int act = cfg->precision == 1 ? ACT_F32 : (cfg->precision == 0 ? ACT_BF16 : ACT_F16);
     if (act != ACT_F32) {
         if (!gemm_tc_block_n(3 * cfg->hidden, EPI_BIAS) || !gemm_tc_block_n(cfg->ffn, EPI_BIAS_GELU) ||
-            !gemm_tc_block_n(cfg->hidden, EPI_BIAS_RES_LN))
+            !gemm_tc_block_n(cfg->hidden, EPI_BIAS_RES_LN) || (ext.embed_dim && !gemm_tc_block_n(cfg->hidden, EPI_BIAS)))
             return fail(nullptr, MX_ERR_SETUP, "hidden %u / ffn %u have no tcgen05 tile configuration", cfg->hidden, cfg->ffn);
     }
     int ndev = 0;
@@ -219,6 +262,8 @@ int32_t mx_embedder_create(const mx_model_cfg *cfg, const mx_tensor *weights, ui
     mx_embedder *e = new mx_embedder();
     e->magic = kEmbedderMagic;
     e->cfg = *cfg;
+    e->ext = ext;
+    e->out_dim = ext.dense_out ? ext.dense_out : cfg->hidden;
     if (e->cfg.max_tokens == 0) e->cfg.max_tokens = 256 * 256;
     if (e->cfg.type_vocab == 0) e->cfg.type_vocab = 2;
     e->device = device;
@@ -239,6 +284,7 @@ int32_t mx_embedder_create(const mx_model_cfg *cfg, const mx_tensor *weights, ui
         if (weights[i].name) tab.by_name[weights[i].name] = &weights[i];
 
     const uint64_t H = cfg->hidden, F = cfg->ffn;
+    const uint64_t E = ext.embed_dim ? ext.embed_dim : H;   // width of the embedding tables
     const size_t asz = act_size(act);
     int32_t rc = MX_OK;
     float *staging = nullptr;
@@ -259,19 +305,36 @@ int32_t mx_embedder_create(const mx_model_cfg *cfg, const mx_tensor *weights, ui
         return upload(e, t->data, numel, dst, act, staging);
     };
 
-    if ((rc = up_f32("embeddings.word_embeddings.weight", (uint64_t)cfg->vocab * H, &e->word)) != MX_OK) return bail(rc);
-    if ((rc = up_f32("embeddings.position_embeddings.weight", (uint64_t)cfg->max_pos * H, &e->pos)) != MX_OK) return bail(rc);
-    {
+    if ((rc = up_f32("embeddings.word_embeddings.weight", (uint64_t)cfg->vocab * E, &e->word)) != MX_OK) return bail(rc);
+    if ((rc = up_f32("embeddings.position_embeddings.weight", (uint64_t)cfg->max_pos * E, &e->pos)) != MX_OK) return bail(rc);
+    if (ext.no_token_type) {
+        // DistilBERT has no token-type table: the kernel adds a row of zeros
+        if ((rc = dev_alloc(e, &e->type0, E)) != MX_OK) return bail(rc);
+        if ((ce = cudaMemsetAsync(e->type0, 0, E * sizeof(float), e->stream)) != cudaSuccess)
+            return bail(fail(e, MX_ERR_SETUP, "cudaMemset: %s", cudaGetErrorString(ce)));
+    } else {
         float *type_all = nullptr;
-        if ((rc = up_f32("embeddings.token_type_embeddings.weight", (uint64_t)e->cfg.type_vocab * H, &type_all)) != MX_OK)
+        if ((rc = up_f32("embeddings.token_type_embeddings.weight", (uint64_t)e->cfg.type_vocab * E, &type_all)) != MX_OK)
             return bail(rc);
         e->type0 = type_all;  // rust-bert / sentence-transformers feed token_type_ids = 0
     }
-    if ((rc = up_f32("embeddings.LayerNorm.weight", H, &e->emb_g)) != MX_OK) return bail(rc);
-    if ((rc = up_f32("embeddings.LayerNorm.bias", H, &e->emb_b)) != MX_OK) return bail(rc);
+    if ((rc = up_f32("embeddings.LayerNorm.weight", E, &e->emb_g)) != MX_OK) return bail(rc);
+    if ((rc = up_f32("embeddings.LayerNorm.bias", E, &e->emb_b)) != MX_OK) return bail(rc);
+    if (E != H) {
+        unsigned char *pw = nullptr;
+        if ((rc = dev_alloc(e, &pw, H * E * asz)) != MX_OK) return bail(rc);
+        e->proj_w = pw;
+        if ((rc = up_act("embeddings.projection.weight", H * E, e->proj_w)) != MX_OK) return bail(rc);
+        if ((rc = up_f32("embeddings.projection.bias", H, &e->proj_b)) != MX_OK) return bail(rc);
+    }
+    if (ext.dense_out) {
+        if ((rc = up_f32("dense.linear.weight", (uint64_t)ext.dense_out * H, &e->dense_w)) != MX_OK) return bail(rc);
+        if (ext.dense_bias && (rc = up_f32("dense.linear.bias", ext.dense_out, &e->dense_b)) != MX_OK) return bail(rc);
+    }
 
-    e->layers.resize(cfg->layers);
-    for (uint32_t l = 0; l < cfg->layers; ++l) {
+    const uint32_t n_layer_sets = ext.share_layers ? 1u : cfg->layers;
+    e->layers.resize(n_layer_sets);
+    for (uint32_t l = 0; l < n_layer_sets; ++l) {
         LayerWeights &w = e->layers[l];
         const std::string p = "encoder.layer." + std::to_string(l) + ".";
         unsigned char *wqkv = nullptr;
@@ -321,7 +384,8 @@ int32_t mx_embedder_create(const mx_model_cfg *cfg, const mx_tensor *weights, ui
     e->max_seqs = (uint32_t)std::min<uint64_t>(T, 8192);
     if ((rc = dev_alloc(e, &e->ids_dev, T)) != MX_OK) return bail(rc);
     if ((rc = dev_alloc(e, &e->lens_dev, e->max_seqs)) != MX_OK) return bail(rc);
-    if ((rc = dev_alloc(e, &e->out_dev, (uint64_t)e->max_seqs * H)) != MX_OK) return bail(rc);
+    if ((rc = dev_alloc(e, &e->out_dev, (uint64_t)e->max_seqs * e->out_dim)) != MX_OK) return bail(rc);
+    if (ext.dense_out && (rc = dev_alloc(e, &e->pooled_dev, (uint64_t)e->max_seqs * H)) != MX_OK) return bail(rc);
     if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess)
         return bail(fail(e, MX_ERR_SETUP, "weight upload failed: %s", cudaGetErrorString(ce)));
     *out = e;
@@ -346,7 +410,8 @@ int32_t mx_embedder_encode_device(mx_embedder *e, const int32_t *ids_dev, const 
     if (!e) return MX_ERR_INVALID;
     if (!ids_dev || !lens || !out_dev) return fail(e, MX_ERR_INVALID, "null buffer");
     if (B == 0) return MX_OK;
-    if (S == 0 || S > e->cfg.max_pos) return fail(e, MX_ERR_ENCODE, "sequence length %u outside [1, max_pos = %u]", S, e->cfg.max_pos);
+    if (S == 0 || S + e->ext.pos_offset > e->cfg.max_pos)
+        return fail(e, MX_ERR_ENCODE, "sequence length %u outside [1, max_pos - pos_offset = %u]", S, e->cfg.max_pos - e->ext.pos_offset);
     if (S > e->cfg.max_tokens) return fail(e, MX_ERR_ENCODE, "sequence length %u exceeds the workspace (%u tokens)", S, e->cfg.max_tokens);
     MX_CUDA(e, MX_ERR_CONNECTION, cudaSetDevice(e->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
@@ -354,7 +419,7 @@ int32_t mx_embedder_encode_device(mx_embedder *e, const int32_t *ids_dev, const 
     for (uint32_t b0 = 0; b0 < B; b0 += chunk) {
         const uint32_t nb = std::min(chunk, B - b0);
         MX_CUDA(e, MX_ERR_ENCODE, cudaMemcpyAsync(e->lens_dev, lens + b0, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        int32_t rc = forward(e, ids_dev + (size_t)b0 * S, e->lens_dev, nb, S, out_dev + (size_t)b0 * e->cfg.hidden, st);
+        int32_t rc = forward(e, ids_dev + (size_t)b0 * S, e->lens_dev, nb, S, out_dev + (size_t)b0 * e->out_dim, st);
         if (rc != MX_OK) return rc;
         if (b0 + chunk < B) MX_CUDA(e, MX_ERR_ENCODE, cudaStreamSynchronize(st));  // lens_dev is reused
     }
@@ -366,10 +431,11 @@ int32_t mx_embedder_encode(mx_embedder *e, const int32_t *ids, const int32_t *le
     if (!e) return MX_ERR_INVALID;
     if (!ids || !lens || !out) return fail(e, MX_ERR_INVALID, "null buffer");
     if (B == 0) return MX_OK;
-    if (S == 0 || S > e->cfg.max_pos) return fail(e, MX_ERR_ENCODE, "sequence length %u outside [1, max_pos = %u]", S, e->cfg.max_pos);
+    if (S == 0 || S + e->ext.pos_offset > e->cfg.max_pos)
+        return fail(e, MX_ERR_ENCODE, "sequence length %u outside [1, max_pos - pos_offset = %u]", S, e->cfg.max_pos - e->ext.pos_offset);
     if (S > e->cfg.max_tokens) return fail(e, MX_ERR_ENCODE, "sequence length %u exceeds the workspace (%u tokens)", S, e->cfg.max_tokens);
     MX_CUDA(e, MX_ERR_CONNECTION, cudaSetDevice(e->device));
-    const uint32_t H = e->cfg.hidden;
+    const uint32_t H = e->out_dim;   // width of one output row
     const uint32_t chunk = std::min(e->cfg.max_tokens / S, e->max_seqs);
     const size_t ids_bytes = (size_t)chunk * S * 4, out_bytes = (size_t)chunk * H * 4;
     const size_t need = ids_bytes + out_bytes;

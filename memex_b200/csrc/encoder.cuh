@@ -41,6 +41,11 @@ cudaError_t launch_add_ln_f32(const float *y, const float *residual, const float
 cudaError_t launch_pool_normalize(const void *x, int act, const int32_t *lens_dev, float *out, uint32_t B, uint32_t S,
                                   uint32_t H, uint32_t normalize, cudaStream_t st);
 
+// sentence-transformers Dense module after pooling: out[b, :] = act(W pooled[b, :] + bias) (act 1 = tanh), optional L2
+// normalise; W [N, H] f32, bias may be null
+cudaError_t launch_dense_tail(const float *pooled, const float *W, const float *bias, float *out, uint32_t B, uint32_t H,
+                              uint32_t N, uint32_t act, uint32_t normalize, cudaStream_t st);
+
 // f32 -> 16-bit weight conversion (rows of `cols`, written at out + row * ldo)
 cudaError_t launch_convert_weight(const float *src, void *dst, int act, uint64_t numel, cudaStream_t st);
 

@@ -483,6 +483,57 @@ cudaError_t launch_pool_normalize(const void *x, int act, const int32_t *lens_de
 }
 
 // ---------------------------------------------------------------------------------------------
+// sentence-transformers Dense module after pooling (DistiluseBaseMultilingualCased: 768 -> 512, Tanh):
+//   out[b, :] = act(W pooled[b, :] + bias), optionally L2-normalised.  One CTA per sequence, the pooled row in shared
+// memory, one warp per output column (coalesced f32 weight rows; the matrix is L2-resident: <= 4 MB).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dense_tail_kernel(const float *__restrict__ pooled, const float *__restrict__ W,
+                                                         const float *__restrict__ bias, float *__restrict__ out,
+                                                         uint32_t H, uint32_t N, uint32_t act, uint32_t normalize)
+{
+    __shared__ float row[1024];    // H <= 1024
+    __shared__ float res[1024];    // N <= 1024
+    __shared__ float red[8];
+    __shared__ float inv_s;
+    const uint32_t b = blockIdx.x, warp = threadIdx.x >> 5, lane = lane_id();
+    for (uint32_t c = threadIdx.x; c < H; c += 256) row[c] = pooled[(size_t)b * H + c];
+    __syncthreads();
+    for (uint32_t n = warp; n < N; n += 8) {
+        const float *w = W + (size_t)n * H;
+        float acc = 0.f;
+        for (uint32_t c = lane; c < H; c += 32) acc = fmaf(w[c], row[c], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            float v = acc + (bias ? bias[n] : 0.f);
+            if (act == 1u) v = tanhf(v);
+            res[n] = v;
+        }
+    }
+    __syncthreads();
+    float sq = 0.f;
+    for (uint32_t n = threadIdx.x; n < N; n += 256) sq = fmaf(res[n], res[n], sq);
+    sq = warp_sum(sq);
+    if (lane == 0) red[warp] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        inv_s = normalize ? 1.0f / fmaxf(sqrtf(t), 1e-12f) : 1.0f;
+    }
+    __syncthreads();
+    for (uint32_t n = threadIdx.x; n < N; n += 256) out[(size_t)b * N + n] = res[n] * inv_s;
+}
+
+cudaError_t launch_dense_tail(const float *pooled, const float *W, const float *bias, float *out, uint32_t B, uint32_t H,
+                              uint32_t N, uint32_t act, uint32_t normalize, cudaStream_t st)
+{
+    if (H > 1024 || N > 1024 || N == 0) return cudaErrorInvalidValue;
+    dense_tail_kernel<<<B, 256, 0, st>>>(pooled, W, bias, out, H, N, act, normalize);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 template <int ACT>
 __global__ void convert_weight_kernel(const float *__restrict__ src, typename Act<ACT>::T *__restrict__ dst, uint64_t n)
 {
@@ -544,6 +595,7 @@ __global__ void __launch_bounds__(256) gemm_ref_kernel(GemmRefParams p)
             if (m < p.M && n < p.N) {
                 float v = acc[i][j] + p.bias[n];
                 if (EPI == EPI_BIAS_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+                if (EPI == EPI_BIAS_GELU_TANH) v = 0.5f * v * (1.0f + tanhf(0.7978845608028654f * (v + 0.044715f * v * v * v)));
                 p.out[(size_t)m * p.N + n] = v;
             }
         }
@@ -554,6 +606,8 @@ cudaError_t launch_gemm_ref(const GemmRefParams &p, int epi, cudaStream_t st)
     dim3 grid(ceil_div<uint32_t>(p.N, 64), ceil_div<uint32_t>(p.M, 64));
     if (epi == EPI_BIAS_GELU)
         gemm_ref_kernel<EPI_BIAS_GELU><<<grid, 256, 0, st>>>(p);
+    else if (epi == EPI_BIAS_GELU_TANH)
+        gemm_ref_kernel<EPI_BIAS_GELU_TANH><<<grid, 256, 0, st>>>(p);
     else
         gemm_ref_kernel<EPI_BIAS><<<grid, 256, 0, st>>>(p);
     count_launch();

@@ -5,7 +5,8 @@
 
 namespace mx {
 
-enum GemmEpilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RES_LN = 2 };
+// EPI_BIAS_GELU_TANH: ALBERT's "gelu_new" (0.5 x (1 + tanh(sqrt(2 / pi) (x + 0.044715 x^3))))
+enum GemmEpilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RES_LN = 2, EPI_BIAS_GELU_TANH = 3 };
 
 // out[M, N] = epi(A[M, K] . W[N, K]^T)
 struct GemmParams {

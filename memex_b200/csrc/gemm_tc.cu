@@ -92,6 +92,19 @@ __device__ __forceinline__ float gelu_erf(float x)
     return fmaf(h, erf_x, h);
 }
 
+// ALBERT's "gelu_new": 0.5 x (1 + tanh(u)), u = sqrt(2 / pi) (x + 0.044715 x^3); tanh(u) = 1 - 2 / (1 + e^(2u)) through one
+// ex2 and one reciprocal (e = inf gives 1, e = 0 gives -1: no clamping needed)
+__device__ __forceinline__ float gelu_tanh(float x)
+{
+    const float u = 0.7978845608028654f * fmaf(0.044715f * x, x * x, x);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * 2.8853900817779268f));   // e^(2u) = 2^(2 u log2 e)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    const float t = fmaf(-2.0f, r, 1.0f);
+    const float h = 0.5f * x;
+    return fmaf(h, t, h);
+}
+
 // The same polynomial for two values at once with the packed f32x2 instructions of sm_100 (FFMA2 / FMUL2: one issue
 // slot for two FMAs -- the epilogue of the intermediate GEMM is bound by instruction issue, not by the FMA pipe).
 __device__ __forceinline__ uint64_t pk_f32x2(float lo, float hi)
@@ -513,6 +526,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
                         if constexpr (EPI == EPI_BIAS_GELU) {
                             bias_gelu_erf2(x0, x1, b2.x, b2.y);
+                        } else if constexpr (EPI == EPI_BIAS_GELU_TANH) {
+                            x0 = gelu_tanh(x0 + b2.x);
+                            x1 = gelu_tanh(x1 + b2.y);
                         } else {
                             x0 += b2.x;
                             x1 += b2.y;
@@ -615,7 +631,7 @@ int gemm_tc_block_n(uint32_t N, int epi)
 
 cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStream_t st, const char **why)
 {
-    const bool res = use_resident(p, epi, sm_count);
+    const bool res = epi != EPI_BIAS_GELU_TANH && use_resident(p, epi, sm_count);
     const int bn = res ? 192 : gemm_tc_block_n(p.N, epi);
     if (bn == 0 || p.K % 8 != 0 || p.lda % 8 != 0 || p.ldw % 8 != 0 || p.ldo % 8 != 0) {
         if (why) *why = "unsupported GEMM shape for the tcgen05 path";
@@ -630,7 +646,7 @@ cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStrea
     // L2, and the lock-step of the two CTAs costs 3-6 % -- so it is opt-in (MX_GEMM_MULTICAST=1; the parity tests
     // run both settings).
     static const bool mc_on = getenv("MX_GEMM_MULTICAST") != nullptr;
-    const bool mc = !res && mc_on && sm_count >= 2 && ceil_div<uint32_t>(p.M, 2 * kBM) * (p.N / bn) >= (uint32_t)sm_count / 2;
+    const bool mc = !res && mc_on && epi != EPI_BIAS_GELU_TANH && sm_count >= 2 && ceil_div<uint32_t>(p.M, 2 * kBM) * (p.N / bn) >= (uint32_t)sm_count / 2;
     CUtensorMap tmA, tmB, tmO;
     uint32_t chunk_rows = mc ? bn / 2 : (bn > 256 ? bn / 2 : bn);
     if (epi == EPI_BIAS_RES_LN && !mc) chunk_rows = 192;   // whole-row 384 (2 chunks), split 2 x 192, split 2 x 384 (2 chunks each)
@@ -674,6 +690,11 @@ cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStrea
         if (bn == 256) MX_GEMM_MC(256, EPI_BIAS_GELU);
         if (bn == 192) MX_GEMM_MC(192, EPI_BIAS_GELU);
         MX_GEMM_MC(128, EPI_BIAS_GELU);
+    }
+    if (epi == EPI_BIAS_GELU_TANH) {   // ALBERT only: the plain streaming variant
+        if (bn == 256) MX_GEMM(256, EPI_BIAS_GELU_TANH, false, false);
+        if (bn == 192) MX_GEMM(192, EPI_BIAS_GELU_TANH, false, false);
+        MX_GEMM(128, EPI_BIAS_GELU_TANH, false, false);
     }
     if (res) MX_GEMM(192, EPI_BIAS, true, false);
     if (bn == 256) MX_GEMM_MC(256, EPI_BIAS);

@@ -62,15 +62,71 @@ class Architecture:
     ln_eps: float = 1e-12
     normalize: bool = True
     max_seq_length: int = 256    # sentence_bert_config.json of the model (what rust-bert truncates to)
+    # the stacks that differ from BERT only around the layers (mx_model_ext in include/memex_b200.h)
+    family: str = "bert"         # "bert" | "roberta" | "distilbert" | "albert": the checkpoint's naming scheme
+    pos_offset: int = 0          # RoBERTa: positions start at padding_idx + 1 = 2
+    pad_id: int = 0              # RoBERTa: 1
+    dense_out: int = 0           # sentence-transformers Dense module after pooling (0 = none)
+    dense_act: str = "identity"  # "identity" | "tanh"
+    dense_bias: bool = True
+    ffn_act: str = "gelu"        # "gelu" (erf) | "gelu_new" (tanh form, ALBERT)
+    embed_dim: int = 0           # ALBERT: factorised embedding width (0 = hidden)
+    share_layers: bool = False   # ALBERT: one set of layer weights
+
+    @property
+    def out_dim(self) -> int:
+        return self.dense_out or self.hidden
 
 
-# BERT-family models of the enum (the others are DistilBERT / RoBERTa / ALBERT / T5 stacks that the
-# reference can only segment for L12 / L6 / distilroberta anyway, embedding.rs:156-161)
+# The models of the enum whose layer is BERT's post-LayerNorm block (embedding.rs:24-55; shapes from the
+# sentence-transformers model cards).  SentenceT5Base is a T5 encoder (relative position bias, RMSNorm, gated FFN)
+# and is not built; the reference can only segment L12 / L6 / distilroberta anyway (embedding.rs:156-161).
 ARCHITECTURES = {
     EmbeddingsModelType.AllMiniLmL6V2: Architecture(6, 384, 12, 1536, max_seq_length=256),
     EmbeddingsModelType.AllMiniLmL12V2: Architecture(12, 384, 12, 1536, max_seq_length=128),
     EmbeddingsModelType.BertBaseNliMeanTokens: Architecture(12, 768, 12, 3072, normalize=False, max_seq_length=128),
+    EmbeddingsModelType.AllDistilrobertaV1: Architecture(
+        6, 768, 12, 3072, vocab=50265, max_pos=514, type_vocab=1, ln_eps=1e-5, max_seq_length=512,
+        family="roberta", pos_offset=2, pad_id=1),
+    EmbeddingsModelType.DistiluseBaseMultilingualCased: Architecture(
+        6, 768, 12, 3072, vocab=119547, max_pos=512, type_vocab=0, normalize=False, max_seq_length=128,
+        family="distilbert", dense_out=512, dense_act="tanh"),
+    EmbeddingsModelType.ParaphraseAlbertSmallV2: Architecture(
+        6, 768, 12, 3072, vocab=30000, max_pos=512, normalize=False, max_seq_length=100,
+        family="albert", ffn_act="gelu_new", embed_dim=128, share_layers=True),
 }
+
+
+def canonical_weights(family: str, state: dict) -> dict:
+    """Checkpoint tensor names of a RoBERTa / DistilBERT / ALBERT stack -> the BERT names the C ABI takes
+    (include/memex_b200.h).  `state` may carry a sentence-transformers Dense module as "linear.weight" /
+    "linear.bias" or "dense.linear.*"; a leading "roberta." / "distilbert." / "albert." / "bert." is dropped."""
+    out = {}
+    for name, arr in state.items():
+        for prefix in ("roberta.", "distilbert.", "albert.", "bert."):
+            if name.startswith(prefix):
+                name = name[len(prefix):]
+        if name in ("linear.weight", "linear.bias"):
+            name = "dense." + name
+        if family == "distilbert":
+            name = name.replace("transformer.layer.", "encoder.layer.")
+            for a, b in ((".attention.q_lin.", ".attention.self.query."), (".attention.k_lin.", ".attention.self.key."),
+                         (".attention.v_lin.", ".attention.self.value."), (".attention.out_lin.", ".attention.output.dense."),
+                         (".sa_layer_norm.", ".attention.output.LayerNorm."), (".ffn.lin1.", ".intermediate.dense."),
+                         (".ffn.lin2.", ".output.dense."), (".output_layer_norm.", ".output.LayerNorm.")):
+                name = name.replace(a, b)
+        elif family == "albert":
+            name = name.replace("encoder.embedding_hidden_mapping_in.", "embeddings.projection.")
+            name = name.replace("encoder.albert_layer_groups.0.albert_layers.0.", "encoder.layer.0.")
+            for a, b in ((".attention.query.", ".attention.self.query."), (".attention.key.", ".attention.self.key."),
+                         (".attention.value.", ".attention.self.value."), (".attention.dense.", ".attention.output.dense."),
+                         (".attention.LayerNorm.", ".attention.output.LayerNorm."), (".ffn_output.", ".output.dense."),
+                         (".ffn.", ".intermediate.dense."), (".full_layer_layer_norm.", ".output.LayerNorm.")):
+                name = name.replace(a, b)
+        if "position_ids" in name or "token_type_ids" in name or name.startswith("pooler."):
+            continue
+        out[name] = arr
+    return out
 
 
 @dataclass(frozen=True)
@@ -84,7 +140,8 @@ PRECISION = {"bf16": 0, "f32": 1, "f16": 2}
 
 
 class B200Encoder:
-    """Owns an mx_embedder handle: ids [B,S] + lens [B] -> unit-norm f32 [B,H]."""
+    """Owns an mx_embedder handle: ids [B,S] + lens [B] -> f32 [B, out_dim] (unit-norm when the model has Normalize).
+    `weights` use the BERT names (canonical_weights renames DistilBERT / ALBERT checkpoints)."""
 
     def __init__(self, arch: Architecture, weights: dict, precision: str = "bf16", device: int = 0,
                  max_tokens: int = 0):
@@ -100,8 +157,12 @@ class B200Encoder:
                             vocab=arch.vocab, max_pos=arch.max_pos, type_vocab=arch.type_vocab,
                             ln_eps=arch.ln_eps, normalize=1 if arch.normalize else 0,
                             precision=PRECISION[precision], max_tokens=max_tokens)
+        ext = capi.ModelExt(pos_offset=arch.pos_offset, no_token_type=1 if arch.family == "distilbert" else 0,
+                            dense_out=arch.dense_out, dense_act={"identity": 0, "tanh": 1}[arch.dense_act],
+                            dense_bias=1 if arch.dense_bias else 0, ffn_act={"gelu": 0, "gelu_new": 1}[arch.ffn_act],
+                            embed_dim=arch.embed_dim, share_layers=1 if arch.share_layers else 0)
         h = C.c_void_p()
-        rc = capi.lib().mx_embedder_create(C.byref(cfg), arr_t, len(tensors), device, C.byref(h))
+        rc = capi.lib().mx_embedder_create_ex(C.byref(cfg), C.byref(ext), arr_t, len(tensors), device, C.byref(h))
         if rc != capi.OK:
             msg = capi.lib().mx_last_error(None)
             raise SetupError(msg.decode(errors="replace") if msg else f"status {rc}")
@@ -116,7 +177,7 @@ class B200Encoder:
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         lens = np.ascontiguousarray(lens, dtype=np.int32)
         B, S = ids.shape
-        out = np.zeros((B, self.arch.hidden), dtype=np.float32)
+        out = np.zeros((B, self.arch.out_dim), dtype=np.float32)
         rc = capi.lib().mx_embedder_encode(self._h, ids.ctypes.data, lens.ctypes.data, B, S, out.ctypes.data)
         if rc != capi.OK:
             msg = capi.lib().mx_last_error(self._h)
@@ -199,7 +260,7 @@ class SentenceEmbedder:
             text, segment, reply = msg
             try:
                 segments = segment_text(model_config, text, tokenizer) if segment else [text]
-                ids, lens = tokenize_batch(tokenizer, segments, encoder.arch.max_seq_length)
+                ids, lens = tokenize_batch(tokenizer, segments, encoder.arch.max_seq_length, encoder.arch.pad_id)
                 embeddings = encoder.encode_ids(ids, lens)        # <- model.encode(&segments), :109
                 if len(segments) != len(embeddings):
                     raise EncodingFailure("# of embeddings doesn't match # of segments")

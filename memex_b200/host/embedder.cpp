@@ -17,13 +17,75 @@ EmbeddingError::EmbeddingError(EmbeddingErrorKind k, const std::string &msg)
 
 std::optional<Architecture> architecture_of(EmbeddingsModelType model)
 {
-    // the others are DistilBERT / RoBERTa / ALBERT / T5 stacks, which the reference can only segment for
-    // L12 / L6 / distilroberta anyway (embedding.rs:156-161)
+    // shapes from the sentence-transformers model cards; the reference can only segment L12 / L6 / distilroberta
+    // (embedding.rs:156-161) but encodes single texts with any of them
     switch (model) {
         case EmbeddingsModelType::AllMiniLmL6V2: return Architecture{6, 384, 12, 1536, 30522, 512, 2, 1e-12f, true, 256};
         case EmbeddingsModelType::AllMiniLmL12V2: return Architecture{12, 384, 12, 1536, 30522, 512, 2, 1e-12f, true, 128};
         case EmbeddingsModelType::BertBaseNliMeanTokens: return Architecture{12, 768, 12, 3072, 30522, 512, 2, 1e-12f, false, 128};
-        default: return std::nullopt;
+        case EmbeddingsModelType::AllDistilrobertaV1: {
+            Architecture a{6, 768, 12, 3072, 50265, 514, 1, 1e-5f, true, 512};
+            a.family = Family::Roberta;
+            a.pos_offset = 2;
+            a.pad_id = 1;
+            return a;
+        }
+        case EmbeddingsModelType::DistiluseBaseMultilingualCased: {
+            Architecture a{6, 768, 12, 3072, 119547, 512, 0, 1e-12f, false, 128};
+            a.family = Family::DistilBert;
+            a.dense_out = 512;
+            a.dense_tanh = true;
+            return a;
+        }
+        case EmbeddingsModelType::ParaphraseAlbertSmallV2: {
+            Architecture a{6, 768, 12, 3072, 30000, 512, 2, 1e-12f, false, 100};
+            a.family = Family::Albert;
+            a.ffn_gelu_new = true;
+            a.embed_dim = 128;
+            a.share_layers = true;
+            return a;
+        }
+        default: return std::nullopt;   // SentenceT5Base: T5 encoder, not built
+    }
+}
+
+namespace {
+void replace_all(std::string &s, const std::string &a, const std::string &b)
+{
+    for (size_t pos = 0; (pos = s.find(a, pos)) != std::string::npos; pos += b.size()) s.replace(pos, a.size(), b);
+}
+}  // namespace
+
+void Weights::canonicalize(Family family)
+{
+    static const char *const kDistil[][2] = {
+        {"transformer.layer.", "encoder.layer."}, {".attention.q_lin.", ".attention.self.query."},
+        {".attention.k_lin.", ".attention.self.key."}, {".attention.v_lin.", ".attention.self.value."},
+        {".attention.out_lin.", ".attention.output.dense."}, {".sa_layer_norm.", ".attention.output.LayerNorm."},
+        {".ffn.lin1.", ".intermediate.dense."}, {".ffn.lin2.", ".output.dense."}, {".output_layer_norm.", ".output.LayerNorm."}};
+    static const char *const kAlbert[][2] = {
+        {"encoder.embedding_hidden_mapping_in.", "embeddings.projection."},
+        {"encoder.albert_layer_groups.0.albert_layers.0.", "encoder.layer.0."},
+        {".attention.query.", ".attention.self.query."}, {".attention.key.", ".attention.self.key."},
+        {".attention.value.", ".attention.self.value."}, {".attention.dense.", ".attention.output.dense."},
+        {".attention.LayerNorm.", ".attention.output.LayerNorm."}, {".ffn_output.", ".output.dense."},
+        {".ffn.", ".intermediate.dense."}, {".full_layer_layer_norm.", ".output.LayerNorm."}};
+    for (std::string &n : names) {
+        for (const char *prefix : {"roberta.", "distilbert.", "albert.", "bert."})
+            if (n.rfind(prefix, 0) == 0) n = n.substr(std::strlen(prefix));
+        if (n == "linear.weight" || n == "linear.bias") n = "dense." + n;
+        if (family == Family::DistilBert)
+            for (const auto &r : kDistil) replace_all(n, r[0], r[1]);
+        else if (family == Family::Albert)
+            for (const auto &r : kAlbert) replace_all(n, r[0], r[1]);
+    }
+}
+
+void Weights::append(Weights &&other)
+{
+    for (size_t i = 0; i < other.names.size(); ++i) {
+        names.push_back(std::move(other.names[i]));
+        data.push_back(std::move(other.data[i]));
     }
 }
 
@@ -126,7 +188,16 @@ B200Encoder::B200Encoder(const Architecture &arch, const Weights &weights, Preci
     cfg.normalize = arch.normalize ? 1 : 0;
     cfg.precision = (uint32_t)precision;
     cfg.max_tokens = max_tokens;
-    int32_t rc = mx_embedder_create(&cfg, ts.data(), (uint32_t)ts.size(), device, &handle_);
+    mx_model_ext ext{};
+    ext.pos_offset = arch.pos_offset;
+    ext.no_token_type = arch.family == Family::DistilBert ? 1 : 0;
+    ext.dense_out = arch.dense_out;
+    ext.dense_act = arch.dense_tanh ? MX_ACT_TANH : MX_ACT_IDENTITY;
+    ext.dense_bias = arch.dense_bias ? 1 : 0;
+    ext.ffn_act = arch.ffn_gelu_new ? MX_FFN_GELU_TANH : MX_FFN_GELU_ERF;
+    ext.embed_dim = arch.embed_dim;
+    ext.share_layers = arch.share_layers ? 1 : 0;
+    int32_t rc = mx_embedder_create_ex(&cfg, &ext, ts.data(), (uint32_t)ts.size(), device, &handle_);
     if (rc != MX_OK) {
         const char *m = mx_last_error(nullptr);
         throw EmbeddingError(EmbeddingErrorKind::SetupError, m && *m ? m : ("status " + std::to_string(rc)));
@@ -140,7 +211,7 @@ B200Encoder::~B200Encoder()
 
 std::vector<float> B200Encoder::encode_ids(const TokenBatch &b)
 {
-    std::vector<float> out((size_t)b.B * arch_.hidden);
+    std::vector<float> out((size_t)b.B * arch_.out_dim());
     if (b.B == 0) return out;
     int32_t rc = mx_embedder_encode(handle_, b.ids.data(), b.lens.data(), b.B, b.S, out.data());
     if (rc != MX_OK) {

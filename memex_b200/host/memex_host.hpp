@@ -224,28 +224,44 @@ struct TokenBatch {
 };
 TokenBatch tokenize_batch(const BertTokenizer &tokenizer, const std::vector<std::string> &segments, size_t max_seq_length);
 
+enum class Family { Bert, Roberta, DistilBert, Albert };   // the checkpoint's naming scheme / embedding layout
 struct Architecture {
     uint32_t layers, hidden, heads, ffn, vocab = 30522, max_pos = 512, type_vocab = 2;
     float ln_eps = 1e-12f;
     bool normalize = true;
     uint32_t max_seq_length = 256;   // sentence_bert_config.json: what rust-bert truncates to
+    // the stacks that differ from BERT only around the layers (mx_model_ext in include/memex_b200.h)
+    Family family = Family::Bert;
+    uint32_t pos_offset = 0;         // RoBERTa: positions start at padding_idx + 1 = 2
+    int32_t pad_id = 0;              // RoBERTa: 1
+    uint32_t dense_out = 0;          // sentence-transformers Dense module after pooling (0 = none)
+    bool dense_tanh = false, dense_bias = true;
+    bool ffn_gelu_new = false;       // ALBERT's tanh-form GELU
+    uint32_t embed_dim = 0;          // ALBERT: factorised embedding width (0 = hidden)
+    bool share_layers = false;       // ALBERT: one set of layer weights
+    uint32_t out_dim() const { return dense_out ? dense_out : hidden; }
 };
-std::optional<Architecture> architecture_of(EmbeddingsModelType model);   // the BERT-family members of the enum
+// every member of the enum whose layer is BERT's post-LayerNorm block; SentenceT5Base (a T5 encoder) has none
+std::optional<Architecture> architecture_of(EmbeddingsModelType model);
 
 // named f32 tensors (HF BertModel names); from_safetensors reads a model.safetensors file (F32 / F16 / BF16)
 struct Weights {
     std::vector<std::string> names;
     std::vector<std::vector<float>> data;
     static Weights from_safetensors(const std::string &path);
+    // RoBERTa / DistilBERT / ALBERT checkpoint names -> the BERT names the C ABI takes ("roberta." / "distilbert." /
+    // "albert." / "bert." prefixes dropped, a sentence-transformers Dense module's "linear.*" -> "dense.linear.*")
+    void canonicalize(Family family);
+    void append(Weights &&other);   // e.g. the 2_Dense/model.safetensors of a sentence-transformers checkpoint
 };
 
 // the forward pass: `model.encode(&segments)` (embedding.rs:109) on ids
 class Encoder {
 public:
     virtual ~Encoder() = default;
-    virtual uint32_t hidden() const = 0;
+    virtual uint32_t hidden() const = 0;                     // width of one output row
     virtual uint32_t max_seq_length() const = 0;
-    virtual std::vector<float> encode_ids(const TokenBatch &batch) = 0;   // [B, hidden], unit-norm rows
+    virtual std::vector<float> encode_ids(const TokenBatch &batch) = 0;   // [B, hidden()]; unit-norm rows if the model normalises
 };
 class B200Encoder : public Encoder {
 public:
@@ -253,7 +269,7 @@ public:
     B200Encoder(const Architecture &arch, const Weights &weights, Precision precision = Precision::BF16, int device = 0,
                 uint32_t max_tokens = 0);
     ~B200Encoder() override;
-    uint32_t hidden() const override { return arch_.hidden; }
+    uint32_t hidden() const override { return arch_.out_dim(); }
     uint32_t max_seq_length() const override { return arch_.max_seq_length; }
     std::vector<float> encode_ids(const TokenBatch &batch) override;
 

@@ -224,6 +224,40 @@ static int run_cpu()
     CHECK(architecture_of(EmbeddingsModelType::AllMiniLmL6V2)->layers == 6);
     CHECK(architecture_of(EmbeddingsModelType::AllMiniLmL12V2)->max_seq_length == 128);
     CHECK(!architecture_of(EmbeddingsModelType::SentenceT5Base).has_value());
+    CHECK(architecture_of(EmbeddingsModelType::AllDistilrobertaV1)->pos_offset == 2);
+    CHECK(architecture_of(EmbeddingsModelType::DistiluseBaseMultilingualCased)->out_dim() == 512);
+    CHECK(architecture_of(EmbeddingsModelType::ParaphraseAlbertSmallV2)->embed_dim == 128);
+    {   // checkpoint names of the other stacks -> the BERT names the C ABI takes
+        Weights w;
+        w.names = {"distilbert.transformer.layer.3.attention.q_lin.weight", "transformer.layer.0.ffn.lin2.bias",
+                   "distilbert.transformer.layer.1.sa_layer_norm.weight", "linear.weight"};
+        w.data.resize(w.names.size());
+        w.canonicalize(Family::DistilBert);
+        CHECK(w.names[0] == "encoder.layer.3.attention.self.query.weight");
+        CHECK(w.names[1] == "encoder.layer.0.output.dense.bias");
+        CHECK(w.names[2] == "encoder.layer.1.attention.output.LayerNorm.weight");
+        CHECK(w.names[3] == "dense.linear.weight");
+        Weights a;
+        a.names = {"albert.encoder.embedding_hidden_mapping_in.weight",
+                   "encoder.albert_layer_groups.0.albert_layers.0.attention.query.bias",
+                   "encoder.albert_layer_groups.0.albert_layers.0.ffn.weight",
+                   "encoder.albert_layer_groups.0.albert_layers.0.ffn_output.weight",
+                   "encoder.albert_layer_groups.0.albert_layers.0.full_layer_layer_norm.bias",
+                   "encoder.albert_layer_groups.0.albert_layers.0.attention.LayerNorm.weight"};
+        a.data.resize(a.names.size());
+        a.canonicalize(Family::Albert);
+        CHECK(a.names[0] == "embeddings.projection.weight");
+        CHECK(a.names[1] == "encoder.layer.0.attention.self.query.bias");
+        CHECK(a.names[2] == "encoder.layer.0.intermediate.dense.weight");
+        CHECK(a.names[3] == "encoder.layer.0.output.dense.weight");
+        CHECK(a.names[4] == "encoder.layer.0.output.LayerNorm.bias");
+        CHECK(a.names[5] == "encoder.layer.0.attention.output.LayerNorm.weight");
+        Weights r;
+        r.names = {"roberta.embeddings.word_embeddings.weight"};
+        r.data.resize(1);
+        r.canonicalize(Family::Roberta);
+        CHECK(r.names[0] == "embeddings.word_embeddings.weight");
+    }
     // ---- no CPU path: creating a store without a CUDA device is a ConnectionError
     try {
         auto s = B200Store::new_("/tmp/mx_host_cpu_probe");

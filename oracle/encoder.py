@@ -13,6 +13,11 @@ implement for the all-MiniLM / BERT sentence-transformers models:
       -> masked mean-pool   sum(h * m) / max(sum(m), 1e-9)
       -> L2 normalise       x / max(||x||_2, 1e-12)
 
+and for the other stacks of the enum that share BERT's layer (embedding.rs:24-55): RoBERTa
+(AllDistilrobertaV1: positions from padding_idx + 1), DistilBERT + Dense/Tanh
+(DistiluseBaseMultilingualCased: no token types, no Normalize) and ALBERT (ParaphraseAlbertSmallV2:
+factorised embeddings, one shared layer, gelu_new).  SentenceT5Base is not restated.
+
 Two independent restatements are kept and checked against each other in tests/:
 ``np_encode`` (plain numpy, float64 accumulation available) and ``hf_encode`` (HuggingFace
 ``transformers.BertModel`` on torch CPU fp32 -- the same libtorch kernels ``tch`` dispatches to).
@@ -39,6 +44,15 @@ class EncoderConfig:
     type_vocab: int = 2
     ln_eps: float = 1e-12
     normalize: bool = True
+    # the other stacks of the enum that share BERT's post-LayerNorm layer (embedding.rs:24-55)
+    family: str = "bert"          # "bert" | "roberta" | "distilbert" | "albert"
+    pos_offset: int = 0           # RoBERTa: create_position_ids_from_input_ids -> padding_idx + 1 + i
+    pad_id: int = 0               # RoBERTa: 1
+    dense_out: int = 0            # sentence-transformers Dense module after pooling
+    dense_act: str = "identity"   # "identity" | "tanh"
+    ffn_act: str = "gelu"         # "gelu" | "gelu_new"
+    embed_dim: int = 0            # ALBERT factorised embeddings (0 = hidden)
+    share_layers: bool = False    # ALBERT
 
     def to_dict(self):
         return asdict(self)
@@ -49,19 +63,41 @@ MINILM_L6 = EncoderConfig(layers=6)
 MINILM_L12 = EncoderConfig(layers=12)              # memex default, embedding.rs:64-73
 BERT_BASE = EncoderConfig(layers=12, hidden=768, heads=12, ffn=3072)  # BertBaseNliMeanTokens / e5-base
 TINY = EncoderConfig(layers=2, hidden=64, heads=2, ffn=128, vocab=200, max_pos=64)
+# AllDistilrobertaV1 (one of the three models segment_text accepts, embedding.rs:156-161)
+DISTILROBERTA = EncoderConfig(layers=6, hidden=768, heads=12, ffn=3072, vocab=50265, max_pos=514, type_vocab=1,
+                              ln_eps=1e-5, family="roberta", pos_offset=2, pad_id=1)
+# DistiluseBaseMultilingualCased: DistilBERT + Dense(768 -> 512, Tanh), no Normalize
+DISTILUSE = EncoderConfig(layers=6, hidden=768, heads=12, ffn=3072, vocab=119547, max_pos=512, type_vocab=0,
+                          normalize=False, family="distilbert", dense_out=512, dense_act="tanh")
+# ParaphraseAlbertSmallV2: ALBERT (128-wide embeddings, one shared layer applied 6 times, gelu_new), no Normalize
+ALBERT_SMALL = EncoderConfig(layers=6, hidden=768, heads=12, ffn=3072, vocab=30000, max_pos=512, normalize=False,
+                             family="albert", ffn_act="gelu_new", embed_dim=128, share_layers=True)
+# the same three stacks at a size the numpy restatement runs in milliseconds
+TINY_ROBERTA = EncoderConfig(layers=2, hidden=64, heads=2, ffn=128, vocab=200, max_pos=66, type_vocab=1, ln_eps=1e-5,
+                             family="roberta", pos_offset=2, pad_id=1)
+TINY_DISTILUSE = EncoderConfig(layers=2, hidden=64, heads=2, ffn=128, vocab=200, max_pos=64, type_vocab=0,
+                               normalize=False, family="distilbert", dense_out=48, dense_act="tanh")
+TINY_ALBERT = EncoderConfig(layers=3, hidden=128, heads=4, ffn=256, vocab=200, max_pos=64, normalize=False,
+                            family="albert", ffn_act="gelu_new", embed_dim=64, share_layers=True)
 
 
 def weight_names(cfg: EncoderConfig):
-    """HF ``BertModel(add_pooling_layer=False)`` state_dict names -> shapes."""
+    """Canonical (HF ``BertModel(add_pooling_layer=False)``) state_dict names -> shapes; the other families use the
+    same names (``hf_state_dict`` renames them for the HF model of the family)."""
     H, F = cfg.hidden, cfg.ffn
+    E = cfg.embed_dim or H
     out = {
-        "embeddings.word_embeddings.weight": (cfg.vocab, H),
-        "embeddings.position_embeddings.weight": (cfg.max_pos, H),
-        "embeddings.token_type_embeddings.weight": (cfg.type_vocab, H),
-        "embeddings.LayerNorm.weight": (H,),
-        "embeddings.LayerNorm.bias": (H,),
+        "embeddings.word_embeddings.weight": (cfg.vocab, E),
+        "embeddings.position_embeddings.weight": (cfg.max_pos, E),
     }
-    for i in range(cfg.layers):
+    if cfg.family != "distilbert":
+        out["embeddings.token_type_embeddings.weight"] = (cfg.type_vocab, E)
+    out["embeddings.LayerNorm.weight"] = (E,)
+    out["embeddings.LayerNorm.bias"] = (E,)
+    if E != H:
+        out["embeddings.projection.weight"] = (H, E)
+        out["embeddings.projection.bias"] = (H,)
+    for i in range(1 if cfg.share_layers else cfg.layers):
         p = f"encoder.layer.{i}."
         out.update({
             p + "attention.self.query.weight": (H, H), p + "attention.self.query.bias": (H,),
@@ -73,6 +109,9 @@ def weight_names(cfg: EncoderConfig):
             p + "output.dense.weight": (H, F), p + "output.dense.bias": (H,),
             p + "output.LayerNorm.weight": (H,), p + "output.LayerNorm.bias": (H,),
         })
+    if cfg.dense_out:
+        out["dense.linear.weight"] = (cfg.dense_out, H)
+        out["dense.linear.bias"] = (cfg.dense_out,)
     return out
 
 
@@ -100,7 +139,7 @@ def make_weights(cfg: EncoderConfig, seed: int = 0) -> dict[str, np.ndarray]:
 
 def make_inputs(cfg: EncoderConfig, batch: int, seq: int, seed: int = 7, ragged: bool = False,
                 min_len: int = 16):
-    """ids [B,S] int32 (0 = [PAD] beyond lens), lens [B] int32 -- SURVEY.md section 8d config 3."""
+    """ids [B,S] int32 (cfg.pad_id beyond lens), lens [B] int32 -- SURVEY.md section 8d config 3."""
     rng = np.random.default_rng(seed)
     lo = min(1000, cfg.vocab // 4)
     hi = min(30000, cfg.vocab)
@@ -110,7 +149,7 @@ def make_inputs(cfg: EncoderConfig, batch: int, seq: int, seed: int = 7, ragged:
     else:
         lens = np.full(batch, seq, dtype=np.int32)
     for b in range(batch):
-        ids[b, lens[b]:] = 0
+        ids[b, lens[b]:] = cfg.pad_id
     return ids, lens
 
 
@@ -142,12 +181,15 @@ def np_encode(cfg: EncoderConfig, w: dict, ids: np.ndarray, lens: np.ndarray, dt
     dh = H // nh
     mask = (np.arange(S)[None, :] < lens[:, None])
     x = (W["embeddings.word_embeddings.weight"][ids]
-         + W["embeddings.position_embeddings.weight"][np.arange(S)][None]
-         + W["embeddings.token_type_embeddings.weight"][0][None, None])
+         + W["embeddings.position_embeddings.weight"][np.arange(S) + cfg.pos_offset][None])
+    if cfg.family != "distilbert":
+        x = x + W["embeddings.token_type_embeddings.weight"][0][None, None]
     x = _layer_norm(x, W["embeddings.LayerNorm.weight"], W["embeddings.LayerNorm.bias"], cfg.ln_eps)
+    if cfg.embed_dim and cfg.embed_dim != H:
+        x = x @ W["embeddings.projection.weight"].T + W["embeddings.projection.bias"]
     addmask = np.where(mask, 0.0, -1e30)[:, None, None, :]
     for i in range(cfg.layers):
-        p = f"encoder.layer.{i}."
+        p = "encoder.layer.0." if cfg.share_layers else f"encoder.layer.{i}."
         q = x @ W[p + "attention.self.query.weight"].T + W[p + "attention.self.query.bias"]
         k = x @ W[p + "attention.self.key.weight"].T + W[p + "attention.self.key.bias"]
         v = x @ W[p + "attention.self.value.weight"].T + W[p + "attention.self.value.bias"]
@@ -163,12 +205,19 @@ def np_encode(cfg: EncoderConfig, w: dict, ids: np.ndarray, lens: np.ndarray, dt
         x = _layer_norm(a + x, W[p + "attention.output.LayerNorm.weight"],
                         W[p + "attention.output.LayerNorm.bias"], cfg.ln_eps)
         h = x @ W[p + "intermediate.dense.weight"].T + W[p + "intermediate.dense.bias"]
-        h = 0.5 * h * (1.0 + _erf(h / np.sqrt(2.0)))
+        if cfg.ffn_act == "gelu_new":
+            h = 0.5 * h * (1.0 + np.tanh(np.sqrt(2.0 / np.pi) * (h + 0.044715 * h ** 3)))
+        else:
+            h = 0.5 * h * (1.0 + _erf(h / np.sqrt(2.0)))
         o = h @ W[p + "output.dense.weight"].T + W[p + "output.dense.bias"]
         x = _layer_norm(o + x, W[p + "output.LayerNorm.weight"], W[p + "output.LayerNorm.bias"],
                         cfg.ln_eps)
     m = mask[..., None].astype(dtype)
     pooled = (x * m).sum(1) / np.maximum(m.sum(1), 1e-9)
+    if cfg.dense_out:   # modules.json order: Transformer, Pooling, Dense, (Normalize)
+        pooled = pooled @ W["dense.linear.weight"].T + W["dense.linear.bias"]
+        if cfg.dense_act == "tanh":
+            pooled = np.tanh(pooled)
     if cfg.normalize:
         pooled = pooled / np.maximum(np.linalg.norm(pooled, axis=1, keepdims=True), 1e-12)
     if return_hidden:
@@ -183,24 +232,77 @@ def np_encode(cfg: EncoderConfig, w: dict, ids: np.ndarray, lens: np.ndarray, dt
 _hf_cache: dict = {}
 
 
+def hf_state_dict(cfg: EncoderConfig, w: dict) -> dict:
+    """canonical (BERT) names -> the state_dict names of the HF model of cfg.family (Dense module left out)"""
+    out = {}
+    for name, arr in w.items():
+        if name.startswith("dense.linear."):
+            continue
+        if cfg.family == "distilbert":
+            name = name.replace("encoder.layer.", "transformer.layer.")
+            for a, b in ((".attention.self.query.", ".attention.q_lin."), (".attention.self.key.", ".attention.k_lin."),
+                         (".attention.self.value.", ".attention.v_lin."), (".attention.output.dense.", ".attention.out_lin."),
+                         (".attention.output.LayerNorm.", ".sa_layer_norm."), (".intermediate.dense.", ".ffn.lin1."),
+                         (".output.dense.", ".ffn.lin2."), (".output.LayerNorm.", ".output_layer_norm.")):
+                name = name.replace(a, b)
+        elif cfg.family == "albert":
+            name = name.replace("embeddings.projection.", "encoder.embedding_hidden_mapping_in.")
+            if name.startswith("encoder.layer.0."):
+                name = name.replace("encoder.layer.0.", "encoder.albert_layer_groups.0.albert_layers.0.")
+                for a, b in ((".attention.self.query.", ".attention.query."), (".attention.self.key.", ".attention.key."),
+                             (".attention.self.value.", ".attention.value."), (".attention.output.dense.", ".attention.dense."),
+                             (".attention.output.LayerNorm.", ".attention.LayerNorm."), (".intermediate.dense.", ".ffn."),
+                             (".output.dense.", ".ffn_output."), (".output.LayerNorm.", ".full_layer_layer_norm.")):
+                    name = name.replace(a, b)
+        out[name] = arr
+    return out
+
+
 def hf_model(cfg: EncoderConfig, w: dict):
     import torch
-    from transformers import BertConfig, BertModel
 
     key = (cfg, id(w))
     if key in _hf_cache:
         return _hf_cache[key]
-    hc = BertConfig(vocab_size=cfg.vocab, hidden_size=cfg.hidden, num_hidden_layers=cfg.layers,
-                    num_attention_heads=cfg.heads, intermediate_size=cfg.ffn,
-                    max_position_embeddings=cfg.max_pos, type_vocab_size=cfg.type_vocab,
-                    layer_norm_eps=cfg.ln_eps, hidden_act="gelu", hidden_dropout_prob=0.0,
-                    attention_probs_dropout_prob=0.0)
+    if cfg.family == "bert":
+        from transformers import BertConfig, BertModel
+        hc = BertConfig(vocab_size=cfg.vocab, hidden_size=cfg.hidden, num_hidden_layers=cfg.layers,
+                        num_attention_heads=cfg.heads, intermediate_size=cfg.ffn,
+                        max_position_embeddings=cfg.max_pos, type_vocab_size=cfg.type_vocab,
+                        layer_norm_eps=cfg.ln_eps, hidden_act="gelu", hidden_dropout_prob=0.0,
+                        attention_probs_dropout_prob=0.0)
+        make = lambda: BertModel(hc, add_pooling_layer=False)
+    elif cfg.family == "roberta":
+        from transformers import RobertaConfig, RobertaModel
+        hc = RobertaConfig(vocab_size=cfg.vocab, hidden_size=cfg.hidden, num_hidden_layers=cfg.layers,
+                           num_attention_heads=cfg.heads, intermediate_size=cfg.ffn,
+                           max_position_embeddings=cfg.max_pos, type_vocab_size=cfg.type_vocab,
+                           layer_norm_eps=cfg.ln_eps, hidden_act="gelu", hidden_dropout_prob=0.0,
+                           attention_probs_dropout_prob=0.0, pad_token_id=cfg.pad_id)
+        make = lambda: RobertaModel(hc, add_pooling_layer=False)
+    elif cfg.family == "distilbert":
+        from transformers import DistilBertConfig, DistilBertModel
+        hc = DistilBertConfig(vocab_size=cfg.vocab, dim=cfg.hidden, n_layers=cfg.layers, n_heads=cfg.heads,
+                              hidden_dim=cfg.ffn, max_position_embeddings=cfg.max_pos, activation="gelu",
+                              dropout=0.0, attention_dropout=0.0, sinusoidal_pos_embds=False, pad_token_id=cfg.pad_id)
+        make = lambda: DistilBertModel(hc)
+    elif cfg.family == "albert":
+        from transformers import AlbertConfig, AlbertModel
+        hc = AlbertConfig(vocab_size=cfg.vocab, embedding_size=cfg.embed_dim or cfg.hidden, hidden_size=cfg.hidden,
+                          num_hidden_layers=cfg.layers, num_hidden_groups=1, inner_group_num=1,
+                          num_attention_heads=cfg.heads, intermediate_size=cfg.ffn,
+                          max_position_embeddings=cfg.max_pos, type_vocab_size=cfg.type_vocab,
+                          layer_norm_eps=cfg.ln_eps, hidden_act=cfg.ffn_act, hidden_dropout_prob=0.0,
+                          attention_probs_dropout_prob=0.0, pad_token_id=cfg.pad_id)
+        make = lambda: AlbertModel(hc, add_pooling_layer=False)
+    else:
+        raise ValueError(cfg.family)
     try:
         hc._attn_implementation = "eager"
     except Exception:
         pass
-    model = BertModel(hc, add_pooling_layer=False)
-    sd = {k: torch.from_numpy(v.copy()) for k, v in w.items()}
+    model = make()
+    sd = {k: torch.from_numpy(v.copy()) for k, v in hf_state_dict(cfg, w).items()}
     missing, unexpected = model.load_state_dict(sd, strict=False)
     real_missing = [m for m in missing if "position_ids" not in m and "token_type_ids" not in m]
     if real_missing or unexpected:
@@ -220,10 +322,17 @@ def hf_encode(cfg: EncoderConfig, w: dict, ids: np.ndarray, lens: np.ndarray, th
     t_ids = torch.from_numpy(ids.astype(np.int64))
     mask = (torch.arange(S)[None, :] < torch.from_numpy(lens.astype(np.int64))[:, None]).to(torch.int64)
     with torch.no_grad():
-        h = model(input_ids=t_ids, attention_mask=mask,
-                  token_type_ids=torch.zeros_like(t_ids)).last_hidden_state
+        if cfg.family == "distilbert":
+            h = model(input_ids=t_ids, attention_mask=mask).last_hidden_state
+        else:   # RoBERTa derives its position ids from the pad id inside the model
+            h = model(input_ids=t_ids, attention_mask=mask,
+                      token_type_ids=torch.zeros_like(t_ids)).last_hidden_state
         m = mask[..., None].to(h.dtype)
         pooled = (h * m).sum(1) / m.sum(1).clamp(min=1e-9)
+        if cfg.dense_out:
+            pooled = pooled @ torch.from_numpy(w["dense.linear.weight"]).T + torch.from_numpy(w["dense.linear.bias"])
+            if cfg.dense_act == "tanh":
+                pooled = torch.tanh(pooled)
         if cfg.normalize:
             pooled = torch.nn.functional.normalize(pooled, p=2, dim=1, eps=1e-12)
     return pooled.numpy().astype(np.float32)

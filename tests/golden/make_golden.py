@@ -10,6 +10,9 @@ Run in the build container (CPU):  python tests/golden/make_golden.py
   restatement (ids, scores as f32 bit patterns).
 * encoder_tiny.npz / encoder_l6.npz -- HF transformers BertModel (torch CPU fp32; the libtorch
   kernels tch dispatches to) outputs for seeded weights and inputs (oracle/encoder.py hf_encode).
+* encoder_tiny_{roberta,distiluse,albert}.npz -- the same for HF RobertaModel, DistilBertModel +
+  Dense/Tanh and AlbertModel (AllDistilrobertaV1, DistiluseBaseMultilingualCased,
+  ParaphraseAlbertSmallV2 of the reference's enum).
 
 The reference itself (Rust; rust-bert / hnsw_rs are un-vendored crates) cannot be imported or
 built here, so these are outputs of independent restatements of its published algorithm.
@@ -58,7 +61,14 @@ def main():
         bits[i] = [int(np.float32(s).view(np.uint32)) for _, s in t]
     np.savez(os.path.join(HERE, "search_small.npz"), corpus=c, queries=q, ids=ids, score_bits=bits)
 
-    for name, cfg, B, S, seed in (("encoder_tiny", encoder.TINY, 5, 24, 3), ("encoder_l6", encoder.MINILM_L6, 4, 48, 5)):
+    for name, cfg, B, S, seed in (("encoder_tiny", encoder.TINY, 5, 24, 3), ("encoder_l6", encoder.MINILM_L6, 4, 48, 5),
+                                  # the other stacks of the enum (embedding.rs:24-55): HF RobertaModel / DistilBertModel
+                                  # (+ Dense, Tanh) / AlbertModel outputs
+                                  ("encoder_tiny_roberta", encoder.TINY_ROBERTA, 5, 24, 13),
+                                  ("encoder_tiny_distiluse", encoder.TINY_DISTILUSE, 5, 24, 14),
+                                  ("encoder_tiny_albert", encoder.TINY_ALBERT, 5, 24, 15)):
+        if os.path.exists(os.path.join(HERE, name + ".npz")) and name in ("encoder_tiny", "encoder_l6"):
+            continue   # committed in an earlier pass; the generator is deterministic, the files stay byte-stable
         w = encoder.make_weights(cfg, seed=seed)
         ids_, lens = encoder.make_inputs(cfg, B, S, seed=seed + 100, ragged=True, min_len=3)
         out = encoder.hf_encode(cfg, w, ids_, lens)

@@ -109,16 +109,39 @@ def test_hnsw_parallel_build_matches_serial_quality(oracle_lib):
     assert recalls[0] > 0.9 and recalls[1] > 0.9, recalls
 
 
-@pytest.mark.parametrize("name,cfg", [("encoder_tiny", encoder.TINY), ("encoder_l6", encoder.MINILM_L6)])
+@pytest.mark.parametrize("name,cfg", [("encoder_tiny", encoder.TINY), ("encoder_l6", encoder.MINILM_L6),
+                                      ("encoder_tiny_roberta", encoder.TINY_ROBERTA),
+                                      ("encoder_tiny_distiluse", encoder.TINY_DISTILUSE),
+                                      ("encoder_tiny_albert", encoder.TINY_ALBERT)])
 def test_encoder_restatements_agree_with_golden(name, cfg):
     g = np.load(os.path.join(GOLD, name + ".npz"))
-    assert json.loads(str(g["cfg"])) == cfg.to_dict()
+    stored = json.loads(str(g["cfg"]))   # the first fixtures predate the family fields
+    assert stored == {k: cfg.to_dict()[k] for k in stored}
     w = encoder.make_weights(cfg, seed=int(g["weight_seed"]))
     out_np = encoder.np_encode(cfg, w, g["ids"], g["lens"])          # numpy, f64 accumulation
     np.testing.assert_allclose(out_np, g["out"], atol=2e-5)          # vs HF/torch fp32 golden
-    cos = (out_np * g["out"]).sum(1)
+    cos = (out_np * g["out"]).sum(1) / (np.linalg.norm(out_np, axis=1) * np.linalg.norm(g["out"], axis=1))
     assert (cos > 1 - 1e-6).all()
-    np.testing.assert_allclose(np.linalg.norm(g["out"], axis=1), 1.0, atol=1e-5)
+    assert g["out"].shape[1] == (cfg.dense_out or cfg.hidden)
+    if cfg.normalize:
+        np.testing.assert_allclose(np.linalg.norm(g["out"], axis=1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("cfg", [encoder.TINY_ROBERTA, encoder.TINY_DISTILUSE, encoder.TINY_ALBERT])
+def test_checkpoint_names_of_the_other_stacks_map_onto_the_c_abi_names(cfg):
+    """memex_b200.embedding.canonical_weights (what the host applies to a RoBERTa / DistilBERT / ALBERT checkpoint)
+    inverts the oracle's canonical -> HF renaming, on the real state_dict key set of the HF model."""
+    from memex_b200.embedding import canonical_weights
+    w = encoder.make_weights(cfg, seed=3)
+    model = encoder.hf_model(cfg, w)
+    state = {k: v.numpy() for k, v in model.state_dict().items()}
+    if cfg.dense_out:   # sentence-transformers 2_Dense/ checkpoint names
+        state["linear.weight"], state["linear.bias"] = w["dense.linear.weight"], w["dense.linear.bias"]
+    back = canonical_weights(cfg.family, {"%s.%s" % (cfg.family, k) if not k.startswith("linear.") else k: v
+                                          for k, v in state.items()})
+    assert set(back) == set(w)
+    for k in w:
+        np.testing.assert_array_equal(back[k], w[k])
 
 
 def test_encoder_hf_matches_golden_tiny():
