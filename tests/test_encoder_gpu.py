@@ -207,7 +207,7 @@ def test_other_stacks_of_the_enum_tensor_core_path(name):
         assert out.shape == ref.shape
         assert (cos >= min_cos).all(), (precision, cos.min())
         if not cfg.normalize:   # the scale matters when the model has no Normalize module
-            assert np.abs(out - ref).max() <= (2e-2 if precision == "bf16" else 3e-3) * max(1.0, np.abs(ref).max())
+            assert np.abs(out - ref).max() <= (5e-2 if precision == "bf16" else 5e-3) * max(1.0, np.abs(ref).max())
         e.close()
 
 
