@@ -114,22 +114,35 @@ __device__ __forceinline__ uint32_t pk2(float a, float b)
 
 struct Unit {
     uint32_t b, h, q0, len;
-    bool skip;   // every query row of the tile is padding
+    uint32_t row0;   // first row of the sequence in qkv / ctx: b S (padded layout) or cu[b] (packed layout)
+    bool skip;       // every query row of the tile is padding
 };
-// The sequence length is the only thing a unit reads from global memory before its barriers; every role fetches it ONE
-// UNIT AHEAD (raw_len_of for the next unit at the top of the current one), so its latency never sits between two units.
-__device__ __forceinline__ int32_t raw_len_of(uint32_t u, uint32_t n_units, uint32_t n_qt, uint32_t heads, const int32_t *lens)
+// The sequence length (and, packed, its first row) is the only thing a unit reads from global memory before its
+// barriers; every role fetches it ONE UNIT AHEAD (meta_of for the next unit at the top of the current one), so its
+// latency never sits between two units.
+struct UnitMeta {
+    int32_t raw_len, row0;
+};
+__device__ __forceinline__ UnitMeta meta_of(uint32_t u, uint32_t n_units, uint32_t n_qt, uint32_t heads, uint32_t S,
+                                            const int32_t *lens, const int32_t *cu)
 {
-    return u < n_units ? __ldg(lens + u / (n_qt * heads)) : 0;
+    UnitMeta m{0, 0};
+    if (u < n_units) {
+        const uint32_t b = u / (n_qt * heads);
+        m.raw_len = __ldg(lens + b);
+        m.row0 = cu ? __ldg(cu + b) : (int32_t)(b * S);
+    }
+    return m;
 }
-__device__ __forceinline__ Unit decode_unit(uint32_t u, int32_t raw_len, uint32_t n_qt, uint32_t heads, uint32_t S)
+__device__ __forceinline__ Unit decode_unit(uint32_t u, UnitMeta m, uint32_t n_qt, uint32_t heads, uint32_t S)
 {
     Unit r;
     const uint32_t qt = u % n_qt, bh = u / n_qt;
     r.h = bh % heads;
     r.b = bh / heads;
     r.q0 = qt * kQT;
-    r.len = min((uint32_t)max(raw_len, 0), S);
+    r.len = min((uint32_t)max(m.raw_len, 0), S);
+    r.row0 = (uint32_t)m.row0;
     r.skip = r.q0 >= r.len;
     return r;
 }
@@ -188,7 +201,7 @@ __device__ __forceinline__ void softmax32(const uint32_t (&v)[32], float sc, flo
 template <bool BF16, int DH, int DIAG = 0>
 __global__ void __launch_bounds__(AttCfg<DH>::kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__restrict__ lens, uint16_t *__restrict__ ctx,
-                    uint32_t B, uint32_t S, uint32_t H, uint32_t heads, float scale_log2e)
+                    uint32_t B, uint32_t S, uint32_t H, uint32_t heads, float scale_log2e, const int32_t *__restrict__ cu)
 {
     using Cfg = AttCfg<DH>;
     constexpr uint32_t kSoftmaxWarps = Cfg::kSoftmaxWarps;
@@ -233,15 +246,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__
         const uint32_t row = quarter * 32 + lane;
         const uint32_t t_s = tmem_base + ((quarter * 32u) << 16) + g * kMaxKeys;
         uint32_t it = 0, cc = 0;
-        int32_t raw_len = raw_len_of(blockIdx.x * kGroups + g, n_units, n_qt, heads, lens);
+        const bool packed = cu != nullptr;   // packed layout: rows of padding do not exist, nothing is written for them
+        UnitMeta meta = meta_of(blockIdx.x * kGroups + g, n_units, n_qt, heads, S, lens, cu);
         for (uint32_t u = blockIdx.x * kGroups + g; u < n_units; u += kGroups * gridDim.x) {
-            const Unit un = decode_unit(u, raw_len, n_qt, heads, S);
-            raw_len = raw_len_of(u + kGroups * gridDim.x, n_units, n_qt, heads, lens);
+            const Unit un = decode_unit(u, meta, n_qt, heads, S);
+            meta = meta_of(u + kGroups * gridDim.x, n_units, n_qt, heads, S, lens, cu);
             const uint32_t q = un.q0 + row;
-            uint16_t *orow = ctx + ((size_t)un.b * S + q) * H + (size_t)un.h * DH;
+            uint16_t *orow = ctx + ((size_t)un.row0 + q) * H + (size_t)un.h * DH;
             if (un.skip) {
                 // padding rows are written as zero: the following GEMMs stay finite
-                if (q < S) {
+                if (q < S && !packed) {
 #pragma unroll
                     for (int j = 0; j < DH / 8; ++j) *reinterpret_cast<uint4 *>(orow + j * 8) = make_uint4(0, 0, 0, 0);
                 }
@@ -302,7 +316,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__
             __syncwarp();
             if (lane == 0) mbar_arrive(bg + B_S_EMPTY);   // the tile may be overwritten by the next unit's Q K^T
             const float inv = q < len ? 1.0f / __uint_as_float(sv[0]) : 0.f;
-            if (q < S && !(DIAG & 16)) {
+            if ((packed ? q < len : q < S) && !(DIAG & 16)) {
 #pragma unroll
                 for (int j = 0; j < DH / 8; ++j) {
                     uint4 w;
@@ -322,13 +336,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__
             uint64_t *bg = bars + g * B_PER_GROUP;
             unsigned char *grp = smem + g * Cfg::kGroupBytes;
             uint32_t it = 0;
-            int32_t raw_len = raw_len_of(blockIdx.x * kGroups + g, n_units, n_qt, heads, lens);
+            UnitMeta meta = meta_of(blockIdx.x * kGroups + g, n_units, n_qt, heads, S, lens, cu);
             for (uint32_t u = blockIdx.x * kGroups + g; u < n_units; u += kGroups * gridDim.x) {
-                const Unit un = decode_unit(u, raw_len, n_qt, heads, S);
-                raw_len = raw_len_of(u + kGroups * gridDim.x, n_units, n_qt, heads, lens);
+                const Unit un = decode_unit(u, meta, n_qt, heads, S);
+                meta = meta_of(u + kGroups * gridDim.x, n_units, n_qt, heads, S, lens, cu);
                 if (un.skip) continue;
                 const uint32_t nch = (un.len + kKC - 1) / kKC;
-                const int32_t row0 = (int32_t)(un.b * S);
+                // packed layout: the boxes may run into the next sequence's rows (finite values; keys >= len are masked,
+                // query rows >= len are not stored) or past the end of the buffer (TMA zero fill)
+                const int32_t row0 = (int32_t)un.row0;
                 const int32_t colq = (int32_t)(un.h * DH);
                 // Q and K: free once the previous unit's Q K^T has completed
                 if (it >= 1) mbar_wait(bg + B_S_FULL, (it - 1) & 1);
@@ -362,10 +378,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__
             constexpr uint32_t idesc_sum = make_idesc(kQT, 16, fmt);               // B = ones, K-major
             const uint32_t ones = smem_u32(smem + Cfg::kOnesOff);
             uint32_t it = 0, cc = 0;
-            int32_t raw_len = raw_len_of(blockIdx.x * kGroups + g, n_units, n_qt, heads, lens);
+            UnitMeta meta = meta_of(blockIdx.x * kGroups + g, n_units, n_qt, heads, S, lens, cu);
             for (uint32_t u = blockIdx.x * kGroups + g; u < n_units; u += kGroups * gridDim.x) {
-                const Unit un = decode_unit(u, raw_len, n_qt, heads, S);
-                raw_len = raw_len_of(u + kGroups * gridDim.x, n_units, n_qt, heads, lens);
+                const Unit un = decode_unit(u, meta, n_qt, heads, S);
+                meta = meta_of(u + kGroups * gridDim.x, n_units, n_qt, heads, S, lens, cu);
                 if (un.skip) continue;
                 const uint32_t nch = (un.len + kKC - 1) / kKC;
                 mbar_wait(bg + B_QK_FULL, it & 1);
@@ -429,7 +445,7 @@ bool make_tmap_qkv(CUtensorMap *out, const void *base, uint64_t T, uint64_t H, u
 
 template <bool BF16, int DH>
 cudaError_t launch_at(const void *qkv, const int32_t *lens, void *ctx, uint32_t B, uint32_t S, uint32_t H, uint32_t heads,
-                      int sm_count, cudaStream_t st)
+                      int sm_count, const int32_t *cu, uint32_t n_rows, cudaStream_t st)
 {
     using Cfg = AttCfg<DH>;
     auto kern = attention_tc_kernel<BF16, DH>;
@@ -449,11 +465,11 @@ cudaError_t launch_at(const void *qkv, const int32_t *lens, void *ctx, uint32_t 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     CUtensorMap tm;
-    if (!make_tmap_qkv(&tm, qkv, (uint64_t)B * S, H, DH, BF16)) return cudaErrorInvalidValue;
+    if (!make_tmap_qkv(&tm, qkv, cu ? (uint64_t)n_rows : (uint64_t)B * S, H, DH, BF16)) return cudaErrorInvalidValue;
     const uint32_t n_units = B * heads * ceil_div<uint32_t>(S, kQT);
     const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count, ceil_div<uint32_t>(n_units, kGroups));
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)DH);
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, lens, (uint16_t *)ctx, B, S, H, heads, scale_log2e);
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, lens, (uint16_t *)ctx, B, S, H, heads, scale_log2e, cu);
     count_launch();
     return cudaGetLastError();
 }
@@ -469,15 +485,15 @@ bool attention_tc_supported(uint32_t S, uint32_t H, uint32_t heads)
 
 // 16-bit activations, head_dim 32 or 64, S <= 256 (attention_tc_supported); same contract as launch_attention_mma
 cudaError_t launch_attention_tc(const void *qkv, const int32_t *lens_dev, void *ctx, int act, uint32_t B, uint32_t S,
-                                uint32_t H, uint32_t heads, int sm_count, cudaStream_t st)
+                                uint32_t H, uint32_t heads, int sm_count, const int32_t *cu, uint32_t n_rows, cudaStream_t st)
 {
-    if (act == ACT_F32 || !attention_tc_supported(S, H, heads) || B == 0) return cudaErrorInvalidValue;
+    if (act == ACT_F32 || !attention_tc_supported(S, H, heads) || B == 0 || (cu && n_rows == 0)) return cudaErrorInvalidValue;
     const bool bf = act == ACT_BF16;
     if (H / heads == 32)
-        return bf ? launch_at<true, 32>(qkv, lens_dev, ctx, B, S, H, heads, sm_count, st)
-                  : launch_at<false, 32>(qkv, lens_dev, ctx, B, S, H, heads, sm_count, st);
-    return bf ? launch_at<true, 64>(qkv, lens_dev, ctx, B, S, H, heads, sm_count, st)
-              : launch_at<false, 64>(qkv, lens_dev, ctx, B, S, H, heads, sm_count, st);
+        return bf ? launch_at<true, 32>(qkv, lens_dev, ctx, B, S, H, heads, sm_count, cu, n_rows, st)
+                  : launch_at<false, 32>(qkv, lens_dev, ctx, B, S, H, heads, sm_count, cu, n_rows, st);
+    return bf ? launch_at<true, 64>(qkv, lens_dev, ctx, B, S, H, heads, sm_count, cu, n_rows, st)
+              : launch_at<false, 64>(qkv, lens_dev, ctx, B, S, H, heads, sm_count, cu, n_rows, st);
 }
 
 }  // namespace mx

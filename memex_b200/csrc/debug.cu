@@ -61,7 +61,7 @@ int32_t mx_debug_attention(const void *qkv, const int32_t *lens_dev, void *ctx, 
             e = cudaGetDeviceProperties(&prop, device);
             if (e == cudaSuccess && impl == 2)
                 e = attention_tc_supported(S, H, heads)
-                        ? launch_attention_tc(qkv, lens_dev, ctx, act, B, S, H, heads, prop.multiProcessorCount, nullptr)
+                        ? launch_attention_tc(qkv, lens_dev, ctx, act, B, S, H, heads, prop.multiProcessorCount, nullptr, 0, nullptr)
                         : cudaErrorNotSupported;
             else if (e == cudaSuccess)
                 e = attention_tc4_supported(S, H, heads)

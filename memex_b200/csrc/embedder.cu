@@ -53,7 +53,8 @@ struct mx_embedder : HandleBase {
     std::vector<LayerWeights> layers;
     // workspaces sized for cfg.max_tokens
     void *x = nullptr, *x1 = nullptr, *qkv = nullptr, *ctx = nullptr, *hh = nullptr;
-    int32_t *ids_dev = nullptr, *lens_dev = nullptr;
+    int32_t *ids_dev = nullptr, *lens_dev = nullptr;   // lens_dev: [max_seqs] lengths, then [max_seqs + 1] row offsets
+    bool packing = true;        // MX_ENCODER_NO_PACKING=1 keeps the padded layout for ragged batches too (A/B measurements)
     float *out_dev = nullptr;
     uint32_t max_seqs = 0;
     void *pinned = nullptr;
@@ -150,11 +151,12 @@ int32_t run_gemm(mx_embedder *e, const void *A, const void *W, const float *bias
 }
 
 // one forward pass over B sequences of S tokens already in ids_dev / lens_dev
-int32_t forward(mx_embedder *e, const int32_t *ids_dev, const int32_t *lens_dev, uint32_t B, uint32_t S, float *out_dev,
-                cudaStream_t st)
+// cu_dev / n_rows: packed layout (encoder.cuh) -- the activations hold only the n_rows real tokens; nullptr = padded
+int32_t forward(mx_embedder *e, const int32_t *ids_dev, const int32_t *lens_dev, const int32_t *cu_dev, uint32_t n_rows,
+                uint32_t B, uint32_t S, float *out_dev, cudaStream_t st)
 {
     const mx_model_cfg &c = e->cfg;
-    const uint32_t T = B * S, H = c.hidden, F = c.ffn;
+    const uint32_t T = cu_dev ? n_rows : B * S, H = c.hidden, F = c.ffn;
     const uint32_t E = e->ext.embed_dim ? e->ext.embed_dim : H;
     const int epi_ffn = e->ext.ffn_act == MX_FFN_GELU_TANH ? EPI_BIAS_GELU_TANH : EPI_BIAS_GELU;
     // RoBERTa numbers its positions from padding_idx + 1: token i of a right-padded row reads row i + pos_offset
@@ -162,8 +164,8 @@ int32_t forward(mx_embedder *e, const int32_t *ids_dev, const int32_t *lens_dev,
     int32_t rc;
     e->timer.begin(st, 1);
     MX_CUDA(e, MX_ERR_ENCODE,
-            launch_embed_ln(ids_dev, e->word, pos, e->type0, e->emb_g, e->emb_b, c.ln_eps, E == H ? e->x : e->ctx, e->act, T, S, E,
-                            c.vocab, st));
+            launch_embed_ln(ids_dev, e->word, pos, e->type0, e->emb_g, e->emb_b, c.ln_eps, E == H ? e->x : e->ctx, e->act, B * S, S,
+                            E, c.vocab, cu_dev, st));
     e->timer.end(st);
     // ALBERT: factorised embeddings, projected to the hidden width
     if (E != H && (rc = run_gemm(e, e->ctx, e->proj_w, e->proj_b, nullptr, nullptr, nullptr, e->x, T, H, E, EPI_BIAS, st)) != MX_OK)
@@ -177,7 +179,7 @@ int32_t forward(mx_embedder *e, const int32_t *ids_dev, const int32_t *lens_dev,
         else if (e->attention_tc4 && attention_tc4_supported(S, H, c.heads))
             MX_CUDA(e, MX_ERR_ENCODE, launch_attention_tc4(e->qkv, lens_dev, e->ctx, e->act, B, S, H, c.heads, e->sm_count, st));
         else if (e->attention_tc && attention_tc_supported(S, H, c.heads))
-            MX_CUDA(e, MX_ERR_ENCODE, launch_attention_tc(e->qkv, lens_dev, e->ctx, e->act, B, S, H, c.heads, e->sm_count, st));
+            MX_CUDA(e, MX_ERR_ENCODE, launch_attention_tc(e->qkv, lens_dev, e->ctx, e->act, B, S, H, c.heads, e->sm_count, cu_dev, n_rows, st));
         else
             MX_CUDA(e, MX_ERR_ENCODE, launch_attention_mma(e->qkv, lens_dev, e->ctx, e->act, B, S, H, c.heads, st));
         e->timer.end(st);
@@ -188,14 +190,37 @@ int32_t forward(mx_embedder *e, const int32_t *ids_dev, const int32_t *lens_dev,
     e->timer.begin(st, 1);
     if (e->ext.dense_out) {
         // Pooling -> Dense -> (Normalize): the order of the sentence-transformers module list
-        MX_CUDA(e, MX_ERR_ENCODE, launch_pool_normalize(e->x, e->act, lens_dev, e->pooled_dev, B, S, H, 0, st));
+        MX_CUDA(e, MX_ERR_ENCODE, launch_pool_normalize(e->x, e->act, lens_dev, e->pooled_dev, B, S, H, 0, cu_dev, st));
         MX_CUDA(e, MX_ERR_ENCODE,
                 launch_dense_tail(e->pooled_dev, e->dense_w, e->dense_b, out_dev, B, H, e->ext.dense_out, e->ext.dense_act,
                                   c.normalize, st));
     } else {
-        MX_CUDA(e, MX_ERR_ENCODE, launch_pool_normalize(e->x, e->act, lens_dev, out_dev, B, S, H, c.normalize, st));
+        MX_CUDA(e, MX_ERR_ENCODE, launch_pool_normalize(e->x, e->act, lens_dev, out_dev, B, S, H, c.normalize, cu_dev, st));
     }
     e->timer.end(st);
+    return MX_OK;
+}
+
+// Uploads the lengths of sequences [b0, b0 + nb) and, when the batch has padding to drop and the tcgen05 attention
+// kernel serves the shape, their row offsets: *cu_dev != nullptr selects the packed layout (encoder.cuh) for this chunk.
+int32_t stage_lengths(mx_embedder *e, const int32_t *lens, uint32_t nb, uint32_t S, cudaStream_t st, const int32_t **cu_dev,
+                      uint32_t *n_rows)
+{
+    *cu_dev = nullptr;
+    *n_rows = nb * S;
+    MX_CUDA(e, MX_ERR_ENCODE, cudaMemcpyAsync(e->lens_dev, lens, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (!e->packing || e->act == ACT_F32 || !e->attention_tc || e->attention_tc4 ||
+        !attention_tc_supported(S, e->cfg.hidden, e->cfg.heads))
+        return MX_OK;
+    std::vector<int32_t> cu(nb + 1);
+    cu[0] = 0;
+    for (uint32_t b = 0; b < nb; ++b) cu[b + 1] = cu[b] + (int32_t)std::min<uint32_t>((uint32_t)std::max(lens[b], 0), S);
+    const uint32_t real = (uint32_t)cu[nb];
+    if (real == 0 || real >= nb * S) return MX_OK;   // nothing to drop (or nothing at all: the padded path writes the zeros)
+    int32_t *dst = e->lens_dev + e->max_seqs;
+    MX_CUDA(e, MX_ERR_ENCODE, cudaMemcpyAsync(dst, cu.data(), (nb + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    *cu_dev = dst;
+    *n_rows = real;
     return MX_OK;
 }
 
@@ -270,6 +295,7 @@ int32_t mx_embedder_create_ex(const mx_model_cfg *cfg, const mx_model_ext *ext_i
     e->sm_count = prop.multiProcessorCount;
     e->attention_tc = getenv("MX_ATTENTION_MMA") == nullptr;
     e->attention_tc4 = e->attention_tc && getenv("MX_ATTENTION_TC4") != nullptr;
+    e->packing = getenv("MX_ENCODER_NO_PACKING") == nullptr;
     e->act = act;
     auto bail = [&](int32_t rc) {
         g_last_error = e->last_error;
@@ -383,7 +409,7 @@ int32_t mx_embedder_create_ex(const mx_model_cfg *cfg, const mx_model_ext *ext_i
     e->hh = ws;
     e->max_seqs = (uint32_t)std::min<uint64_t>(T, 8192);
     if ((rc = dev_alloc(e, &e->ids_dev, T)) != MX_OK) return bail(rc);
-    if ((rc = dev_alloc(e, &e->lens_dev, e->max_seqs)) != MX_OK) return bail(rc);
+    if ((rc = dev_alloc(e, &e->lens_dev, 2 * (uint64_t)e->max_seqs + 1)) != MX_OK) return bail(rc);
     if ((rc = dev_alloc(e, &e->out_dev, (uint64_t)e->max_seqs * e->out_dim)) != MX_OK) return bail(rc);
     if (ext.dense_out && (rc = dev_alloc(e, &e->pooled_dev, (uint64_t)e->max_seqs * H)) != MX_OK) return bail(rc);
     if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess)
@@ -418,8 +444,11 @@ int32_t mx_embedder_encode_device(mx_embedder *e, const int32_t *ids_dev, const 
     const uint32_t chunk = std::min(e->cfg.max_tokens / S, e->max_seqs);
     for (uint32_t b0 = 0; b0 < B; b0 += chunk) {
         const uint32_t nb = std::min(chunk, B - b0);
-        MX_CUDA(e, MX_ERR_ENCODE, cudaMemcpyAsync(e->lens_dev, lens + b0, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        int32_t rc = forward(e, ids_dev + (size_t)b0 * S, e->lens_dev, nb, S, out_dev + (size_t)b0 * e->out_dim, st);
+        const int32_t *cu_dev = nullptr;
+        uint32_t n_rows = 0;
+        int32_t rc = stage_lengths(e, lens + b0, nb, S, st, &cu_dev, &n_rows);
+        if (rc != MX_OK) return rc;
+        rc = forward(e, ids_dev + (size_t)b0 * S, e->lens_dev, cu_dev, n_rows, nb, S, out_dev + (size_t)b0 * e->out_dim, st);
         if (rc != MX_OK) return rc;
         if (b0 + chunk < B) MX_CUDA(e, MX_ERR_ENCODE, cudaStreamSynchronize(st));  // lens_dev is reused
     }
@@ -452,8 +481,11 @@ int32_t mx_embedder_encode(mx_embedder *e, const int32_t *ids, const int32_t *le
         const uint32_t nb = std::min(chunk, B - b0);
         memcpy(pin_ids, ids + (size_t)b0 * S, (size_t)nb * S * 4);
         MX_CUDA(e, MX_ERR_ENCODE, cudaMemcpyAsync(e->ids_dev, pin_ids, (size_t)nb * S * 4, cudaMemcpyHostToDevice, e->stream));
-        MX_CUDA(e, MX_ERR_ENCODE, cudaMemcpyAsync(e->lens_dev, lens + b0, nb * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-        int32_t rc = forward(e, e->ids_dev, e->lens_dev, nb, S, e->out_dev, e->stream);
+        const int32_t *cu_dev = nullptr;
+        uint32_t n_rows = 0;
+        int32_t rc = stage_lengths(e, lens + b0, nb, S, e->stream, &cu_dev, &n_rows);
+        if (rc != MX_OK) return rc;
+        rc = forward(e, e->ids_dev, e->lens_dev, cu_dev, n_rows, nb, S, e->out_dev, e->stream);
         if (rc != MX_OK) return rc;
         MX_CUDA(e, MX_ERR_ENCODE, cudaMemcpyAsync(pin_out, e->out_dev, (size_t)nb * H * 4, cudaMemcpyDeviceToHost, e->stream));
         cudaError_t ce = cudaStreamSynchronize(e->stream);

@@ -9,10 +9,14 @@ namespace mx {
 enum ActType { ACT_F32 = 0, ACT_BF16 = 1, ACT_F16 = 2 };
 inline size_t act_size(int act) { return act == ACT_F32 ? 4 : 2; }
 
-// K4: x[t, :] = LayerNorm(word[ids[t]] + pos[t % S] + type[0])
+// PACKED LAYOUT.  ids arrive padded [B, S]; when `cu` ([B + 1] prefix sums of the clamped lengths, device memory) is not
+// null the activations are stored without the padding -- token i of sequence b in row cu[b] + i of [cu[B], H] -- so the
+// GEMMs only see real tokens.  cu == nullptr is the padded layout (row b S + i).
+
+// K4: x[row, :] = LayerNorm(word[ids[t]] + pos[t % S] + type[0]) for the padded token index t = b S + i
 cudaError_t launch_embed_ln(const int32_t *ids, const float *word, const float *pos, const float *type0,
                             const float *gamma, const float *beta, float eps, void *x, int act, uint32_t n_tokens,
-                            uint32_t S, uint32_t H, uint32_t vocab, cudaStream_t st);
+                            uint32_t S, uint32_t H, uint32_t vocab, const int32_t *cu, cudaStream_t st);
 
 // K6 (CUDA-core version): ctx = softmax(q k^T / sqrt(dh) + mask(lens)) v, from the fused qkv buffer
 // [T, 3H] (q | k | v, heads contiguous inside each).  Rows at or beyond lens[b] are written as zero.
@@ -25,8 +29,9 @@ cudaError_t launch_attention_mma(const void *qkv, const int32_t *lens_dev, void 
 
 // K6 (tcgen05 version, attention_tc.cu): same contract; head_dim 32 or 64 and S <= 256 only
 bool attention_tc_supported(uint32_t S, uint32_t H, uint32_t heads);
+// (cu, n_rows): packed layout, qkv / ctx have n_rows = cu[B] rows; cu == nullptr: padded, B S rows
 cudaError_t launch_attention_tc(const void *qkv, const int32_t *lens_dev, void *ctx, int act, uint32_t B, uint32_t S,
-                                uint32_t H, uint32_t heads, int sm_count, cudaStream_t st);
+                                uint32_t H, uint32_t heads, int sm_count, const int32_t *cu, uint32_t n_rows, cudaStream_t st);
 
 // K6 (tcgen05, four-stream form, attention_tc4.cu): same contract; head_dim 32 and S <= 256 only
 bool attention_tc4_supported(uint32_t S, uint32_t H, uint32_t heads);
@@ -39,7 +44,7 @@ cudaError_t launch_add_ln_f32(const float *y, const float *residual, const float
 
 // K10: masked mean-pool over the first lens[b] tokens, optional L2 normalise -> out [B, H] f32
 cudaError_t launch_pool_normalize(const void *x, int act, const int32_t *lens_dev, float *out, uint32_t B, uint32_t S,
-                                  uint32_t H, uint32_t normalize, cudaStream_t st);
+                                  uint32_t H, uint32_t normalize, const int32_t *cu, cudaStream_t st);
 
 // sentence-transformers Dense module after pooling: out[b, :] = act(W pooled[b, :] + bias) (act 1 = tanh), optional L2
 // normalise; W [N, H] f32, bias may be null

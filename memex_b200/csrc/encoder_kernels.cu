@@ -77,11 +77,17 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int32_t *__restrict
                                                        const float *__restrict__ pos, const float *__restrict__ type0,
                                                        const float *__restrict__ gamma, const float *__restrict__ beta,
                                                        float eps, typename Act<ACT>::T *__restrict__ x, uint32_t n_tokens,
-                                                       uint32_t S, uint32_t H, uint32_t vocab)
+                                                       uint32_t S, uint32_t H, uint32_t vocab, const int32_t *__restrict__ cu)
 {
     const uint32_t t = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
     if (t >= n_tokens) return;
     const uint32_t lane = lane_id();
+    uint32_t orow = t;   // packed layout (cu != null): token i of sequence b goes to row cu[b] + i, padding is dropped
+    if (cu) {
+        const int32_t lo = cu[t / S], hi = cu[t / S + 1];
+        if ((int32_t)(t % S) >= hi - lo) return;
+        orow = (uint32_t)lo + t % S;
+    }
     uint32_t id = (uint32_t)ids[t];
     if (id >= vocab) id = 0;  // out-of-vocabulary ids read the [PAD] row instead of faulting
     const float *wr = word + (size_t)id * H;
@@ -97,7 +103,7 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int32_t *__restrict
 #pragma unroll
     for (int i = 0; i < kMaxHPerLane; ++i) {
         const uint32_t c = lane + 32 * i;
-        if (c < H) Act<ACT>::st(x + (size_t)t * H + c, (vals[i] - mean) * rstd * gamma[c] + beta[c]);
+        if (c < H) Act<ACT>::st(x + (size_t)orow * H + c, (vals[i] - mean) * rstd * gamma[c] + beta[c]);
     }
 }
 
@@ -107,12 +113,18 @@ __global__ void __launch_bounds__(256) embed_ln_vec_kernel(const int32_t *__rest
                                                            const float *__restrict__ pos, const float *__restrict__ type0,
                                                            const float *__restrict__ gamma, const float *__restrict__ beta,
                                                            float eps, typename Act<ACT>::T *__restrict__ x, uint32_t n_tokens,
-                                                           uint32_t S, uint32_t vocab)
+                                                           uint32_t S, uint32_t vocab, const int32_t *__restrict__ cu)
 {
     constexpr uint32_t H = 128 * V;
     const uint32_t t = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
     if (t >= n_tokens) return;
     const uint32_t lane = lane_id();
+    uint32_t orow = t;   // packed layout: see embed_ln_kernel
+    if (cu) {
+        const int32_t lo = cu[t / S], hi = cu[t / S + 1];
+        if ((int32_t)(t % S) >= hi - lo) return;
+        orow = (uint32_t)lo + t % S;
+    }
     uint32_t id = (uint32_t)ids[t];
     if (id >= vocab) id = 0;
     const float4 *wr = reinterpret_cast<const float4 *>(word + (size_t)id * H);
@@ -138,7 +150,7 @@ __global__ void __launch_bounds__(256) embed_ln_vec_kernel(const int32_t *__rest
     for (int i = 0; i < V; ++i) {
         const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma) + lane + 32 * i);
         const float4 b = __ldg(reinterpret_cast<const float4 *>(beta) + lane + 32 * i);
-        typename Act<ACT>::T *o = x + (size_t)t * H + (lane + 32 * i) * 4;
+        typename Act<ACT>::T *o = x + (size_t)orow * H + (lane + 32 * i) * 4;
         const float y0 = (v[i].x - mean) * rstd * g.x + b.x, y1 = (v[i].y - mean) * rstd * g.y + b.y;
         const float y2 = (v[i].z - mean) * rstd * g.z + b.z, y3 = (v[i].w - mean) * rstd * g.w + b.w;
         if constexpr (ACT == ACT_F32) {
@@ -157,13 +169,13 @@ __global__ void __launch_bounds__(256) embed_ln_vec_kernel(const int32_t *__rest
 
 cudaError_t launch_embed_ln(const int32_t *ids, const float *word, const float *pos, const float *type0,
                             const float *gamma, const float *beta, float eps, void *x, int act, uint32_t n_tokens,
-                            uint32_t S, uint32_t H, uint32_t vocab, cudaStream_t st)
+                            uint32_t S, uint32_t H, uint32_t vocab, const int32_t *cu, cudaStream_t st)
 {
     if (H > 32 * kMaxHPerLane) return cudaErrorInvalidValue;
     const unsigned grid = ceil_div<uint32_t>(n_tokens, 8);
 #define MX_LV(A, V)                                                                                                     \
     embed_ln_vec_kernel<A, V><<<grid, 256, 0, st>>>(ids, word, pos, type0, gamma, beta, eps, (typename Act<A>::T *)x, \
-                                                    n_tokens, S, vocab)
+                                                    n_tokens, S, vocab, cu)
     if (H == 384 || H == 768) {
         if (act == ACT_F32) { if (H == 384) MX_LV(ACT_F32, 3); else MX_LV(ACT_F32, 6); }
         else if (act == ACT_BF16) { if (H == 384) MX_LV(ACT_BF16, 3); else MX_LV(ACT_BF16, 6); }
@@ -174,7 +186,7 @@ cudaError_t launch_embed_ln(const int32_t *ids, const float *word, const float *
 #undef MX_LV
 #define MX_L(A)                                                                                              \
     embed_ln_kernel<A><<<grid, 256, 0, st>>>(ids, word, pos, type0, gamma, beta, eps, (typename Act<A>::T *)x, \
-                                             n_tokens, S, H, vocab)
+                                             n_tokens, S, H, vocab, cu)
     if (act == ACT_F32) MX_L(ACT_F32);
     else if (act == ACT_BF16) MX_L(ACT_BF16);
     else MX_L(ACT_F16);
@@ -374,13 +386,15 @@ cudaError_t launch_add_ln_f32(const float *y, const float *residual, const float
 template <int ACT>
 __global__ void __launch_bounds__(256) pool_normalize_kernel(const typename Act<ACT>::T *__restrict__ x,
                                                              const int32_t *__restrict__ lens, float *__restrict__ out,
-                                                             uint32_t S, uint32_t H, uint32_t normalize)
+                                                             uint32_t S, uint32_t H, uint32_t normalize,
+                                                             const int32_t *__restrict__ cu)
 {
     __shared__ float part[8][1024];   // H <= 1024
     __shared__ float red[8];
     __shared__ float inv_s;
     const uint32_t b = blockIdx.x;
     const uint32_t len = min((uint32_t)max(lens[b], 0), S);
+    const size_t row0 = cu ? (size_t)cu[b] : (size_t)b * S;   // packed layout: the sequence starts at row cu[b]
     const float denom = fmaxf((float)len, 1e-9f);   // sentence-transformers Pooling: clamp(sum_mask, 1e-9)
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     if constexpr (ACT != ACT_F32) {
@@ -397,7 +411,7 @@ __global__ void __launch_bounds__(256) pool_normalize_kernel(const typename Act<
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t t = t0 + 8 * k;
-                const uint4 *row = reinterpret_cast<const uint4 *>(x + ((size_t)b * S + min(t, len - 1)) * H);
+                const uint4 *row = reinterpret_cast<const uint4 *>(x + (row0 + min(t, len - 1)) * H);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const uint32_t ch = lane + 32 * i;
@@ -425,7 +439,7 @@ __global__ void __launch_bounds__(256) pool_normalize_kernel(const typename Act<
 #pragma unroll
         for (int i = 0; i < kMaxHPerLane; ++i) acc[i] = 0.f;
         for (uint32_t t = warp; t < len; t += 8) {
-            const typename Act<ACT>::T *row = x + ((size_t)b * S + t) * H;
+            const typename Act<ACT>::T *row = x + (row0 + t) * H;
 #pragma unroll
             for (int i = 0; i < kMaxHPerLane; ++i) {
                 const uint32_t c = lane + 32 * i;
@@ -469,15 +483,15 @@ __global__ void __launch_bounds__(256) pool_normalize_kernel(const typename Act<
 }
 
 cudaError_t launch_pool_normalize(const void *x, int act, const int32_t *lens_dev, float *out, uint32_t B, uint32_t S,
-                                  uint32_t H, uint32_t normalize, cudaStream_t st)
+                                  uint32_t H, uint32_t normalize, const int32_t *cu, cudaStream_t st)
 {
     if (H > 1024) return cudaErrorInvalidValue;
     if (act == ACT_F32)
-        pool_normalize_kernel<ACT_F32><<<B, 256, 0, st>>>((const float *)x, lens_dev, out, S, H, normalize);
+        pool_normalize_kernel<ACT_F32><<<B, 256, 0, st>>>((const float *)x, lens_dev, out, S, H, normalize, cu);
     else if (act == ACT_BF16)
-        pool_normalize_kernel<ACT_BF16><<<B, 256, 0, st>>>((const __nv_bfloat16 *)x, lens_dev, out, S, H, normalize);
+        pool_normalize_kernel<ACT_BF16><<<B, 256, 0, st>>>((const __nv_bfloat16 *)x, lens_dev, out, S, H, normalize, cu);
     else
-        pool_normalize_kernel<ACT_F16><<<B, 256, 0, st>>>((const __half *)x, lens_dev, out, S, H, normalize);
+        pool_normalize_kernel<ACT_F16><<<B, 256, 0, st>>>((const __half *)x, lens_dev, out, S, H, normalize, cu);
     count_launch();
     return cudaGetLastError();
 }

@@ -157,6 +157,37 @@ def test_tensor_core_paths_vs_oracle(precision, min_cos, max_abs):
     assert ((out * out32).sum(1) >= min_cos).all()
 
 
+@pytest.mark.parametrize("precision", ["bf16", "f16"])
+def test_packed_layout_matches_padded_layout_and_oracle(precision, monkeypatch):
+    """Ragged batches run without their padding (token i of sequence b in row cu[b] + i, encoder.cuh): same rows, same
+    arithmetic per row, so the result must equal the padded layout's (MX_ENCODER_NO_PACKING=1) and the oracle's."""
+    cfg = enc_oracle.MINILM_L6
+    w = enc_oracle.make_weights(cfg, seed=51)
+    ids, lens = enc_oracle.make_inputs(cfg, 9, 160, seed=52, ragged=True, min_len=2)
+    lens[0], lens[3], lens[8] = 160, 1, 129          # a full row, a single token, one key past a 128-row tile
+    for b in range(9):
+        ids[b, lens[b]:] = 0
+    ref = enc_oracle.hf_encode(cfg, w, ids, lens)
+    e = B200Encoder(arch_of(cfg), w, precision=precision, max_tokens=5 * 160)     # two chunks of 5 and 4 sequences
+    out = e.encode_ids(ids, lens)
+    monkeypatch.setenv("MX_ENCODER_NO_PACKING", "1")
+    e_pad = B200Encoder(arch_of(cfg), w, precision=precision, max_tokens=5 * 160)
+    monkeypatch.delenv("MX_ENCODER_NO_PACKING")
+    out_pad = e_pad.encode_ids(ids, lens)
+    print(f"packed vs padded ({precision}): max abs diff {np.abs(out - out_pad).max():.2e}")
+    np.testing.assert_allclose(out, out_pad, atol=1e-6)
+    assert ((out * ref).sum(1) >= (1 - 2e-4 if precision == "bf16" else 1 - 1e-5)).all()
+    # garbage in the padded tail of the ids must not matter, and an empty sequence gives a zero row in both layouts
+    ids2 = ids.copy()
+    ids2[1, lens[1]:] = 777
+    np.testing.assert_array_equal(e.encode_ids(ids2, lens), out)
+    lens0 = lens.copy()
+    lens0[4] = 0
+    out0, out0_pad = e.encode_ids(ids, lens0), e_pad.encode_ids(ids, lens0)
+    assert np.abs(out0[4]).max() == 0.0 and np.abs(out0_pad[4]).max() == 0.0
+    np.testing.assert_allclose(np.delete(out0, 4, 0), np.delete(out, 4, 0), atol=1e-6)
+
+
 def test_encode_errors():
     cfg = enc_oracle.TINY
     w = enc_oracle.make_weights(cfg, seed=1)
