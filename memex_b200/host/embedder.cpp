@@ -225,7 +225,7 @@ std::vector<float> B200Encoder::encode_ids(const TokenBatch &b)
 // SentenceEmbedder
 // ------------------------------------------------------------------------------------------------
 std::shared_ptr<SentenceEmbedder> SentenceEmbedder::spawn(const ModelConfig &model_config, std::shared_ptr<Encoder> encoder,
-                                                          std::shared_ptr<BertTokenizer> tokenizer)
+                                                          std::shared_ptr<Tokenizer> tokenizer)
 {
     std::shared_ptr<SentenceEmbedder> e(new SentenceEmbedder());
     e->handle_ = std::thread([p = e.get(), model_config, encoder, tokenizer] { p->runner(model_config, encoder, tokenizer); });
@@ -243,7 +243,7 @@ SentenceEmbedder::~SentenceEmbedder()
     if (handle_.joinable()) handle_.join();
 }
 
-void SentenceEmbedder::runner(ModelConfig model_config, std::shared_ptr<Encoder> encoder, std::shared_ptr<BertTokenizer> tokenizer)
+void SentenceEmbedder::runner(ModelConfig model_config, std::shared_ptr<Encoder> encoder, std::shared_ptr<Tokenizer> tokenizer)
 {
     while (true) {
         Message msg;

@@ -186,21 +186,32 @@ struct ModelConfig {   // embedding.rs:57-73
     size_t stride = 86;   // overlap roughly a third of the previous text
 };
 
+// What segment_text / the embedder need from `tokenizers::Tokenizer` (embedding.rs:163-195): ids without and with the
+// model's special tokens, decoding back to text, and truncation windows.
+class Tokenizer {
+public:
+    virtual ~Tokenizer() = default;
+    virtual std::vector<int32_t> encode(const std::string &text, bool add_special_tokens) const = 0;
+    virtual std::string decode(const std::vector<int32_t> &ids, bool skip_special_tokens) const = 0;
+    // Tokenizer::with_truncation(max_length, stride) + encode(text, false): the first window and the overflowing ones
+    std::vector<std::vector<int32_t>> encode_windows(const std::string &text, size_t max_length, size_t stride) const;
+
+    int32_t pad_id = 0, cls_id = 101, sep_id = 102;   // [PAD] [CLS] [SEP]; RoBERTa: <pad> 1, <s> 0, </s> 2
+};
+
 // BERT WordPiece tokenizer (what `tokenizers` builds from the models' tokenizer.json: BertNormalizer(clean_text,
 // handle_chinese_chars, strip_accents, lowercase) -> BertPreTokenizer -> WordPiece("##", "[UNK]", 100) with the
-// WordPiece decoder, cleanup = true).  Accent stripping / lower-casing cover ASCII, Latin-1 Supplement, Latin
-// Extended-A, Greek and Cyrillic; other scripts pass through unchanged (no Unicode tables in this image).
-class BertTokenizer {
+// WordPiece decoder, cleanup = true).  Accent stripping / lower-casing cover the BMP (tables generated from Python's
+// unicodedata, gen_unicode_tables.py).
+class BertTokenizer : public Tokenizer {
 public:
     static std::shared_ptr<BertTokenizer> from_vocab_file(const std::string &vocab_txt, bool lowercase = true);
     static std::shared_ptr<BertTokenizer> from_vocab(const std::vector<std::string> &tokens, bool lowercase = true);
 
-    std::vector<int32_t> encode(const std::string &text, bool add_special_tokens) const;
-    std::string decode(const std::vector<int32_t> &ids, bool skip_special_tokens) const;
-    // Tokenizer::with_truncation(max_length, stride) + encode(text, false): the first window and the overflowing ones
-    std::vector<std::vector<int32_t>> encode_windows(const std::string &text, size_t max_length, size_t stride) const;
+    std::vector<int32_t> encode(const std::string &text, bool add_special_tokens) const override;
+    std::string decode(const std::vector<int32_t> &ids, bool skip_special_tokens) const override;
 
-    int32_t pad_id = 0, unk_id = 100, cls_id = 101, sep_id = 102, mask_id = 103;
+    int32_t unk_id = 100, mask_id = 103;
     size_t vocab_size() const { return id_to_token_.size(); }
 
 private:
@@ -211,10 +222,35 @@ private:
     void wordpiece(const std::u32string &word, std::vector<int32_t> &out) const;
 };
 
+// Byte-level BPE tokenizer of the RoBERTa stacks (AllDistilrobertaV1 -- the third model segment_text accepts,
+// embedding.rs:156-161): what `tokenizers` builds from that model's tokenizer.json -- no normalizer, ByteLevel
+// pre-tokenizer (GPT-2 regex, add_prefix_space = false), BPE merges, ByteLevel decoder, RobertaProcessing
+// (<s> ... </s>).  Specials: <s> 0, <pad> 1, </s> 2, <unk> 3, <mask> the last id the vocabulary gives it.
+class ByteLevelBpeTokenizer : public Tokenizer {
+public:
+    // vocab.json ({"token": id}) + merges.txt ("a b" per line, first line may be a #version comment)
+    static std::shared_ptr<ByteLevelBpeTokenizer> from_files(const std::string &vocab_json, const std::string &merges_txt);
+    // tokens in id order (byte-level spelling, as in vocab.json), merges in rank order
+    static std::shared_ptr<ByteLevelBpeTokenizer> from_vocab(const std::vector<std::string> &tokens,
+                                                             const std::vector<std::pair<std::string, std::string>> &merges);
+
+    std::vector<int32_t> encode(const std::string &text, bool add_special_tokens) const override;
+    std::string decode(const std::vector<int32_t> &ids, bool skip_special_tokens) const override;
+
+    int32_t unk_id = 3, mask_id = -1;
+    size_t vocab_size() const { return id_to_token_.size(); }
+
+private:
+    std::vector<std::string> id_to_token_;
+    std::unordered_map<std::string, int32_t> token_to_id_;
+    std::unordered_map<std::string, uint32_t> merge_rank_;   // "left right" -> rank
+    void bpe(const std::string &piece, std::vector<int32_t> &out) const;
+};
+
 // segment_text (embedding.rs:155-198): windows of max_length tokens overlapping by stride, each decoded back to
 // TEXT (the first one also gets .replace(" ' ", "'"), :183).  The tokenizer is passed in: the reference re-loads it
 // from the hub on every call (:163).
-std::vector<std::string> segment_text(const ModelConfig &model_config, const std::string &text, const BertTokenizer &tokenizer);
+std::vector<std::string> segment_text(const ModelConfig &model_config, const std::string &text, const Tokenizer &tokenizer);
 
 // rust-bert's SentenceEmbeddingsModel::tokenize step: [CLS] .. [SEP], truncate to max_seq_length, pad to the longest.
 struct TokenBatch {
@@ -222,7 +258,7 @@ struct TokenBatch {
     std::vector<int32_t> lens;   // [B]
     uint32_t B = 0, S = 0;
 };
-TokenBatch tokenize_batch(const BertTokenizer &tokenizer, const std::vector<std::string> &segments, size_t max_seq_length);
+TokenBatch tokenize_batch(const Tokenizer &tokenizer, const std::vector<std::string> &segments, size_t max_seq_length);
 
 enum class Family { Bert, Roberta, DistilBert, Albert };   // the checkpoint's naming scheme / embedding layout
 struct Architecture {
@@ -284,7 +320,7 @@ class SentenceEmbedder {
 public:
     // the already-loaded encoder / tokenizer are handed in (process-wide, N1); the reference loads both inside the runner
     static std::shared_ptr<SentenceEmbedder> spawn(const ModelConfig &model_config, std::shared_ptr<Encoder> encoder,
-                                                   std::shared_ptr<BertTokenizer> tokenizer);
+                                                   std::shared_ptr<Tokenizer> tokenizer);
     ~SentenceEmbedder();
     std::vector<EmbeddingResult> encode(const std::string &text);                    // segment + embed each window
     std::optional<EmbeddingResult> encode_single(const std::string &text);           // one shot, truncated by the model
@@ -297,7 +333,7 @@ private:
         std::promise<std::vector<EmbeddingResult>> sender;
     };
     SentenceEmbedder() = default;
-    void runner(ModelConfig model_config, std::shared_ptr<Encoder> encoder, std::shared_ptr<BertTokenizer> tokenizer);
+    void runner(ModelConfig model_config, std::shared_ptr<Encoder> encoder, std::shared_ptr<Tokenizer> tokenizer);
     static constexpr size_t kChannel = 100;
     std::mutex mu_;
     std::condition_variable not_empty_, not_full_;

@@ -96,6 +96,62 @@ static int run_tokenizer(const std::string &golden)
     return 0;
 }
 
+// byte-level BPE (all-distilroberta-v1's pipeline) against tests/golden/bpe_golden.json
+static int run_bpe(const std::string &golden)
+{
+    json::Value g = json::parse(slurp(golden));
+    std::vector<std::string> vocab;
+    for (const auto &t : g.get("vocab")->arr) vocab.push_back(t.str);
+    std::vector<std::pair<std::string, std::string>> merges;
+    for (const auto &m : g.get("merges")->arr) merges.emplace_back(m.arr[0].str, m.arr[1].str);
+    auto tok = ByteLevelBpeTokenizer::from_vocab(vocab, merges);
+    CHECK(tok->cls_id == 0 && tok->pad_id == 1 && tok->sep_id == 2 && tok->unk_id == 3 && tok->mask_id == 4);
+    int n = 0;
+    for (const auto &c : g.get("cases")->arr) {
+        const std::string text = c.get("text")->str;
+        const auto ids = tok->encode(text, false);
+        if (ids != ints(*c.get("ids"))) {
+            std::fprintf(stderr, "ids differ for case %d: %s\n got:", n, text.c_str());
+            for (auto i : ids) std::fprintf(stderr, " %d", i);
+            std::fprintf(stderr, "\nwant:");
+            for (auto i : ints(*c.get("ids"))) std::fprintf(stderr, " %d", i);
+            std::fprintf(stderr, "\n");
+            return 1;
+        }
+        CHECK(tok->encode(text, true) == ints(*c.get("ids_special")));
+        const std::string dec = tok->decode(ids, true);
+        if (dec != c.get("decoded")->str) {
+            std::fprintf(stderr, "decode differs for case %d:\n got  %s\n want %s\n", n, dec.c_str(), c.get("decoded")->str.c_str());
+            return 1;
+        }
+        const size_t max_length = (size_t)c.get("max_length")->num, stride = (size_t)c.get("stride")->num;
+        const auto windows = tok->encode_windows(text, max_length, stride);
+        const auto &gw = c.get("windows")->arr;
+        CHECK(windows.size() == gw.size());
+        for (size_t i = 0; i < gw.size(); ++i) CHECK(windows[i] == ints(gw[i]));
+        ModelConfig cfg;
+        cfg.model = EmbeddingsModelType::AllDistilrobertaV1;
+        cfg.max_length = max_length;
+        cfg.stride = stride;
+        const auto segs = segment_text(cfg, text, *tok);
+        const auto &gs = c.get("segments")->arr;
+        CHECK(segs.size() == gs.size());
+        for (size_t i = 0; i < gs.size(); ++i) {
+            if (segs[i] != gs[i].str) {
+                std::fprintf(stderr, "segment %zu differs for case %d:\n got  %s\n want %s\n", i, n, segs[i].c_str(), gs[i].str.c_str());
+                return 1;
+            }
+        }
+        // the embedder's batch: <s> .. </s>, padded with <pad>
+        const TokenBatch tb = tokenize_batch(*tok, {text, "a"}, 12);
+        CHECK(tb.B == 2 && tb.ids[0] == tok->cls_id && tb.ids[tb.lens[0] - 1] == tok->sep_id && tb.lens[0] <= 12);
+        for (uint32_t i = (uint32_t)tb.lens[1]; i < tb.S; ++i) CHECK(tb.ids[tb.S + i] == tok->pad_id);
+        ++n;
+    }
+    std::printf("bpe ok: %d cases, %d checks\n", n, g_checks);
+    return 0;
+}
+
 // ---- fakes for the CPU tests --------------------------------------------------------------------
 struct FakeEncoder : Encoder {
     std::atomic<int> calls{0};
@@ -404,6 +460,7 @@ int main(int argc, char **argv)
 {
     try {
         if (argc >= 3 && !std::strcmp(argv[1], "tokenizer")) return run_tokenizer(argv[2]);
+        if (argc >= 3 && !std::strcmp(argv[1], "bpe")) return run_bpe(argv[2]);
         if (argc >= 2 && !std::strcmp(argv[1], "cpu")) return run_cpu();
         if (argc >= 3 && !std::strcmp(argv[1], "gpu")) return run_gpu(argv[2]);
         if (argc >= 2 && !std::strcmp(argv[1], "encode")) return run_encode(argc, argv);

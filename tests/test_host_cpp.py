@@ -15,6 +15,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden", "tokenizer_golden.json")
+BPE_GOLDEN = os.path.join(ROOT, "tests", "golden", "bpe_golden.json")
 
 
 @pytest.fixture(scope="module")
@@ -33,6 +34,26 @@ def run(binary, *args):
 def test_tokenizer_matches_tokenizers_package(test_host):
     out = run(test_host, "tokenizer", GOLDEN)
     assert "tokenizer ok" in out
+
+
+def test_bpe_tokenizer_matches_tokenizers_package(test_host):
+    """ByteLevelBpeTokenizer (all-distilroberta-v1's pipeline, the third model segment_text accepts, embedding.rs:159):
+    ids, <s> .. </s>, decode, windows and segments identical to the `tokenizers` package on tests/golden/bpe_golden.json"""
+    out = run(test_host, "bpe", BPE_GOLDEN)
+    assert "bpe ok: 18 cases" in out
+
+
+def test_bpe_golden_is_reproducible_here():
+    """the committed BPE fixture is what the installed `tokenizers` gives for the stored vocabulary and merges"""
+    pytest.importorskip("tokenizers")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mkbpe", os.path.join(ROOT, "tests", "golden", "make_bpe_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    g = json.load(open(BPE_GOLDEN))
+    t = mk.build(g["vocab"], g["merges"])
+    assert [c["text"] for c in g["cases"]] == [x[0] for x in mk.texts()]
+    assert mk.cases_for(t, g["vocab"]) == g["cases"]
 
 
 def test_golden_is_reproducible_here():
@@ -75,7 +96,7 @@ def test_host_library_exports():
     syms = subprocess.run(["nm", "-D", "--defined-only", "-C", mx_build.HOST_LIB], capture_output=True, text=True).stdout
     for name in ("memex::get_vector_storage", "memex::B200Store::load", "memex::B200Store::search", "memex::segment_text",
                  "memex::SentenceEmbedder::spawn", "memex::SentenceEmbedder::encode_single", "memex::SearchBatcher::submit",
-                 "memex::BertTokenizer::encode_windows", "memex::Weights::from_safetensors"):
+                 "memex::Tokenizer::encode_windows", "memex::ByteLevelBpeTokenizer::encode", "memex::Weights::from_safetensors"):
         assert name in syms, name
 
 
