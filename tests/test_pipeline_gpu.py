@@ -138,3 +138,64 @@ def test_streamed_ingest_with_concurrent_search(tmp_path):
     assert storage.search(probe, 8)[0][0] == "doc0-seg0"
     enc.close()
     store.close()
+
+
+@pytest.mark.parametrize("model", ["AllMiniLmL6V2", "AllDistilrobertaV1"])
+def test_sentence_embedder_from_text(model):
+    """SentenceEmbedder::{encode, encode_single} (embedding.rs:138-151) from raw text for two of the three models
+    segment_text accepts: WordPiece + BERT, and byte-level BPE + RoBERTa (pad id 1, positions from 2).  Tokenizers are
+    built from the committed golden vocabularies; the vectors are checked against the HF oracle on the same ids."""
+    import dataclasses
+    import importlib.util
+    import json
+    import os
+
+    from memex_b200.embedding import (ARCHITECTURES, EmbeddingsModelType, ModelConfig, SentenceEmbedder, segment_text,
+                                      tokenize_batch)
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(gold, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    kind = EmbeddingsModelType[model]
+    if kind is EmbeddingsModelType.AllDistilrobertaV1:
+        mk = load("make_bpe_golden")
+        g = json.load(open(os.path.join(gold, "bpe_golden.json")))
+        tok = mk.build(g["vocab"], g["merges"])
+        base = enc_oracle.DISTILROBERTA
+    else:
+        mk = load("make_tokenizer_golden")
+        vocab, tok = mk.build()
+        from tokenizers import processors
+        tok.post_processor = processors.TemplateProcessing(single="[CLS] $A [SEP]", special_tokens=[
+            ("[CLS]", vocab.index("[CLS]")), ("[SEP]", vocab.index("[SEP]"))])
+        g = json.load(open(os.path.join(gold, "tokenizer_golden.json")))
+        base = enc_oracle.MINILM_L6
+    cfg = dataclasses.replace(base, layers=2, vocab=tok.get_vocab_size())
+    arch = dataclasses.replace(ARCHITECTURES[kind], layers=2, vocab=cfg.vocab, max_seq_length=64)
+    w = enc_oracle.make_weights(cfg, seed=61)
+    enc = B200Encoder(arch, w, precision="bf16", max_tokens=64 * 64)
+    mc = ModelConfig(model=kind, max_length=48, stride=16)
+    text = max((c["text"] for c in g["cases"]), key=len)
+    handle, embedder = SentenceEmbedder.spawn(mc, enc, tok)
+    try:
+        results = embedder.encode(text)
+        single = embedder.encode_single("the quick brown fox")
+    finally:
+        embedder.shutdown()
+        handle.join(timeout=10)
+    segments = segment_text(mc, text, tok)
+    assert len(segments) > 4 and [r.content for r in results] == segments
+    ids, lens = tokenize_batch(tok, segments, arch.max_seq_length, arch.pad_id)
+    assert ids.shape[1] <= 64 and (ids[:, 0] == (0 if arch.family == "roberta" else ids[0, 0])).all()
+    ref = enc_oracle.hf_encode(cfg, w, ids, lens)
+    got = np.array([r.vector for r in results], dtype=np.float32)
+    assert got.shape == ref.shape
+    assert ((got * ref).sum(1) >= 1 - 2e-4).all()
+    ids1, lens1 = tokenize_batch(tok, ["the quick brown fox"], arch.max_seq_length, arch.pad_id)
+    ref1 = enc_oracle.hf_encode(cfg, w, ids1, lens1)
+    assert (np.array(single.vector, dtype=np.float32) * ref1[0]).sum() >= 1 - 2e-4
+    enc.close()
