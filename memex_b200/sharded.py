@@ -140,18 +140,25 @@ class ShardedStore:
         if key not in self._bufs:
             dev = torch.device("cuda", self.device)
             blob = int(capi.lib().mx_topk_blob_bytes(nq, k))
+            # the answer {ids i64 [nq,k] | scores f32 [nq,k] | counts i32 [nq]} lives in ONE buffer on each side, so the
+            # end-to-end call reads it back with a single device-to-host copy
+            a, c = nq * k * 8, nq * k * 12
+
+            def views(buf):
+                return (buf[:a].view(torch.int64).view(nq, k), buf[a:c].view(torch.float32).view(nq, k),
+                        buf[c:].view(torch.int32))
+            out = torch.zeros(c + nq * 4, dtype=torch.uint8, device=dev)
+            out_pin = torch.zeros(c + nq * 4, dtype=torch.uint8).pin_memory()
+            ids, scores, counts = views(out)
+            ids_pin, scores_pin, counts_pin = views(out_pin)
             self._bufs[key] = dict(
                 blob_bytes=blob,
                 gathered=torch.zeros((self.world, blob), dtype=torch.uint8, device=dev),
                 mine=torch.zeros(blob, dtype=torch.uint8, device=dev),
                 q=torch.zeros((nq, self.dim), dtype=torch.float32, device=dev),
-                ids=torch.zeros((nq, k), dtype=torch.int64, device=dev),
-                scores=torch.zeros((nq, k), dtype=torch.float32, device=dev),
-                counts=torch.zeros(nq, dtype=torch.int32, device=dev),
+                out=out, ids=ids, scores=scores, counts=counts,
                 q_pin=torch.zeros((nq, self.dim), dtype=torch.float32).pin_memory(),
-                ids_pin=torch.zeros((nq, k), dtype=torch.int64).pin_memory(),
-                scores_pin=torch.zeros((nq, k), dtype=torch.float32).pin_memory(),
-                counts_pin=torch.zeros(nq, dtype=torch.int32).pin_memory(),
+                out_pin=out_pin, ids_pin=ids_pin, scores_pin=scores_pin, counts_pin=counts_pin,
             )
         return self._bufs[key]
 
@@ -220,10 +227,8 @@ class ShardedStore:
             b["q"].copy_(b["q_pin"], non_blocking=True)
         if self.world > 1:
             dist.broadcast(b["q"], src=0, group=self.group)
-        ids, scores, counts = self.search_device(b["q"], k)
-        b["ids_pin"].copy_(ids, non_blocking=True)
-        b["scores_pin"].copy_(scores, non_blocking=True)
-        b["counts_pin"].copy_(counts, non_blocking=True)
+        self.search_device(b["q"], k)                     # fills b["out"] (ids | scores | counts)
+        b["out_pin"].copy_(b["out"], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return (b["ids_pin"].numpy().astype(np.uint64), b["scores_pin"].numpy().copy(),
                 b["counts_pin"].numpy().astype(np.uint32))
