@@ -32,7 +32,9 @@ constexpr int kResMaxKB = 6;   // resident-weights variant: K <= 384
 // RES = the CTA keeps its [BN, K] weight slice resident in shared memory and streams only activations
 // (K <= 384): weights are read from L2 once per CTA instead of once per tile, which takes the K = 384
 // GEMMs off the L2 -> SM bandwidth limit (a 128 x 192 x 384 tile would otherwise pull 240 KB for 2304 MMA cycles).
-template <int BN, bool RES, bool LN>
+// CG != 0 overrides the number of epilogue column groups (CG = 2 at BN = 256: 8 epilogue warps of 128 columns, which
+// halves the output staging and, with the bias staging cut to 3072 entries, leaves room for a FOURTH 48 KB stage)
+template <int BN, bool RES, bool LN, int CG = 0>
 struct GemmCfg {
     static constexpr int kChunks = BN > 256 ? 2 : 1;          // one tcgen05.mma covers N <= 256
     static constexpr int kChunkN = BN / kChunks;
@@ -44,13 +46,13 @@ struct GemmCfg {
     static constexpr int kResBytes = RES ? kResMaxKB * kBBytes : 0;
     // epilogue: 4 TMEM lane quarters x kColGroups column groups, one warp each -- several warps per SM
     // sub-partition so that the bias / GELU / LayerNorm arithmetic is issue-bound, not latency-bound
-    static constexpr int kColGroups = (BN % 128 == 0) ? 4 : 3;   // 192 -> 3 x 64 columns
+    static constexpr int kColGroups = CG ? CG : ((BN % 128 == 0) ? 4 : 3);   // 192 -> 3 x 64 columns
     static constexpr int kColsPerWarp = BN / kColGroups;
     static constexpr int kEpiWarps = 4 * kColGroups;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
     // LayerNorm partial (sum, sq) per column group, double buffered, + the peer CTA's row totals (split-N variant)
     static constexpr int kStatBytes = LN ? 2 * kColGroups * kBM * 8 + 2 * kBM * 8 : 0;
-    static constexpr int kMaxBiasN = RES ? 2048 : 4096;
+    static constexpr int kMaxBiasN = RES ? 2048 : (CG ? 3072 : 4096);
     static constexpr int kVecBytes = LN ? 3 * BN * 4 : kMaxBiasN * 4;      // bias | gamma | beta, or the whole bias vector
     // output staging for TMA stores: one [32 rows x 32 columns] 16-bit tile (2 KB, 64-byte swizzle) per epilogue warp
     // (LayerNorm with 64 columns per warp: a [32 rows x 128 bytes] tile per warp, used to transpose the residual
@@ -177,12 +179,12 @@ __device__ __forceinline__ float2 unpack16(uint32_t u)
 // memory and each normalises its half.  With N = 384 that makes BN = 192: two TMEM accumulator stages fit, so the
 // two-pass LayerNorm epilogue overlaps the next tile's MMAs; with N = 768 (BERT-base) it is what makes the fused
 // epilogue possible at all (768 f32 columns do not fit the 512 TMEM columns of one SM).
-template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT>
-__global__ void __launch_bounds__(GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN>::kThreads, 1)
+template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT, int CG = 0>
+__global__ void __launch_bounds__(GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN, CG>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, GemmParams p)
 {
-    using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN>;
+    using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN, CG>;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment by OFFSET (keeps the pointer in the shared address space: LDS/STS, not generic LD/ST)
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -570,12 +572,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT = false>
+template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT = false, int CG = 0>
 static cudaError_t launch_cfg(const GemmParams &p, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO,
                               int sm_count, cudaStream_t st)
 {
-    using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN>;
-    auto kern = gemm_tc_kernel<BN, EPI, FMT, RES, MC, SPLIT>;
+    using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN, CG>;
+    auto kern = gemm_tc_kernel<BN, EPI, FMT, RES, MC, SPLIT, CG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     const uint32_t tiles_m = ceil_div<uint32_t>(p.M, kBM), tiles_n = p.N / BN;
@@ -687,6 +689,12 @@ cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStrea
     }
     if (epi == EPI_BIAS_GELU) {
         if (res) MX_GEMM(192, EPI_BIAS_GELU, true, false);
+        // BN = 256 with 8 epilogue warps and four 48 KB stages instead of 16 warps and three (GemmCfg, CG): opt-in
+        // until measured (MX_GEMM_EPI8=1)
+        static const bool epi8 = getenv("MX_GEMM_EPI8") != nullptr;
+        if (bn == 256 && epi8 && !mc && p.N <= 3072)
+            return p.fmt == 1 ? launch_cfg<256, EPI_BIAS_GELU, 1, false, false, false, 2>(p, tmA, tmB, tmO, sm_count, st)
+                              : launch_cfg<256, EPI_BIAS_GELU, 0, false, false, false, 2>(p, tmA, tmB, tmO, sm_count, st);
         if (bn == 256) MX_GEMM_MC(256, EPI_BIAS_GELU);
         if (bn == 192) MX_GEMM_MC(192, EPI_BIAS_GELU);
         MX_GEMM_MC(128, EPI_BIAS_GELU);
