@@ -750,7 +750,7 @@ def main():
         if args.only == "ingest":
             res = bench_ingest(dev, peaks(), args.ingest_rows, args.ingest_seconds)
         elif args.only == "embed":
-            res = bench_embed(dev, args.steps, args.warmup, peaks(), False)
+            res = bench_embed(dev, args.steps, args.warmup, peaks(), False, not args.skip_extras)
         else:
             res = bench_single_query(dev, args.steps, args.warmup, peaks())
         print(json.dumps(res), flush=True)

@@ -179,7 +179,9 @@ __device__ __forceinline__ float2 unpack16(uint32_t u)
 // memory and each normalises its half.  With N = 384 that makes BN = 192: two TMEM accumulator stages fit, so the
 // two-pass LayerNorm epilogue overlaps the next tile's MMAs; with N = 768 (BERT-base) it is what makes the fused
 // epilogue possible at all (768 f32 columns do not fit the 512 TMEM columns of one SM).
-template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT, int CG = 0>
+// AMC (split-row LayerNorm variant only): the two CTAs of a cluster work on the SAME row tile, so each loads half of
+// every activation k-block and multicasts it to both -- the activations cross the L2 -> SM path once per cluster
+template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT, int CG = 0, bool AMC = false>
 __global__ void __launch_bounds__(GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN, CG>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, GemmParams p)
@@ -244,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < Cfg::kStages; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], MC ? 2 : 1);   // MC: a stage is free once BOTH CTAs' MMAs have read it
+            mbar_init(&empty[i], (MC || AMC) ? 2 : 1);   // multicast: a stage is free once BOTH CTAs' MMAs have read it
         }
         for (int i = 0; i < Cfg::kAccStages; ++i) {
             mbar_init(&tmem_full[i], 1);
@@ -284,7 +286,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char *sa = ring + stage * Cfg::kStageBytes;
                     mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-                    tma_load_2d(sa, &tmA, &full[stage], kb * kBK, m_blk * kBM, RES ? kEvictLast : kEvictFirst);
+                    if constexpr (AMC) {
+                        // this CTA's 64 rows of the activation k-block, delivered to both CTAs (and both `full` barriers)
+                        tma_load_2d_multicast(sa + cta_rank * (Cfg::kABytes / 2), &tmA, &full[stage], kb * kBK,
+                                              m_blk * kBM + cta_rank * (kBM / 2), (uint16_t)3, kEvictFirst);
+                    } else {
+                        tma_load_2d(sa, &tmA, &full[stage], kb * kBK, m_blk * kBM, RES ? kEvictLast : kEvictFirst);
+                    }
                     if constexpr (!RES) {
                         unsigned char *sb = sa + Cfg::kABytes;
                         if constexpr (MC) {
@@ -338,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             umma(tmem_base + as * BN + c * Cfg::kChunkN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                     }
-                    if constexpr (MC)
+                    if constexpr (MC || AMC)
                         umma_commit_multicast(&empty[stage], (uint16_t)3);
                     else
                         umma_commit(&empty[stage]);
@@ -572,12 +580,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT = false, int CG = 0>
+template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT = false, int CG = 0, bool AMC = false>
 static cudaError_t launch_cfg(const GemmParams &p, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO,
                               int sm_count, cudaStream_t st)
 {
     using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN, CG>;
-    auto kern = gemm_tc_kernel<BN, EPI, FMT, RES, MC, SPLIT, CG>;
+    auto kern = gemm_tc_kernel<BN, EPI, FMT, RES, MC, SPLIT, CG, AMC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     const uint32_t tiles_m = ceil_div<uint32_t>(p.M, kBM), tiles_n = p.N / BN;
@@ -652,7 +660,12 @@ cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStrea
     CUtensorMap tmA, tmB, tmO;
     uint32_t chunk_rows = mc ? bn / 2 : (bn > 256 ? bn / 2 : bn);
     if (epi == EPI_BIAS_RES_LN && !mc) chunk_rows = 192;   // whole-row 384 (2 chunks), split 2 x 192, split 2 x 384 (2 chunks each)
-    if (!make_tmap_k_major_16bit(&tmA, p.A, p.M, p.K, p.lda, kBM, p.fmt == 1) ||
+    // split-row LayerNorm variant with activation multicast (MX_GEMM_LN_AMC=1, opt-in until measured): each CTA of the
+    // pair loads 64 of the tile's 128 rows
+    static const bool amc_on = getenv("MX_GEMM_LN_AMC") != nullptr;
+    static const bool ln_no_split = getenv("MX_GEMM_LN_NO_SPLIT") != nullptr;
+    const bool amc = amc_on && epi == EPI_BIAS_RES_LN && !mc && sm_count >= 2 && (p.N == 768 || !ln_no_split);
+    if (!make_tmap_k_major_16bit(&tmA, p.A, p.M, p.K, p.lda, amc ? kBM / 2 : kBM, p.fmt == 1) ||
         !make_tmap_k_major_16bit(&tmB, p.W, p.N, p.K, p.ldw, chunk_rows, p.fmt == 1) ||
         !make_tmap_store_32x32_16bit(&tmO, p.out, p.M, p.N, p.ldo, p.fmt == 1)) {
         if (why) *why = "cuTensorMapEncodeTiled failed";
@@ -679,12 +692,19 @@ cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStrea
                 if (why) *why = "N = 768 LayerNorm epilogue needs a 2-CTA cluster";
                 return cudaErrorInvalidValue;
             }
+            if (amc)
+                return p.fmt == 1 ? launch_cfg<384, EPI_BIAS_RES_LN, 1, false, false, true, 0, true>(p, tmA, tmB, tmO, sm_count, st)
+                                  : launch_cfg<384, EPI_BIAS_RES_LN, 0, false, false, true, 0, true>(p, tmA, tmB, tmO, sm_count, st);
             return p.fmt == 1 ? launch_cfg<384, EPI_BIAS_RES_LN, 1, false, false, true>(p, tmA, tmB, tmO, sm_count, st)
                               : launch_cfg<384, EPI_BIAS_RES_LN, 0, false, false, true>(p, tmA, tmB, tmO, sm_count, st);
         }
-        if (can_split && !no_split && !mc)
+        if (can_split && !no_split && !mc) {
+            if (amc)
+                return p.fmt == 1 ? launch_cfg<192, EPI_BIAS_RES_LN, 1, false, false, true, 0, true>(p, tmA, tmB, tmO, sm_count, st)
+                                  : launch_cfg<192, EPI_BIAS_RES_LN, 0, false, false, true, 0, true>(p, tmA, tmB, tmO, sm_count, st);
             return p.fmt == 1 ? launch_cfg<192, EPI_BIAS_RES_LN, 1, false, false, true>(p, tmA, tmB, tmO, sm_count, st)
                               : launch_cfg<192, EPI_BIAS_RES_LN, 0, false, false, true>(p, tmA, tmB, tmO, sm_count, st);
+        }
         MX_GEMM_MC(384, EPI_BIAS_RES_LN);
     }
     if (epi == EPI_BIAS_GELU) {
