@@ -32,8 +32,10 @@ constexpr int kResMaxKB = 6;   // resident-weights variant: K <= 384
 // RES = the CTA keeps its [BN, K] weight slice resident in shared memory and streams only activations
 // (K <= 384): weights are read from L2 once per CTA instead of once per tile, which takes the K = 384
 // GEMMs off the L2 -> SM bandwidth limit (a 128 x 192 x 384 tile would otherwise pull 240 KB for 2304 MMA cycles).
-// CG != 0 overrides the number of epilogue column groups (CG = 2 at BN = 256: 8 epilogue warps of 128 columns, which
-// halves the output staging and, with the bias staging cut to 3072 entries, leaves room for a FOURTH 48 KB stage)
+// CG != 0 overrides the number of epilogue column groups.  CG = 2 gives 8 epilogue warps instead of 16 / 12, which
+// halves the output staging and, with a smaller bias staging, leaves room for one more ring stage: four 48 KB stages at
+// BN = 256 (three before: 1.4 us of MMA work in flight against a ~1.9 us TMA round trip; measured r1: the
+// intermediate GEMM 93 -> 81 us), five 40 KB stages at BN = 192.
 template <int BN, bool RES, bool LN, int CG = 0>
 struct GemmCfg {
     static constexpr int kChunks = BN > 256 ? 2 : 1;          // one tcgen05.mma covers N <= 256
@@ -52,7 +54,7 @@ struct GemmCfg {
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
     // LayerNorm partial (sum, sq) per column group, double buffered, + the peer CTA's row totals (split-N variant)
     static constexpr int kStatBytes = LN ? 2 * kColGroups * kBM * 8 + 2 * kBM * 8 : 0;
-    static constexpr int kMaxBiasN = RES ? 2048 : (CG ? 3072 : 4096);
+    static constexpr int kMaxBiasN = RES ? 2048 : (CG ? (BN == 192 ? 2304 : 3072) : 4096);
     static constexpr int kVecBytes = LN ? 3 * BN * 4 : kMaxBiasN * 4;      // bias | gamma | beta, or the whole bias vector
     // output staging for TMA stores: one [32 rows x 32 columns] 16-bit tile (2 KB, 64-byte swizzle) per epilogue warp
     // (LayerNorm with 64 columns per warp: a [32 rows x 128 bytes] tile per warp, used to transpose the residual
@@ -709,9 +711,9 @@ cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStrea
     }
     if (epi == EPI_BIAS_GELU) {
         if (res) MX_GEMM(192, EPI_BIAS_GELU, true, false);
-        // BN = 256 with 8 epilogue warps and four 48 KB stages instead of 16 warps and three (GemmCfg, CG): opt-in
-        // until measured (MX_GEMM_EPI8=1)
-        static const bool epi8 = getenv("MX_GEMM_EPI8") != nullptr;
+        // BN = 256 with 8 epilogue warps and four 48 KB stages instead of 16 warps and three (GemmCfg, CG): +3.4 % on the
+        // whole encoder step (r1); MX_GEMM_EPI16=1 keeps the 16-warp form for A/B measurements
+        static const bool epi8 = getenv("MX_GEMM_EPI16") == nullptr;
         if (bn == 256 && epi8 && !mc && p.N <= 3072)
             return p.fmt == 1 ? launch_cfg<256, EPI_BIAS_GELU, 1, false, false, false, 2>(p, tmA, tmB, tmO, sm_count, st)
                               : launch_cfg<256, EPI_BIAS_GELU, 0, false, false, false, 2>(p, tmA, tmB, tmO, sm_count, st);
@@ -725,6 +727,11 @@ cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStrea
         MX_GEMM(128, EPI_BIAS_GELU_TANH, false, false);
     }
     if (res) MX_GEMM(192, EPI_BIAS, true, false);
+    // BN = 192 with 8 epilogue warps and five 40 KB stages instead of 12 warps and four: opt-in until measured
+    static const bool qkv8 = getenv("MX_GEMM_QKV8") != nullptr;
+    if (bn == 192 && qkv8 && !mc && p.N <= 2304)
+        return p.fmt == 1 ? launch_cfg<192, EPI_BIAS, 1, false, false, false, 2>(p, tmA, tmB, tmO, sm_count, st)
+                          : launch_cfg<192, EPI_BIAS, 0, false, false, false, 2>(p, tmA, tmB, tmO, sm_count, st);
     if (bn == 256) MX_GEMM_MC(256, EPI_BIAS);
     if (bn == 192) MX_GEMM_MC(192, EPI_BIAS);
     MX_GEMM_MC(128, EPI_BIAS);

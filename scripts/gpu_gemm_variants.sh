@@ -3,7 +3,7 @@
 # sub-bench under each.   gpurun --timeout 600 -- bash scripts/gpu_gemm_variants.sh
 set -u
 mkdir -p gpurun_out
-for sw in MX_GEMM_EPI8 MX_GEMM_LN_AMC; do
+for sw in MX_NONE MX_GEMM_QKV8; do
     env $sw=1 timeout 200 python -m pytest tests/test_encoder_gpu.py -q -x -m gpu \
         -k "tcgen05_gemm_against_torch or tensor_core_paths_vs_oracle or bert_base_shape" > gpurun_out/t_$sw.log 2>&1
     echo "$sw: $(tail -1 gpurun_out/t_$sw.log)"
@@ -23,6 +23,7 @@ for l in open(f"gpurun_out/embed_{name}.json"):
 PY
 }
 run base MX_NONE=1
-run epi8 MX_GEMM_EPI8=1
-run amc MX_GEMM_LN_AMC=1
-run both MX_GEMM_EPI8=1 MX_GEMM_LN_AMC=1
+run qkv8 MX_GEMM_QKV8=1
+run epi16 MX_GEMM_EPI16=1
+run qkv8b MX_GEMM_QKV8=1
+run base2 MX_NONE=1
