@@ -253,7 +253,7 @@ def test_roberta_position_offset_limits_the_sequence_length():
         e.encode_ids(np.full((1, 65), 5, np.int32), np.full(1, 65, np.int32))
 
 
-@pytest.mark.parametrize("switch", ["MX_GEMM_MULTICAST", "MX_GEMM_RESIDENT", "MX_GEMM_LN_NO_SPLIT", "MX_GEMM_EPI16", "MX_GEMM_LN_AMC", "MX_GEMM_QKV8"])
+@pytest.mark.parametrize("switch", ["MX_GEMM_MULTICAST", "MX_GEMM_RESIDENT", "MX_GEMM_LN_NO_SPLIT", "MX_GEMM_EPI16", "MX_GEMM_LN_AMC", "MX_GEMM_QKV12"])
 def test_gemm_opt_in_variants_in_a_fresh_process(switch):
     """the 2-CTA weight-multicast and resident-weight GEMM variants are selected by an environment switch that
     the library reads once, so they are exercised in a child process: same GEMM parity cases + the end-to-end
