@@ -368,11 +368,11 @@ def bench_embed(device, steps: int, warmup: int, pk, cpu: bool, extras: bool = T
         step()
     torch.cuda.synchronize(device)
 
-    def timed():
+    def timed(fn):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            step()
+            fn()
         e1.record()
         torch.cuda.synchronize(device)
         return e0.elapsed_time(e1) / steps
@@ -381,10 +381,10 @@ def bench_embed(device, steps: int, warmup: int, pk, cpu: bool, extras: bool = T
     # the library's per-kernel CUDA events on (two event records around each of the 32 launches of a step, which cost
     # 2-3 % of the step) and gives the GEMM / other split the roofline is computed from
     l0 = L.mx_launch_count()
-    ms = timed()
+    ms = timed(step)
     launches = L.mx_launch_count() - l0
     L.mx_embedder_set_timing(enc.handle, 1)
-    ms_events = timed()
+    ms_events = timed(step)
     g_ms, g_n, o_ms, o_n = C.c_double(), C.c_uint64(), C.c_double(), C.c_uint64()
     L.mx_embedder_get_timing(enc.handle, C.byref(g_ms), C.byref(g_n), C.byref(o_ms), C.byref(o_n))
     L.mx_embedder_set_timing(enc.handle, 0)
@@ -425,12 +425,7 @@ def bench_embed(device, steps: int, warmup: int, pk, cpu: bool, extras: bool = T
     for _ in range(3):
         step_ragged()
     torch.cuda.synchronize(device)
-    e0.record()
-    for _ in range(steps):
-        step_ragged()
-    e1.record()
-    torch.cuda.synchronize(device)
-    ms_r = e0.elapsed_time(e1) / steps
+    ms_r = timed(step_ragged)
     real = int(lens_r.sum())
     flops_r = Lyr * (real * 24 * H * H + 4 * H * int((lens_r.astype(np.int64) ** 2).sum()))
     res["ragged"] = {"workload": "same batch, lengths ~ U[16, 256]; packed layout (padding rows dropped before the first GEMM)", "value": B * 1e3 / ms_r, "unit": "segments/s",
@@ -450,12 +445,7 @@ def bench_embed(device, steps: int, warmup: int, pk, cpu: bool, extras: bool = T
     for _ in range(3):
         step12()
     torch.cuda.synchronize(device)
-    e0.record()
-    for _ in range(steps):
-        step12()
-    e1.record()
-    torch.cuda.synchronize(device)
-    ms12 = e0.elapsed_time(e1) / steps
+    ms12 = timed(step12)
     f12 = 12 * B * 128 * (24 * H * H + 4 * 128 * H)
     res["default_model"] = {"workload": "all-MiniLM-L12-v2 shape (memex's default), B = 256, S = 128, bf16", "value": B * 1e3 / ms12,
                             "unit": "segments/s", "ms_per_step": ms12, "tflops": f12 / (ms12 * 1e-3) / 1e12}
