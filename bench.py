@@ -140,6 +140,26 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # synthetic corpus / queries (N(0,1) rows, L2-normalised; queries = rows + noise)
 # ------------------------------------------------------------------------------------------------
+def box_copy_bandwidth(device, nbytes: int = 1 << 30, reps: int = 5) -> float:
+    """device-to-device copy bandwidth of THIS box in GB/s (bytes read + bytes written per second), measured the way
+    MEASURED_PEAKS.json's figure was: context for roofline.frac, whose denominator is the pool-wide recorded number --
+    individual B200s of the pool copy at 6.5-7.0 TB/s"""
+    import torch
+    a = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    b = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    for _ in range(2):
+        b.copy_(a)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        b.copy_(a)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / reps
+    del a, b
+    return 2 * nbytes / (ms * 1e-3) / 1e9
+
+
 def corpus_chunk_device(chunk: int, rows: int, device):
     import torch
     g = torch.Generator(device=device)
@@ -684,6 +704,8 @@ def run_ours(args):
     }
     if rank == 0:
         line["clocks"] = sampler.summary(t_begin, t_end)
+        # outside the timed region: what a plain 1 GiB device-to-device copy reaches on this very GPU
+        line["roofline"]["copy_gbs_this_box"] = box_copy_bandwidth(device)
     store.close()
     del store
     torch.cuda.empty_cache()
