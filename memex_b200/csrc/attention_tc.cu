@@ -30,7 +30,9 @@
 // two such instruction streams per SM sub-partition.  Variants tried and measured slower: two threads per row
 // (148-177 us), single group with ping-pong score slots + P kept in TMEM as the A operand + auxiliary max / drain
 // warps (140-165 us; kept as experiments/attention_tc_pingpong.cu.txt), a rolled 8-key software pipeline (184 us).
-// Next step: 128-key sub-units (four score tiles in TMEM -> four independent streams per sub-partition).
+// Also measured slower (r1): announcing a P chunk half a chunk late so that tcgen05.wait::st never stalls the softmax warp
+// (+6 % kernel time: the last two chunks' P V products then queue up behind the final announcement and lengthen the unit's
+// tail).  Next step: 128-key sub-units (four score tiles in TMEM -> four independent streams per sub-partition).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -287,39 +289,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__
             const float msc = m * scale_log2e;
             // ---- pass 2: p = 2^(s scale log2e - max) -> packed 16-bit pairs written back over the score columns (key k ->
             //      column k / 2, always behind this thread's read position); the tensor pipe reads them as the A operand ----
-            //      A chunk is announced HALF A CHUNK LATE: the wait for its stores sits behind the exponentials of the next
-            //      chunk's first half, by which time they have long completed (tcgen05.wait::st right behind the stores
-            //      stalled the warp for the store latency four times per unit).
             for (uint32_t c = 0; c < nch; ++c, ++cc) {
                 uint32_t o[16];
                 if constexpr (!(DIAG & 8)) {
                     tmem_ld_wait();
                     tmem_ld32(t_s + c * kKC + 32, vb);
                     softmax32<BF16, (DIAG & 1) != 0>(va, scale_log2e, msc, c * kKC, len, o);
-                    if (c > 0) {   // chunk c - 1 is complete in TMEM: hand it to the tensor pipe
-                        tmem_st_wait();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bg + B_P_READY + (cc - 1) % kPRing);
-                    }
                     if constexpr (!(DIAG & 4)) tmem_st16(t_s + c * (kKC / 2), o);
                     tmem_ld_wait();
                     if (c + 1 < nch) tmem_ld32(t_s + (c + 1) * kKC, va);
                     softmax32<BF16, (DIAG & 1) != 0>(vb, scale_log2e, msc, c * kKC + 32, len, o);
                     if constexpr (!(DIAG & 4)) tmem_st16(t_s + c * (kKC / 2) + 16, o);
-                } else {
-                    if (c > 0) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bg + B_P_READY + (cc - 1) % kPRing);
-                    }
+                    tmem_st_wait();
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bg + B_P_READY + cc % kPRing);
             }
-            // the last chunk of the unit
-            if constexpr (!(DIAG & 8)) tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bg + B_P_READY + (cc - 1) % kPRing);
             // ---- O = P V in columns [128, 128 + DH) of the tile, the row sums of P (P times ones) next to it ----
             mbar_wait(bg + B_O_FULL, it & 1);
             tc_fence_after();
