@@ -3,7 +3,7 @@
 # sub-bench under each.   gpurun --timeout 600 -- bash scripts/gpu_gemm_variants.sh
 set -u
 mkdir -p gpurun_out
-for sw in MX_NONE MX_GEMM_QKV8; do
+for sw in ${PARITY_SWITCHES:-}; do
     env $sw=1 timeout 200 python -m pytest tests/test_encoder_gpu.py -q -x -m gpu \
         -k "tcgen05_gemm_against_torch or tensor_core_paths_vs_oracle or bert_base_shape" > gpurun_out/t_$sw.log 2>&1
     echo "$sw: $(tail -1 gpurun_out/t_$sw.log)"
@@ -22,8 +22,8 @@ for l in open(f"gpurun_out/embed_{name}.json"):
         print(f"{name:10s} {d['value']:10.0f} seg/s  step {d['ms_per_step']:.3f} ms  gemm {r['gemm_ms_per_step']:.3f} ms  other {r['other_ms_per_step']:.3f} ms")
 PY
 }
-run base MX_NONE=1
-run qkv8 MX_GEMM_QKV8=1
-run epi16 MX_GEMM_EPI16=1
-run qkv8b MX_GEMM_QKV8=1
-run base2 MX_NONE=1
+# A/B pairs on the same box: default, then each switch given on the command line, twice
+for rep in 1 2; do
+    run base$rep MX_NONE=1
+    for sw in "$@"; do run ${sw#MX_GEMM_}$rep $sw=1; done
+done
