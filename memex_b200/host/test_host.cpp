@@ -46,7 +46,8 @@ static int run_tokenizer(const std::string &golden)
     json::Value g = json::parse(slurp(golden));
     std::vector<std::string> vocab;
     for (const auto &t : g.get("vocab")->arr) vocab.push_back(t.str);
-    auto tok = BertTokenizer::from_vocab(vocab);
+    const bool lowercase = !g.get("lowercase") || g.get("lowercase")->b;   // the cased fixture says false
+    auto tok = BertTokenizer::from_vocab(vocab, lowercase);
     int n = 0;
     for (const auto &c : g.get("cases")->arr) {
         const std::string text = c.get("text")->str;
@@ -54,6 +55,8 @@ static int run_tokenizer(const std::string &golden)
         if (ids != ints(*c.get("ids"))) {
             std::fprintf(stderr, "ids differ for case %d: %s\n got:", n, text.c_str());
             for (auto i : ids) std::fprintf(stderr, " %d", i);
+            std::fprintf(stderr, "\nwant:");
+            for (auto i : ints(*c.get("ids"))) std::fprintf(stderr, " %d", i);
             std::fprintf(stderr, "\n");
             return 1;
         }

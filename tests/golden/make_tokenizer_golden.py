@@ -50,6 +50,56 @@ def build():
     return vocab, t
 
 
+def build_cased():
+    """distiluse-base-multilingual-cased's tokenizer.json: the same pipeline with lowercase = false (and with it no accent
+    stripping), on a vocabulary that keeps case and accents"""
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"]
+    seen = set(vocab)
+    words = BASE.split() + [w.capitalize() for w in BASE.split()[:80]] + ["Café", "café", "naïve", "Über", "über", "Zürich",
+                                                                            "François", "STRASSE", "Straße", "Привет", "МИР", "мир"]
+    for w in words + list("abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZéèïüßñç") + SUFFIX + PUNCT + EXTRA:
+        if w not in seen:
+            vocab.append(w)
+            seen.add(w)
+    t = Tokenizer(models.WordPiece({w: i for i, w in enumerate(vocab)}, unk_token="[UNK]", max_input_chars_per_word=100))
+    t.normalizer = normalizers.BertNormalizer(clean_text=True, handle_chinese_chars=True, strip_accents=None, lowercase=False)
+    t.pre_tokenizer = pre_tokenizers.BertPreTokenizer()
+    t.decoder = decoders.WordPiece(prefix="##", cleanup=True)
+    t.add_special_tokens(["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"])
+    return vocab, t
+
+
+def cases_for(vocab, t, texts):
+    cases = []
+    for text, max_length, stride in texts:
+        t.no_truncation()
+        enc = t.encode(text, add_special_tokens=False)
+        ids = enc.ids
+        ids_special = [vocab.index("[CLS]")] + ids + [vocab.index("[SEP]")]
+        decoded = t.decode(ids, skip_special_tokens=True)
+        t.enable_truncation(max_length=max_length, stride=stride)
+        e2 = t.encode(text, add_special_tokens=False)
+        windows = [e2.ids] + [o.ids for o in e2.overflowing]
+        segments = [t.decode(e2.ids, skip_special_tokens=True).replace(" ' ", "'")]
+        segments += [t.decode(o.ids, skip_special_tokens=True) for o in e2.overflowing]
+        t.no_truncation()
+        cases.append(dict(text=text, ids=ids, ids_special=ids_special, decoded=decoded, max_length=max_length, stride=stride,
+                          windows=windows, segments=segments))
+    return cases
+
+
+def cased_texts():
+    rng = random.Random(20260103)
+    doc = long_document(rng, 300)
+    return [
+        ("The Quick brown Fox jumps over the lazy Dog.", 256, 86),
+        ("Café café CAFÉ naïve Naïve Über über Zürich François STRASSE Straße straße", 256, 86),
+        ("Привет МИР мир α β Γεια 中文 mixed中Text", 256, 86),
+        ("don't It's We're I'M   tabs\tand\nnewlines \u00e9 vs e\u0301 combining", 256, 86),
+        (" ".join(w.capitalize() if i % 3 == 0 else w for i, w in enumerate(doc.split())), 32, 8),
+    ]
+
+
 def long_document(rng, n_words):
     words = BASE.split()
     out = []
@@ -111,6 +161,11 @@ def main():
     with open(os.path.join(HERE, "tokenizer_golden.json"), "w") as f:
         json.dump(out, f, ensure_ascii=True)
     print(f"{len(cases)} cases, {len(vocab)} vocab entries, windows per case: {[len(c['windows']) for c in cases]}")
+    vocab_c, t_c = build_cased()
+    cased = cases_for(vocab_c, t_c, cased_texts())
+    with open(os.path.join(HERE, "tokenizer_cased_golden.json"), "w") as f:
+        json.dump(dict(tokenizers_version=tokenizers.__version__, lowercase=False, vocab=vocab_c, cases=cased), f, ensure_ascii=True)
+    print(f"cased: {len(cased)} cases, {len(vocab_c)} vocab entries, windows per case: {[len(c['windows']) for c in cased]}")
 
 
 if __name__ == "__main__":

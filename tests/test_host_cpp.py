@@ -36,6 +36,12 @@ def test_tokenizer_matches_tokenizers_package(test_host):
     assert "tokenizer ok" in out
 
 
+def test_cased_tokenizer_matches_tokenizers_package(test_host):
+    """lowercase = false (no accent stripping): the tokenizer of DistiluseBaseMultilingualCased"""
+    out = run(test_host, "tokenizer", os.path.join(ROOT, "tests", "golden", "tokenizer_cased_golden.json"))
+    assert "tokenizer ok: 5 cases" in out
+
+
 def test_bpe_tokenizer_matches_tokenizers_package(test_host):
     """ByteLevelBpeTokenizer (all-distilroberta-v1's pipeline, the third model segment_text accepts, embedding.rs:159):
     ids, <s> .. </s>, decode, windows and segments identical to the `tokenizers` package on tests/golden/bpe_golden.json"""
