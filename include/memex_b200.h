@@ -204,7 +204,8 @@ int32_t mx_embedder_create_ex(const mx_model_cfg *cfg, const mx_model_ext *ext, 
 int32_t mx_embedder_out_dim(mx_embedder *e, uint32_t *dim);
 void mx_embedder_destroy(mx_embedder *e);
 /* ids [B, S] int32 padded, lens [B] (tokens beyond lens[b] are ignored), out [B, out_dim] f32;
- * HOST buffers. */
+ * HOST buffers.  Padding costs nothing: the activations are stored without it (row offsets from
+ * lens), so the GEMMs run on sum(lens) rows; the result is bit-identical to the padded layout. */
 int32_t mx_embedder_encode(mx_embedder *e, const int32_t *ids, const int32_t *lens, uint32_t B,
                            uint32_t S, float *out);
 /* ids / out in DEVICE memory, lens on the HOST; asynchronous on cuda_stream (NULL = own) */
