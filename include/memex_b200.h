@@ -148,6 +148,15 @@ int32_t mx_store_info(mx_store *s, uint32_t *dim, uint32_t *dtype, uint32_t *met
  * 1 = fp16 CUDA-core stream, 2 = fp16 tcgen05.  force >= 0 pins a path (tests / bench). */
 int32_t mx_store_scan_path(mx_store *s, uint32_t nq, uint32_t k, int32_t force);
 
+/* Superset certificate.  The scan kernels rank rows by an approximate score and the answer is
+ * re-scored exactly; after every search the library checks, per query, that no row it turned away could have reached
+ * the k-th exact score (approximation radius from the fp16 query rounding and the f32 accumulation), and answers the
+ * queries that fail the check again with an exact f64 scan -- so results equal the reference's (distance, id) order on
+ * ANY data (near-tie crowds, mass duplicates).  mx_store_verify_stats: lifetime counts of queries answered / sent to the
+ * exact scan (synchronises the device).  mx_store_set_verify(0) turns the check off (A/B measurements only). */
+int32_t mx_store_verify_stats(mx_store *s, uint64_t *queries_out, uint64_t *flagged_out);
+int32_t mx_store_set_verify(mx_store *s, int32_t on);
+
 /* device-side timing of the store's own kernels (CUDA events on the launching stream) */
 int32_t mx_store_set_timing(mx_store *s, int32_t on);
 int32_t mx_store_get_timing(mx_store *s, double *scan_ms_total, uint64_t *scan_launches,

@@ -107,6 +107,8 @@ def lib() -> C.CDLL:
     sig("mx_store_sync", C.c_int32, vp)
     sig("mx_store_info", C.c_int32, vp, u32p, u32p, u32p, u64p)
     sig("mx_store_scan_path", C.c_int32, vp, C.c_uint32, C.c_uint32, C.c_int32)
+    sig("mx_store_verify_stats", C.c_int32, vp, u64p, u64p)
+    sig("mx_store_set_verify", C.c_int32, vp, C.c_int32)
     sig("mx_store_set_timing", C.c_int32, vp, C.c_int32)
     sig("mx_store_get_timing", C.c_int32, vp, f64p, u64p, f64p, u64p)
     sig("mx_embedder_create", C.c_int32, C.POINTER(ModelCfg), C.POINTER(Tensor), C.c_uint32,

@@ -13,46 +13,10 @@
 // double sqrt and division are correctly rounded on the device), evaluated in the same order,
 // so scores are bit-identical to oracle/cosine_oracle.c and ordering is (d asc, id asc).
 #include "common.cuh"
+#include "exact.cuh"
 #include "scan.cuh"
 
 namespace mx {
-
-__device__ __forceinline__ float load_elem(const void *rows, uint32_t dtype, size_t idx)
-{
-    return dtype == MX_DTYPE_F32 ? reinterpret_cast<const float *>(rows)[idx]
-                                 : __half2float(reinterpret_cast<const __half *>(rows)[idx]);
-}
-
-// exact key of (query, row): cosine distance, or -dot for the dot metric
-__device__ float exact_key(const float *q, const void *rows, uint32_t dtype, uint32_t metric, size_t row_off,
-                           uint32_t dim, double *aa_out)
-{
-    double ab = 0.0, aa = 0.0, bb = 0.0;
-    if (dtype == MX_DTYPE_F32) {
-        const float *r = reinterpret_cast<const float *>(rows) + row_off;
-        for (uint32_t i = 0; i < dim; ++i) {
-            const float a = q[i], b = r[i];
-            ab = __dadd_rn(ab, (double)__fmul_rn(a, b));
-            aa = __dadd_rn(aa, (double)__fmul_rn(a, a));
-            bb = __dadd_rn(bb, (double)__fmul_rn(b, b));
-        }
-    } else {
-        const __half *r = reinterpret_cast<const __half *>(rows) + row_off;
-        for (uint32_t i = 0; i < dim; ++i) {
-            const float a = q[i], b = __half2float(r[i]);
-            ab = __dadd_rn(ab, (double)__fmul_rn(a, b));
-            aa = __dadd_rn(aa, (double)__fmul_rn(a, a));
-            bb = __dadd_rn(bb, (double)__fmul_rn(b, b));
-        }
-    }
-    if (aa_out) *aa_out = aa;
-    if (metric == MX_METRIC_DOT) return -(float)ab;
-    if (aa > 0.0 && bb > 0.0) {
-        const double du = __dsub_rn(1.0, __ddiv_rn(ab, __dsqrt_rn(__dmul_rn(aa, bb))));
-        return (float)fmax(du, 0.0);
-    }
-    return 0.f;
-}
 
 __device__ __forceinline__ float key_to_score(float key, uint32_t metric)
 {
@@ -131,9 +95,20 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
     float *rowbuf = reinterpret_cast<float *>(erow + kMaxEntries);   // [kFoldBatches * 32][kFoldPitch]
     __shared__ uint32_t n_entries_s;
     __shared__ int zero_query_s;
+    __shared__ float sel_v_s, kth_key_s, red_s[kRerankWarps];
+    __shared__ uint32_t sel_r_s;
 
-    const uint32_t q = blockIdx.x;
+    // second pass (exact fallback): CTA b answers flagged query active_map[b] from candidate lists b
+    const bool second_pass = p.active_n != nullptr;
+    if (second_pass && blockIdx.x >= *p.active_n) return;
+    const uint32_t q = second_pass ? p.active_map[blockIdx.x] : blockIdx.x;
+    const bool certify = !second_pass && p.n_flagged != nullptr;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        sel_r_s = kNoRow;
+        sel_v_s = kNegInf;
+        kth_key_s = 0.f;
+    }
     const float *qg = p.queries + (size_t)q * p.ldq;
 
     for (uint32_t j = threadIdx.x; j < kMaxEntries; j += blockDim.x) {
@@ -141,7 +116,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
         erow[j] = kNoRow;
     }
     const uint32_t total = p.n_lists * p.lcap;   // the (query, list) candidate lists are contiguous
-    const size_t cbase = (size_t)q * total;
+    const size_t cbase = (size_t)blockIdx.x * total;
     if constexpr (E == 1) {
         // 1+2 (k <= 24): sorted-list algebra.  Each warp sorts 32 candidates at a time and merges them
         // into its running sorted top-32; warp 0 then merges the 16 warp lists.
@@ -173,7 +148,13 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
                 }
             }
         }
-        if (warp == 0) erow[lane] = br;
+        if (warp == 0) {
+            erow[lane] = br;
+            if (lane == 31) {   // the worst entry that made the cut (kNoRow: nothing was cut)
+                sel_v_s = bv;
+                sel_r_s = br;
+            }
+        }
     } else {
         // 1. every warp folds a slice of the candidate lists into its own list
         WarpTopK<E> top;
@@ -200,7 +181,42 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
             uint32_t rank = 0;
             for (uint32_t i = 0; i < kRerankWarps * kList; ++i) rank += cand_before(ws[i], wr[i], v, r) ? 1u : 0u;
             if (rank < kList) erow[rank] = r;
+            if (rank == kList - 1) {
+                sel_v_s = v;
+                sel_r_s = r;
+            }
         }
+    }
+    // certificate, part 1: the best APPROXIMATE score among everything that was rejected before the exact re-scoring --
+    // by a scan CTA (a full list's minimum bounds whatever that CTA turned away, and the global threshold tau is the
+    // maximum of such minima), by the seeding floor, or by the top-(32 E) cut above
+    float a_rej = kNegInf;
+    if (certify) {
+        __syncthreads();
+        for (uint32_t c = threadIdx.x; c < p.n_lists; c += blockDim.x) {
+            float mn = __int_as_float(0x7f800000);
+            bool full = true;
+            for (uint32_t e = 0; e < p.lcap; ++e) {
+                full &= p.cand_r[cbase + (size_t)c * p.lcap + e] != kNoRow;
+                mn = fminf(mn, p.cand_s[cbase + (size_t)c * p.lcap + e]);
+            }
+            if (full) a_rej = fmaxf(a_rej, mn);
+        }
+        const float sv = sel_v_s;
+        const uint32_t sr = sel_r_s;
+        if (sr != kNoRow)
+            for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+                const float v = p.cand_s[cbase + i];
+                const uint32_t r = p.cand_r[cbase + i];
+                if (r != kNoRow && cand_before(sv, sr, v, r)) a_rej = fmaxf(a_rej, v);
+            }
+        if (threadIdx.x == 0 && p.scan_floor) a_rej = fmaxf(a_rej, p.scan_floor[q]);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) a_rej = fmaxf(a_rej, __shfl_xor_sync(0xffffffffu, a_rej, o));
+        if (lane == 0) red_s[warp] = a_rej;
+        __syncthreads();
+        a_rej = red_s[0];
+        for (int w = 1; w < kRerankWarps; ++w) a_rej = fmaxf(a_rej, red_s[w]);
     }
     // 3. the lowest-id zero-norm rows (cosine: d = 0)
     if (threadIdx.x == 0) {
@@ -324,7 +340,10 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
             p.scores_out[(size_t)q * p.k + j] = ok ? key_to_score(0.f, p.metric) : 0.f;
             if (p.dists_out) p.dists_out[(size_t)q * p.k + j] = 0.f;
         }
-        if (threadIdx.x == 0) p.counts_out[q] = count;
+        if (threadIdx.x == 0) {
+            p.counts_out[q] = count;
+            if (certify && p.stats) atomicAdd(p.stats, 1ull);
+        }
         return;
     }
 
@@ -362,9 +381,46 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
             p.ids_out[(size_t)q * p.k + rank] = p.id_offset + (uint64_t)row * p.id_stride + 1;
             p.scores_out[(size_t)q * p.k + rank] = key_to_score(key, p.metric);
             if (p.dists_out) p.dists_out[(size_t)q * p.k + rank] = key;
+            if (rank + 1 == count) kth_key_s = key;
         }
     }
     if (threadIdx.x == 0) p.counts_out[q] = count;
+    if (!certify) return;
+    // certificate, part 2.  In the exact score's units (cosine: cos; dot: q . c) the approximate score of a row is within
+    //   eps = [ |q16 - q/|q||_2  (tcgen05 scan: fp16 query, Cauchy-Schwarz) + (dim + 64) 2^-23  (f32 / tensor-core
+    //           accumulation, inverse norm, the f32 products of the exact fold) + 4e-6 ]  x  (dot: |q| max|row|)
+    // of its exact score, so no rejected row can reach the k-th exact score X when  a_rej + eps < X.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (p.stats) atomicAdd(p.stats, 1ull);
+        const double qn = sqrt(aa_s);
+        if (count > 0 && a_rej > kNegInf && qn > 0.0) {
+            const float rel1 = (float)(p.dim + 64) * 1.1920929e-7f + 4e-6f;
+            const float rel = rel1 + (p.qerr ? p.qerr[q] : 0.f);
+            const double mn = p.metric == MX_METRIC_DOT ? (double)*p.max_norm : 1.0;
+            double a_eu, eps, eps1, X;
+            if (p.metric == MX_METRIC_COSINE) {
+                a_eu = p.unit_queries ? (double)a_rej : (double)a_rej / qn;
+                eps = rel;
+                eps1 = rel1;
+                X = 1.0 - (double)kth_key_s;
+            } else {
+                a_eu = p.unit_queries ? (double)a_rej * qn : (double)a_rej;
+                eps = (double)rel * qn * mn;
+                eps1 = (double)rel1 * qn * mn;
+                X = -(double)kth_key_s;
+            }
+            if (!(a_eu + eps < X)) {
+                // threshold of the exact scan's f32 pre-filter, in ITS units (cosine: q . c / |c|; dot: q . c)
+                double t1 = p.metric == MX_METRIC_COSINE ? (X - eps1) * qn : X - eps1;
+                t1 -= fabs(t1) * 1e-6 + 1e-30;
+                const uint32_t pos = atomicAdd(p.n_flagged, 1u);
+                p.q_map[pos] = q;
+                p.fb_thr[pos] = __double2float_rd(t1);
+                if (p.stats) atomicAdd(p.stats + 1, 1ull);
+            }
+        }
+    }
 }
 
 cudaError_t launch_rerank(const RerankParams &p, cudaStream_t st)
@@ -526,6 +582,12 @@ __global__ void __launch_bounds__(256) ingest_kernel(IngestParams p)
         if (bad) atomicOr(p.bad_flag, 1u);
         const bool zero = !(ss > 0.f);
         p.inv_norm[dst_row] = zero ? 0.f : 1.0f / sqrtf(ss);
+        if (p.max_norm && !bad) {
+            // running maximum of the row norms (rounded up): the dot metric's approximation radius scales with it
+            const float nrm = sqrtf(ss) * 1.0001f;
+            if (nrm > *reinterpret_cast<volatile float *>(p.max_norm))
+                atomicMax(reinterpret_cast<unsigned int *>(p.max_norm), __float_as_uint(nrm));
+        }
         if (zero && p.metric == MX_METRIC_COSINE) atomicOr(p.bad_flag, 2u);
     }
 }

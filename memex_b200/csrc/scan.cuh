@@ -42,8 +42,35 @@ struct RerankParams {
     uint32_t n_rows, ld, ldq, dim, nq, k;
     uint32_t n_lists, lcap;
     uint32_t dtype, metric;
+    // ---- superset certificate ----
+    // The scan ranks rows by an APPROXIMATE score; the answer is provably the exact one when every row the scan or the
+    // rerank's own top-(32 E) cut rejected scored, approximately, more than the approximation radius below the k-th
+    // exact score.  Queries that fail the test are appended to q_map / fb_thr and answered again by the exact scan.
+    const float *qerr = nullptr;        // [nq] fp16 rounding radius of the prepared query (tcgen05 scan) or nullptr
+    const float *scan_floor = nullptr;  // [nq] tau0 of the tcgen05 scan's threshold seeding or nullptr
+    const float *max_norm = nullptr;    // device scalar: largest stored row norm (dot metric radius)
+    uint32_t unit_queries = 0;          // 1: approximate scores are those of the unit-norm query (tcgen05 scan)
+    uint32_t *n_flagged = nullptr;      // device scalar, zero on entry; nullptr = no certificate
+    uint32_t *q_map = nullptr;          // [nq] flagged query indices
+    float *fb_thr = nullptr;            // [nq] fp32-scan threshold below which a row cannot be in the flagged query's top k
+    unsigned long long *stats = nullptr;  // [2] lifetime counters: queries answered, queries flagged
+    // ---- second pass over the flagged queries only: CTA b answers query active_map[b] from candidate lists b ----
+    const uint32_t *active_n = nullptr;
+    const uint32_t *active_map = nullptr;
 };
 cudaError_t launch_rerank(const RerankParams &p, cudaStream_t st);
+
+// exact fallback scan (scan_stream.cu): for each flagged query, every row whose fp32 score reaches fb_thr is re-scored
+// with the reference's f64 arithmetic IN the scan, and the lists are kept on the exact key -- no approximation left.
+// Candidate lists [flagged index][cta][lcap] with score field = -key.
+struct ExactScanParams {
+    ScanParams scan;              // queries = all queries of the batch; cand_* = the lists
+    const uint32_t *active_n;     // device scalar: flagged queries
+    const uint32_t *active_map;   // [nq]
+    const float *fb_thr;          // [nq]
+    uint32_t dim, metric;
+};
+cudaError_t launch_scan_exact(const ExactScanParams &p, uint32_t dtype, uint32_t k, uint32_t n_ctas, cudaStream_t st);
 
 struct MergeParams {
     const uint64_t *ids;     // shard g: [nq, k] at (char *)ids + g * stride_ids
@@ -80,6 +107,7 @@ struct IngestParams {
     uint32_t *zero_rows;
     uint32_t *n_zero;
     uint32_t *bad_flag;
+    float *max_norm;      // device scalar: running maximum of the stored rows' norms
     uint64_t first_row, n;
     uint32_t dim, ld, dtype, metric;
 };
@@ -98,6 +126,8 @@ bool tc_scan_supports(const TcScanState *t, uint32_t k);
 uint32_t tc_scan_max_k();
 uint32_t tc_scan_lists(const TcScanState *t, uint64_t n_rows);
 uint32_t tc_scan_lcap(uint32_t k);
+const float *tc_scan_qerr(const TcScanState *t);    // valid after tc_scan_launch, [nq]
+const float *tc_scan_floor(const TcScanState *t);
 cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacity, uint32_t k, KernelTimer *timer,
                            cudaStream_t st, const char **why);
 

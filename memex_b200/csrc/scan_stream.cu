@@ -14,6 +14,7 @@
 // lane per row offers (score, row) to a warp-resident top-k list; lists are merged per CTA and
 // written as [query][cta][LCAP] candidates.
 #include "common.cuh"
+#include "exact.cuh"
 #include "scan.cuh"
 
 namespace mx {
@@ -56,10 +57,21 @@ constexpr int kScanWarps = kScanThreads / 32;
 
 // T: stored element type; LPR: lanes per row; CPL: 16-byte chunks per lane (0 = runtime loop);
 // R: row slots in flight per lane group; NQ: queries per pass; E: list entries per lane.
-template <typename T, int LPR, int CPL, int R, int NQ, int E>
-__global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(ScanParams p)
+// EXACT (the fallback of the superset certificate, NQ = 1): the query is flagged query number `slot`
+// (x.active_map[slot]); a row whose f32 score reaches x.fb_thr[slot] is re-scored with the reference's f64 fold right
+// here, by the lane that speaks for it, and offered to the list with score = -key.  The lists then rank by the EXACT key
+// (ties -> lower row), so their union holds the exact top 32 E whatever the data looks like.
+struct ExactExtra {
+    const uint32_t *active_map;
+    const float *fb_thr;
+    uint32_t dim, metric;
+};
+
+template <typename T, int LPR, int CPL, int R, int NQ, int E, bool EXACT>
+__device__ __forceinline__ void scan_stream_body(const ScanParams &p, const ExactExtra &x, uint32_t slot)
 {
     static_assert(LPR >= R && (LPR & (LPR - 1)) == 0 && (R & (R - 1)) == 0, "bad LPR / R");
+    static_assert(!EXACT || NQ == 1, "the exact scan takes one query per pass");
     constexpr int kGroups = 32 / LPR;           // rows per slot per warp
     constexpr int kRowsPerIter = R * kGroups;   // rows per warp iteration
     constexpr int kCE = Chunk<T>::kElems;
@@ -68,8 +80,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(ScanParams
 
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t q0 = blockIdx.y * NQ;
-    const uint32_t nq_here = min((uint32_t)NQ, p.nq - q0);
+    const uint32_t q0 = EXACT ? x.active_map[slot] : blockIdx.y * NQ;
+    const uint32_t nq_here = EXACT ? 1u : min((uint32_t)NQ, p.nq - q0);
+    const float exact_thr = EXACT ? x.fb_thr[slot] : 0.f;
 
     for (uint32_t i = threadIdx.x; i < NQ * p.ldq; i += blockDim.x) {
         const uint32_t qi = i / p.ldq;
@@ -174,8 +187,17 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(ScanParams
         const bool valid = speaker && row64 < p.n_rows;
         const uint32_t row = (uint32_t)row64;
         const float inv = (valid && p.use_inv) ? __ldg(p.inv_norm + row) : 1.f;
+        if constexpr (EXACT) {
+            const bool pass = valid && acc[0][0] * inv >= exact_thr;
+            float v = kNegInf;
+            if (pass)
+                v = -exact_key(qs, p.rows, sizeof(T) == 4 ? MX_DTYPE_F32 : MX_DTYPE_F16, x.metric, (size_t)row * p.ld, x.dim,
+                               nullptr);
+            top[0].offer(pass, v, row);
+        } else {
 #pragma unroll
-        for (int qi = 0; qi < NQ; ++qi) top[qi].offer(valid, acc[qi][0] * inv, row);
+            for (int qi = 0; qi < NQ; ++qi) top[qi].offer(valid, acc[qi][0] * inv, row);
+        }
     }
 
     // ---- per-CTA merge of the warp lists, then one list per (query, cta) to global ----
@@ -200,7 +222,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(ScanParams
                     fin.offer(r != kNoRow, v, r);
                 }
             if ((uint32_t)qi < nq_here) {
-                const size_t o = ((size_t)(q0 + qi) * p.n_lists + blockIdx.x) * (32 * E);
+                const size_t o = ((size_t)(EXACT ? slot : q0 + qi) * p.n_lists + blockIdx.x) * (32 * E);
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     p.cand_s[o + e * 32 + lane] = fin.s[e];
@@ -210,6 +232,20 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(ScanParams
         }
         __syncthreads();
     }
+}
+
+template <typename T, int LPR, int CPL, int R, int NQ, int E>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(ScanParams p)
+{
+    scan_stream_body<T, LPR, CPL, R, NQ, E, false>(p, ExactExtra{}, 0);
+}
+
+// one pass over the corpus per flagged query; normally there is none and the kernel returns at once
+template <typename T, int LPR, int CPL, int R, int E>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(ScanParams p, ExactExtra x, const uint32_t *active_n)
+{
+    const uint32_t n = *active_n;
+    for (uint32_t slot = 0; slot < n; ++slot) scan_stream_body<T, LPR, CPL, R, 1, E, true>(p, x, slot);
 }
 
 template <typename T, int LPR, int CPL, int R, int NQ, int E>
@@ -259,6 +295,49 @@ cudaError_t launch_scan_stream(const ScanParams &p, uint32_t dtype, uint32_t k, 
         MX_DISPATCH(__half)
     }
 #undef MX_DISPATCH
+}
+
+template <typename T, int LPR, int CPL, int R, int E>
+static cudaError_t launch_exact_one(const ExactScanParams &p, uint32_t n_ctas, cudaStream_t st)
+{
+    auto kern = scan_exact_kernel<T, LPR, CPL, R, E>;
+    size_t smem = std::max((size_t)p.scan.ldq * sizeof(float), (size_t)kScanWarps * 32 * E * 8);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<n_ctas, kScanThreads, smem, st>>>(p.scan, ExactExtra{p.active_map, p.fb_thr, p.dim, p.metric}, p.active_n);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <typename T, int E>
+static cudaError_t launch_exact_shape(const ExactScanParams &p, uint32_t n_ctas, cudaStream_t st)
+{
+    const uint32_t V = p.scan.ld / Chunk<T>::kElems;
+    if (V == 96) return launch_exact_one<T, 32, 3, 8, E>(p, n_ctas, st);
+    if (V == 48) return launch_exact_one<T, 16, 3, 8, E>(p, n_ctas, st);
+    if (V >= 32) return launch_exact_one<T, 32, 0, 4, E>(p, n_ctas, st);
+    if (V >= 8) return launch_exact_one<T, 8, 0, 4, E>(p, n_ctas, st);
+    return launch_exact_one<T, 1, 0, 1, E>(p, n_ctas, st);
+}
+
+cudaError_t launch_scan_exact(const ExactScanParams &p, uint32_t dtype, uint32_t k, uint32_t n_ctas, cudaStream_t st)
+{
+    const uint32_t E = scan_stream_lcap(k) / 32;
+#define MX_DISPATCH_EXACT(T)                                      \
+    switch (E) {                                                  \
+        case 1: return launch_exact_shape<T, 1>(p, n_ctas, st);   \
+        case 2: return launch_exact_shape<T, 2>(p, n_ctas, st);   \
+        case 4: return launch_exact_shape<T, 4>(p, n_ctas, st);   \
+        default: return launch_exact_shape<T, 8>(p, n_ctas, st);  \
+    }
+    if (dtype == MX_DTYPE_F32) {
+        MX_DISPATCH_EXACT(float)
+    } else {
+        MX_DISPATCH_EXACT(__half)
+    }
+#undef MX_DISPATCH_EXACT
 }
 
 // queries-per-pass the dispatch above uses for (nq, k): lets the caller size grid.y / candidates

@@ -26,7 +26,9 @@
 // per query (no list), publishes the second best, and after ONE grid-wide barrier (cooperative launch) every thread
 // takes tau0 = the (L/2)-th largest of the published values: L/2 CTAs hold two rows each scoring >= tau0, so tau0 is a
 // valid lower bound for the top L, and it sits at the ~0.07 % quantile instead of -inf.  The P tiles are then scanned
-// again, normally, at the end of the CTA's range.
+// again, normally, RIGHT AFTER the barrier (they are still in L2: the sampling pass loads them with the normal eviction
+// priority, everything after it evict-first), so a CTA visits its rows in increasing order and the strict `>` admission
+// of the list keeps the LOWER row of two equal scores -- the (distance, id) order of the reference's result.
 //
 // Roofline: HBM.  Algorithmic bytes per launch = N * ld * 2 (+ 4 N inv_norm).
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 tcgen05.mma issuer + TMEM owner,
@@ -105,6 +107,7 @@ struct TcParams {
     uint32_t sample_tiles, nq_pad;
     float *samp;
     uint32_t *sync;
+    float *floor_out;       // [nq_pad] tau0 of each query (-inf without seeding), read by the rerank's certificate
 };
 
 // QM = 128: TMEM lane = query.  QM = 64 (cta_group::1, M = 64): accumulator row r sits in TMEM lane
@@ -136,11 +139,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t n_tiles = (p.n_rows + kTileN - 1) / kTileN;
     const uint32_t q0 = blockIdx.y * QM;
     // this CTA's tiles: blockIdx.x + i * gridDim.x, i < n_local; with seeding the first P of them come twice:
-    // position i of the sequence -> tile index (i < n_local ? i : i - n_local), positions < P are the sampling pass
+    // positions [0, P) of the sequence are the sampling pass over local tiles 0 .. P-1, positions [P, P + n_local) the
+    // real scan over local tiles 0 .. n_local-1 -- rows in increasing order
     const uint32_t n_local = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const uint32_t n_sample = p.sample_tiles;
     const uint32_t n_seq = n_local + n_sample;
-    auto tile_of = [&](uint32_t i) { return blockIdx.x + (i < n_local ? i : i - n_local) * gridDim.x; };
+    auto tile_of = [&](uint32_t i) { return blockIdx.x + (i < n_sample ? i : i - n_sample) * gridDim.x; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -180,7 +184,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], kKBBytes);
-                    tma_load_2d(ring + stage * kKBBytes, &tmC, &full[stage], kb * kBK, tile * kTileN, kEvictFirst);
+                    tma_load_2d(ring + stage * kKBBytes, &tmC, &full[stage], kb * kBK, tile * kTileN,
+                                local < n_sample ? kEvictNormal : kEvictFirst);
                     if (++stage == n_stages) {
                         stage = 0;
                         phase ^= 1;
@@ -300,6 +305,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         }
                         g_floor = top[L / 2 - 1];
                     }
+                    if (q_ok && blockIdx.x == 0) p.floor_out[q0 + t] = g_floor;   // rerank's certificate needs every threshold
                 }
                 continue;
             }
@@ -401,8 +407,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // queries f32 [nq, ldq] -> unit-norm fp16 [nq_pad, ld] (zero rows beyond nq), tau[nq_pad] = -inf.
 // Scaling a query by a positive constant changes neither the cosine nor the dot ranking, and keeps
 // every fp16 component in [-1, 1].
+// qerr[row] = |q16 - q / |q||_2: by Cauchy-Schwarz the tensor-core score of ANY unit row differs from the exact cosine by at
+// most this (plus accumulation error) -- the rerank's certificate uses it as the approximation radius.
 __global__ void __launch_bounds__(128) tc_prepare_queries_kernel(const float *q, uint32_t nq, uint32_t dim, uint32_t ldq,
-                                                                 __half *q16, uint32_t ld, float *tau, uint32_t *sync)
+                                                                 __half *q16, uint32_t ld, float *tau, uint32_t *sync,
+                                                                 float *qerr, float *floor_out)
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) *sync = 0;
     const uint32_t row = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -416,9 +425,21 @@ __global__ void __launch_bounds__(128) tc_prepare_queries_kernel(const float *q,
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
-    for (uint32_t c = lane; c < ld; c += 32)
-        q16[(size_t)row * ld + c] = __float2half_rn((row < nq && c < dim) ? q[(size_t)row * ldq + c] * inv : 0.f);
-    if (lane == 0) tau[row] = kNegInf;
+    float ee = 0.f;
+    for (uint32_t c = lane; c < ld; c += 32) {
+        const float u = (row < nq && c < dim) ? q[(size_t)row * ldq + c] * inv : 0.f;
+        const __half h = __float2half_rn(u);
+        q16[(size_t)row * ld + c] = h;
+        const float e = __half2float(h) - u;
+        ee = fmaf(e, e, ee);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) ee += __shfl_xor_sync(0xffffffffu, ee, o);
+    if (lane == 0) {
+        tau[row] = kNegInf;
+        qerr[row] = sqrtf(ee) * 1.001f;
+        floor_out[row] = kNegInf;
+    }
 }
 
 }  // namespace
@@ -430,6 +451,8 @@ struct TcScanState {
     float *tau = nullptr;
     float *samp = nullptr;      // [sm_count][q_cap]
     uint32_t *sync = nullptr;
+    float *qerr = nullptr;      // [q_cap] fp16 rounding radius of each prepared query
+    float *floor_out = nullptr; // [q_cap] tau0 of the last launch
     uint32_t q_cap = 0;  // rows
 };
 
@@ -452,6 +475,8 @@ void tc_scan_destroy(TcScanState *t)
     cudaFree(t->tau);
     cudaFree(t->samp);
     cudaFree(t->sync);
+    cudaFree(t->qerr);
+    cudaFree(t->floor_out);
     delete t;
 }
 
@@ -460,6 +485,8 @@ void tc_scan_invalidate(TcScanState *) {}  // tensor maps are rebuilt on every l
 uint32_t tc_scan_max_k() { return 26; }
 bool tc_scan_supports(const TcScanState *t, uint32_t k) { return t != nullptr && k <= tc_scan_max_k(); }
 uint32_t tc_scan_lcap(uint32_t k) { return k <= 10 ? 16u : 32u; }
+const float *tc_scan_qerr(const TcScanState *t) { return t->qerr; }
+const float *tc_scan_floor(const TcScanState *t) { return t->floor_out; }
 uint32_t tc_scan_lists(const TcScanState *t, uint64_t n_rows)
 {
     return (uint32_t)std::min<uint64_t>((uint64_t)t->sm_count, ceil_div<uint64_t>(n_rows, kTileN));
@@ -527,15 +554,21 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
         cudaFree(t->tau);
         cudaFree(t->samp);
         cudaFree(t->sync);
+        cudaFree(t->qerr);
+        cudaFree(t->floor_out);
         t->q16 = nullptr;
         t->tau = nullptr;
         t->samp = nullptr;
         t->sync = nullptr;
+        t->qerr = nullptr;
+        t->floor_out = nullptr;
         t->q_cap = 0;
         cudaError_t e = cudaMalloc(&t->q16, (size_t)nq_pad * t->ld * sizeof(__half));
         if (e == cudaSuccess) e = cudaMalloc(&t->tau, (size_t)nq_pad * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&t->samp, (size_t)t->sm_count * nq_pad * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&t->sync, 256);
+        if (e == cudaSuccess) e = cudaMalloc(&t->qerr, (size_t)nq_pad * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&t->floor_out, (size_t)nq_pad * sizeof(float));
         if (e != cudaSuccess) {
             if (why) *why = "query staging allocation failed";
             return e;
@@ -543,7 +576,8 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
         t->q_cap = nq_pad;
     }
     if (timer) timer->begin(st, 1);
-    tc_prepare_queries_kernel<<<nq_pad / 4, 128, 0, st>>>(p.queries, p.nq, t->dim, p.ldq, t->q16, t->ld, t->tau, t->sync);
+    tc_prepare_queries_kernel<<<nq_pad / 4, 128, 0, st>>>(p.queries, p.nq, t->dim, p.ldq, t->q16, t->ld, t->tau, t->sync,
+                                                           t->qerr, t->floor_out);
     count_launch();
     if (timer) timer->end(st);
     cudaError_t e = cudaGetLastError();
@@ -567,6 +601,7 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
     tp.nq_pad = nq_pad;
     tp.samp = t->samp;
     tp.sync = t->sync;
+    tp.floor_out = t->floor_out;
     dim3 grid(p.n_lists, nq_pad / qm);
     // threshold seeding needs every CTA at the barrier: one query pass (grid.y == 1), a full grid, enough tiles per CTA
     // that scanning P of them twice is cheap; MX_SCAN_TC_SAMPLE=0 turns it off (A/B measurements)

@@ -68,6 +68,14 @@ struct mx_store : HandleBase {
     TcScanState *tc = nullptr;
     float *blob_scores = nullptr;  // scratch of mx_store_search_blob_device
     size_t blob_scores_cap = 0;
+    // superset certificate + exact fallback
+    bool verify = true;
+    uint32_t *n_flagged = nullptr;   // device scalar
+    uint32_t *q_map = nullptr;       // [verify_cap]
+    float *fb_thr = nullptr;         // [verify_cap]
+    size_t verify_cap = 0;
+    unsigned long long *stats = nullptr;   // device [2]: queries answered, queries flagged
+    float *max_norm = nullptr;       // device scalar
     KernelTimer timer;
 };
 
@@ -138,6 +146,7 @@ int32_t ingest_device(mx_store *s, const float *src_dev, uint64_t n, cudaStream_
     ip.zero_rows = s->zero_rows;
     ip.n_zero = s->n_zero;
     ip.bad_flag = s->flags;
+    ip.max_norm = s->max_norm;
     ip.first_row = s->n;
     ip.n = n;
     ip.dim = s->cfg.dim;
@@ -174,8 +183,76 @@ uint32_t pick_path(mx_store *s, uint32_t nq, uint32_t k)
     return s->cfg.dtype == MX_DTYPE_F16 ? 1 : 0;
 }
 
+uint32_t stream_lists(const mx_store *s)
+{
+    const uint64_t rows_per_cta = 16 * 16;  // a CTA iteration covers at least this many rows
+    return (uint32_t)std::min<uint64_t>((uint64_t)s->sm_count, ceil_div<uint64_t>(s->n, rows_per_cta));
+}
+
+// Second pass over the queries the certificate flagged (normally none: both kernels return at once).  The exact scan
+// re-scores every row that can still matter with the reference's f64 fold and keeps its lists on the exact key; the
+// rerank kernel then answers the flagged queries from those lists, overwriting their slots in the outputs.
+int32_t search_fallback(mx_store *s, const float *q_use, uint32_t nq, uint32_t k, uint64_t *ids_dev, float *scores_dev,
+                        float *dists_dev, uint32_t *counts_dev, cudaStream_t st)
+{
+    const uint32_t n_lists = stream_lists(s), lcap = scan_stream_lcap(k);
+    ExactScanParams ep{};
+    ep.scan.rows = s->rows;
+    ep.scan.inv_norm = s->inv_norm;
+    ep.scan.queries = q_use;
+    ep.scan.cand_s = s->cand_s;
+    ep.scan.cand_r = s->cand_r;
+    ep.scan.n_rows = (uint32_t)s->n;
+    ep.scan.ld = s->ld;
+    ep.scan.ldq = s->ldq;
+    ep.scan.nq = nq;
+    ep.scan.n_lists = n_lists;
+    ep.scan.use_inv = s->cfg.metric == MX_METRIC_COSINE ? 1u : 0u;
+    ep.active_n = s->n_flagged;
+    ep.active_map = s->q_map;
+    ep.fb_thr = s->fb_thr;
+    ep.dim = s->cfg.dim;
+    ep.metric = s->cfg.metric;
+    s->timer.begin(st, 1);
+    MX_CUDA(s, MX_ERR_SEARCH, launch_scan_exact(ep, s->cfg.dtype, k, n_lists, st));
+    s->timer.end(st);
+    RerankParams rp{};
+    rp.rows = s->rows;
+    rp.queries = q_use;
+    rp.cand_s = s->cand_s;
+    rp.cand_r = s->cand_r;
+    rp.zero_rows = s->zero_rows;
+    rp.n_zero = s->n_zero;
+    rp.ids_out = ids_dev;
+    rp.scores_out = scores_dev;
+    rp.dists_out = dists_dev;
+    rp.counts_out = counts_dev;
+    rp.id_offset = s->cfg.id_offset;
+    rp.id_stride = s->cfg.id_stride;
+    rp.n_rows = (uint32_t)s->n;
+    rp.ld = s->ld;
+    rp.ldq = s->ldq;
+    rp.dim = s->cfg.dim;
+    rp.nq = nq;
+    rp.k = k;
+    rp.n_lists = n_lists;
+    rp.lcap = lcap;
+    rp.dtype = s->cfg.dtype;
+    rp.metric = s->cfg.metric;
+    rp.active_n = s->n_flagged;
+    rp.active_map = s->q_map;
+    s->timer.begin(st, 1);
+    MX_CUDA(s, MX_ERR_SEARCH, launch_rerank(rp, st));
+    s->timer.end(st);
+    return MX_OK;
+}
+
+// defer_fallback: the caller reads *n_flagged back itself and runs search_fallback only when it is non-zero (the
+// host-buffer call synchronises anyway); otherwise the two fallback kernels are always enqueued and exit at once
+// when nothing was flagged (the asynchronous device-buffer call cannot look)
 int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_t k, uint64_t *ids_dev,
-                           float *scores_dev, float *dists_dev, uint32_t *counts_dev, cudaStream_t st)
+                           float *scores_dev, float *dists_dev, uint32_t *counts_dev, cudaStream_t st,
+                           bool defer_fallback = false, const float **q_used = nullptr)
 {
     if (!q_dev || !ids_dev || !scores_dev || !counts_dev) return fail(s, MX_ERR_INVALID, "null buffer");
     if (k == 0 || k > MX_MAX_K) return fail(s, MX_ERR_INVALID, "k must be in [1, %u]", MX_MAX_K);
@@ -215,17 +292,18 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
         s->timer.end(st);
         q_use = s->q_stage;
     }
+    if (q_used) *q_used = q_use;
 
     uint32_t n_lists, lcap;
     if (path == 2) {
         n_lists = tc_scan_lists(s->tc, s->n);
         lcap = tc_scan_lcap(k);
     } else {
-        const uint64_t rows_per_cta = 16 * 16;  // a CTA iteration covers at least this many rows
-        n_lists = (uint32_t)std::min<uint64_t>((uint64_t)s->sm_count, ceil_div<uint64_t>(s->n, rows_per_cta));
+        n_lists = stream_lists(s);
         lcap = scan_stream_lcap(k);
     }
-    const size_t cand = (size_t)nq * n_lists * lcap;
+    // the exact fallback writes [flagged][stream lists][stream lcap] into the same candidate buffer
+    const size_t cand = std::max((size_t)nq * n_lists * lcap, (size_t)nq * stream_lists(s) * scan_stream_lcap(k));
     if (cand > s->cand_cap) {
         if (s->cand_s) cudaFree(s->cand_s);
         if (s->cand_r) cudaFree(s->cand_r);
@@ -236,6 +314,17 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
         MX_CUDA(s, MX_ERR_SEARCH, cudaMalloc(&s->cand_r, cand * sizeof(uint32_t)));
         s->cand_cap = cand;
     }
+    if (s->verify && nq > s->verify_cap) {
+        cudaFree(s->q_map);
+        cudaFree(s->fb_thr);
+        s->q_map = nullptr;
+        s->fb_thr = nullptr;
+        s->verify_cap = 0;
+        MX_CUDA(s, MX_ERR_SEARCH, cudaMalloc(&s->q_map, (size_t)nq * sizeof(uint32_t)));
+        MX_CUDA(s, MX_ERR_SEARCH, cudaMalloc(&s->fb_thr, (size_t)nq * sizeof(float)));
+        s->verify_cap = nq;
+    }
+    if (s->verify) MX_CUDA(s, MX_ERR_SEARCH, cudaMemsetAsync(s->n_flagged, 0, sizeof(uint32_t), st));
 
     ScanParams sp{};
     sp.rows = s->rows;
@@ -283,9 +372,22 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
     rp.lcap = lcap;
     rp.dtype = s->cfg.dtype;
     rp.metric = s->cfg.metric;
+    if (s->verify) {
+        rp.n_flagged = s->n_flagged;
+        rp.q_map = s->q_map;
+        rp.fb_thr = s->fb_thr;
+        rp.stats = s->stats;
+        rp.max_norm = s->max_norm;
+        if (path == 2) {
+            rp.qerr = tc_scan_qerr(s->tc);
+            rp.scan_floor = tc_scan_floor(s->tc);
+            rp.unit_queries = 1;
+        }
+    }
     s->timer.begin(st, 1);
     MX_CUDA(s, MX_ERR_SEARCH, launch_rerank(rp, st));
     s->timer.end(st);
+    if (s->verify && !defer_fallback) return search_fallback(s, q_use, nq, k, ids_dev, scores_dev, dists_dev, counts_dev, st);
     return MX_OK;
 }
 
@@ -366,8 +468,15 @@ int32_t mx_store_create(const mx_store_cfg *cfg, mx_store **out)
     if ((e = cudaMalloc(&s->zero_rows, sizeof(uint32_t) * MX_MAX_K)) != cudaSuccess ||
         (e = cudaMalloc(&s->n_zero, 4)) != cudaSuccess || (e = cudaMalloc(&s->flags, 4)) != cudaSuccess)
         return bail(MX_ERR_CONNECTION, "cudaMalloc", e);
+    if ((e = cudaMalloc(&s->n_flagged, 4)) != cudaSuccess || (e = cudaMalloc(&s->stats, 16)) != cudaSuccess ||
+        (e = cudaMalloc(&s->max_norm, 4)) != cudaSuccess)
+        return bail(MX_ERR_CONNECTION, "cudaMalloc", e);
     cudaMemsetAsync(s->n_zero, 0, 4, s->stream);
     cudaMemsetAsync(s->flags, 0, 4, s->stream);
+    cudaMemsetAsync(s->n_flagged, 0, 4, s->stream);
+    cudaMemsetAsync(s->stats, 0, 16, s->stream);
+    cudaMemsetAsync(s->max_norm, 0, 4, s->stream);
+    if (const char *v = getenv("MX_SEARCH_VERIFY")) s->verify = atoi(v) != 0;   // A/B measurements only
     if (cfg->dtype == MX_DTYPE_F16) s->tc = tc_scan_create(s->sm_count, s->ld, cfg->dim);
     int32_t rc = reserve(s, cfg->capacity ? cfg->capacity : 1024, MX_ERR_CONNECTION);
     if (rc != MX_OK) {
@@ -395,6 +504,11 @@ void mx_store_destroy(mx_store *s)
     cudaFree(s->cand_r);
     cudaFree(s->dev_io);
     cudaFree(s->blob_scores);
+    cudaFree(s->n_flagged);
+    cudaFree(s->q_map);
+    cudaFree(s->fb_thr);
+    cudaFree(s->stats);
+    cudaFree(s->max_norm);
     if (s->pinned) cudaFreeHost(s->pinned);
     if (s->stream) cudaStreamDestroy(s->stream);
     s->magic = 0;
@@ -479,17 +593,31 @@ int32_t mx_store_search(mx_store *s, const float *queries, uint32_t nq, uint32_t
     const size_t ib = (size_t)nq * k * sizeof(uint64_t), sb = (size_t)nq * k * sizeof(float), cb = (size_t)nq * 4;
     const size_t off_i = (qb + 255) & ~(size_t)255, off_s = off_i + ((ib + 255) & ~(size_t)255),
                  off_c = off_s + ((sb + 255) & ~(size_t)255), total = off_c + ((cb + 255) & ~(size_t)255);
-    if ((rc = ensure_pinned(s, total)) != MX_OK) return rc;
+    if ((rc = ensure_pinned(s, total + 16)) != MX_OK) return rc;
     if ((rc = ensure_dev_io(s, total)) != MX_OK) return rc;
     char *hp = (char *)s->pinned, *dp = (char *)s->dev_io;
     memcpy(hp, queries, qb);
     MX_CUDA(s, MX_ERR_SEARCH, cudaMemcpyAsync(dp, hp, qb, cudaMemcpyHostToDevice, s->stream));
+    const float *q_used = nullptr;
     rc = search_device_impl(s, (const float *)dp, nq, k, (uint64_t *)(dp + off_i), (float *)(dp + off_s), nullptr,
-                            (uint32_t *)(dp + off_c), s->stream);
+                            (uint32_t *)(dp + off_c), s->stream, true, &q_used);
     if (rc != MX_OK) return rc;
     MX_CUDA(s, MX_ERR_SEARCH,
             cudaMemcpyAsync(hp + off_i, dp + off_i, total - off_i, cudaMemcpyDeviceToHost, s->stream));
+    uint32_t *flagged_h = reinterpret_cast<uint32_t *>(hp + total);
+    *flagged_h = 0;
+    if (s->verify && s->n > 0)
+        MX_CUDA(s, MX_ERR_SEARCH, cudaMemcpyAsync(flagged_h, s->n_flagged, 4, cudaMemcpyDeviceToHost, s->stream));
     MX_CUDA(s, MX_ERR_SEARCH, cudaStreamSynchronize(s->stream));
+    if (*flagged_h > 0) {
+        // the certificate could not vouch for some queries: answer those again with the exact scan
+        rc = search_fallback(s, q_used, nq, k, (uint64_t *)(dp + off_i), (float *)(dp + off_s), nullptr,
+                             (uint32_t *)(dp + off_c), s->stream);
+        if (rc != MX_OK) return rc;
+        MX_CUDA(s, MX_ERR_SEARCH,
+                cudaMemcpyAsync(hp + off_i, dp + off_i, total - off_i, cudaMemcpyDeviceToHost, s->stream));
+        MX_CUDA(s, MX_ERR_SEARCH, cudaStreamSynchronize(s->stream));
+    }
     memcpy(ids_out, hp + off_i, ib);
     memcpy(scores_out, hp + off_s, sb);
     memcpy(counts_out, hp + off_c, cb);
@@ -616,6 +744,7 @@ int32_t mx_store_clear(mx_store *s)
     s->n = 0;
     s->zero_dirty = false;
     MX_CUDA(s, MX_ERR_DELETE, cudaMemsetAsync(s->n_zero, 0, 4, s->stream));
+    MX_CUDA(s, MX_ERR_DELETE, cudaMemsetAsync(s->max_norm, 0, 4, s->stream));
     return MX_OK;
 }
 
@@ -671,6 +800,26 @@ int32_t mx_store_get_timing(mx_store *s, double *scan_ms_total, uint64_t *scan_l
     if (scan_launches) *scan_launches = s->timer.launches[0];
     if (other_ms_total) *other_ms_total = s->timer.total_ms[1];
     if (other_launches) *other_launches = s->timer.launches[1];
+    return MX_OK;
+}
+
+int32_t mx_store_verify_stats(mx_store *s, uint64_t *queries_out, uint64_t *flagged_out)
+{
+    if (!s) return MX_ERR_INVALID;
+    int32_t rc;
+    if ((rc = set_device(s)) != MX_OK) return rc;
+    unsigned long long h[2] = {0, 0};
+    MX_CUDA(s, MX_ERR_CONNECTION, cudaDeviceSynchronize());
+    MX_CUDA(s, MX_ERR_CONNECTION, cudaMemcpy(h, s->stats, sizeof h, cudaMemcpyDeviceToHost));
+    if (queries_out) *queries_out = h[0];
+    if (flagged_out) *flagged_out = h[1];
+    return MX_OK;
+}
+
+int32_t mx_store_set_verify(mx_store *s, int32_t on)
+{
+    if (!s) return MX_ERR_INVALID;
+    s->verify = on != 0;
     return MX_OK;
 }
 

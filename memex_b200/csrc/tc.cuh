@@ -142,6 +142,7 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m)
 }
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // stream-once data (corpus tiles, activations)
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // re-used data (weights, queries)
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;  // read again soon, then streamed past
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int32_t c0,
                                             int32_t c1, uint64_t hint)
 {

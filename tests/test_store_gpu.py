@@ -449,3 +449,158 @@ def test_full_size_properties_tcgen05_2m(tmp_path):
     oi, os_, _ = cosine.exact_topk(stored, queries[:2], k)
     np.testing.assert_array_equal(ids[:2], oi)
     np.testing.assert_array_equal(scores[:2].view(np.uint32), os_.view(np.uint32))
+
+
+# ---- seeded-scan tie order, the superset certificate and the exact fallback -----------------------
+
+def _verify_stats(store):
+    q, f = C.c_uint64(), C.c_uint64()
+    assert capi.lib().mx_store_verify_stats(store.handle, C.byref(q), C.byref(f)) == 0
+    return q.value, f.value
+
+
+def test_tcgen05_seeded_scan_keeps_lowest_ids_of_a_tie_group(tmp_path):
+    """20 bit-identical rows inside ONE CTA's stripe -- two of them in the tile the sampling pass
+    scans (rows 3 and 70 of CTA 0's first tile), the rest in CTA 0's later tiles (tile 148 j) -- more than the L = 16 list
+    holds.  The scan alone (certificate off) must already keep the lowest rows: a CTA visits its rows in increasing
+    order, so the strict admission test never trades a lower row for an equal-score higher one."""
+    n, d, nq, k = 400_000, 64, 16, 10
+    rng = np.random.default_rng(5)
+    corpus = rng.standard_normal((n, d)).astype(np.float32)
+    dup = rng.standard_normal(d).astype(np.float32)
+    dup_rows = np.array([3, 70] + [148 * 128 * j + int(rng.integers(0, 128)) for j in range(1, 19)])
+    corpus[dup_rows] = dup
+    queries = rng.standard_normal((nq, d)).astype(np.float32)
+    queries[0] = dup
+    queries[5] = dup * 3.0 + 0.001 * rng.standard_normal(d).astype(np.float32)
+    store = B200Store.new(tmp_path, dim=d, dtype="f16", capacity=n)
+    store.add_matrix(corpus)
+    L = capi.lib()
+    assert L.mx_store_scan_path(store.handle, nq, k, -1) == 2
+    stored = corpus.astype(np.float16).astype(np.float32)
+    want = np.sort(dup_rows)[:k] + 1
+    assert L.mx_store_set_verify(store.handle, 0) == 0
+    ids, scores, _ = store.search_matrix(queries, k)
+    np.testing.assert_array_equal(ids[0], want)
+    np.testing.assert_array_equal(ids[5], want)
+    oi, os_, _ = cosine.exact_topk(stored, queries, k)
+    np.testing.assert_array_equal(ids, oi)
+    np.testing.assert_array_equal(scores.view(np.uint32), os_.view(np.uint32))
+    # with the certificate on the answer is the same, and the tie group that spills over the lists is noticed
+    assert L.mx_store_set_verify(store.handle, 1) == 0
+    check_parity(store, stored, queries, k)
+    _, flagged = _verify_stats(store)
+    assert flagged >= 2
+
+
+def _near_tie_crowd(rng, q, d, m, alpha=0.8):
+    """m rows at (in real arithmetic) the SAME cosine alpha to q: alpha q + sqrt(1 - alpha^2) h_i, h_i unit, h_i . q = 0.
+    Rounding the rows for storage then decides their exact order; rounding the QUERY to fp16 (tcgen05 scan) or
+    accumulating in f32 (stream scan) shuffles the approximate one."""
+    qn = q / np.linalg.norm(q)
+    h = rng.standard_normal((m, d))
+    h -= (h @ qn)[:, None] * qn[None, :]
+    h /= np.linalg.norm(h, axis=1, keepdims=True)
+    return (alpha * qn[None, :] + np.sqrt(1 - alpha * alpha) * h).astype(np.float32)
+
+
+def test_certificate_catches_a_near_tie_crowd_tcgen05(tmp_path):
+    """40 rows within ~1e-5 of each other inside one CTA's stripe, more than the 16-entry list holds and
+    closer than the fp16-query approximation resolves.  The certificate must flag the query and the exact scan must
+    return the reference's order; the other queries of the batch stay on the fast path."""
+    d, nq, k = 384, 16, 10
+    n = 148 * 128 * 6
+    rng = np.random.default_rng(11)
+    corpus = unit_rows(n, d, 12)
+    queries = unit_rows(nq, d, 13)
+    crowd = _near_tie_crowd(rng, queries[3].astype(np.float64), d, 40)
+    rows = np.array([(5 + 148 * j) * 128 + i for j in range(4) for i in range(0, 120, 12)])   # tiles 5, 153, 301, 449: CTA 5
+    corpus[rows] = crowd
+    store = B200Store.new(tmp_path, dim=d, dtype="f16", capacity=n)
+    store.add_matrix(corpus)
+    L = capi.lib()
+    assert L.mx_store_scan_path(store.handle, nq, k, -1) == 2
+    stored = corpus.astype(np.float16).astype(np.float32)
+    oi, os_, _ = cosine.exact_topk(stored, queries, k)
+    assert set(oi[3] - 1) <= set(rows)          # the crowd IS the answer of query 3
+    q0, f0 = _verify_stats(store)
+    check_parity(store, stored, queries, k)
+    q1, f1 = _verify_stats(store)
+    assert q1 - q0 == nq and 1 <= f1 - f0 <= 2
+    # the device-buffer call (fallback kernels always enqueued) gives the same answer
+    import torch
+    qd = torch.from_numpy(queries).cuda()
+    ids_d = torch.zeros((nq, k), dtype=torch.int64, device="cuda")
+    sc_d = torch.zeros((nq, k), dtype=torch.float32, device="cuda")
+    cn_d = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    assert L.mx_store_search_device(store.handle, qd.data_ptr(), nq, k, ids_d.data_ptr(), sc_d.data_ptr(), None,
+                                    cn_d.data_ptr(), None) == 0
+    assert L.mx_store_sync(store.handle) == 0
+    np.testing.assert_array_equal(ids_d.cpu().numpy().astype(np.uint64), oi)
+    np.testing.assert_array_equal(sc_d.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+    # what the approximate stage alone would have answered: recorded, not asserted (it may get lucky)
+    L.mx_store_set_verify(store.handle, 0)
+    ids_off, _, _ = store.search_matrix(queries, k)
+    L.mx_store_set_verify(store.handle, 1)
+    print("crowd query without the certificate:", "same" if (ids_off[3] == oi[3]).all() else "DIFFERENT", "ids")
+    np.testing.assert_array_equal(np.delete(ids_off, 3, 0), np.delete(oi, 3, 0))
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f16"])
+def test_certificate_catches_a_near_tie_crowd_stream_scan(tmp_path, dtype):
+    """the same for the CUDA-core stream scan (single query): 100 contiguous near-tie rows sit in one CTA's range, its
+    32-entry list cannot hold them, f32 accumulation cannot order them"""
+    d, k, n = 384, 10, 60_000
+    rng = np.random.default_rng(21)
+    corpus = unit_rows(n, d, 22)
+    q = unit_rows(1, d, 23)
+    corpus[1000:1100] = _near_tie_crowd(rng, q[0].astype(np.float64), d, 100)
+    store = B200Store.new(tmp_path, dim=d, dtype=dtype, capacity=n)
+    store.add_matrix(corpus)
+    stored = corpus if dtype == "f32" else corpus.astype(np.float16).astype(np.float32)
+    _, f0 = _verify_stats(store)
+    check_parity(store, stored, q, k)
+    _, f1 = _verify_stats(store)
+    assert f1 - f0 == 1
+    check_parity(store, stored, unit_rows(3, d, 24), k)       # ordinary queries are not flagged
+    _, f2 = _verify_stats(store)
+    assert f2 == f1
+
+
+@pytest.mark.parametrize("metric", ["cosine", "dot"])
+def test_mass_duplicates_answered_by_the_exact_scan(tmp_path, metric):
+    """memex has no dedup: the same document ingested thousands of times.  5000 bit-identical rows tie for every place
+    of the top k; whatever the lists kept, the exact scan ranks them by (distance, id)"""
+    d, nq, k, n = 128, 12, 10, 120_000
+    rng = np.random.default_rng(31)
+    corpus = rng.standard_normal((n, d)).astype(np.float32)
+    dup = rng.standard_normal(d).astype(np.float32)
+    dup_rows = np.sort(rng.choice(n, 5000, replace=False))
+    corpus[dup_rows] = dup
+    queries = rng.standard_normal((nq, d)).astype(np.float32)
+    queries[7] = dup + 0.01 * rng.standard_normal(d).astype(np.float32)
+    store = B200Store.new(tmp_path, dim=d, dtype="f16", metric=metric, capacity=n)
+    store.add_matrix(corpus)
+    stored = corpus.astype(np.float16).astype(np.float32)
+    check_parity(store, stored, queries, k, metric=metric)
+    ids, _, _ = store.search_matrix(queries, k)
+    np.testing.assert_array_equal(ids[7], dup_rows[:k] + 1)
+    _, flagged = _verify_stats(store)
+    assert flagged >= 2
+    # k = 40 goes through the stream scan's 64-entry lists (E = 2) and the E = 2 exact scan
+    check_parity(store, stored, queries[6:8], 40, metric=metric)
+
+
+def test_ordinary_corpus_is_never_flagged(tmp_path):
+    """the certificate costs nothing on well-separated data: no query of the parity cases above takes the exact scan"""
+    n, d, nq, k = 200_000, 384, 64, 10
+    corpus = unit_rows(n, d, 41)
+    rng = np.random.default_rng(42)
+    queries = corpus[rng.integers(0, n, nq)] + 0.1 * unit_rows(nq, d, 43)
+    store = B200Store.new(tmp_path, dim=d, dtype="f16", capacity=n)
+    store.add_matrix(corpus)
+    stored = corpus.astype(np.float16).astype(np.float32)
+    check_parity(store, stored, queries, k)
+    check_parity(store, stored, queries[:1], k)
+    qn, flagged = _verify_stats(store)
+    assert qn == nq + 1 and flagged == 0
