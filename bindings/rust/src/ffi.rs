@@ -93,6 +93,7 @@ extern "C" {
         counts_out: *mut u32,
     ) -> i32;
     pub fn mx_store_len(s: *mut mx_store, n_out: *mut u64) -> i32;
+    pub fn mx_store_info(s: *mut mx_store, dim: *mut u32, dtype: *mut u32, metric: *mut u32, capacity: *mut u64) -> i32;
     pub fn mx_store_clear(s: *mut mx_store) -> i32;
     pub fn mx_store_delete(s: *mut mx_store, id: u64) -> i32; // always MX_ERR_UNSUPPORTED (local.rs:29-32)
     pub fn mx_store_save(s: *mut mx_store, dir: *const c_char) -> i32;

@@ -28,6 +28,7 @@ pub struct B200Store {
     handle: *mut ffi::mx_store, // created on the first insert, when the dimension is known
     half: bool,                 // fp16 rows (b200+f16://): the tensor-core scan serves batched queries
     device: i32,
+    dim: usize, // width of the device store (0 until the first insert / load); every FFI call is checked against it
     pub _id_map: HashMap<usize, String>,
 }
 
@@ -61,7 +62,7 @@ fn check(rc: i32, handle: *const c_void) -> StoreResult<()> {
 impl B200Store {
     pub fn new(storage_path: &Path, half: bool) -> Self {
         log::info!("Initializing B200 vector storage @ \"{}\"", storage_path.display());
-        Self { storage_path: storage_path.to_path_buf(), handle: std::ptr::null_mut(), half, device: 0, _id_map: HashMap::new() }
+        Self { storage_path: storage_path.to_path_buf(), handle: std::ptr::null_mut(), half, device: 0, dim: 0, _id_map: HashMap::new() }
     }
 
     pub fn has_store(store_path: &Path) -> bool {
@@ -77,17 +78,30 @@ impl B200Store {
         }
         let meta_reader = BufReader::new(File::open(store_path.join(META_FILE))?);
         let _id_map: HashMap<usize, String> = serde_json::from_reader(meta_reader)?;
-        Ok(Self { storage_path: store_path.to_path_buf(), handle, half: false, device: 0, _id_map })
+        // the C ABI's add / search take no width: read it back so that every slice can be checked before the call
+        let (mut dim, mut dtype, mut metric, mut cap) = (0u32, 0u32, 0u32, 0u64);
+        if !handle.is_null() {
+            check(unsafe { ffi::mx_store_info(handle, &mut dim, &mut dtype, &mut metric, &mut cap) }, handle as *const c_void)?;
+        }
+        Ok(Self {
+            storage_path: store_path.to_path_buf(),
+            handle,
+            half: dtype == ffi::MX_DTYPE_F16,
+            device: 0,
+            dim: dim as usize,
+            _id_map,
+        })
     }
 
     pub fn save(&self, store_path: PathBuf) -> Result<(), VectorStoreError> {
         if !store_path.exists() {
             let _ = std::fs::create_dir_all(store_path.clone());
         }
-        if !self.handle.is_null() {
-            let dir = cstr(&store_path);
-            check(unsafe { ffi::mx_store_save(self.handle, dir.as_ptr()) }, self.handle as *const c_void)?;
+        if self.handle.is_null() {
+            return Ok(()); // nothing was ever inserted: no files, so has_store() stays false
         }
+        let dir = cstr(&store_path);
+        check(unsafe { ffi::mx_store_save(self.handle, dir.as_ptr()) }, self.handle as *const c_void)?;
         // the id map, byte-compatible with local.rs:155-161
         let result = serde_json::to_string(&self._id_map).map_err(|err| VectorStoreError::SaveError(err.to_string()))?;
         let mut f = File::create(store_path.join(META_FILE))?;
@@ -98,7 +112,12 @@ impl B200Store {
 
     fn ensure(&mut self, dim: usize) -> StoreResult<()> {
         if !self.handle.is_null() {
-            return Ok(());
+            // an existing (or loaded) store has ONE width: a narrower slice would make the device read past its end
+            return if dim == self.dim {
+                Ok(())
+            } else {
+                Err(VectorStoreError::InsertionError(format!("vector has dimension {dim}, store has {}", self.dim)))
+            };
         }
         let cfg = ffi::mx_store_cfg {
             dim: if dim == 0 { DEFAULT_DIM } else { dim as u32 },
@@ -109,7 +128,9 @@ impl B200Store {
             id_offset: 0,
             id_stride: 1,
         };
-        check(unsafe { ffi::mx_store_create(&cfg, &mut self.handle) }, std::ptr::null())
+        check(unsafe { ffi::mx_store_create(&cfg, &mut self.handle) }, std::ptr::null())?;
+        self.dim = cfg.dim as usize;
+        Ok(())
     }
 }
 
@@ -172,10 +193,17 @@ impl VectorStore for B200Store {
 
     async fn search(&self, vec: &[f32], limit: usize) -> StoreResult<Vec<VectorSearchResult>> {
         // local.rs:71-91
-        let k = limit.min(ffi::MX_MAX_K as usize) as u32;
-        if k == 0 || self.handle.is_null() {
+        if limit == 0 || self.handle.is_null() {
             return Ok(Vec::new());
         }
+        // one behaviour in every host (C++, Python, Rust): more than MX_MAX_K neighbours is an error, never a silent cut
+        if limit > ffi::MX_MAX_K as usize {
+            return Err(VectorStoreError::SearchError(format!("limit {limit} exceeds the store's maximum of {}", ffi::MX_MAX_K)));
+        }
+        if vec.len() != self.dim {
+            return Err(VectorStoreError::SearchError(format!("query has dimension {}, store has {}", vec.len(), self.dim)));
+        }
+        let k = limit as u32;
         let (mut ids, mut scores, mut count) = (vec![0u64; k as usize], vec![0f32; k as usize], 0u32);
         check(
             unsafe {

@@ -532,23 +532,29 @@ int32_t mx_store_add(mx_store *s, const float *vecs, uint64_t n, uint64_t *first
     if ((rc = ensure_pinned(s, chunk_rows * row_bytes)) != MX_OK) return rc;
     if ((rc = ensure_dev_io(s, chunk_rows * row_bytes)) != MX_OK) return rc;
     const uint64_t n_before = s->n;
+    // ingest appends at s->n, so the count moves with the chunks; EVERY exit below puts it back, and only finish_add
+    // commits the batch (a failed copy must not leave rows the host's id map knows nothing about)
+    struct Rollback {
+        mx_store *s;
+        uint64_t n;
+        ~Rollback() { s->n = n; }
+    } rollback{s, n_before};
     uint64_t done = 0;
     while (done < n) {
         const uint64_t c = std::min(chunk_rows, n - done);
         memcpy(s->pinned, vecs + done * s->cfg.dim, c * row_bytes);
         MX_CUDA(s, MX_ERR_INSERTION,
                 cudaMemcpyAsync(s->dev_io, s->pinned, c * row_bytes, cudaMemcpyHostToDevice, s->stream));
-        s->n = n_before + done;  // ingest appends at s->n
+        s->n = n_before + done;
         rc = ingest_device(s, (const float *)s->dev_io, c, s->stream);
-        if (rc != MX_OK) {
-            s->n = n_before;
-            return rc;
-        }
+        if (rc != MX_OK) return rc;
         MX_CUDA(s, MX_ERR_INSERTION, cudaStreamSynchronize(s->stream));  // pinned buffer is reused
         done += c;
     }
     s->n = n_before;
-    return finish_add(s, n, s->stream, first_id_out);
+    rc = finish_add(s, n, s->stream, first_id_out);
+    rollback.n = s->n;   // committed (or unchanged when the batch was rejected)
+    return rc;
 }
 
 int32_t mx_store_add_device(mx_store *s, const float *vecs_dev, uint64_t n, uint64_t *first_id_out)
@@ -953,6 +959,7 @@ int32_t mx_store_load(const char *dir, int32_t device, mx_store **out)
         return bail(MX_ERR_CONNECTION, "cudaMalloc failed");
     }
     rc = ensure_pinned(s, chunk_rows * row_bytes);
+    if (rc != MX_OK) g_last_error = s->last_error;   // the handle is destroyed below: keep its message
     for (uint64_t done = 0; rc == MX_OK && done < h.n;) {
         const uint64_t c = std::min(chunk_rows, h.n - done);
         if (fread(s->pinned, row_bytes, c, f) != c) {

@@ -80,7 +80,7 @@ public:
 class B200Store : public VectorStore {
 public:
     struct Options {
-        uint32_t dim = 384;     // mod.rs:126: the embedding dimension of the MiniLM models
+        uint32_t dim = 0;       // 0 = sized by the first insert (HnswStore takes any width; mod.rs:126 only hints 384)
         bool fp16 = false;      // rows kept as fp16 in HBM (north_star's 10Mx384 configuration)
         bool dot = false;       // dot-product metric instead of 1 - DistCosine
         int device = 0;
@@ -109,6 +109,7 @@ public:
 
 private:
     B200Store() = default;
+    void create_handle(uint32_t dim);   // the device store is made when the width is known (Options::dim or first insert)
     mx_store *handle_ = nullptr;
 };
 
@@ -129,7 +130,9 @@ private:
 // get_vector_storage (mod.rs:95-139): URI-scheme factory.  "b200://<dir>" -> <dir>/<collection>/, loaded if a
 // vectors.meta.json exists there, else new.  Unlike the reference (which re-opens the index on every task and
 // request, worker/src/tasks.rs:17, api handlers.rs:35,63) handles are kept in a process-wide registry keyed by
-// (uri, collection) -- SURVEY.md 8(f) N1.  Options after '?': dtype=f16|f32, metric=cosine|dot, device=<n>, dim=<n>.
+// (uri, collection) -- SURVEY.md 8(f) N1.  Options after '?' (stripped from the directory): dtype=f16|f32,
+// metric=cosine|dot, device=<n>, dim=<n>; unknown keys or values -> Unsupported.  Without dim= the store takes the
+// width of its first insert, as HnswStore does (so 768-d / 512-d models work behind the same URI).
 VectorStorage get_vector_storage(const std::string &uri, const std::string &collection);
 void drop_vector_storage_registry();   // tests
 

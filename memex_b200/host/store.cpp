@@ -104,29 +104,37 @@ std::unique_ptr<B200Store> B200Store::new_(const std::string &storage_path, cons
     std::unique_ptr<B200Store> s(new B200Store());
     s->storage_path = storage_path;
     s->options = opt;
+    if (opt.dim) s->create_handle(opt.dim);
+    return s;
+}
+
+void B200Store::create_handle(uint32_t dim)
+{
     mx_store_cfg cfg{};
-    cfg.dim = opt.dim;
-    cfg.dtype = opt.fp16 ? MX_DTYPE_F16 : MX_DTYPE_F32;
-    cfg.metric = opt.dot ? MX_METRIC_DOT : MX_METRIC_COSINE;
-    cfg.device = opt.device;
-    cfg.capacity = opt.capacity;
+    cfg.dim = dim;
+    cfg.dtype = options.fp16 ? MX_DTYPE_F16 : MX_DTYPE_F32;
+    cfg.metric = options.dot ? MX_METRIC_DOT : MX_METRIC_COSINE;
+    cfg.device = options.device;
+    cfg.capacity = options.capacity;
     cfg.id_offset = 0;
     cfg.id_stride = 1;
-    int32_t rc = mx_store_create(&cfg, &s->handle_);
+    int32_t rc = mx_store_create(&cfg, &handle_);
     if (rc != MX_OK) raise(rc, nullptr, StoreErrorKind::ConnectionError);
-    return s;
+    options.dim = dim;
 }
 
 bool B200Store::has_store(const std::string &store_path) { return exists(join(store_path, kMetaFile)); }
 
 std::unique_ptr<B200Store> B200Store::load(const std::string &store_path, int device)
 {
-    if (!mx_store_has_file(store_path.c_str()))
-        throw VectorStoreError(StoreErrorKind::FileIOError, join(store_path, "vectors.b200.bin") + ": No such file or directory");
     std::unique_ptr<B200Store> s(new B200Store());
     s->storage_path = store_path;
-    int32_t rc = mx_store_load(store_path.c_str(), device, &s->handle_);
-    if (rc != MX_OK) raise(rc, nullptr, StoreErrorKind::FileIOError);
+    s->options.device = device;
+    const bool has_bin = mx_store_has_file(store_path.c_str()) != 0;
+    if (has_bin) {
+        int32_t rc = mx_store_load(store_path.c_str(), device, &s->handle_);
+        if (rc != MX_OK) raise(rc, nullptr, StoreErrorKind::FileIOError);
+    }
     std::ifstream f(join(store_path, kMetaFile), std::ios::binary);
     if (!f) throw VectorStoreError(StoreErrorKind::FileIOError, join(store_path, kMetaFile) + ": " + std::strerror(errno));
     std::stringstream ss;
@@ -144,6 +152,13 @@ std::unique_ptr<B200Store> B200Store::load(const std::string &store_path, int de
     } catch (const std::runtime_error &e) {
         throw VectorStoreError(StoreErrorKind::SerdeError, e.what());
     }
+    if (!has_bin) {
+        // a meta file without its matrix: only an EMPTY map is a store (one that never received a row); anything
+        // else is the reference's load failure (local.rs:127-129)
+        if (!s->_id_map.empty())
+            throw VectorStoreError(StoreErrorKind::FileIOError, join(store_path, "vectors.b200.bin") + ": No such file or directory");
+        return s;
+    }
     uint32_t dim = 0, dtype = 0, metric = 0;
     uint64_t cap = 0;
     mx_store_info(s->handle_, &dim, &dtype, &metric, &cap);
@@ -156,6 +171,7 @@ std::unique_ptr<B200Store> B200Store::load(const std::string &store_path, int de
 
 void B200Store::save(const std::string &store_path) const
 {
+    if (!handle_) return;   // nothing was ever inserted: no files, so has_store() stays false (as a fresh HnswStore dir)
     make_dirs(store_path);
     int32_t rc = mx_store_save(handle_, store_path.c_str());
     if (rc != MX_OK) raise(rc, handle_, StoreErrorKind::SaveError);
@@ -189,6 +205,7 @@ B200Store::~B200Store()
 void B200Store::delete_(const std::string &)
 {
     // local.rs:29-32 is `unimplemented!()`: a panic.  The ABI reports it instead.
+    if (!handle_) throw VectorStoreError(StoreErrorKind::Unsupported, "removing a single point is not supported by the file store");
     raise(mx_store_delete(handle_, 0), handle_, StoreErrorKind::Unsupported);
 }
 
@@ -196,14 +213,20 @@ void B200Store::delete_all()
 {
     mx_store_remove_file(storage_path.c_str());                 // the data file ...
     std::remove(join(storage_path, kMetaFile).c_str());         // ... and the id map (local.rs:36-46)
-    int32_t rc = mx_store_clear(handle_);
-    if (rc != MX_OK) raise(rc, handle_, StoreErrorKind::DeleteError);
+    if (handle_) {
+        int32_t rc = mx_store_clear(handle_);
+        if (rc != MX_OK) raise(rc, handle_, StoreErrorKind::DeleteError);
+    }
     _id_map.clear();
 }
 
 void B200Store::bulk_insert(const std::vector<VectorData> &data)
 {
     if (data.empty()) return;
+    if (!handle_) {
+        if (data[0].vector.empty()) throw VectorStoreError(StoreErrorKind::InsertionError, "empty vector");
+        create_handle((uint32_t)data[0].vector.size());
+    }
     const size_t dim = options.dim;
     std::vector<float> rows(data.size() * dim);
     for (size_t i = 0; i < data.size(); ++i) {
@@ -230,9 +253,13 @@ void B200Store::insert(const VectorData &data) { bulk_insert({data}); }
 std::vector<std::vector<VectorSearchResult>> B200Store::search_batch(const std::vector<std::vector<float>> &vecs, size_t limit) const
 {
     std::vector<std::vector<VectorSearchResult>> out(vecs.size());
-    if (vecs.empty() || limit == 0 || _id_map.empty()) return out;
+    if (vecs.empty() || limit == 0 || _id_map.empty() || !handle_) return out;
+    // one behaviour in every host (C++, Python, Rust): more than MX_MAX_K neighbours is an error, never a silent cut
+    if (limit > MX_MAX_K)
+        throw VectorStoreError(StoreErrorKind::SearchError, "limit " + std::to_string(limit) + " exceeds the store's maximum of " +
+                                                                std::to_string(MX_MAX_K) + " neighbours per query");
     const size_t dim = options.dim, nq = vecs.size();
-    const uint32_t k = (uint32_t)std::min<size_t>(limit, MX_MAX_K);
+    const uint32_t k = (uint32_t)limit;
     std::vector<float> q(nq * dim);
     for (size_t i = 0; i < nq; ++i) {
         if (vecs[i].size() != dim)
@@ -265,7 +292,7 @@ std::vector<VectorSearchResult> B200Store::search(const std::vector<float> &vec,
 uint64_t B200Store::len() const
 {
     uint64_t n = 0;
-    mx_store_len(handle_, &n);
+    if (handle_) mx_store_len(handle_, &n);
     return n;
 }
 
@@ -317,19 +344,48 @@ VectorStorage get_vector_storage(const std::string &uri, const std::string &coll
     if (sep == std::string::npos || sep == 0) throw VectorStoreError(StoreErrorKind::Unsupported, uri);
     const std::string scheme = uri.substr(0, sep);
     if (scheme != "b200" && scheme != "b200+f16" && scheme != "b200+f32") throw VectorStoreError(StoreErrorKind::Unsupported, uri);
+    // "<dir>?key=value&..." -- the options never reach the directory name
+    std::string rest = uri.substr(sep + 3);
+    B200Store::Options opt;
+    opt.fp16 = scheme == "b200+f16";
+    const size_t qm = rest.find('?');
+    if (qm != std::string::npos) {
+        std::string query = rest.substr(qm + 1);
+        rest.resize(qm);
+        size_t pos = 0;
+        while (pos <= query.size()) {
+            size_t amp = query.find('&', pos);
+            if (amp == std::string::npos) amp = query.size();
+            const std::string kv = query.substr(pos, amp - pos);
+            pos = amp + 1;
+            if (kv.empty()) continue;
+            const size_t eq = kv.find('=');
+            const std::string k = kv.substr(0, eq), v = eq == std::string::npos ? "" : kv.substr(eq + 1);
+            auto number = [&](uint64_t max) -> uint64_t {
+                char *end = nullptr;
+                errno = 0;
+                unsigned long long x = std::strtoull(v.c_str(), &end, 10);
+                if (v.empty() || *end || errno || x > max) throw VectorStoreError(StoreErrorKind::Unsupported, uri + " (bad value for " + k + ")");
+                return x;
+            };
+            if (k == "dtype" && (v == "f16" || v == "f32")) opt.fp16 = v == "f16";
+            else if (k == "metric" && (v == "cosine" || v == "dot")) opt.dot = v == "dot";
+            else if (k == "device") opt.device = (int)number(1023);
+            else if (k == "dim") opt.dim = (uint32_t)number(1u << 20);
+            else throw VectorStoreError(StoreErrorKind::Unsupported, uri + " (unknown option " + kv + ")");
+        }
+    }
     const std::string key = uri + "\n" + collection;
     std::lock_guard<std::mutex> g(g_registry_mu);
     auto it = registry().find(key);
     if (it != registry().end()) return it->second;
     // collections are stored as folders (mod.rs:109-113)
-    const std::string storage = join(uri.substr(sep + 3), collection);
+    const std::string storage = join(rest, collection);
     make_dirs(storage);
     std::shared_ptr<VectorStore> store;
     if (B200Store::has_store(storage)) {
-        store = B200Store::load(storage);
+        store = B200Store::load(storage, opt.device);
     } else {
-        B200Store::Options opt;
-        opt.fp16 = scheme == "b200+f16";
         store = B200Store::new_(storage, opt);
     }
     VectorStorage vs(store);

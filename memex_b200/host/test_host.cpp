@@ -10,6 +10,7 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <sys/stat.h>
 
 #include "json.hpp"
 #include "memex_host.hpp"
@@ -25,6 +26,8 @@ static int g_checks = 0;
             std::exit(1);                                                                \
         }                                                                                \
     } while (0)
+
+static void make_dir(const std::string &p) { ::mkdir(p.c_str(), 0777); }
 
 static std::string slurp(const std::string &p)
 {
@@ -319,7 +322,9 @@ static int run_cpu()
     }
     // ---- no CPU path: creating a store without a CUDA device is a ConnectionError
     try {
-        auto s = B200Store::new_("/tmp/mx_host_cpu_probe");
+        B200Store::Options o;
+        o.dim = 384;   // a given width makes the device store at once (dim = 0 waits for the first insert)
+        auto s = B200Store::new_("/tmp/mx_host_cpu_probe", o);
         std::printf("cpu ok (a CUDA device is present): %d checks\n", g_checks);
     } catch (const VectorStoreError &e) {
         CHECK(e.kind == StoreErrorKind::ConnectionError);
@@ -428,8 +433,66 @@ static int run_gpu(const std::string &tmp)
             if (i % 50 == 0) CHECK(r == c.search(pts[i].vector, 5));
         }
         CHECK(batcher.batches_issued() < 200);
+        // more than MX_MAX_K neighbours: an error in every host, never a silent cut
+        try {
+            c.search(pts[0].vector, 257);
+            CHECK(false);
+        } catch (const VectorStoreError &e) {
+            CHECK(e.kind == StoreErrorKind::SearchError);
+        }
+        CHECK(c.search(pts[0].vector, 256).size() == 256);
         c.delete_collection();
         CHECK(c.search(pts[0].vector, 3).empty());
+        drop_vector_storage_registry();
+    }
+    // the factory sizes a store by its first insert (HnswStore takes any width): the 768-d and 512-d models of the
+    // enum work behind the same URI; '?' options are parsed and never reach the directory name
+    {
+        const std::string base = tmp + "/lazy";
+        VectorStorage w768 = get_vector_storage("b200+f16://" + base, "wide");
+        CHECK(w768.search(std::vector<float>(768, 1.f), 3).empty());   // nothing inserted yet
+        CHECK(!B200Store::has_store(base + "/wide"));
+        w768.add_vectors({});                                           // an empty batch leaves no files behind
+        CHECK(!B200Store::has_store(base + "/wide"));
+        std::vector<VectorData> pts;
+        for (int i = 0; i < 40; ++i) {
+            VectorData d;
+            d._id = "w-" + std::to_string(i);
+            d.vector.assign(768, 0.01f);
+            d.vector[i * 3] = 1.f;
+            pts.push_back(d);
+        }
+        w768.add_vectors(pts);
+        auto r = w768.search(pts[7].vector, 4);
+        CHECK(r.size() == 4 && r[0].first == "w-7");
+        auto *st = dynamic_cast<B200Store *>(w768.client.get());
+        CHECK(st && st->options.dim == 768 && st->options.fp16);
+        try {
+            VectorData bad;
+            bad._id = "narrow";
+            bad.vector.assign(384, 1.f);
+            w768.add_vectors({bad});
+            CHECK(false);
+        } catch (const VectorStoreError &e) {
+            CHECK(e.kind == StoreErrorKind::InsertionError);
+        }
+        VectorStorage opt = get_vector_storage("b200://" + base + "?dtype=f16&metric=dot&dim=512&device=0", "opts");
+        auto *so = dynamic_cast<B200Store *>(opt.client.get());
+        CHECK(so && so->options.dim == 512 && so->options.fp16 && so->options.dot);
+        CHECK(so->storage_path == base + "/opts");
+        for (const char *bad_uri : {"?dtype=f64", "?colour=red", "?dim=abc"}) {
+            try {
+                get_vector_storage("b200://" + base + bad_uri, "x");
+                CHECK(false);
+            } catch (const VectorStoreError &e) {
+                CHECK(e.kind == StoreErrorKind::Unsupported);
+            }
+        }
+        // a meta file with an empty map and no matrix (what older builds left after add_vectors([])) is an empty store
+        make_dir(base + "/orphan");
+        { std::ofstream f(base + "/orphan/vectors.meta.json"); f << "{}"; }
+        auto orphan = B200Store::load(base + "/orphan");
+        CHECK(orphan->len() == 0 && orphan->search({1.f, 0.f}, 3).empty());
         drop_vector_storage_registry();
     }
     std::printf("gpu ok: %d checks\n", g_checks);

@@ -118,6 +118,14 @@ class B200Store(VectorStore):
         L = capi.lib()
         h = C.c_void_p()
         if not L.mx_store_has_file(store_path.encode()):
+            # a meta file without its matrix: only an EMPTY map is a store (one that never received a row, e.g.
+            # left by an older build after add_vectors([])); anything else is the reference's load failure
+            try:
+                with open(meta_path) as f:
+                    if json.load(f) == {}:
+                        return cls(store_path, device=device)
+            except (OSError, ValueError):
+                pass
             raise FileIOError(f"{os.path.join(store_path, DATA_FILE)}: No such file or directory")
         rc = L.mx_store_load(store_path.encode(), device, C.byref(h))
         if rc != capi.OK:
@@ -142,11 +150,12 @@ class B200Store(VectorStore):
 
     def save(self, store_path=None) -> None:
         store_path = str(store_path) if store_path is not None else self.storage_path
+        if self._h is None:
+            return   # nothing was ever inserted: no files, so has_store() stays false (a fresh HnswStore directory)
         os.makedirs(store_path, exist_ok=True)
-        if self._h is not None:
-            rc = capi.lib().mx_store_save(self._h, store_path.encode())
-            if rc != capi.OK:
-                _raise(rc, self._h, SaveError)
+        rc = capi.lib().mx_store_save(self._h, store_path.encode())
+        if rc != capi.OK:
+            _raise(rc, self._h, SaveError)
         try:
             tmp = os.path.join(store_path, META_FILE + ".tmp")
             with open(tmp, "w") as f:
@@ -234,6 +243,8 @@ class B200Store(VectorStore):
         queries = np.ascontiguousarray(queries, dtype=np.float32)
         if queries.ndim != 2 or queries.shape[1] != self._dim:
             raise SearchError(f"query has dimension {queries.shape[-1]}, store has {self._dim}")
+        if k > capi.MAX_K:   # one behaviour in every host (C++, Python, Rust): an error, never a silent cut
+            raise SearchError(f"limit {k} exceeds the store's maximum of {capi.MAX_K} neighbours per query")
         nq = queries.shape[0]
         ids = np.zeros((nq, k), dtype=np.uint64)
         scores = np.zeros((nq, k), dtype=np.float32)

@@ -94,6 +94,28 @@ def test_factory_new_then_load(tmp_path):
     assert vs2.search([0.1, 0.1, 0.1], 3) == []
 
 
+def test_empty_batch_leaves_no_files_and_limit_cap(tmp_path):
+    """an empty add on a fresh collection must not leave a meta file without its matrix (the directory would be
+    unusable on the next open); limit > MX_MAX_K is a SearchError in every host, never a shorter list"""
+    vs = get_vector_storage(f"b200://{tmp_path}", "fresh")
+    vs.add_vectors([])
+    assert not B200Store.has_store(tmp_path / "fresh")
+    vs = get_vector_storage(f"b200://{tmp_path}", "fresh")           # opens as new again
+    vs.add_vectors(reference_test_data())
+    assert vs.search([0.1, 0.1, 0.1], 256)[0][0] == "test-two"
+    with pytest.raises(VectorStoreError) as ei:
+        vs.search([0.1, 0.1, 0.1], 257)
+    assert ei.value.variant == "SearchError"
+    # what an older build left behind: "{}" and no matrix -> an empty store, not a FileIOError
+    orphan = tmp_path / "orphan"
+    orphan.mkdir()
+    (orphan / "vectors.meta.json").write_text("{}")
+    vo = get_vector_storage(f"b200://{tmp_path}", "orphan")
+    assert vo.search([0.1, 0.1, 0.1], 3) == []
+    vo.add_vectors(reference_test_data())
+    assert vo.search([0.1, 0.1, 0.1], 1)[0][0] == "test-two"
+
+
 # ---- parity against the oracle -------------------------------------------------------------------
 
 def unit_rows(n, d, seed):
