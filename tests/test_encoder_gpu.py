@@ -139,7 +139,7 @@ def test_attention_kernels_against_torch(B, S, H, heads, fmt, tol, impl):
     assert np.isfinite(err) and err <= tol * max(1.0, ref.abs().max().item()), err
 
 
-@pytest.mark.parametrize("precision,min_cos,max_abs", [("bf16", 1 - 2e-4, 2e-3), ("f16", 1 - 1e-5, 5e-4)])
+@pytest.mark.parametrize("precision,min_cos,max_abs", [("bf16", 1 - 1e-4, 2e-3), ("f16", 1 - 1e-5, 5e-4)])
 def test_tensor_core_paths_vs_oracle(precision, min_cos, max_abs):
     cfg = enc_oracle.MINILM_L6
     w = enc_oracle.make_weights(cfg, seed=21)
@@ -176,7 +176,7 @@ def test_packed_layout_matches_padded_layout_and_oracle(precision, monkeypatch):
     out_pad = e_pad.encode_ids(ids, lens)
     print(f"packed vs padded ({precision}): max abs diff {np.abs(out - out_pad).max():.2e}")
     np.testing.assert_allclose(out, out_pad, atol=1e-6)
-    assert ((out * ref).sum(1) >= (1 - 2e-4 if precision == "bf16" else 1 - 1e-5)).all()
+    assert ((out * ref).sum(1) >= (1 - 1e-4 if precision == "bf16" else 1 - 1e-5)).all()
     # garbage in the padded tail of the ids must not matter, and an empty sequence gives a zero row in both layouts
     ids2 = ids.copy()
     ids2[1, lens[1]:] = 777
@@ -207,13 +207,43 @@ def test_bert_base_shape_tensor_core_path():
     w = enc_oracle.make_weights(cfg, seed=31)
     ids, lens = enc_oracle.make_inputs(cfg, 6, 96, seed=32, ragged=True, min_len=3)
     ref = enc_oracle.hf_encode(cfg, w, ids, lens)
-    for precision, min_cos in (("bf16", 1 - 2e-4), ("f16", 1 - 1e-5), ("f32", 1 - 1e-6)):
+    for precision, min_cos in (("bf16", 1 - 1e-4), ("f16", 1 - 1e-5), ("f32", 1 - 1e-6)):
         e = B200Encoder(arch_of(cfg), w, precision=precision, max_tokens=6 * 96)
         out = e.encode_ids(ids, lens)
         cos = (out * ref).sum(1)
         print(f"bert-base shape {precision}: min cosine {cos.min():.7f}")
         assert (cos >= min_cos).all(), (precision, cos.min())
         e.close()
+
+
+@pytest.mark.parametrize("name,cfg,B,S,sample", [
+    ("config 3: MiniLM-L6, B=256, S=256", enc_oracle.MINILM_L6, 256, 256, 16),
+    ("memex default: MiniLM-L12, B=256, S=128", enc_oracle.MINILM_L12, 256, 128, 16),
+    ("config 5 ingest: BERT-base 12 layers, B=16, S=512", enc_oracle.BERT_BASE, 16, 512, 6),
+])
+def test_bf16_parity_at_the_benchmark_shapes(name, cfg, B, S, sample):
+    """The product path (bf16 activations, tcgen05 GEMMs + attention) at the shapes the numbers are quoted on
+    (BASELINE.json configs 3 and 5, and memex's default model embedding.rs:64-72) -- full depth, full batch.  The GPU
+    encodes the WHOLE batch; the oracle (HF BertModel fp32 on torch-CPU) re-computes a spread sample of its rows
+    (rows are independent, so a sample row's answer does not depend on the rest of the batch).
+    Gate: BASELINE.md section 3 / north_star -- cosine >= 1 - 1e-4 per row for the Normalize models."""
+    w = enc_oracle.make_weights(cfg, seed=61)
+    ids, lens = enc_oracle.make_inputs(cfg, B, S, seed=62)
+    # a few ragged rows inside the full-length batch (padding mask + packed layout at this size)
+    lens[1], lens[B // 2] = max(3, S // 3), S - 1
+    ids[1, lens[1]:] = cfg.pad_id
+    ids[B // 2, lens[B // 2]:] = cfg.pad_id
+    rows = sorted(set([0, 1, B // 2, B - 1] + list(np.linspace(2, B - 2, sample - 4).astype(int))))
+    ref = enc_oracle.hf_encode(cfg, w, ids[rows], lens[rows])
+    e = B200Encoder(arch_of(cfg), w, precision="bf16", max_tokens=B * S)
+    out = e.encode_ids(ids, lens)
+    e.close()
+    assert out.shape == (B, cfg.hidden) and np.isfinite(out).all()
+    np.testing.assert_allclose(np.linalg.norm(out, axis=1), 1.0, atol=1e-5)
+    cos = (out[rows] * ref).sum(1)
+    print(f"{name}: bf16 min cosine to the oracle over {len(rows)} sampled rows {cos.min():.7f}, "
+          f"max abs diff {np.abs(out[rows] - ref).max():.2e}")
+    assert (cos >= 1 - 1e-4).all(), cos.min()
 
 
 @pytest.mark.parametrize("name", ["roberta", "distiluse", "albert"])
