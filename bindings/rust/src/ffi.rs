@@ -11,6 +11,10 @@ pub struct mx_store {
 pub struct mx_embedder {
     _p: [u8; 0],
 }
+#[repr(C)]
+pub struct mx_shard_group {
+    _p: [u8; 0],
+}
 
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
@@ -79,6 +83,7 @@ pub const MX_DTYPE_F16: u32 = 1;
 pub const MX_METRIC_COSINE: u32 = 0;
 pub const MX_METRIC_DOT: u32 = 1;
 pub const MX_MAX_K: u32 = 256;
+pub const MX_IPC_HANDLE_BYTES: usize = 64;
 pub const MX_ACT_IDENTITY: u32 = 0;
 pub const MX_ACT_TANH: u32 = 1;
 pub const MX_FFN_GELU_ERF: u32 = 0;
@@ -100,6 +105,24 @@ extern "C" {
     pub fn mx_store_load(dir: *const c_char, device: i32, out: *mut *mut mx_store) -> i32;
     pub fn mx_store_has_file(dir: *const c_char) -> i32;
     pub fn mx_store_remove_file(dir: *const c_char) -> i32;
+
+    // mx_shard_group: the multi-GPU search below the C ABI (one member per GPU; rendezvous by CUDA IPC handles between
+    // processes, or mx_shard_group_connect_local inside one process) -- what a sharded `impl VectorStore` calls
+    pub fn mx_shard_group_create(
+        device: i32, world: u32, rank: u32, dim: u32, max_nq: u32, max_k: u32, out: *mut *mut mx_shard_group,
+    ) -> i32;
+    pub fn mx_shard_group_destroy(g: *mut mx_shard_group);
+    pub fn mx_shard_group_export(g: *mut mx_shard_group, handle_out: *mut u8) -> i32; // MX_IPC_HANDLE_BYTES
+    pub fn mx_shard_group_connect(g: *mut mx_shard_group, handles: *const u8) -> i32; // [world][MX_IPC_HANDLE_BYTES]
+    pub fn mx_shard_group_connect_local(groups: *const *mut mx_shard_group, world: u32) -> i32;
+    pub fn mx_shard_group_search(
+        g: *mut mx_shard_group, s: *mut mx_store, queries: *const f32, query_root: i32, nq: u32, k: u32,
+        ids_out: *mut u64, scores_out: *mut f32, counts_out: *mut u32,
+    ) -> i32;
+    pub fn mx_shard_group_search_local(
+        groups: *const *mut mx_shard_group, stores: *const *mut mx_store, world: u32, queries: *const f32, nq: u32,
+        k: u32, ids_out: *mut u64, scores_out: *mut f32, counts_out: *mut u32,
+    ) -> i32;
 
     pub fn mx_embedder_create(
         cfg: *const mx_model_cfg, w: *const mx_tensor, n: u32, device: i32, out: *mut *mut mx_embedder,

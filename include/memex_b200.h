@@ -130,6 +130,48 @@ int32_t mx_merge_topk_blobs_wait_device(const void *blobs_dev, uint64_t blob_str
                                         float *scores_out_dev, uint32_t *counts_out_dev, const uint32_t *flags_dev,
                                         uint32_t epoch, int32_t device, void *cuda_stream);
 
+/* ------------------------------------------------------------------------------------------
+ * mx_shard_group -- the multi-GPU search of a row-sharded corpus, rendezvous included, with no
+ * torch and no collective library: what lets `VectorStorage::search` (storage/mod.rs:85-92)
+ * reach the 8 GPUs of a box from a C++ or Rust host.
+ *
+ * Every member owns one exchange buffer in its GPU's memory ([2][world] blob slots, [2] query
+ * slots, world + 1 epoch flags) that all peers address over NVLink.  Rendezvous, either
+ *   - one PROCESS per GPU: mx_shard_group_export -> 64-byte CUDA IPC handle; the host moves the
+ *     `world` handles over its own transport (file, socket, MPI, torch.distributed);
+ *     mx_shard_group_connect(handles [world][64], rank order) opens them; or
+ *   - one process driving SEVERAL GPUs (memex's server is one process): create one member per
+ *     device and call mx_shard_group_connect_local (peer access + raw pointers).
+ * A search = the shard's own scan + rerank (mx_store_search_blob_device), one push of the blob into
+ * every peer's slot (P2P stores + release-stored epoch flag), one merge that waits for its `world`
+ * flags inside the kernel.  All members make the same sequence of search calls (SPMD).
+ *   query_root < 0 : every member passes the same queries.
+ *   query_root = r : member r passes them and pushes the block into every peer's query slot; the
+ *                    others pass NULL and their first kernel waits for the root's flag -- the
+ *                    host-buffer call needs no broadcast.
+ * Stores of a group report GLOBAL ids (mx_store_cfg.id_offset / id_stride). */
+typedef struct mx_shard_group mx_shard_group;
+#define MX_IPC_HANDLE_BYTES 64
+int32_t mx_shard_group_create(int32_t device, uint32_t world, uint32_t rank, uint32_t dim, uint32_t max_nq,
+                              uint32_t max_k, mx_shard_group **out);
+void mx_shard_group_destroy(mx_shard_group *g);
+int32_t mx_shard_group_export(mx_shard_group *g, void *handle_out /* MX_IPC_HANDLE_BYTES */);
+int32_t mx_shard_group_connect(mx_shard_group *g, const void *handles /* [world][MX_IPC_HANDLE_BYTES] */);
+int32_t mx_shard_group_connect_local(mx_shard_group *const *groups, uint32_t world);
+/* DEVICE buffers, asynchronous on cuda_stream (NULL = the member's own stream) */
+int32_t mx_shard_group_search_device(mx_shard_group *g, mx_store *s, const float *queries_dev, int32_t query_root,
+                                     uint32_t nq, uint32_t k, uint64_t *ids_dev, float *scores_dev,
+                                     uint32_t *counts_dev, void *cuda_stream);
+/* HOST buffers: H2D of the queries (where this member has them), the search, ONE D2H of the answer */
+int32_t mx_shard_group_search(mx_shard_group *g, mx_store *s, const float *queries, int32_t query_root, uint32_t nq,
+                              uint32_t k, uint64_t *ids_out, float *scores_out, uint32_t *counts_out);
+/* single-process form: `world` members / stores in rank order; HOST buffers; the answer is member 0's */
+int32_t mx_shard_group_search_local(mx_shard_group *const *groups, mx_store *const *stores, uint32_t world,
+                                    const float *queries, uint32_t nq, uint32_t k, uint64_t *ids_out,
+                                    float *scores_out, uint32_t *counts_out);
+int32_t mx_shard_group_info(const mx_shard_group *g, uint32_t *world, uint32_t *rank, uint32_t *epoch,
+                            int32_t *connected);
+
 int32_t mx_store_len(mx_store *s, uint64_t *n_out); /* hnsw.get_nb_point(), local.rs:238 */
 int32_t mx_store_clear(mx_store *s);                /* delete_all's index reset, local.rs:48-50 */
 int32_t mx_store_delete(mx_store *s, uint64_t id);  /* local.rs:29-32: always MX_ERR_UNSUPPORTED */

@@ -21,6 +21,7 @@ ERR_SERDE, ERR_SAVE, ERR_UNSUPPORTED, ERR_INVALID, ERR_ENCODE, ERR_SETUP = -6, -
 DTYPE_F32, DTYPE_F16 = 0, 1
 METRIC_COSINE, METRIC_DOT = 0, 1
 MAX_K = 256
+IPC_HANDLE_BYTES = 64
 
 ERROR_NAMES = {
     ERR_CONNECTION: "ConnectionError", ERR_DELETE: "DeleteError", ERR_FILE_IO: "FileIOError",
@@ -96,6 +97,15 @@ def lib() -> C.CDLL:
         C.c_int32, vp)
     sig("mx_merge_topk_blobs_wait_device", C.c_int32, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp,
         vp, C.c_uint32, C.c_int32, vp)
+    sig("mx_shard_group_create", C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp))
+    sig("mx_shard_group_destroy", None, vp)
+    sig("mx_shard_group_export", C.c_int32, vp, vp)
+    sig("mx_shard_group_connect", C.c_int32, vp, vp)
+    sig("mx_shard_group_connect_local", C.c_int32, C.POINTER(vp), C.c_uint32)
+    sig("mx_shard_group_search_device", C.c_int32, vp, vp, vp, C.c_int32, C.c_uint32, C.c_uint32, vp, vp, vp, vp)
+    sig("mx_shard_group_search", C.c_int32, vp, vp, vp, C.c_int32, C.c_uint32, C.c_uint32, vp, vp, vp)
+    sig("mx_shard_group_search_local", C.c_int32, C.POINTER(vp), C.POINTER(vp), C.c_uint32, vp, C.c_uint32, C.c_uint32, vp, vp, vp)
+    sig("mx_shard_group_info", C.c_int32, vp, u32p, u32p, u32p, i32p)
     sig("mx_store_len", C.c_int32, vp, u64p)
     sig("mx_store_clear", C.c_int32, vp)
     sig("mx_store_delete", C.c_int32, vp, C.c_uint64)

@@ -21,6 +21,7 @@
 // release-stored epoch flags), and the merge that waits for its `world` flags inside the kernel.
 // Slot reuse is safe with two parities: a peer can only push epoch e + 2 after its own merge of e + 1, which waited for
 // this rank's push of e + 1, which is stream-ordered after this rank's merge (and scan) of epoch e.
+#include <cmath>
 #include <cstring>
 
 #include "common.cuh"
@@ -298,6 +299,63 @@ int32_t mx_shard_group_search(mx_shard_group *g, mx_store *s, const float *queri
     // ids | scores | counts are contiguous: ONE device-to-host copy
     MX_CUDA(g, MX_ERR_SEARCH, cudaMemcpyAsync(hp + off_i, dp + off_i, total - off_i, cudaMemcpyDeviceToHost, g->stream));
     MX_CUDA(g, MX_ERR_SEARCH, cudaStreamSynchronize(g->stream));
+    memcpy(ids_out, hp + off_i, ib);
+    memcpy(scores_out, hp + off_s, sb);
+    memcpy(counts_out, hp + off_c, cb);
+    return MX_OK;
+}
+
+// One process, `world` members on `world` devices: H2D of the query block on every member, every member's search
+// enqueued (asynchronously: member 0's merge waits inside its kernel for pushes that are enqueued after it), then ONE
+// D2H of member 0's answer.  This is the call behind a single-process host's VectorStore::search.
+int32_t mx_shard_group_search_local(mx_shard_group *const *groups, mx_store *const *stores, uint32_t world, const float *queries,
+                                    uint32_t nq, uint32_t k, uint64_t *ids_out, float *scores_out, uint32_t *counts_out)
+{
+    if (!groups || !stores || world == 0 || world > (uint32_t)kMaxPeers) return fail(nullptr, MX_ERR_INVALID, "bad group list");
+    for (uint32_t i = 0; i < world; ++i)
+        if (!groups[i] || !stores[i] || groups[i]->world != world || groups[i]->rank != i)
+            return fail(nullptr, MX_ERR_INVALID, "member %u does not belong to a group of %u in rank order", i, world);
+    mx_shard_group *g0 = groups[0];
+    if (!queries || !ids_out || !scores_out || !counts_out) return fail(g0, MX_ERR_INVALID, "null buffer");
+    if (nq == 0) return MX_OK;
+    if (nq > g0->max_nq || k == 0 || k > g0->max_k) return fail(g0, MX_ERR_INVALID, "batch of %u x top-%u exceeds the group's %u x %u", nq, k, g0->max_nq, g0->max_k);
+    for (size_t i = 0; i < (size_t)nq * g0->dim; ++i)
+        if (!std::isfinite(queries[i])) return fail(g0, MX_ERR_SEARCH, "non-finite value in query %zu", i / g0->dim);
+    const size_t qb = (size_t)nq * g0->dim * sizeof(float);
+    const size_t ib = (size_t)nq * k * sizeof(uint64_t), sb = (size_t)nq * k * sizeof(float), cb = (size_t)nq * 4;
+    const size_t off_i = (qb + 255) & ~(size_t)255, off_s = off_i + ib, off_c = off_s + sb, total = off_c + cb;
+    for (uint32_t i = 0; i < world; ++i) {
+        mx_shard_group *g = groups[i];
+        MX_CUDA(g0, MX_ERR_CONNECTION, cudaSetDevice(g->device));
+        if (total > g->pinned_cap) {
+            if (g->pinned) cudaFreeHost(g->pinned);
+            cudaFree(g->dev_io);
+            g->pinned = nullptr;
+            g->dev_io = nullptr;
+            g->pinned_cap = g->dev_io_cap = 0;
+            MX_CUDA(g0, MX_ERR_CONNECTION, cudaMallocHost(&g->pinned, total));
+            MX_CUDA(g0, MX_ERR_CONNECTION, cudaMalloc(&g->dev_io, total));
+            g->pinned_cap = g->dev_io_cap = total;
+        }
+        char *hp = static_cast<char *>(g->pinned), *dp = static_cast<char *>(g->dev_io);
+        memcpy(hp, queries, qb);
+        MX_CUDA(g0, MX_ERR_SEARCH, cudaMemcpyAsync(dp, hp, qb, cudaMemcpyHostToDevice, g->stream));
+        int32_t rc = mx_shard_group_search_device(g, stores[i], reinterpret_cast<const float *>(dp), -1, nq, k,
+                                                  reinterpret_cast<uint64_t *>(dp + off_i), reinterpret_cast<float *>(dp + off_s),
+                                                  reinterpret_cast<uint32_t *>(dp + off_c), g->stream);
+        if (rc != MX_OK) {
+            if (g != g0) g0->last_error = g->last_error;
+            return rc;
+        }
+    }
+    MX_CUDA(g0, MX_ERR_CONNECTION, cudaSetDevice(g0->device));
+    char *hp = static_cast<char *>(g0->pinned), *dp = static_cast<char *>(g0->dev_io);
+    MX_CUDA(g0, MX_ERR_SEARCH, cudaMemcpyAsync(hp + off_i, dp + off_i, total - off_i, cudaMemcpyDeviceToHost, g0->stream));
+    // every member's stream drains (their merges ran too: the next call may reuse the slots at once)
+    for (uint32_t i = 0; i < world; ++i) {
+        MX_CUDA(g0, MX_ERR_CONNECTION, cudaSetDevice(groups[i]->device));
+        MX_CUDA(g0, MX_ERR_SEARCH, cudaStreamSynchronize(groups[i]->stream));
+    }
     memcpy(ids_out, hp + off_i, ib);
     memcpy(scores_out, hp + off_s, sb);
     memcpy(counts_out, hp + off_c, cb);

@@ -34,6 +34,7 @@
 #include <vector>
 
 struct mx_store;
+struct mx_shard_group;
 struct mx_embedder;
 
 namespace memex {
@@ -111,6 +112,49 @@ private:
     B200Store() = default;
     void create_handle(uint32_t dim);   // the device store is made when the width is known (Options::dim or first insert)
     mx_store *handle_ = nullptr;
+};
+
+// The same store over SEVERAL GPUs of one box, driven by ONE process (memex's server is one process: mod.rs:68-93).
+// Row i of the insertion order lives on shard i % G as local row i / G, and the shard's device reports the GLOBAL
+// 1-based id (mx_store_cfg.id_offset = g, id_stride = G), so `_id_map` is keyed exactly as HnswStore's (local.rs:63).
+// search = mx_shard_group_search_local: every GPU scans its shard, one peer-memory exchange of the per-shard top-k
+// over NVLink, merge -- no torch, no collective library (include/memex_b200.h, mx_shard_group).
+// Files: <storage_path>/shard-<g>/vectors.b200.bin next to the one vectors.meta.json.
+class ShardedB200Store : public VectorStore {
+public:
+    struct Options {
+        std::vector<int> devices;   // one shard per entry; the same device may appear twice (tests on a 1-GPU box)
+        uint32_t dim = 0;           // 0 = sized by the first insert
+        bool fp16 = true;
+        bool dot = false;
+        uint64_t capacity_per_shard = 0;
+        uint32_t max_batch = 64;    // queries per search_batch call the exchange buffers are sized for
+        bool save_on_insert = false;
+    };
+    static std::unique_ptr<ShardedB200Store> new_(const std::string &storage_path, const Options &opt);
+    static bool has_store(const std::string &store_path) { return B200Store::has_store(store_path); }
+    static std::unique_ptr<ShardedB200Store> load(const std::string &store_path, const Options &opt);
+    void save(const std::string &store_path) const;
+    ~ShardedB200Store() override;
+
+    void delete_(const std::string &id) override;
+    void delete_all() override;
+    void bulk_insert(const std::vector<VectorData> &data) override;
+    void insert(const VectorData &data) override;
+    std::vector<VectorSearchResult> search(const std::vector<float> &vec, size_t limit) const override;
+    std::vector<std::vector<VectorSearchResult>> search_batch(const std::vector<std::vector<float>> &vecs,
+                                                              size_t limit) const override;
+    uint64_t len() const;
+    size_t shards() const { return options.devices.size(); }
+    std::string storage_path;
+    std::unordered_map<size_t, std::string> _id_map;
+    Options options;
+
+private:
+    ShardedB200Store() = default;
+    void create_handles(uint32_t dim);
+    std::vector<mx_store *> stores_;
+    std::vector<mx_shard_group *> groups_;
 };
 
 // VectorStorage (mod.rs:68-93): every call takes the one lock, as the tokio Mutex does.

@@ -297,6 +297,269 @@ uint64_t B200Store::len() const
 }
 
 // ------------------------------------------------------------------------------------------------
+// ShardedB200Store: one process, G GPUs
+// ------------------------------------------------------------------------------------------------
+namespace {
+std::string shard_dir(const std::string &base, size_t g) { return join(base, "shard-" + std::to_string(g)); }
+
+void write_id_map(const std::string &store_path, const std::unordered_map<size_t, std::string> &id_map)
+{
+    std::string out = "{";
+    bool first = true;
+    for (const auto &kv : id_map) {
+        if (!first) out += ',';
+        first = false;
+        out += '"' + std::to_string(kv.first) + "\":";
+        json::escape_into(kv.second, out);
+    }
+    out += '}';
+    const std::string tmp = join(store_path, std::string(kMetaFile) + ".tmp");
+    {
+        std::ofstream f(tmp, std::ios::binary | std::ios::trunc);
+        if (!f) throw VectorStoreError(StoreErrorKind::FileIOError, tmp + ": " + std::strerror(errno));
+        f << out;
+        f.flush();
+        if (!f) throw VectorStoreError(StoreErrorKind::FileIOError, tmp + ": write failed");
+    }
+    if (std::rename(tmp.c_str(), join(store_path, kMetaFile).c_str()) != 0)
+        throw VectorStoreError(StoreErrorKind::FileIOError, std::string("rename: ") + std::strerror(errno));
+}
+
+std::unordered_map<size_t, std::string> read_id_map(const std::string &store_path)
+{
+    std::ifstream f(join(store_path, kMetaFile), std::ios::binary);
+    if (!f) throw VectorStoreError(StoreErrorKind::FileIOError, join(store_path, kMetaFile) + ": " + std::strerror(errno));
+    std::stringstream ss;
+    ss << f.rdbuf();
+    std::unordered_map<size_t, std::string> out;
+    try {
+        json::Value v = json::parse(ss.str());
+        if (v.kind != json::Value::Object) throw std::runtime_error("expected an object");
+        for (const auto &kv : v.obj) {
+            if (kv.second.kind != json::Value::String) throw std::runtime_error("expected string values");
+            char *end = nullptr;
+            unsigned long long id = std::strtoull(kv.first.c_str(), &end, 10);
+            if (end == kv.first.c_str() || *end) throw std::runtime_error("key is not an integer: " + kv.first);
+            out[(size_t)id] = kv.second.str;
+        }
+    } catch (const std::runtime_error &e) {
+        throw VectorStoreError(StoreErrorKind::SerdeError, e.what());
+    }
+    return out;
+}
+}  // namespace
+
+std::unique_ptr<ShardedB200Store> ShardedB200Store::new_(const std::string &storage_path, const Options &opt)
+{
+    if (opt.devices.empty() || opt.devices.size() > 16)
+        throw VectorStoreError(StoreErrorKind::ConnectionError, "a sharded store needs 1..16 devices");
+    std::unique_ptr<ShardedB200Store> s(new ShardedB200Store());
+    s->storage_path = storage_path;
+    s->options = opt;
+    if (opt.dim) s->create_handles(opt.dim);
+    return s;
+}
+
+void ShardedB200Store::create_handles(uint32_t dim)
+{
+    const size_t G = options.devices.size();
+    for (size_t g = 0; g < G; ++g) {
+        mx_store_cfg cfg{};
+        cfg.dim = dim;
+        cfg.dtype = options.fp16 ? MX_DTYPE_F16 : MX_DTYPE_F32;
+        cfg.metric = options.dot ? MX_METRIC_DOT : MX_METRIC_COSINE;
+        cfg.device = options.devices[g];
+        cfg.capacity = options.capacity_per_shard;
+        cfg.id_offset = g;          // global id = local_row * G + g + 1: row i of the insertion order -> shard i % G
+        cfg.id_stride = G;
+        mx_store *h = nullptr;
+        int32_t rc = mx_store_create(&cfg, &h);
+        if (rc != MX_OK) raise(rc, nullptr, StoreErrorKind::ConnectionError);
+        stores_.push_back(h);
+        mx_shard_group *grp = nullptr;
+        rc = mx_shard_group_create(options.devices[g], (uint32_t)G, (uint32_t)g, dim, std::max<uint32_t>(1, options.max_batch), MX_MAX_K, &grp);
+        if (rc != MX_OK) raise(rc, nullptr, StoreErrorKind::ConnectionError);
+        groups_.push_back(grp);
+    }
+    int32_t rc = mx_shard_group_connect_local(groups_.data(), (uint32_t)G);
+    if (rc != MX_OK) raise(rc, groups_[0], StoreErrorKind::ConnectionError);
+    options.dim = dim;
+}
+
+ShardedB200Store::~ShardedB200Store()
+{
+    for (mx_shard_group *g : groups_) mx_shard_group_destroy(g);
+    for (mx_store *h : stores_) mx_store_destroy(h);
+}
+
+std::unique_ptr<ShardedB200Store> ShardedB200Store::load(const std::string &store_path, const Options &opt)
+{
+    if (opt.devices.empty()) throw VectorStoreError(StoreErrorKind::ConnectionError, "a sharded store needs devices");
+    std::unique_ptr<ShardedB200Store> s(new ShardedB200Store());
+    s->storage_path = store_path;
+    s->options = opt;
+    s->_id_map = read_id_map(store_path);
+    const size_t G = opt.devices.size();
+    if (!mx_store_has_file(shard_dir(store_path, 0).c_str())) {
+        if (!s->_id_map.empty())
+            throw VectorStoreError(StoreErrorKind::FileIOError, join(shard_dir(store_path, 0), "vectors.b200.bin") + ": No such file or directory");
+        return s;
+    }
+    // the shard files hold rows in local order; ids are rebuilt from (g, G), so the files must be read with the G they
+    // were written with
+    uint32_t dim = 0;
+    for (size_t g = 0; g < G; ++g) {
+        mx_store *tmp = nullptr;
+        int32_t rc = mx_store_load(shard_dir(store_path, g).c_str(), opt.devices[g], &tmp);
+        if (rc != MX_OK) raise(rc, nullptr, StoreErrorKind::FileIOError);
+        uint32_t d = 0, dtype = 0, metric = 0;
+        uint64_t cap = 0, n = 0;
+        mx_store_info(tmp, &d, &dtype, &metric, &cap);
+        mx_store_len(tmp, &n);
+        if (g == 0) {
+            dim = d;
+            s->options.fp16 = dtype == MX_DTYPE_F16;
+            s->options.dot = metric == MX_METRIC_DOT;
+            s->create_handles(dim);
+        }
+        // re-ingest through the sharded handles (global ids need id_offset / id_stride, which a plain load does not carry)
+        std::vector<float> rows((size_t)std::min<uint64_t>(n, 65536) * d);
+        for (uint64_t done = 0; done < n;) {
+            const uint64_t c = std::min<uint64_t>(65536, n - done);
+            rc = mx_store_get_rows(tmp, done, c, rows.data());
+            if (rc == MX_OK) rc = mx_store_add(s->stores_[g], rows.data(), c, nullptr);
+            if (rc != MX_OK) {
+                mx_store_destroy(tmp);
+                raise(rc, s->stores_[g], StoreErrorKind::FileIOError);
+            }
+            done += c;
+        }
+        mx_store_destroy(tmp);
+    }
+    if (s->len() != s->_id_map.size())
+        throw VectorStoreError(StoreErrorKind::SerdeError, "shard files hold " + std::to_string(s->len()) + " rows, the id map " +
+                                                               std::to_string(s->_id_map.size()) + " (written with another shard count?)");
+    return s;
+}
+
+void ShardedB200Store::save(const std::string &store_path) const
+{
+    if (stores_.empty()) return;
+    make_dirs(store_path);
+    for (size_t g = 0; g < stores_.size(); ++g) {
+        make_dirs(shard_dir(store_path, g));
+        int32_t rc = mx_store_save(stores_[g], shard_dir(store_path, g).c_str());
+        if (rc != MX_OK) raise(rc, stores_[g], StoreErrorKind::SaveError);
+    }
+    write_id_map(store_path, _id_map);
+}
+
+void ShardedB200Store::delete_(const std::string &)
+{
+    throw VectorStoreError(StoreErrorKind::Unsupported, "removing a single point is not supported by the file store");
+}
+
+void ShardedB200Store::delete_all()
+{
+    for (size_t g = 0; g < options.devices.size(); ++g) mx_store_remove_file(shard_dir(storage_path, g).c_str());
+    std::remove(join(storage_path, kMetaFile).c_str());
+    for (mx_store *h : stores_) {
+        int32_t rc = mx_store_clear(h);
+        if (rc != MX_OK) raise(rc, h, StoreErrorKind::DeleteError);
+    }
+    _id_map.clear();
+}
+
+void ShardedB200Store::bulk_insert(const std::vector<VectorData> &data)
+{
+    if (data.empty()) return;
+    if (stores_.empty()) {
+        if (data[0].vector.empty()) throw VectorStoreError(StoreErrorKind::InsertionError, "empty vector");
+        create_handles((uint32_t)data[0].vector.size());
+    }
+    const size_t dim = options.dim, G = stores_.size();
+    for (const auto &d : data)
+        if (d.vector.size() != dim)
+            throw VectorStoreError(StoreErrorKind::InsertionError, "vector has dimension " + std::to_string(d.vector.size()) +
+                                                                       ", store has " + std::to_string(dim));
+    const size_t n0 = _id_map.size();   // rows so far == next global index (next_id = len + 1, local.rs:63)
+    std::vector<std::vector<float>> part(G);
+    for (size_t i = 0; i < data.size(); ++i) {
+        auto &p = part[(n0 + i) % G];
+        p.insert(p.end(), data[i].vector.begin(), data[i].vector.end());
+    }
+    for (size_t g = 0; g < G; ++g) {
+        if (part[g].empty()) continue;
+        uint64_t first = 0;
+        int32_t rc = mx_store_add(stores_[g], part[g].data(), part[g].size() / dim, &first);
+        if (rc != MX_OK) raise(rc, stores_[g], StoreErrorKind::InsertionError);
+    }
+    for (size_t i = 0; i < data.size(); ++i) _id_map[n0 + i + 1] = data[i]._id;
+    if (options.save_on_insert) {
+        try {
+            save(storage_path);
+        } catch (const VectorStoreError &) {
+        }
+    }
+}
+
+void ShardedB200Store::insert(const VectorData &data) { bulk_insert({data}); }
+
+std::vector<std::vector<VectorSearchResult>> ShardedB200Store::search_batch(const std::vector<std::vector<float>> &vecs, size_t limit) const
+{
+    std::vector<std::vector<VectorSearchResult>> out(vecs.size());
+    if (vecs.empty() || limit == 0 || _id_map.empty() || stores_.empty()) return out;
+    if (limit > MX_MAX_K)
+        throw VectorStoreError(StoreErrorKind::SearchError, "limit " + std::to_string(limit) + " exceeds the store's maximum of " +
+                                                                std::to_string(MX_MAX_K) + " neighbours per query");
+    const size_t dim = options.dim;
+    const uint32_t k = (uint32_t)limit;
+    const size_t step = std::max<uint32_t>(1, options.max_batch);
+    for (size_t q0 = 0; q0 < vecs.size(); q0 += step) {
+        const size_t nq = std::min(step, vecs.size() - q0);
+        std::vector<float> q(nq * dim);
+        for (size_t i = 0; i < nq; ++i) {
+            if (vecs[q0 + i].size() != dim)
+                throw VectorStoreError(StoreErrorKind::SearchError, "query has dimension " + std::to_string(vecs[q0 + i].size()) +
+                                                                        ", store has " + std::to_string(dim));
+            std::copy(vecs[q0 + i].begin(), vecs[q0 + i].end(), q.begin() + i * dim);
+        }
+        std::vector<uint64_t> ids(nq * k);
+        std::vector<float> scores(nq * k);
+        std::vector<uint32_t> counts(nq);
+        int32_t rc = mx_shard_group_search_local(groups_.data(), stores_.data(), (uint32_t)stores_.size(), q.data(), (uint32_t)nq, k,
+                                                 ids.data(), scores.data(), counts.data());
+        if (rc != MX_OK) raise(rc, groups_[0], StoreErrorKind::SearchError);
+        for (size_t i = 0; i < nq; ++i) {
+            out[q0 + i].reserve(counts[i]);
+            for (uint32_t j = 0; j < counts[i]; ++j) {
+                auto it = _id_map.find((size_t)ids[i * k + j]);
+                if (it == _id_map.end())
+                    throw VectorStoreError(StoreErrorKind::SearchError, "Internal inconsistency. Id from vector store not mapped.");
+                out[q0 + i].emplace_back(it->second, scores[i * k + j]);
+            }
+        }
+    }
+    return out;
+}
+
+std::vector<VectorSearchResult> ShardedB200Store::search(const std::vector<float> &vec, size_t limit) const
+{
+    return search_batch({vec}, limit)[0];
+}
+
+uint64_t ShardedB200Store::len() const
+{
+    uint64_t total = 0;
+    for (mx_store *h : stores_) {
+        uint64_t n = 0;
+        mx_store_len(h, &n);
+        total += n;
+    }
+    return total;
+}
+
+// ------------------------------------------------------------------------------------------------
 // VectorStorage / factory / registry
 // ------------------------------------------------------------------------------------------------
 VectorStorage::VectorStorage(std::shared_ptr<VectorStore> c) : client(std::move(c)), lock_(std::make_shared<std::mutex>()) {}

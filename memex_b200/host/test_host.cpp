@@ -12,6 +12,7 @@
 #include <sstream>
 #include <sys/stat.h>
 
+#include "../../include/memex_b200.h"
 #include "json.hpp"
 #include "memex_host.hpp"
 
@@ -494,6 +495,56 @@ static int run_gpu(const std::string &tmp)
         auto orphan = B200Store::load(base + "/orphan");
         CHECK(orphan->len() == 0 && orphan->search({1.f, 0.f}, 3).empty());
         drop_vector_storage_registry();
+    }
+    // ShardedB200Store: ONE process, several GPUs (or, on a 1-GPU box, two shards on the same device), rendezvous and
+    // exchange below the C ABI (mx_shard_group).  Answers must equal the single store's: same doc ids, same score bits.
+    {
+        const int ndev = mx_device_count();
+        ShardedB200Store::Options so;
+        so.devices = ndev >= 2 ? std::vector<int>{0, 1} : std::vector<int>{0, 0};
+        if (ndev >= 4) so.devices = {0, 1, 2, 3};
+        so.fp16 = true;
+        auto sharded = ShardedB200Store::new_(tmp + "/sharded", so);
+        B200Store::Options o1;
+        o1.fp16 = true;
+        o1.save_on_insert = false;
+        auto single = B200Store::new_(tmp + "/sharded_ref", o1);
+        std::vector<VectorData> pts;
+        uint32_t rng = 12345;
+        auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return ((rng >> 8) & 0xffff) / 65536.0f - 0.5f; };
+        const int n = 6001, d = 96;
+        for (int i = 0; i < n; ++i) {
+            VectorData v;
+            v._id = "doc-" + std::to_string(i);
+            v.vector.resize(d);
+            for (auto &x : v.vector) x = rnd();
+            pts.push_back(v);
+        }
+        pts[4000].vector = pts[17].vector;     // exact ties across shards: the lower global id must come first
+        pts[4001].vector = pts[17].vector;
+        // two batches, the second starting at an odd global index
+        sharded->bulk_insert(std::vector<VectorData>(pts.begin(), pts.begin() + 2501));
+        sharded->bulk_insert(std::vector<VectorData>(pts.begin() + 2501, pts.end()));
+        single->bulk_insert(pts);
+        CHECK(sharded->len() == (uint64_t)n && sharded->_id_map.size() == (size_t)n);
+        for (int qi : {17, 0, 2500, 4001, 6000}) {
+            auto a = sharded->search(pts[qi].vector, 10), b = single->search(pts[qi].vector, 10);
+            CHECK(a.size() == 10 && a == b);
+        }
+        auto tie = sharded->search(pts[17].vector, 3);
+        CHECK(tie[0].first == "doc-17" && tie[1].first == "doc-4000" && tie[2].first == "doc-4001");
+        std::vector<std::vector<float>> batch;
+        for (int i = 0; i < 20; ++i) batch.push_back(pts[i * 300].vector);     // >= 8 queries: the tcgen05 scan
+        auto ra = sharded->search_batch(batch, 10), rb = single->search_batch(batch, 10);
+        CHECK(ra == rb);
+        // save / load with the same shard count
+        sharded->save(tmp + "/sharded");
+        auto again = ShardedB200Store::load(tmp + "/sharded", so);
+        CHECK(again->len() == (uint64_t)n);
+        CHECK(again->search_batch(batch, 10) == rb);
+        again->delete_all();
+        CHECK(again->len() == 0 && !ShardedB200Store::has_store(tmp + "/sharded"));
+        std::printf("sharded store ok over %zu shard(s) on %d visible device(s)\n", so.devices.size(), ndev);
     }
     std::printf("gpu ok: %d checks\n", g_checks);
     return 0;

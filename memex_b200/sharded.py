@@ -86,38 +86,42 @@ class ShardedStore:
         self._bufs = {}
         self.exchange = "none" if world == 1 else "nccl"
         self._want_p2p = world > 1 and os.environ.get("MX_EXCHANGE", "p2p") != "nccl"
+        self._shard_group = None          # mx_shard_group member (peer-memory exchange), made on the first search
+        self._group_nq, self._group_k = 64, 16
+        self._group_error = ""
 
-    def _setup_p2p(self, b, blob: int):
-        """exchange buffer addressable by every peer: [2][world] blob slots + world u32 flags; all ranks or none"""
+    def _setup_group(self, nq: int, k: int) -> bool:
+        """The peer-memory exchange below the C ABI (mx_shard_group, csrc/shard_group.cu): every rank creates its member,
+        exports the 64-byte CUDA IPC handle of its exchange buffer, the handles travel over torch.distributed (plumbing:
+        any transport would do) and every rank opens its peers'.  All ranks or none."""
         import torch
         import torch.distributed as dist
-        ok, peers, buf = 1, None, None
-        try:
-            import torch.distributed._symmetric_memory as symm_mem
-            stride = (blob + 15) & ~15
-            nbytes = 2 * self.world * stride + 64
-            dev = torch.device("cuda", self.device)
-            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
-            buf.zero_()
-            torch.cuda.synchronize(dev)
-            name = getattr(self.group, "group_name", None) or dist.group.WORLD.group_name
-            try:
-                hdl = symm_mem.rendezvous(buf, name)
-            except TypeError:
-                hdl = symm_mem.rendezvous(buf, group=name)
-            peers = [int(p) for p in hdl.buffer_ptrs]
-            if len(peers) != self.world or not all(peers):
-                ok = 0
-        except Exception as e:  # noqa: BLE001 -- any failure means "use the collective"
-            b["p2p_error"] = repr(e)
+        L = capi.lib()
+        dev = torch.device("cuda", self.device)
+        ok = 1
+        g = C.c_void_p()
+        handle = torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8)
+        rc = L.mx_shard_group_create(self.device, self.world, self.rank, self.dim, max(nq, self._group_nq), max(k, self._group_k),
+                                     C.byref(g))
+        if rc != capi.OK or L.mx_shard_group_export(g, handle.data_ptr()) != capi.OK:
+            self._group_error = (L.mx_last_error(g if g.value else None) or b"").decode(errors="replace")
             ok = 0
-        flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", self.device))
+        gathered = [torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev) for _ in range(self.world)]
+        dist.all_gather(gathered, handle.to(dev), group=self.group)
+        if ok:
+            handles = torch.stack(gathered).cpu().contiguous()
+            if L.mx_shard_group_connect(g, handles.data_ptr()) != capi.OK:
+                self._group_error = (L.mx_last_error(g) or b"").decode(errors="replace")
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) != 1:
+            if g.value:
+                L.mx_shard_group_destroy(g)
             return False
-        b["xbuf"], b["xstride"] = buf, stride
-        b["peers"] = (C.c_uint64 * self.world)(*peers)
-        dist.barrier(group=self.group)   # every rank's flags are zero before anyone pushes
+        self._shard_group = g
+        self._group_nq, self._group_k = max(nq, self._group_nq), max(k, self._group_k)
+        dist.barrier(group=self.group)   # every member is connected before anyone pushes
         return True
 
     # ---- ingest: rows already on this rank's device (f32 [n, dim]); ids follow the plan ----
@@ -162,42 +166,44 @@ class ShardedStore:
             )
         return self._bufs[key]
 
-    def search_device(self, q_dev, k: int):
-        """q_dev: torch f32 [nq, dim] on this rank's device, identical on every rank.
+    def search_device(self, q_dev, k: int, nq: int | None = None, query_root: int = -1):
+        """q_dev: torch f32 [nq, dim] on this rank's device, identical on every rank (query_root = -1); or, with the
+        peer-memory exchange, only on rank `query_root` (the others pass None and `nq`: the root's block arrives through
+        their exchange buffer).
         -> (ids i64 [nq,k], scores f32 [nq,k], counts i32 [nq]) device tensors, identical on every
         rank, enqueued on torch's current stream (no host synchronisation)."""
         import torch
         import torch.distributed as dist
-        nq = q_dev.shape[0]
+        if q_dev is not None:
+            nq = q_dev.shape[0]
         b = self._buffers(nq, k)
         L = capi.lib()
         # torch's default stream has handle 0, which the C ABI reads as "the store's own stream": name the
         # legacy default stream explicitly (cudaStreamLegacy == 0x1) so the work is ordered with torch's
         st = torch.cuda.current_stream(self.device).cuda_stream or 1
+        metric = capi.METRIC_DOT if self.metric == "dot" else capi.METRIC_COSINE
+        if self._want_p2p and (self._shard_group is None or nq > self._group_nq or k > self._group_k):
+            if self._shard_group is not None:        # a larger batch than the group was sized for: make a new one
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=self.group)
+                L.mx_shard_group_destroy(self._shard_group)
+                self._shard_group = None
+            if self._setup_group(nq, k):
+                self.exchange = "p2p"
+            else:
+                self._want_p2p = False
+        if self._shard_group is not None:
+            # scan + rerank, push to every peer, merge-with-wait: all below the C ABI (csrc/shard_group.cu)
+            rc = L.mx_shard_group_search_device(self._shard_group, self.local.handle,
+                                                q_dev.data_ptr() if q_dev is not None else None, query_root, nq, k,
+                                                b["ids"].data_ptr(), b["scores"].data_ptr(), b["counts"].data_ptr(), st)
+            if rc != capi.OK:
+                _raise(rc, self._shard_group, SearchError)
+            return b["ids"], b["scores"], b["counts"]
         mine = b["mine"]
         rc = L.mx_store_search_blob_device(self.local.handle, q_dev.data_ptr(), nq, k, mine.data_ptr(), st)
         if rc != capi.OK:
             _raise(rc, self.local.handle, SearchError)
-        metric = capi.METRIC_DOT if self.metric == "dot" else capi.METRIC_COSINE
-        if self.world > 1 and self._want_p2p and "p2p" not in b:
-            b["p2p"] = self._setup_p2p(b, b["blob_bytes"])
-            if b["p2p"]:
-                self.exchange = "p2p"
-        if self.world > 1 and b.get("p2p"):
-            # the one exchange step, peer-memory form: push to every peer's slot [epoch parity][rank], wait inside the merge
-            b["epoch"] = epoch = b.get("epoch", 0) + 1
-            stride, base = b["xstride"], b["xbuf"].data_ptr()
-            half = (epoch & 1) * self.world * stride
-            rc = L.mx_exchange_push_device(mine.data_ptr(), stride, b["peers"], self.world, self.rank, half + self.rank * stride,
-                                           2 * self.world * stride, epoch, self.device, st)
-            if rc != capi.OK:
-                _raise(rc, None, SearchError)
-            rc = L.mx_merge_topk_blobs_wait_device(base + half, stride, self.world, nq, k, metric, b["ids"].data_ptr(),
-                                                   b["scores"].data_ptr(), b["counts"].data_ptr(),
-                                                   base + 2 * self.world * stride, epoch, self.device, st)
-            if rc != capi.OK:
-                _raise(rc, None, SearchError)
-            return b["ids"], b["scores"], b["counts"]
         if self.world > 1:
             # the one exchange step, collective form: each rank contributes blob_bytes
             dist.all_gather_into_tensor(b["gathered"].view(-1), mine, group=self.group)
@@ -225,13 +231,20 @@ class ShardedStore:
         if queries is not None:
             b["q_pin"].numpy()[...] = queries
             b["q"].copy_(b["q_pin"], non_blocking=True)
-        if self.world > 1:
-            dist.broadcast(b["q"], src=0, group=self.group)
-        self.search_device(b["q"], k)                     # fills b["out"] (ids | scores | counts)
+        if self.world > 1 and self._shard_group is not None and nq <= self._group_nq and k <= self._group_k:
+            # rank 0's block goes to the peers through the exchange buffers (one push kernel, no collective call)
+            self.search_device(b["q"] if self.rank == 0 else None, k, nq=nq, query_root=0)
+        else:
+            if self.world > 1:
+                dist.broadcast(b["q"], src=0, group=self.group)
+            self.search_device(b["q"], k)                 # fills b["out"] (ids | scores | counts)
         b["out_pin"].copy_(b["out"], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return (b["ids_pin"].numpy().astype(np.uint64), b["scores_pin"].numpy().copy(),
                 b["counts_pin"].numpy().astype(np.uint32))
 
     def close(self):
+        if self._shard_group is not None:
+            capi.lib().mx_shard_group_destroy(self._shard_group)
+            self._shard_group = None
         self.local.close()
