@@ -117,22 +117,59 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
     }
     const uint32_t total = p.n_lists * p.lcap;   // the (query, list) candidate lists are contiguous
     const size_t cbase = (size_t)blockIdx.x * total;
-    if constexpr (E == 1) {
-        // 1+2 (k <= 24): sorted-list algebra.  Each warp sorts 32 candidates at a time and merges them
-        // into its running sorted top-32; warp 0 then merges the 16 warp lists.
+    // certificate, part 1 (see below): the best APPROXIMATE score among everything that was rejected before the exact
+    // re-scoring -- by a scan CTA (a full list's minimum bounds whatever that CTA turned away, and the global threshold tau
+    // is the maximum of such minima), by the seeding floor, or by the top-(32 E) cut
+    float a_rej = kNegInf;
+    if (certify && p.n_flagged_next && blockIdx.x == 0 && threadIdx.x == 0) *p.n_flagged_next = 0;
+    constexpr int kRegSlots = 10;   // candidates per thread held in registers by the E == 1 fast path
+    bool reg_path = false;
+    if constexpr (E == 1) reg_path = total <= (uint32_t)kRegSlots * kRerankThreads && (p.lcap == 16 || p.lcap == 32);
+    if (E == 1 && reg_path) {
+        // 1+2 (k <= 24), ONE pass over global memory: every candidate of the query goes to a register first (all loads
+        // in flight together), the certificate's per-list facts come from segmented warp reductions of those registers
+        // (a list is 16 or 32 consecutive entries = half a warp-load or a whole one), then sorted-list algebra: each
+        // warp sorts 32 candidates at a time and merges them into its running sorted top-32, a tree merges the 16 warps.
+        float cv[kRegSlots];
+        uint32_t cr[kRegSlots];
+#pragma unroll
+        for (int i = 0; i < kRegSlots; ++i) {
+            const uint32_t idx = (uint32_t)i * kRerankThreads + threadIdx.x;
+            const bool in = idx < total;
+            cv[i] = in ? p.cand_s[cbase + idx] : kNegInf;
+            cr[i] = in ? p.cand_r[cbase + idx] : kNoRow;
+        }
+        if (certify) {
+            const uint32_t segmask = p.lcap == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
+#pragma unroll
+            for (int i = 0; i < kRegSlots; ++i) {
+                if ((uint32_t)i * kRerankThreads + warp * 32 < total) {            // warp-uniform
+                    const uint32_t have = __ballot_sync(0xffffffffu, cr[i] != kNoRow);
+                    float mn = cv[i];
+                    if (p.lcap == 32) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, 16));
+#pragma unroll
+                    for (int o = 8; o >= 1; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    if ((have & segmask) == segmask) a_rej = fmaxf(a_rej, mn);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kRegSlots; ++i)
+            if (cr[i] == kNoRow) cv[i] = kNegInf;
         float bv = kNegInf;
         uint32_t br = kNoRow;
-        for (uint32_t i = warp * 32; i < total; i += kRerankWarps * 32) {
-            const uint32_t idx = i + lane;
-            float v = idx < total ? p.cand_s[cbase + idx] : kNegInf;
-            uint32_t r = idx < total ? p.cand_r[cbase + idx] : kNoRow;
-            if (r == kNoRow) v = kNegInf;
-            warp_sort32(v, r);
-            if (i == warp * 32) {
-                bv = v;
-                br = r;
-            } else {
-                warp_merge32(bv, br, v, r);
+#pragma unroll
+        for (int i = 0; i < kRegSlots; ++i) {
+            if ((uint32_t)i * kRerankThreads + warp * 32 < total) {               // warp-uniform
+                float v = cv[i];
+                uint32_t r = cr[i];
+                warp_sort32(v, r);
+                if (i == 0) {
+                    bv = v;
+                    br = r;
+                } else {
+                    warp_merge32(bv, br, v, r);
+                }
             }
         }
         ws[warp * 32 + lane] = bv;
@@ -151,6 +188,53 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
         if (warp == 0) {
             erow[lane] = br;
             if (lane == 31) {   // the worst entry that made the cut (kNoRow: nothing was cut)
+                sel_v_s = bv;
+                sel_r_s = br;
+            }
+        }
+        if (certify) {
+            __syncthreads();
+            const float sv = sel_v_s;
+            const uint32_t sr = sel_r_s;
+            if (sr != kNoRow) {
+#pragma unroll
+                for (int i = 0; i < kRegSlots; ++i)
+                    if (cr[i] != kNoRow && cand_before(sv, sr, cv[i], cr[i])) a_rej = fmaxf(a_rej, cv[i]);
+            }
+        }
+    } else if constexpr (E == 1) {
+        // generic form of the same (more candidates than the register path holds): each warp sorts 32 candidates at a
+        // time and merges them into its running sorted top-32; warp 0 then merges the 16 warp lists.
+        float bv = kNegInf;
+        uint32_t br = kNoRow;
+        for (uint32_t i = warp * 32; i < total; i += kRerankWarps * 32) {
+            const uint32_t idx = i + lane;
+            float v = idx < total ? p.cand_s[cbase + idx] : kNegInf;
+            uint32_t r = idx < total ? p.cand_r[cbase + idx] : kNoRow;
+            if (r == kNoRow) v = kNegInf;
+            warp_sort32(v, r);
+            if (i == warp * 32) {
+                bv = v;
+                br = r;
+            } else {
+                warp_merge32(bv, br, v, r);
+            }
+        }
+        ws[warp * 32 + lane] = bv;
+        wr[warp * 32 + lane] = br;
+        for (int half = kRerankWarps / 2; half >= 1; half >>= 1) {
+            __syncthreads();
+            if ((int)warp < half) {
+                warp_merge32(bv, br, ws[(warp + half) * 32 + lane], wr[(warp + half) * 32 + lane]);
+                if (half > 1) {
+                    ws[warp * 32 + lane] = bv;
+                    wr[warp * 32 + lane] = br;
+                }
+            }
+        }
+        if (warp == 0) {
+            erow[lane] = br;
+            if (lane == 31) {
                 sel_v_s = bv;
                 sel_r_s = br;
             }
@@ -187,29 +271,27 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
             }
         }
     }
-    // certificate, part 1: the best APPROXIMATE score among everything that was rejected before the exact re-scoring --
-    // by a scan CTA (a full list's minimum bounds whatever that CTA turned away, and the global threshold tau is the
-    // maximum of such minima), by the seeding floor, or by the top-(32 E) cut above
-    float a_rej = kNegInf;
     if (certify) {
         __syncthreads();
-        for (uint32_t c = threadIdx.x; c < p.n_lists; c += blockDim.x) {
-            float mn = __int_as_float(0x7f800000);
-            bool full = true;
-            for (uint32_t e = 0; e < p.lcap; ++e) {
-                full &= p.cand_r[cbase + (size_t)c * p.lcap + e] != kNoRow;
-                mn = fminf(mn, p.cand_s[cbase + (size_t)c * p.lcap + e]);
+        if (!(E == 1 && reg_path)) {
+            for (uint32_t c = threadIdx.x; c < p.n_lists; c += blockDim.x) {
+                float mn = __int_as_float(0x7f800000);
+                bool full = true;
+                for (uint32_t e = 0; e < p.lcap; ++e) {
+                    full &= p.cand_r[cbase + (size_t)c * p.lcap + e] != kNoRow;
+                    mn = fminf(mn, p.cand_s[cbase + (size_t)c * p.lcap + e]);
+                }
+                if (full) a_rej = fmaxf(a_rej, mn);
             }
-            if (full) a_rej = fmaxf(a_rej, mn);
+            const float sv = sel_v_s;
+            const uint32_t sr = sel_r_s;
+            if (sr != kNoRow)
+                for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+                    const float v = p.cand_s[cbase + i];
+                    const uint32_t r = p.cand_r[cbase + i];
+                    if (r != kNoRow && cand_before(sv, sr, v, r)) a_rej = fmaxf(a_rej, v);
+                }
         }
-        const float sv = sel_v_s;
-        const uint32_t sr = sel_r_s;
-        if (sr != kNoRow)
-            for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-                const float v = p.cand_s[cbase + i];
-                const uint32_t r = p.cand_r[cbase + i];
-                if (r != kNoRow && cand_before(sv, sr, v, r)) a_rej = fmaxf(a_rej, v);
-            }
         if (threadIdx.x == 0 && p.scan_floor) a_rej = fmaxf(a_rej, p.scan_floor[q]);
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) a_rej = fmaxf(a_rej, __shfl_xor_sync(0xffffffffu, a_rej, o));

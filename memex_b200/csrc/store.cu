@@ -70,7 +70,9 @@ struct mx_store : HandleBase {
     size_t blob_scores_cap = 0;
     // superset certificate + exact fallback
     bool verify = true;
-    uint32_t *n_flagged = nullptr;   // device scalar
+    uint32_t *n_flagged_buf = nullptr;   // device [2]: search i counts into [i & 1]; its rerank zeroes the other one for search i + 1
+    uint32_t flag_cur = 0;
+    uint32_t *n_flagged = nullptr;       // = n_flagged_buf + flag_cur during a search
     uint32_t *q_map = nullptr;       // [verify_cap]
     float *fb_thr = nullptr;         // [verify_cap]
     size_t verify_cap = 0;
@@ -324,7 +326,10 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
         MX_CUDA(s, MX_ERR_SEARCH, cudaMalloc(&s->fb_thr, (size_t)nq * sizeof(float)));
         s->verify_cap = nq;
     }
-    if (s->verify) MX_CUDA(s, MX_ERR_SEARCH, cudaMemsetAsync(s->n_flagged, 0, sizeof(uint32_t), st));
+    // the flagged-query counter alternates between two cells: this search's rerank zeroes the other cell for the next
+    // search (no memset node in the stream)
+    s->flag_cur ^= 1u;
+    s->n_flagged = s->n_flagged_buf + s->flag_cur;
 
     ScanParams sp{};
     sp.rows = s->rows;
@@ -374,6 +379,7 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
     rp.metric = s->cfg.metric;
     if (s->verify) {
         rp.n_flagged = s->n_flagged;
+        rp.n_flagged_next = s->n_flagged_buf + (s->flag_cur ^ 1u);
         rp.q_map = s->q_map;
         rp.fb_thr = s->fb_thr;
         rp.stats = s->stats;
@@ -468,12 +474,13 @@ int32_t mx_store_create(const mx_store_cfg *cfg, mx_store **out)
     if ((e = cudaMalloc(&s->zero_rows, sizeof(uint32_t) * MX_MAX_K)) != cudaSuccess ||
         (e = cudaMalloc(&s->n_zero, 4)) != cudaSuccess || (e = cudaMalloc(&s->flags, 4)) != cudaSuccess)
         return bail(MX_ERR_CONNECTION, "cudaMalloc", e);
-    if ((e = cudaMalloc(&s->n_flagged, 4)) != cudaSuccess || (e = cudaMalloc(&s->stats, 16)) != cudaSuccess ||
+    if ((e = cudaMalloc(&s->n_flagged_buf, 8)) != cudaSuccess || (e = cudaMalloc(&s->stats, 16)) != cudaSuccess ||
         (e = cudaMalloc(&s->max_norm, 4)) != cudaSuccess)
         return bail(MX_ERR_CONNECTION, "cudaMalloc", e);
     cudaMemsetAsync(s->n_zero, 0, 4, s->stream);
     cudaMemsetAsync(s->flags, 0, 4, s->stream);
-    cudaMemsetAsync(s->n_flagged, 0, 4, s->stream);
+    cudaMemsetAsync(s->n_flagged_buf, 0, 8, s->stream);
+    s->n_flagged = s->n_flagged_buf;
     cudaMemsetAsync(s->stats, 0, 16, s->stream);
     cudaMemsetAsync(s->max_norm, 0, 4, s->stream);
     if (const char *v = getenv("MX_SEARCH_VERIFY")) s->verify = atoi(v) != 0;   // A/B measurements only
@@ -504,7 +511,7 @@ void mx_store_destroy(mx_store *s)
     cudaFree(s->cand_r);
     cudaFree(s->dev_io);
     cudaFree(s->blob_scores);
-    cudaFree(s->n_flagged);
+    cudaFree(s->n_flagged_buf);
     cudaFree(s->q_map);
     cudaFree(s->fb_thr);
     cudaFree(s->stats);
