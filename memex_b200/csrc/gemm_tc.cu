@@ -36,14 +36,19 @@ constexpr int kResMaxKB = 6;   // resident-weights variant: K <= 384
 // halves the output staging and, with a smaller bias staging, leaves room for one more ring stage: four 48 KB stages at
 // BN = 256 (three before: 1.4 us of MMA work in flight against a ~1.9 us TMA round trip; measured r1: the
 // intermediate GEMM 93 -> 81 us), five 40 KB stages at BN = 192.
-template <int BN, bool RES, bool LN, int CG = 0>
+// PAIR = cta_group::2: the two CTAs of a cluster run ONE MMA of M = 256 on vertically adjacent row tiles; each CTA streams
+// its own 128 activation rows and only HALF of every weight k-block (BN / 2 rows), and the tensor cores of both SMs read
+// both halves.  Shared memory bandwidth is what paces these GEMMs (every operand byte is written once by TMA and read once
+// by the MMA: 188 B / clk at 128 x 256 against ~128 B / clk per SM, plus 42 B / clk of output staging -- which is where the
+// measured ~50 % tensor-pipe activity of the single-CTA kernels comes from); the pair form removes a quarter of it.
+template <int BN, bool RES, bool LN, int CG = 0, bool PAIR = false>
 struct GemmCfg {
     static constexpr int kChunks = BN > 256 ? 2 : 1;          // one tcgen05.mma covers N <= 256
     static constexpr int kChunkN = BN / kChunks;
     static constexpr int kAccStages = (2 * BN <= 512) ? 2 : 1;
     static constexpr int kTmemCols = (kAccStages * BN <= 128) ? 128 : (kAccStages * BN <= 256 ? 256 : 512);
     static constexpr int kABytes = kBM * kBK * 2;             // one k-block of activations
-    static constexpr int kBBytes = BN * kBK * 2;              // one k-block of weights
+    static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBK * 2;   // one k-block of weights (PAIR: this CTA's half)
     static constexpr int kStageBytes = RES ? kABytes : kABytes + kBBytes;
     static constexpr int kResBytes = RES ? kResMaxKB * kBBytes : 0;
     // epilogue: 4 TMEM lane quarters x kColGroups column groups, one warp each -- several warps per SM
@@ -72,6 +77,7 @@ struct GemmCfg {
     static constexpr int kSmemBytes = kBarOff + 1024 /*align*/ + kTailBytes;
     static_assert(kChunkN % 16 == 0 && kChunkN <= 256, "invalid UMMA N");
     static_assert((BN * kBK * 2 / kChunks) % 1024 == 0, "B chunks must stay 1024-byte aligned");
+    static_assert(!PAIR || (kChunks == 1 && !RES && !LN && (BN / 2 * kBK * 2) % 1024 == 0), "pair variant: streaming, BN <= 256");
     static_assert(kColsPerWarp % 32 == 0, "an epilogue warp works in 32-column chunks");
     static_assert(kStages >= 2, "ring too small");
     static_assert(!RES || kChunks == 1, "resident variant: BN <= 256");
@@ -183,12 +189,13 @@ __device__ __forceinline__ float2 unpack16(uint32_t u)
 // epilogue possible at all (768 f32 columns do not fit the 512 TMEM columns of one SM).
 // AMC (split-row LayerNorm variant only): the two CTAs of a cluster work on the SAME row tile, so each loads half of
 // every activation k-block and multicasts it to both -- the activations cross the L2 -> SM path once per cluster
-template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT, int CG = 0, bool AMC = false>
-__global__ void __launch_bounds__(GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN, CG>::kThreads, 1)
+template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT, int CG = 0, bool AMC = false, bool PAIR = false>
+__global__ void __launch_bounds__(GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN, CG, PAIR>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, GemmParams p)
 {
-    using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN, CG>;
+    using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN, CG, PAIR>;
+    static_assert(!PAIR || (!MC && !SPLIT && !AMC && !RES), "the pair variant is a form of its own");
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment by OFFSET (keeps the pointer in the shared address space: LDS/STS, not generic LD/ST)
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -217,13 +224,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // resident: a contiguous range of the n-major list, so a CTA changes its weight slice at most a few times.
     uint32_t t_begin, t_end, t_step;
     uint32_t cta_rank = 0;
-    if constexpr (MC || SPLIT) cta_rank = cluster_ctarank();
+    if constexpr (MC || SPLIT || PAIR) cta_rank = cluster_ctarank();
     if constexpr (SPLIT) {
         // a cluster strides over the row tiles; the rank picks the column half
         t_begin = blockIdx.x >> 1;
         t_end = tiles_m;
         t_step = gridDim.x >> 1;
-    } else if constexpr (MC) {
+    } else if constexpr (MC || PAIR) {
         // units = (pair of vertically adjacent tiles); a cluster strides over them, n fastest
         t_begin = blockIdx.x >> 1;
         t_end = ((tiles_m + 1) / 2) * tiles_n;
@@ -239,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         t_step = gridDim.x;
     }
     auto tile_m = [&](uint32_t t) {
-        return SPLIT ? t : (MC ? 2 * (t / tiles_n) + cta_rank : (RES ? t % tiles_m : t / tiles_n));
+        return SPLIT ? t : ((MC || PAIR) ? 2 * (t / tiles_n) + cta_rank : (RES ? t % tiles_m : t / tiles_n));
     };
     auto tile_n = [&](uint32_t t) { return SPLIT ? cta_rank : (RES ? t / tiles_m : t % tiles_n); };
 
@@ -252,7 +259,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < Cfg::kAccStages; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], Cfg::kEpiWarps);
+            // pair: the leader's MMA warp waits for the epilogue warps of BOTH CTAs (the peer's arrive remotely)
+            mbar_init(&tmem_empty[i], PAIR ? 2 * Cfg::kEpiWarps : Cfg::kEpiWarps);
         }
         mbar_init(b_full, 1);
         mbar_init(b_empty, 1);
@@ -260,10 +268,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(&x_full[1], kBM);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    if (warp == 1) {
+        if constexpr (PAIR)
+            tmem_alloc_pair(tmem_ptr, Cfg::kTmemCols);
+        else
+            tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    }
     tc_fence_before();
     __syncthreads();
-    if constexpr (MC || SPLIT) cluster_sync_all();   // the peer's barriers exist before anything is sent at them
+    if constexpr (MC || SPLIT || PAIR) cluster_sync_all();   // the peer's barriers exist before anything is sent at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -287,6 +300,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (uint32_t kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char *sa = ring + stage * Cfg::kStageBytes;
+                    if constexpr (PAIR) {
+                        // both CTAs load into their own ring; the bytes of both are counted on the LEADER's barrier, which
+                        // the leader arms for the two stages' worth (the phase cannot complete before that arrive)
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+                        tma_load_2d_pair(sa, &tmA, &full[stage], kb * kBK, m_blk * kBM, kEvictFirst);
+                        tma_load_2d_pair(sa + Cfg::kABytes, &tmB, &full[stage], kb * kBK, n_blk * BN + cta_rank * (BN / 2),
+                                         kEvictLast);
+                        if (++stage == Cfg::kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
                     if constexpr (AMC) {
                         // this CTA's 64 rows of the activation k-block, delivered to both CTAs (and both `full` barriers)
@@ -318,8 +344,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(kBM, Cfg::kChunkN, FMT);
+        if (lane == 0 && (!PAIR || cta_rank == 0)) {   // pair: the leader issues for both SMs
+            constexpr uint32_t idesc = make_idesc(PAIR ? 2 * kBM : kBM, Cfg::kChunkN, FMT);
             uint32_t stage = 0, phase = 0, local = 0, seg = 0, cur_n = 0xffffffffu;
             for (uint32_t tile = t_begin; tile < t_end; tile += t_step, ++local) {
                 const uint32_t as = local % Cfg::kAccStages, aphase = (local / Cfg::kAccStages) & 1;
@@ -345,10 +371,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int c = 0; c < Cfg::kChunks; ++c) {
                             const uint64_t bdesc = make_smem_desc(sb + c * (Cfg::kChunkN * kBK * 2) + k * 32);
-                            umma(tmem_base + as * BN + c * Cfg::kChunkN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                            if constexpr (PAIR)
+                                umma_pair(tmem_base + as * BN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                            else
+                                umma(tmem_base + as * BN + c * Cfg::kChunkN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                     }
-                    if constexpr (MC || AMC)
+                    if constexpr (PAIR)
+                        umma_commit_pair(&empty[stage]);      // frees the stage in BOTH CTAs' rings
+                    else if constexpr (MC || AMC)
                         umma_commit_multicast(&empty[stage], (uint16_t)3);
                     else
                         umma_commit(&empty[stage]);
@@ -357,7 +388,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tmem_full[as]);
+                if constexpr (PAIR)
+                    umma_commit_pair(&tmem_full[as]);         // each CTA's epilogue reads its own 128 rows
+                else
+                    umma_commit(&tmem_full[as]);
                 if constexpr (RES) {
                     // last tile that reads this weight slice: its completion frees the resident buffer
                     const uint32_t next = tile + t_step;
@@ -566,7 +600,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) {
+                if constexpr (PAIR) {
+                    if (cta_rank == 0)
+                        mbar_arrive(&tmem_empty[as]);
+                    else
+                        mbar_arrive_remote_release(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+                } else {
+                    mbar_arrive(&tmem_empty[as]);
+                }
+            }
         }
         if constexpr (EPI != EPI_BIAS_RES_LN) {
             if (lane == 0) bulk_wait_read0();
@@ -575,23 +618,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
-    if constexpr (MC || SPLIT) cluster_sync_all();   // no CTA leaves while the peer can still signal its barriers
+    if constexpr (MC || SPLIT || PAIR) cluster_sync_all();   // no CTA leaves while the peer can still signal its barriers
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if constexpr (PAIR)
+            tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+        else
+            tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
-template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT = false, int CG = 0, bool AMC = false>
+template <int BN, int EPI, int FMT, bool RES, bool MC, bool SPLIT = false, int CG = 0, bool AMC = false, bool PAIR = false>
 static cudaError_t launch_cfg(const GemmParams &p, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO,
                               int sm_count, cudaStream_t st)
 {
-    using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN, CG>;
-    auto kern = gemm_tc_kernel<BN, EPI, FMT, RES, MC, SPLIT, CG, AMC>;
+    using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN, CG, PAIR>;
+    auto kern = gemm_tc_kernel<BN, EPI, FMT, RES, MC, SPLIT, CG, AMC, PAIR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     const uint32_t tiles_m = ceil_div<uint32_t>(p.M, kBM), tiles_n = p.N / BN;
-    if constexpr (MC || SPLIT) {
+    if constexpr (MC || SPLIT || PAIR) {
         const uint32_t units = SPLIT ? tiles_m : ceil_div<uint32_t>(tiles_m, 2) * tiles_n;
         const uint32_t clusters = std::min<uint32_t>(units, (uint32_t)sm_count / 2);
         cudaLaunchConfig_t cfg{};
@@ -659,8 +705,13 @@ cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStrea
     // run both settings).
     static const bool mc_on = getenv("MX_GEMM_MULTICAST") != nullptr;
     const bool mc = !res && mc_on && epi != EPI_BIAS_GELU_TANH && sm_count >= 2 && ceil_div<uint32_t>(p.M, 2 * kBM) * (p.N / bn) >= (uint32_t)sm_count / 2;
+    // CTA pairs (cta_group::2, GemmCfg): MX_GEMM_PAIR=0 turns them off (A/B measurements)
+    static const bool pair_on = getenv("MX_GEMM_PAIR") == nullptr || atoi(getenv("MX_GEMM_PAIR")) != 0;
+    const bool pair = pair_on && !res && !mc && (epi == EPI_BIAS || epi == EPI_BIAS_GELU) && (bn == 192 || bn == 256) &&
+                      sm_count >= 2 && ceil_div<uint32_t>(p.M, 2 * kBM) * (p.N / bn) >= (uint32_t)sm_count / 2 &&
+                      p.N <= (bn == 192 ? 2304u : 3072u);
     CUtensorMap tmA, tmB, tmO;
-    uint32_t chunk_rows = mc ? bn / 2 : (bn > 256 ? bn / 2 : bn);
+    uint32_t chunk_rows = (mc || pair) ? bn / 2 : (bn > 256 ? bn / 2 : bn);
     if (epi == EPI_BIAS_RES_LN && !mc) chunk_rows = 192;   // whole-row 384 (2 chunks), split 2 x 192, split 2 x 384 (2 chunks each)
     // split-row LayerNorm variant with activation multicast (MX_GEMM_LN_AMC=1, opt-in until measured): each CTA of the
     // pair loads 64 of the tile's 128 rows
@@ -708,6 +759,19 @@ cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStrea
                               : launch_cfg<192, EPI_BIAS_RES_LN, 0, false, false, true>(p, tmA, tmB, tmO, sm_count, st);
         }
         MX_GEMM_MC(384, EPI_BIAS_RES_LN);
+    }
+    if (pair) {
+        if (epi == EPI_BIAS_GELU && bn == 256)
+            return p.fmt == 1 ? launch_cfg<256, EPI_BIAS_GELU, 1, false, false, false, 2, false, true>(p, tmA, tmB, tmO, sm_count, st)
+                              : launch_cfg<256, EPI_BIAS_GELU, 0, false, false, false, 2, false, true>(p, tmA, tmB, tmO, sm_count, st);
+        if (epi == EPI_BIAS_GELU)
+            return p.fmt == 1 ? launch_cfg<192, EPI_BIAS_GELU, 1, false, false, false, 2, false, true>(p, tmA, tmB, tmO, sm_count, st)
+                              : launch_cfg<192, EPI_BIAS_GELU, 0, false, false, false, 2, false, true>(p, tmA, tmB, tmO, sm_count, st);
+        if (bn == 256)
+            return p.fmt == 1 ? launch_cfg<256, EPI_BIAS, 1, false, false, false, 2, false, true>(p, tmA, tmB, tmO, sm_count, st)
+                              : launch_cfg<256, EPI_BIAS, 0, false, false, false, 2, false, true>(p, tmA, tmB, tmO, sm_count, st);
+        return p.fmt == 1 ? launch_cfg<192, EPI_BIAS, 1, false, false, false, 2, false, true>(p, tmA, tmB, tmO, sm_count, st)
+                          : launch_cfg<192, EPI_BIAS, 0, false, false, false, 2, false, true>(p, tmA, tmB, tmO, sm_count, st);
     }
     if (epi == EPI_BIAS_GELU) {
         if (res) MX_GEMM(192, EPI_BIAS_GELU, true, false);

@@ -68,6 +68,15 @@ __device__ __forceinline__ void warp_merge32(float &v, uint32_t &r, float bv, ui
     }
 }
 
+__device__ __forceinline__ void prof_mark(const RerankParams &p, int slot)
+{
+    if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        p.prof[slot] = t;
+    }
+}
+
 constexpr int kRerankThreads = 512;
 constexpr int kRerankWarps = kRerankThreads / 32;
 constexpr int kFoldChunk = 384;           // elements of a row staged per pass
@@ -110,6 +119,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
         kth_key_s = 0.f;
     }
     const float *qg = p.queries + (size_t)q * p.ldq;
+    prof_mark(p, 0);
 
     for (uint32_t j = threadIdx.x; j < kMaxEntries; j += blockDim.x) {
         ekey[j] = 0.f;
@@ -139,6 +149,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
             cv[i] = in ? p.cand_s[cbase + idx] : kNegInf;
             cr[i] = in ? p.cand_r[cbase + idx] : kNoRow;
         }
+        prof_mark(p, 1);   // (issue only: the loads complete at their first use)
         if (certify) {
             const uint32_t segmask = p.lcap == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
 #pragma unroll
@@ -172,6 +183,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
                 }
             }
         }
+        prof_mark(p, 2);
         ws[warp * 32 + lane] = bv;
         wr[warp * 32 + lane] = br;
         // tree merge of the 16 warp lists (the top 32 of a union does not depend on the merge order)
@@ -300,6 +312,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
         a_rej = red_s[0];
         for (int w = 1; w < kRerankWarps; ++w) a_rej = fmaxf(a_rej, red_s[w]);
     }
+    prof_mark(p, 3);
     // 3. the lowest-id zero-norm rows (cosine: d = 0)
     if (threadIdx.x == 0) {
         uint32_t n = kList;
@@ -319,6 +332,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
     //    operations per sum as the reference, hence the same bits.
     __shared__ double bb_s[kFoldBatches * 32];
     __shared__ double aa_s;
+    prof_mark(p, 4);
     const uint32_t n_batches = (n_entries + 31) / 32;
     const uint32_t frole = warp / kFoldBatches, fb = warp % kFoldBatches;   // role 0: a.b, 1: b.b, warp 2F: a.a
     for (uint32_t b0 = 0; b0 < n_batches; b0 += kFoldBatches) {
@@ -413,6 +427,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
     }
     __syncthreads();
 
+    prof_mark(p, 5);
     const uint32_t count = min(p.k, p.n_rows);
     if (zero_query_s) {
         // all distances are 0 -> (d asc, id asc) is simply the first rows
@@ -467,6 +482,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
         }
     }
     if (threadIdx.x == 0) p.counts_out[q] = count;
+    prof_mark(p, 6);
     if (!certify) return;
     // certificate, part 2.  In the exact score's units (cosine: cos; dot: q . c) the approximate score of a row is within
     //   eps = [ |q16 - q/|q||_2  (tcgen05 scan: fp16 query, Cauchy-Schwarz) + (dim + 64) 2^-23  (f32 / tensor-core

@@ -52,6 +52,7 @@ struct RerankParams {
     uint32_t unit_queries = 0;          // 1: approximate scores are those of the unit-norm query (tcgen05 scan)
     uint32_t *n_flagged = nullptr;      // device scalar, zero on entry; nullptr = no certificate
     uint32_t *n_flagged_next = nullptr; // the counter of the NEXT search: zeroed here (nobody reads it during this one)
+    unsigned long long *prof = nullptr; // test-only (MX_RERANK_PROF=1): %globaltimer of CTA 0 at the phase boundaries, [8]
     uint32_t *q_map = nullptr;          // [nq] flagged query indices
     float *fb_thr = nullptr;            // [nq] fp32-scan threshold below which a row cannot be in the flagged query's top k
     unsigned long long *stats = nullptr;  // [2] lifetime counters: queries answered, queries flagged

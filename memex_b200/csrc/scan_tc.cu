@@ -108,13 +108,18 @@ struct TcParams {
     float *samp;
     uint32_t *sync;
     float *floor_out;       // [nq_pad] tau0 of each query (-inf without seeding), read by the rerank's certificate
+    // query preparation in the prologue (no separate launch, no fp16 staging buffer): queries f32 [nq, ldq], zero padded
+    const float *queries;
+    uint32_t ldq, dim;
+    float *qerr;            // [nq_pad] fp16 rounding radius of each prepared query (written by CTA x = 0)
+    uint32_t *done;         // exit ticket: the LAST CTA out resets tau / sync / done for the next launch
 };
 
 // QM = 128: TMEM lane = query.  QM = 64 (cta_group::1, M = 64): accumulator row r sits in TMEM lane
 // 32 * (r / 16) + r % 16, i.e. the first 16 lanes of each 32-lane quarter -- epilogue lanes 16..31 idle.
 template <int L, bool USE_INV, int QM>
 __global__ void __launch_bounds__(kTcThreads, 1)
-scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, TcParams p)
+scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
 {
     using Cfg = TcCfg<L>;
     extern __shared__ unsigned char smem_raw[];
@@ -147,7 +152,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     auto tile_of = [&](uint32_t i) { return blockIdx.x + (i < n_sample ? i : i - n_sample) * gridDim.x; };
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmC);
         for (uint32_t i = 0; i < n_stages; ++i) {
             mbar_init(&full[i], 1);
@@ -158,7 +162,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_init(&tmem_empty[i], 4);
         }
         for (int i = 0; i < kInvSlots; ++i) mbar_init(&inv_full[i], 1);
-        mbar_init(q_full, 1);
+        mbar_init(q_full, 4);   // one arrive per epilogue warp once its share of the query block is in shared memory
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -170,10 +174,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, p.k_blocks * kQKB);
-            for (uint32_t kb = 0; kb < p.k_blocks; ++kb)
-                tma_load_2d(sq + kb * kQKB, &tmQ, q_full, kb * kBK, q0, kEvictLast);
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, phase = 0;   // the corpus ring fills while the epilogue warps prepare the queries
             for (uint32_t local = 0; local < n_seq; ++local) {
                 const uint32_t tile = tile_of(local);
                 if (USE_INV) {
@@ -226,6 +227,74 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     } else {
         // ================= epilogue: thread = query (TMEM lane), columns = corpus rows =================
         const uint32_t quarter = warp & 3;
+        // ---- query preparation (was a kernel of its own): rows q0 .. q0 + QM of the f32 query block -> unit norm ->
+        // fp16 -> the K-major SWIZZLE_128B layout the UMMA descriptor expects ([k-block][QM rows][64 halfs], 16-byte chunk
+        // index ^= row & 7), zero rows beyond nq.  Scaling a query by a positive constant changes neither ranking, and keeps
+        // every fp16 component in [-1, 1].  qerr[row] = |q16 - q / |q||_2: by Cauchy-Schwarz the tensor-core score of ANY
+        // unit row differs from the exact cosine by at most this -- the rerank's certificate uses it as the radius.
+        {
+            const uint32_t n_chunks = p.k_blocks * 8;            // 8-element (16-byte) chunks per prepared row
+            constexpr int kRowsInFlight = 4;                     // the loads of 4 rows are issued before the first reduction
+            for (uint32_t rb = quarter; rb < (uint32_t)QM; rb += 4 * kRowsInFlight) {
+                float4 va[kRowsInFlight][3], vb[kRowsInFlight][3];
+#pragma unroll
+                for (int j = 0; j < kRowsInFlight; ++j) {
+                    const uint32_t gq = q0 + rb + 4 * j;
+                    const bool live = rb + 4 * j < (uint32_t)QM && gq < p.nq;
+                    const float *src = p.queries + (size_t)gq * p.ldq;
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const uint32_t c = lane + 32 * u;
+                        va[j][u] = vb[j][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live && c < n_chunks && c * 8 < p.ldq) {     // ldq is a multiple of 8, zero beyond dim
+                            va[j][u] = __ldg(reinterpret_cast<const float4 *>(src + c * 8));
+                            vb[j][u] = __ldg(reinterpret_cast<const float4 *>(src + c * 8 + 4));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kRowsInFlight; ++j) {
+                    const uint32_t r = rb + 4 * j;
+                    if (r >= (uint32_t)QM) break;
+                    float ss = 0.f;
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        ss = fmaf(va[j][u].x, va[j][u].x, fmaf(va[j][u].y, va[j][u].y, fmaf(va[j][u].z, va[j][u].z, fmaf(va[j][u].w, va[j][u].w, ss))));
+                        ss = fmaf(vb[j][u].x, vb[j][u].x, fmaf(vb[j][u].y, vb[j][u].y, fmaf(vb[j][u].z, vb[j][u].z, fmaf(vb[j][u].w, vb[j][u].w, ss))));
+                    }
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                    const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+                    float ee = 0.f;
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const uint32_t c = lane + 32 * u;
+                        if (c >= n_chunks) continue;
+                        const float f[8] = {va[j][u].x * inv, va[j][u].y * inv, va[j][u].z * inv, va[j][u].w * inv,
+                                            vb[j][u].x * inv, vb[j][u].y * inv, vb[j][u].z * inv, vb[j][u].w * inv};
+                        uint32_t w[4];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            const __half2 h2 = __floats2half2_rn(f[2 * x], f[2 * x + 1]);
+                            const float2 back = __half22float2(h2);
+                            const float e0 = back.x - f[2 * x], e1 = back.y - f[2 * x + 1];
+                            ee = fmaf(e0, e0, fmaf(e1, e1, ee));
+                            w[x] = *reinterpret_cast<const uint32_t *>(&h2);
+                        }
+                        const uint32_t kb = c >> 3, cj = c & 7;
+                        *reinterpret_cast<uint4 *>(sq + kb * kQKB + r * 128 + ((cj ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    if (blockIdx.x == 0) {
+#pragma unroll
+                        for (int o = 16; o >= 1; o >>= 1) ee += __shfl_xor_sync(0xffffffffu, ee, o);
+                        if (lane == 0) p.qerr[q0 + r] = sqrtf(ee) * 1.001f;
+                    }
+                }
+            }
+            fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_full);
+        }
         const uint32_t t = QM == 128 ? quarter * 32 + lane : quarter * 16 + (lane & 15);   // query row of this thread
         const bool q_ok = (QM == 128 || lane < 16) && q0 + t < p.nq;
         float *ls = list_s + quarter * 32 + lane;    // one list column per thread (idle lanes own an unused one)
@@ -241,6 +310,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const float *tau = p.tau + q0 + t;
         const float kPosInf = __int_as_float(0x7f800000);
         float g_floor = kNegInf;          // tau0 from the sampling pass
+        if (n_sample == 0 && q_ok && blockIdx.x == 0) p.floor_out[q0 + t] = kNegInf;
         float b1 = kNegInf, b2 = kNegInf; // two best scores of the sampling pass
         for (uint32_t local = 0; local < n_seq; ++local) {
             const uint32_t tile = tile_of(local);
@@ -402,43 +472,39 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    if (warp == 0) {
+        // last CTA out leaves the cross-launch state as the next launch expects it: tau = -inf, counters zero (every other
+        // CTA made its last tau / sync access before taking its ticket)
+        uint32_t ticket = 0;
+        if (lane == 0) {
+            __threadfence();
+            ticket = atomicAdd(p.done, 1u);
+        }
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket == gridDim.x * gridDim.y - 1) {
+            for (uint32_t i = lane; i < p.nq_pad; i += 32) p.tau[i] = kNegInf;
+            if (lane == 0) {
+                *p.sync = 0;
+                __threadfence();
+                *p.done = 0;
+            }
+        }
+    }
 }
 
-// queries f32 [nq, ldq] -> unit-norm fp16 [nq_pad, ld] (zero rows beyond nq), tau[nq_pad] = -inf.
-// Scaling a query by a positive constant changes neither the cosine nor the dot ranking, and keeps
-// every fp16 component in [-1, 1].
-// qerr[row] = |q16 - q / |q||_2: by Cauchy-Schwarz the tensor-core score of ANY unit row differs from the exact cosine by at
-// most this (plus accumulation error) -- the rerank's certificate uses it as the approximation radius.
-__global__ void __launch_bounds__(128) tc_prepare_queries_kernel(const float *q, uint32_t nq, uint32_t dim, uint32_t ldq,
-                                                                 __half *q16, uint32_t ld, float *tau, uint32_t *sync,
-                                                                 float *qerr, float *floor_out)
+// cross-launch state of a freshly (re)allocated query capacity: tau = -inf, counters zero.  Every launch's last CTA puts
+// it back, so this runs once per allocation, not once per search.
+__global__ void tc_init_state_kernel(float *tau, float *floor_out, float *qerr, uint32_t n, uint32_t *sync, uint32_t *done)
 {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *sync = 0;
-    const uint32_t row = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const uint32_t lane = lane_id();
-    float ss = 0.f;
-    if (row < nq)
-        for (uint32_t c = lane; c < dim; c += 32) {
-            const float v = q[(size_t)row * ldq + c];
-            ss = fmaf(v, v, ss);
-        }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
-    float ee = 0.f;
-    for (uint32_t c = lane; c < ld; c += 32) {
-        const float u = (row < nq && c < dim) ? q[(size_t)row * ldq + c] * inv : 0.f;
-        const __half h = __float2half_rn(u);
-        q16[(size_t)row * ld + c] = h;
-        const float e = __half2float(h) - u;
-        ee = fmaf(e, e, ee);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        tau[i] = kNegInf;
+        floor_out[i] = kNegInf;
+        qerr[i] = 0.f;
     }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) ee += __shfl_xor_sync(0xffffffffu, ee, o);
-    if (lane == 0) {
-        tau[row] = kNegInf;
-        qerr[row] = sqrtf(ee) * 1.001f;
-        floor_out[row] = kNegInf;
+    if (i == 0) {
+        *sync = 0;
+        *done = 0;
     }
 }
 
@@ -447,10 +513,9 @@ __global__ void __launch_bounds__(128) tc_prepare_queries_kernel(const float *q,
 struct TcScanState {
     int sm_count;
     uint32_t ld, dim, k_blocks;
-    __half *q16 = nullptr;
     float *tau = nullptr;
     float *samp = nullptr;      // [sm_count][q_cap]
-    uint32_t *sync = nullptr;
+    uint32_t *sync = nullptr;   // [0] grid barrier arrivals, [32] exit tickets (separate 128-byte lines)
     float *qerr = nullptr;      // [q_cap] fp16 rounding radius of each prepared query
     float *floor_out = nullptr; // [q_cap] tau0 of the last launch
     uint32_t q_cap = 0;  // rows
@@ -471,7 +536,6 @@ TcScanState *tc_scan_create(int sm_count, uint32_t ld, uint32_t dim)
 void tc_scan_destroy(TcScanState *t)
 {
     if (!t) return;
-    cudaFree(t->q16);
     cudaFree(t->tau);
     cudaFree(t->samp);
     cudaFree(t->sync);
@@ -493,7 +557,7 @@ uint32_t tc_scan_lists(const TcScanState *t, uint64_t n_rows)
 }
 
 template <int L, bool USE_INV, int QM>
-static cudaError_t launch_tc_one(const CUtensorMap &tmQ, const CUtensorMap &tmC, TcParams tp, dim3 grid, cudaStream_t st)
+static cudaError_t launch_tc_one(const CUtensorMap &tmC, TcParams tp, dim3 grid, cudaStream_t st)
 {
     int n_stages = TcCfg<L>::stages((int)tp.k_blocks, QM);
     static const int cap = getenv("MX_SCAN_TC_STAGES") ? atoi(getenv("MX_SCAN_TC_STAGES")) : kMaxStages;   // measurement aid
@@ -516,7 +580,7 @@ static cudaError_t launch_tc_one(const CUtensorMap &tmQ, const CUtensorMap &tmC,
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, kern, tmQ, tmC, tp);
+        e = cudaLaunchKernelEx(&cfg, kern, tmC, tp);
         if (e == cudaSuccess) {
             count_launch();
             return cudaGetLastError();
@@ -524,18 +588,17 @@ static cudaError_t launch_tc_one(const CUtensorMap &tmQ, const CUtensorMap &tmC,
         cudaGetLastError();   // not launchable cooperatively here: plain launch without seeding
         tp.sample_tiles = 0;
     }
-    kern<<<grid, kTcThreads, smem, st>>>(tmQ, tmC, tp);
+    kern<<<grid, kTcThreads, smem, st>>>(tmC, tp);
     count_launch();
     return cudaGetLastError();
 }
 
 template <int L>
-static cudaError_t launch_tc(const CUtensorMap &tmQ, const CUtensorMap &tmC, const TcParams &tp, bool use_inv, uint32_t qm,
-                             dim3 grid, cudaStream_t st)
+static cudaError_t launch_tc(const CUtensorMap &tmC, const TcParams &tp, bool use_inv, uint32_t qm, dim3 grid, cudaStream_t st)
 {
     if (qm == 128)
-        return use_inv ? launch_tc_one<L, true, 128>(tmQ, tmC, tp, grid, st) : launch_tc_one<L, false, 128>(tmQ, tmC, tp, grid, st);
-    return use_inv ? launch_tc_one<L, true, 64>(tmQ, tmC, tp, grid, st) : launch_tc_one<L, false, 64>(tmQ, tmC, tp, grid, st);
+        return use_inv ? launch_tc_one<L, true, 128>(tmC, tp, grid, st) : launch_tc_one<L, false, 128>(tmC, tp, grid, st);
+    return use_inv ? launch_tc_one<L, true, 64>(tmC, tp, grid, st) : launch_tc_one<L, false, 64>(tmC, tp, grid, st);
 }
 
 cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacity, uint32_t k, KernelTimer *timer,
@@ -550,21 +613,18 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
     if (qm_force == 64) qm = 64u;
     const uint32_t nq_pad = ceil_div<uint32_t>(p.nq, qm) * qm;
     if (nq_pad > t->q_cap) {
-        cudaFree(t->q16);
         cudaFree(t->tau);
         cudaFree(t->samp);
         cudaFree(t->sync);
         cudaFree(t->qerr);
         cudaFree(t->floor_out);
-        t->q16 = nullptr;
         t->tau = nullptr;
         t->samp = nullptr;
         t->sync = nullptr;
         t->qerr = nullptr;
         t->floor_out = nullptr;
         t->q_cap = 0;
-        cudaError_t e = cudaMalloc(&t->q16, (size_t)nq_pad * t->ld * sizeof(__half));
-        if (e == cudaSuccess) e = cudaMalloc(&t->tau, (size_t)nq_pad * sizeof(float));
+        cudaError_t e = cudaMalloc(&t->tau, (size_t)nq_pad * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&t->samp, (size_t)t->sm_count * nq_pad * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&t->sync, 256);
         if (e == cudaSuccess) e = cudaMalloc(&t->qerr, (size_t)nq_pad * sizeof(float));
@@ -573,19 +633,15 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
             if (why) *why = "query staging allocation failed";
             return e;
         }
+        tc_init_state_kernel<<<ceil_div<uint32_t>(nq_pad, 128), 128, 0, st>>>(t->tau, t->floor_out, t->qerr, nq_pad, t->sync, t->sync + 32);
+        count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
         t->q_cap = nq_pad;
     }
-    if (timer) timer->begin(st, 1);
-    tc_prepare_queries_kernel<<<nq_pad / 4, 128, 0, st>>>(p.queries, p.nq, t->dim, p.ldq, t->q16, t->ld, t->tau, t->sync,
-                                                           t->qerr, t->floor_out);
-    count_launch();
-    if (timer) timer->end(st);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
 
-    CUtensorMap tmQ, tmC;
-    if (!make_tmap_k_major_16bit(&tmQ, t->q16, nq_pad, t->dim, t->ld, qm, false) ||
-        !make_tmap_k_major_16bit(&tmC, p.rows, p.n_rows, t->dim, p.ld, kTileN, false)) {
+    CUtensorMap tmC;
+    if (!make_tmap_k_major_16bit(&tmC, p.rows, p.n_rows, t->dim, p.ld, kTileN, false)) {
         if (why) *why = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
     }
@@ -602,6 +658,11 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
     tp.samp = t->samp;
     tp.sync = t->sync;
     tp.floor_out = t->floor_out;
+    tp.queries = p.queries;
+    tp.ldq = p.ldq;
+    tp.dim = t->dim;
+    tp.qerr = t->qerr;
+    tp.done = t->sync + 32;
     dim3 grid(p.n_lists, nq_pad / qm);
     // threshold seeding needs every CTA at the barrier: one query pass (grid.y == 1), a full grid, enough tiles per CTA
     // that scanning P of them twice is cheap; MX_SCAN_TC_SAMPLE=0 turns it off (A/B measurements)
@@ -611,8 +672,8 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
                           ? std::min<uint32_t>((uint32_t)sample_cap, tiles_per_cta / 16)
                           : 0u;
     if (timer) timer->begin(st, 0);
-    e = tc_scan_lcap(k) == 16 ? launch_tc<16>(tmQ, tmC, tp, p.use_inv != 0, qm, grid, st)
-                              : launch_tc<32>(tmQ, tmC, tp, p.use_inv != 0, qm, grid, st);
+    cudaError_t e = tc_scan_lcap(k) == 16 ? launch_tc<16>(tmC, tp, p.use_inv != 0, qm, grid, st)
+                                          : launch_tc<32>(tmC, tp, p.use_inv != 0, qm, grid, st);
     if (timer) timer->end(st);
     if (e != cudaSuccess && why) *why = "scan_tc_kernel launch failed";
     return e;

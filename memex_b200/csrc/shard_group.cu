@@ -197,21 +197,20 @@ int32_t mx_shard_group_connect_local(mx_shard_group *const *groups, uint32_t wor
     return MX_OK;
 }
 
-int32_t mx_shard_group_search_device(mx_shard_group *g, mx_store *s, const float *queries_dev, int32_t query_root, uint32_t nq,
-                                     uint32_t k, uint64_t *ids_dev, float *scores_dev, uint32_t *counts_dev, void *cuda_stream)
+// phase 1 of a member's search: (queries through peer memory,) the shard's own scan + rerank into the member's blob, the
+// push of that blob into every peer's slot.  Nothing in it waits for another member.
+static int32_t group_scan_and_push(mx_shard_group *g, mx_store *s, const float *queries_dev, int32_t query_root, uint32_t nq,
+                                   uint32_t k, cudaStream_t st, uint32_t *metric_out)
 {
-    if (!g || !s) return MX_ERR_INVALID;
     if (!g->connected) return fail(g, MX_ERR_CONNECTION, "group is not connected (mx_shard_group_connect[_local] first)");
-    if (nq == 0) return MX_OK;
     if (nq > g->max_nq || k == 0 || k > g->max_k) return fail(g, MX_ERR_INVALID, "batch of %u x top-%u exceeds the group's %u x %u", nq, k, g->max_nq, g->max_k);
-    if (!ids_dev || !scores_dev || !counts_dev) return fail(g, MX_ERR_INVALID, "null buffer");
     if (query_root >= (int32_t)g->world) return fail(g, MX_ERR_INVALID, "query root %d outside the group", query_root);
     uint32_t sdim = 0, metric = 0;
     mx_store_info(s, &sdim, nullptr, &metric, nullptr);
     if (sdim != g->dim) return fail(g, MX_ERR_INVALID, "store has dimension %u, group %u", sdim, g->dim);
+    *metric_out = metric;
     int32_t rc;
     if ((rc = group_set_device(g)) != MX_OK) return rc;
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g->stream;
     const uint32_t epoch = ++g->epoch;
     const uint64_t half = (uint64_t)(epoch & 1u);
     const float *q_use = queries_dev;
@@ -241,12 +240,10 @@ int32_t mx_shard_group_search_device(mx_shard_group *g, mx_store *s, const float
     if (!q_use) return fail(g, MX_ERR_INVALID, "null queries");
     rc = mx_store_search_blob_device(s, q_use, nq, k, g->mine, st);
     if (rc != MX_OK) return fail(g, rc, "shard search failed: %s", mx_last_error(s));
-    const uint64_t blob = mx_topk_blob_bytes(nq, k);
-    if (g->world == 1)
-        return mx_merge_topk_blobs_device(g->mine, blob, 1, nq, k, metric, ids_dev, scores_dev, counts_dev, g->device, st);
+    if (g->world == 1) return MX_OK;
     PushParams pp{};
     pp.blob = g->mine;
-    pp.blob_bytes = blob;
+    pp.blob_bytes = mx_topk_blob_bytes(nq, k);
     for (uint32_t i = 0; i < g->world; ++i) pp.peer_base[i] = g->peer[i];
     pp.slot_offset = (half * g->world + g->rank) * g->stride;
     pp.flag_offset = g->off_flags;
@@ -254,11 +251,37 @@ int32_t mx_shard_group_search_device(mx_shard_group *g, mx_store *s, const float
     pp.rank = g->rank;
     pp.epoch = epoch;
     MX_CUDA(g, MX_ERR_SEARCH, launch_exchange_push(pp, st));
+    return MX_OK;
+}
+
+// phase 2: the merge of the `world` blobs of the current epoch; its kernel waits for the peers' flags
+static int32_t group_merge(mx_shard_group *g, uint32_t metric, uint32_t nq, uint32_t k, uint64_t *ids_dev, float *scores_dev,
+                           uint32_t *counts_dev, cudaStream_t st)
+{
+    int32_t rc;
+    if ((rc = group_set_device(g)) != MX_OK) return rc;
+    if (g->world == 1)
+        return mx_merge_topk_blobs_device(g->mine, mx_topk_blob_bytes(nq, k), 1, nq, k, metric, ids_dev, scores_dev, counts_dev,
+                                          g->device, st);
+    const uint64_t half = (uint64_t)(g->epoch & 1u);
     rc = mx_merge_topk_blobs_wait_device(g->buf + half * g->world * g->stride, g->stride, g->world, nq, k, metric, ids_dev,
                                          scores_dev, counts_dev, reinterpret_cast<const uint32_t *>(g->buf + g->off_flags),
-                                         epoch, g->device, st);
+                                         g->epoch, g->device, st);
     if (rc != MX_OK) return fail(g, rc, "merge failed: %s", mx_last_error(nullptr));
     return MX_OK;
+}
+
+int32_t mx_shard_group_search_device(mx_shard_group *g, mx_store *s, const float *queries_dev, int32_t query_root, uint32_t nq,
+                                     uint32_t k, uint64_t *ids_dev, float *scores_dev, uint32_t *counts_dev, void *cuda_stream)
+{
+    if (!g || !s) return MX_ERR_INVALID;
+    if (nq == 0) return MX_OK;
+    if (!ids_dev || !scores_dev || !counts_dev) return fail(g, MX_ERR_INVALID, "null buffer");
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g->stream;
+    uint32_t metric = 0;
+    int32_t rc = group_scan_and_push(g, s, queries_dev, query_root, nq, k, st, &metric);
+    if (rc != MX_OK) return rc;
+    return group_merge(g, metric, nq, k, ids_dev, scores_dev, counts_dev, st);
 }
 
 int32_t mx_shard_group_search(mx_shard_group *g, mx_store *s, const float *queries, int32_t query_root, uint32_t nq, uint32_t k,
@@ -324,6 +347,7 @@ int32_t mx_shard_group_search_local(mx_shard_group *const *groups, mx_store *con
     const size_t qb = (size_t)nq * g0->dim * sizeof(float);
     const size_t ib = (size_t)nq * k * sizeof(uint64_t), sb = (size_t)nq * k * sizeof(float), cb = (size_t)nq * 4;
     const size_t off_i = (qb + 255) & ~(size_t)255, off_s = off_i + ib, off_c = off_s + sb, total = off_c + cb;
+    // buffers first: an allocation synchronises its device, which must not happen while a member's merge is waiting
     for (uint32_t i = 0; i < world; ++i) {
         mx_shard_group *g = groups[i];
         MX_CUDA(g0, MX_ERR_CONNECTION, cudaSetDevice(g->device));
@@ -337,12 +361,28 @@ int32_t mx_shard_group_search_local(mx_shard_group *const *groups, mx_store *con
             MX_CUDA(g0, MX_ERR_CONNECTION, cudaMalloc(&g->dev_io, total));
             g->pinned_cap = g->dev_io_cap = total;
         }
+    }
+    // phase 1 on every member (scan + rerank + push: waits for nobody), THEN phase 2 on every member (the merges wait for
+    // the pushes inside their kernels): whatever the order in which the devices run, nothing waits for work that has not
+    // been enqueued -- two members may even share a device (tests on a 1-GPU box)
+    uint32_t metric = 0;
+    for (uint32_t i = 0; i < world; ++i) {
+        mx_shard_group *g = groups[i];
+        MX_CUDA(g0, MX_ERR_CONNECTION, cudaSetDevice(g->device));
         char *hp = static_cast<char *>(g->pinned), *dp = static_cast<char *>(g->dev_io);
         memcpy(hp, queries, qb);
         MX_CUDA(g0, MX_ERR_SEARCH, cudaMemcpyAsync(dp, hp, qb, cudaMemcpyHostToDevice, g->stream));
-        int32_t rc = mx_shard_group_search_device(g, stores[i], reinterpret_cast<const float *>(dp), -1, nq, k,
-                                                  reinterpret_cast<uint64_t *>(dp + off_i), reinterpret_cast<float *>(dp + off_s),
-                                                  reinterpret_cast<uint32_t *>(dp + off_c), g->stream);
+        int32_t rc = group_scan_and_push(g, stores[i], reinterpret_cast<const float *>(dp), -1, nq, k, g->stream, &metric);
+        if (rc != MX_OK) {
+            if (g != g0) g0->last_error = g->last_error;
+            return rc;
+        }
+    }
+    for (uint32_t i = 0; i < world; ++i) {
+        mx_shard_group *g = groups[i];
+        char *dp = static_cast<char *>(g->dev_io);
+        int32_t rc = group_merge(g, metric, nq, k, reinterpret_cast<uint64_t *>(dp + off_i), reinterpret_cast<float *>(dp + off_s),
+                                 reinterpret_cast<uint32_t *>(dp + off_c), g->stream);
         if (rc != MX_OK) {
             if (g != g0) g0->last_error = g->last_error;
             return rc;

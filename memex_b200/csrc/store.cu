@@ -15,6 +15,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include "../../include/memex_b200_debug.h"
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -78,6 +79,7 @@ struct mx_store : HandleBase {
     size_t verify_cap = 0;
     unsigned long long *stats = nullptr;   // device [2]: queries answered, queries flagged
     float *max_norm = nullptr;       // device scalar
+    unsigned long long *prof = nullptr;   // test-only: rerank phase timestamps (MX_RERANK_PROF=1)
     KernelTimer timer;
 };
 
@@ -380,6 +382,7 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
     if (s->verify) {
         rp.n_flagged = s->n_flagged;
         rp.n_flagged_next = s->n_flagged_buf + (s->flag_cur ^ 1u);
+        rp.prof = s->prof;
         rp.q_map = s->q_map;
         rp.fb_thr = s->fb_thr;
         rp.stats = s->stats;
@@ -484,6 +487,9 @@ int32_t mx_store_create(const mx_store_cfg *cfg, mx_store **out)
     cudaMemsetAsync(s->stats, 0, 16, s->stream);
     cudaMemsetAsync(s->max_norm, 0, 4, s->stream);
     if (const char *v = getenv("MX_SEARCH_VERIFY")) s->verify = atoi(v) != 0;   // A/B measurements only
+    if (getenv("MX_RERANK_PROF")) {
+        if (cudaMalloc(&s->prof, 64) == cudaSuccess) cudaMemsetAsync(s->prof, 0, 64, s->stream);
+    }
     if (cfg->dtype == MX_DTYPE_F16) s->tc = tc_scan_create(s->sm_count, s->ld, cfg->dim);
     int32_t rc = reserve(s, cfg->capacity ? cfg->capacity : 1024, MX_ERR_CONNECTION);
     if (rc != MX_OK) {
@@ -516,6 +522,7 @@ void mx_store_destroy(mx_store *s)
     cudaFree(s->fb_thr);
     cudaFree(s->stats);
     cudaFree(s->max_norm);
+    cudaFree(s->prof);
     if (s->pinned) cudaFreeHost(s->pinned);
     if (s->stream) cudaStreamDestroy(s->stream);
     s->magic = 0;
@@ -739,6 +746,14 @@ int32_t mx_exchange_push_device(const void *blob_dev, uint64_t blob_bytes, const
     MX_CUDA(nullptr, MX_ERR_CONNECTION, cudaSetDevice(device));
     MX_CUDA(nullptr, MX_ERR_SEARCH, launch_exchange_push(pp, (cudaStream_t)cuda_stream));
     return MX_OK;
+}
+
+int32_t mx_debug_rerank_prof(void *store, uint64_t *out8)
+{
+    mx_store *s = static_cast<mx_store *>(store);
+    if (!s || !out8 || !s->prof) return MX_ERR_INVALID;
+    cudaSetDevice(s->cfg.device);
+    return cudaMemcpy(out8, s->prof, 64, cudaMemcpyDeviceToHost) == cudaSuccess ? MX_OK : MX_ERR_CONNECTION;
 }
 
 int32_t mx_store_len(mx_store *s, uint64_t *n_out)

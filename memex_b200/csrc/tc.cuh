@@ -234,6 +234,17 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)     
 {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// ---- CTA pair (cta_group::2): the two CTAs of a 2-CTA cluster run ONE MMA of M = 256; the same warp of EACH CTA allocates
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t cols)   // one full warp in each CTA of the pair
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -287,6 +298,38 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t *bar, uint16_t ct
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(cta_mask)
                  : "memory");
+}
+
+// CTA pair: D[256 x N] (+)= A[256 x 16] * B[N x 16]^T, issued by ONE thread of the LEADER CTA (cluster rank 0).  Each CTA
+// holds its 128 rows of A and its N / 2 rows of B at the SAME shared-memory offsets (the descriptors are the leader's), and
+// gets its 128 rows x N columns of D in its own tensor memory.
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs of the pair when every pair MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+// TMA load into THIS CTA's shared memory whose transaction bytes are counted on the LEADER's mbarrier at the same offset
+// (bit 24 of a shared::cluster address is the rank within the pair: cleared = the even CTA)
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int32_t c0, int32_t c1,
+                                                 uint64_t hint)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1),
+          "l"(hint)
+        : "memory");
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive columns (thread t <- lane base + t)

@@ -143,9 +143,21 @@ class B200Encoder:
     """Owns an mx_embedder handle: ids [B,S] + lens [B] -> f32 [B, out_dim] (unit-norm when the model has Normalize).
     `weights` use the BERT names (canonical_weights renames DistilBERT / ALBERT checkpoints)."""
 
-    def __init__(self, arch: Architecture, weights: dict, precision: str = "bf16", device: int = 0,
+    def __init__(self, arch: Architecture, weights: dict, precision: str = "auto", device: int = 0,
                  max_tokens: int = 0):
+        """precision: "bf16" | "f16" (tensor-core paths, tcgen05 kind::f16 at the same speed) | "f32" (CUDA-core validation
+        path) | "auto" = bf16 up to 6 layers, f16 beyond.  Measured against the fp32 oracle (tests/test_encoder_gpu.py):
+        bf16 activations + weights give cosine 1 - 3e-5 at 6 layers but 1 - 1.05e-4 at 12 (the rounding of an 8-bit
+        mantissa compounds per layer), f16's 11 bits give 1 - 2e-6 at 12 layers, so the deeper stacks of the enum
+        (memex's default all-MiniLM-L12-v2, BERT-base) default to f16.  f16's range ends at 65504: should an exotic
+        checkpoint overflow it, the batch comes back non-finite and `encode_ids` re-runs it on a bf16 twin of the model
+        (still the GPU path; there is no CPU fallback)."""
         self.arch = arch
+        self._auto = precision == "auto"
+        if self._auto:
+            precision = "bf16" if arch.layers <= 6 else "f16"
+        self._twin = None
+        self._args = (arch, weights, device, max_tokens)
         names, tensors, keep = [], [], []
         for name, arr in weights.items():
             a = np.ascontiguousarray(arr, dtype=np.float32)
@@ -182,9 +194,17 @@ class B200Encoder:
         if rc != capi.OK:
             msg = capi.lib().mx_last_error(self._h)
             raise EncodingFailure(msg.decode(errors="replace") if msg else f"status {rc}")
+        if self._auto and self.precision == "f16" and not np.isfinite(out).all():
+            if self._twin is None:   # the model overflowed f16 somewhere: the wider exponent of bf16 takes this batch
+                arch, weights, device, max_tokens = self._args
+                self._twin = B200Encoder(arch, weights, precision="bf16", device=device, max_tokens=max_tokens)
+            return self._twin.encode_ids(ids, lens)
         return out
 
     def close(self):
+        if getattr(self, "_twin", None) is not None:
+            self._twin.close()
+            self._twin = None
         if getattr(self, "_h", None) is not None:
             capi.lib().mx_embedder_destroy(self._h)
             self._h = None

@@ -1,5 +1,6 @@
 // embedder.cpp -- B200Encoder, SentenceEmbedder (the actor of reference llm/embedding.rs:77-152), model table and
 // the .safetensors reader.  See memex_host.hpp.
+#include <cmath>
 #include <cstring>
 #include <fstream>
 
@@ -186,6 +187,8 @@ B200Encoder::B200Encoder(const Architecture &arch, const Weights &weights, Preci
     cfg.type_vocab = arch.type_vocab;
     cfg.ln_eps = arch.ln_eps;
     cfg.normalize = arch.normalize ? 1 : 0;
+    if (precision == Precision::AUTO) precision = arch.layers <= 6 ? Precision::BF16 : Precision::F16;
+    f16_ = precision == Precision::F16;
     cfg.precision = (uint32_t)precision;
     cfg.max_tokens = max_tokens;
     mx_model_ext ext{};
@@ -218,6 +221,12 @@ std::vector<float> B200Encoder::encode_ids(const TokenBatch &b)
         const char *m = mx_last_error(handle_);
         throw EmbeddingError(EmbeddingErrorKind::EncodingFailure, m && *m ? m : ("status " + std::to_string(rc)));
     }
+    if (f16_)
+        for (float v : out)
+            if (!std::isfinite(v))
+                throw EmbeddingError(EmbeddingErrorKind::EncodingFailure,
+                                     "non-finite embedding: the model overflowed f16 activations (|x| > 65504); construct the "
+                                     "encoder with Precision::BF16");
     return out;
 }
 

@@ -348,8 +348,12 @@ public:
 };
 class B200Encoder : public Encoder {
 public:
-    enum class Precision { BF16 = 0, F32 = 1, F16 = 2 };
-    B200Encoder(const Architecture &arch, const Weights &weights, Precision precision = Precision::BF16, int device = 0,
+    // BF16 / F16: the tensor-core paths (same tcgen05 kernels and speed); F32: CUDA-core validation path; AUTO = BF16 up
+    // to 6 layers, F16 beyond (bf16's 8-bit mantissa compounds to cosine 1 - 1.05e-4 against the fp32 oracle at 12 layers,
+    // f16's 11 bits stay at 1 - 2e-6: tests/test_encoder_gpu.py).  An f16 overflow (|x| > 65504, exotic checkpoints)
+    // surfaces as EncodingFailure naming Precision::BF16.
+    enum class Precision { BF16 = 0, F32 = 1, F16 = 2, AUTO = 3 };
+    B200Encoder(const Architecture &arch, const Weights &weights, Precision precision = Precision::AUTO, int device = 0,
                 uint32_t max_tokens = 0);
     ~B200Encoder() override;
     uint32_t hidden() const override { return arch_.out_dim(); }
@@ -359,6 +363,7 @@ public:
 private:
     Architecture arch_;
     mx_embedder *handle_ = nullptr;
+    bool f16_ = false;
 };
 
 // SentenceEmbedder (embedding.rs:77-152): `spawn` starts the runner thread that owns the model; requests arrive
