@@ -108,7 +108,7 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self, t0: float, t1: float):
-        sm, mx, reasons = [], 0.0, set()
+        sm, mx, reasons, power = [], 0.0, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for t, line in self.rows:
             if not (t0 - 0.15 <= t <= t1 + 0.15):
@@ -121,6 +121,10 @@ class ClockSampler:
                 mx = max(mx, float(f[1]))
             except ValueError:
                 continue
+            try:
+                power.append(float(f[2]))
+            except ValueError:
+                pass
             for name, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
@@ -134,7 +138,7 @@ class ClockSampler:
                 except (ValueError, IndexError):
                     pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w": float(np.median(power)) if power else None}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -527,6 +531,18 @@ def bench_embed(device, steps: int, warmup: int, pk, cpu: bool, extras: bool = T
     l0 = L.mx_launch_count()
     ms = timed(step)
     launches = L.mx_launch_count() - l0
+    # SM clock and board power under THIS kernel mix (a tensor-heavy step runs into the power cap long before the tensor pipe
+    # is full: MEASURED_PEAKS.json's cuBLAS figure was taken at ~1335 MHz): ~0.4 s of back-to-back steps, sampled at 20 ms
+    sampler = ClockSampler(device.index)
+    sampler.start()
+    time.sleep(0.2)
+    t_a = sampler.mark()
+    for _ in range(max(1, int(400.0 / max(ms, 1e-3)))):
+        step()
+    torch.cuda.synchronize(device)
+    t_b = sampler.mark()
+    sampler.stop()
+    clocks = sampler.summary(t_a + 0.05, t_b - 0.02)
     L.mx_embedder_set_timing(enc.handle, 1)
     ms_events = timed(step)
     g_ms, g_n, o_ms, o_n = C.c_double(), C.c_uint64(), C.c_double(), C.c_uint64()
@@ -548,7 +564,7 @@ def bench_embed(device, steps: int, warmup: int, pk, cpu: bool, extras: bool = T
     res = {"workload": "batch-256 segment embedding, MiniLM-L6, seq_len 256, bf16 activations (seeded random weights)",
            "value": B * 1e3 / ms, "unit": "segments/s", "ms_per_step": ms, "dtype": "bf16",
            "e2e": {"value": e2e, "unit": "segments/s", "h2d_bytes_per_step": B * S * 4 + B * 4, "d2h_bytes_per_step": B * H * 4},
-           "gpu_launches_per_step": launches // max(1, steps),
+           "gpu_launches_per_step": launches // max(1, steps), "clocks": clocks,
            # the timed region is tens of milliseconds, not seconds: the BURST bf16 figure is the apt denominator
            "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                         "frac": gemm_tf / pk["tf_burst"], "traffic": ncu_traffic("gemm_tc"),
@@ -614,26 +630,37 @@ def bench_embed(device, steps: int, warmup: int, pk, cpu: bool, extras: bool = T
     return res
 
 
-def bench_ingest(device, pk, rows: int, seconds: float):
-    """config 5 at one GPU's share: a 768-d fp16 shard (50 M x 768 over 8 GPUs = 6.25 M rows, 9.6 GB) searched with
-    64-query batches WHILE segments are embedded (BERT-base shape, S = 512) and appended to the same shard.
-    Two host threads, searcher and ingester, take turns behind one FIFO lock (the store is behind one lock in the
-    reference too, storage/mod.rs:70-92): one 64-query scan, one embedded + appended batch, and so on.  Reports each role
-    alone, then both.  (True overlap of the HBM-bound scan with the tensor-bound forward pass needs the SMs partitioned
-    between the two persistent kernels -- green contexts -- and is not built yet.)"""
+def bench_ingest(device, pk, rows: int, seconds: float, rank: int = 0, world: int = 1, group=None, scan_sms: int = 104):
+    """config 5 (BASELINE.json configs[4]): a 50 M x 768 fp16 corpus row-sharded over 8 GPUs (6.25 M rows = 9.6 GB per GPU)
+    searched with 64-query batches WHILE BERT-base-shape segments (L = 12, H = 768, S = 512) are embedded and appended to the
+    local shard -- the worker's `embed + add_vectors` (reference lib/worker/src/tasks.rs:15-59) next to the API's search
+    (lib/api/src/endpoints/collections/handlers.rs:61-81).
+
+    Both roles are persistent kernels that each fill every SM when alone, so the SMs are PARTITIONED while they run
+    together: the scan grid gets `scan_sms` CTAs (mx_store_set_sm_limit; it stays HBM-bound far below the full chip), the
+    embedder's grids the rest (mx_embedder_set_sm_limit).  One host thread per role and per rank, each with its own
+    stream; the ingester appends with mx_store_add_device_stream (the rows join the searchable range -- the committed-rows
+    watermark -- when the append has completed; the store is created with the capacity it will reach, so the matrix never
+    moves under a running scan).  At N ranks every rank runs both roles on its own shard; a search is the sharded one
+    (peer-memory exchange of the per-shard top-k, memex_b200/sharded.py) and new rows get round-robin global ids
+    (local_row * N + rank + 1), so ingest needs no exchange.  Three windows: search alone and ingest alone (whole GPU
+    each), then both (partitioned).  Wall clock over `seconds` per window: throughput figures, not kernel times."""
     import torch
+    import torch.distributed as dist
     from memex_b200 import capi
     from memex_b200.embedding import Architecture, B200Encoder
     from memex_b200.sharded import ShardedStore
     L = capi.lib()
     dim, Lyr, heads, F, vocab, max_pos = 768, 12, 12, 3072, 30522, 512
     B, S = 16, 512
-    st = ShardedStore("/tmp/mx_bench_ingest", dim, rows + 400_000, dtype="f16", device=device.index)
+    headroom = 400_000
+    st = ShardedStore(f"/tmp/mx_bench_ingest_{rank}", dim, (rows + headroom) * world, dtype="f16", device=device.index,
+                      rank=rank, world=world, group=group, id_stride=world)
     g = torch.Generator(device=device)
     done = 0
     while done < rows:
         take = min(250_000, rows - done)
-        g.manual_seed(CORPUS_SEED + done // 250_000)
+        g.manual_seed(CORPUS_SEED + 1000 * rank + done // 250_000)
         x = torch.nn.functional.normalize(torch.randn((take, dim), generator=g, device=device), dim=1).contiguous()
         torch.cuda.synchronize(device)
         st.add_local_device(x.data_ptr(), take)
@@ -643,94 +670,136 @@ def bench_ingest(device, pk, rows: int, seconds: float):
     q = torch.nn.functional.normalize(torch.randn((NQ, dim), generator=g, device=device), dim=1).contiguous()
     enc = B200Encoder(Architecture(Lyr, dim, heads, F, vocab, max_pos), random_bert_weights(Lyr, dim, F, vocab, max_pos),
                       precision="bf16", device=device.index, max_tokens=B * S)
-    ids_d = torch.from_numpy(np.random.default_rng(7).integers(1000, 30000, size=(B, S)).astype(np.int32)).to(device)
+    ids_d = torch.from_numpy(np.random.default_rng(7 + rank).integers(1000, 30000, size=(B, S)).astype(np.int32)).to(device)
     lens = np.full(B, S, dtype=np.int32)
-    class TicketLock:
-        """FIFO hand-over: threading.Lock lets the releasing thread win the lock again and starves the other role"""
-
-        def __init__(self):
-            self.cv = threading.Condition()
-            self.next_ticket = 0
-            self.serving = 0
-
-        def __enter__(self):
-            with self.cv:
-                t = self.next_ticket
-                self.next_ticket += 1
-                while self.serving != t:
-                    self.cv.wait()
-
-        def __exit__(self, *a):
-            with self.cv:
-                self.serving += 1
-                self.cv.notify_all()
-
-    lock = TicketLock()
     s_search, s_ingest = torch.cuda.Stream(device), torch.cuda.Stream(device)
     out_d = torch.zeros((B, dim), dtype=torch.float32, device=device)
-    stop = threading.Event()
     counts = {"queries": 0, "segments": 0, "rows_scanned": 0}
+    n_sms = torch.cuda.get_device_properties(device).multi_processor_count
 
-    def searcher():
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier(group=group)
+
+    def searcher(n_batches):
+        # every rank issues the SAME number of batches: the sharded search is a collective step (SPMD)
         torch.cuda.set_device(device)
         with torch.cuda.stream(s_search):
-            while not stop.is_set():
-                with lock:
-                    n_now = len(st)
-                    st.search_device(q, TOPK)
-                    s_search.synchronize()
+            for _ in range(n_batches):
+                n_now = len(st)
+                st.search_device(q, TOPK)
+                s_search.synchronize()
                 counts["queries"] += NQ
                 counts["rows_scanned"] += n_now
 
-    def ingester():
+    def ingester(stop):
         torch.cuda.set_device(device)
         first = C.c_uint64()
         while not stop.is_set():
-            # the forward pass runs under the lock too: the scan is a persistent kernel that fills every SM, so kernels of
-            # another stream only get in at its boundaries -- the two roles take turns on the GPU, batch by batch
-            with lock:
-                rc = L.mx_embedder_encode_device(enc.handle, ids_d.data_ptr(), lens.ctypes.data, B, S, out_d.data_ptr(),
-                                                 s_ingest.cuda_stream)
-                assert rc == 0, L.mx_last_error(enc.handle)
-                s_ingest.synchronize()
-                rc = L.mx_store_add_device(st.local.handle, out_d.data_ptr(), B, C.byref(first))
-                assert rc == 0, L.mx_last_error(st.local.handle)
+            rc = L.mx_embedder_encode_device(enc.handle, ids_d.data_ptr(), lens.ctypes.data, B, S, out_d.data_ptr(),
+                                             s_ingest.cuda_stream)
+            assert rc == 0, L.mx_last_error(enc.handle)
+            rc = L.mx_store_add_device_stream(st.local.handle, out_d.data_ptr(), B, C.byref(first), s_ingest.cuda_stream)
+            assert rc == 0, L.mx_last_error(st.local.handle)
             counts["segments"] += B
 
-    def window(fns):
+    def window(search: bool, ingest: bool, n_batches: int):
         for k in counts:
             counts[k] = 0
-        stop.clear()
-        ths = [threading.Thread(target=f) for f in fns]
+        stop = threading.Event()
+        barrier()
         t0 = time.perf_counter()
-        for t in ths:
-            t.start()
-        time.sleep(seconds)
+        ti = threading.Thread(target=ingester, args=(stop,)) if ingest else None
+        if ti:
+            ti.start()
+        if search:
+            searcher(n_batches)          # fixed number of batches on every rank
+        else:
+            time.sleep(seconds)
+        t_search = time.perf_counter() - t0
         stop.set()
-        for t in ths:
-            t.join()
+        if ti:
+            ti.join()
         torch.cuda.synchronize(device)
         dt = time.perf_counter() - t0
-        return {k: v / dt for k, v in counts.items()}
+        res = {"queries": counts["queries"] / t_search if search else 0.0, "segments": counts["segments"] / dt,
+               "rows_scanned": counts["rows_scanned"] / t_search if search else 0.0}
+        t = torch.tensor([res["queries"], res["segments"], res["rows_scanned"]], dtype=torch.float64, device=device)
+        if world > 1:
+            # queries/s: every rank answers the same batches -> the slowest rank's rate; segments and bytes add up
+            qmin = t[:1].clone()
+            dist.all_reduce(qmin, op=dist.ReduceOp.MIN, group=group)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            t[0] = qmin[0]
+        return {"queries": t[0].item(), "segments": t[1].item(), "rows_scanned": t[2].item()}
 
     for _ in range(3):
         st.search_device(q, TOPK)
     torch.cuda.synchronize(device)
-    alone_s = window([searcher])
-    alone_i = window([ingester])
-    both = window([searcher, ingester])
+    # calibrate the batch count of a window from the scan-alone rate (same number on every rank)
+    barrier()
+    t0 = time.perf_counter()
+    searcher(10)
+    per_batch = torch.tensor([(time.perf_counter() - t0) / 10], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(per_batch, op=dist.ReduceOp.MAX, group=group)
+    n_alone = max(10, int(seconds / per_batch.item()))
+    alone_s = window(True, False, n_alone)
+    alone_i = window(False, True, 0)
+    # together: partition the SMs -- green contexts confine EVERY kernel of a role to its share; the grid budgets size the
+    # persistent kernels for it
+    part = C.c_void_p()
+    partition = "CUDA green contexts"
+    if L.mx_sm_partition_create(device.index, scan_sms, C.byref(part)) == capi.OK:
+        scan_sms = int(L.mx_sm_partition_sms(part, 0))
+        emb_sms = int(L.mx_sm_partition_sms(part, 1))
+        s_search = torch.cuda.ExternalStream(L.mx_sm_partition_stream(part, 0), device=device)
+        s_ingest = torch.cuda.ExternalStream(L.mx_sm_partition_stream(part, 1), device=device)
+    else:
+        part = None
+        emb_sms = n_sms - scan_sms
+        partition = "grid budgets only (no green contexts on this driver: " + (L.mx_last_error(None) or b"").decode() + ")"
+    L.mx_store_set_sm_limit(st.local.handle, scan_sms)
+    L.mx_embedder_set_sm_limit(enc.handle, emb_sms)
+    with torch.cuda.stream(s_search):
+        for _ in range(3):
+            st.search_device(q, TOPK)
+    torch.cuda.synchronize(device)
+    both = window(True, True, max(10, n_alone * 2 // 3))
+    rows_end = torch.tensor([len(st)], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(rows_end, op=dist.ReduceOp.SUM, group=group)
+    # the freshly ingested rows are searchable: the last appended segment must come back as its own nearest neighbour
+    torch.cuda.synchronize(device)
+    probe = out_d[-1:].clone()
+    ids_p, scores_p, _ = st.search_device(probe.contiguous(), 1) if world == 1 else (None, None, None)   # default stream
+    found = None
+    if world == 1:
+        torch.cuda.synchronize(device)
+        found = bool(abs(float(scores_p[0, 0]) - 1.0) < 1e-3)
     seg_flops = Lyr * S * (24 * dim * dim + 4 * S * dim)
-    res = {"workload": f"{rows}x{dim} fp16 shard (50Mx768 / 8), 64-query batches, while embedding BERT-base-shape segments "
-                       f"(L=12, H=768, S=512, B={B}) and appending them to the shard",
-           "rows_at_end": len(st),
-           "search_alone": {"queries_per_s": alone_s["queries"], "hbm_gbs": alone_s["rows_scanned"] * (dim * 2 + 4) / 1e9},
-           "ingest_alone": {"segments_per_s": alone_i["segments"], "tflops": alone_i["segments"] * seg_flops / 1e12},
+    bytes_per_row = dim * 2 + 4
+    res = {"workload": f"{rows * world}x{dim} fp16 corpus over {world} GPU(s) ({rows} rows = {rows * bytes_per_row / 1e9:.1f} GB per GPU; "
+                       f"config 5 is 50Mx768 over 8), {NQ}-query batches, WHILE BERT-base-shape segments (L=12, H=768, S={S}, "
+                       f"B={B}) are embedded and appended to the local shards",
+           "n_gpus": world, "rows_at_end": int(rows_end.item()),
+           "sm_partition_when_concurrent": {"scan_sms": scan_sms, "embedder_sms": emb_sms, "how": partition},
+           "search_alone": {"queries_per_s": alone_s["queries"], "hbm_gbs_summed": alone_s["rows_scanned"] * bytes_per_row / 1e9},
+           "ingest_alone": {"segments_per_s": alone_i["segments"], "tflops_summed": alone_i["segments"] * seg_flops / 1e12},
            "concurrent": {"queries_per_s": both["queries"], "segments_per_s": both["segments"],
-                          "hbm_gbs": both["rows_scanned"] * (dim * 2 + 4) / 1e9, "tflops": both["segments"] * seg_flops / 1e12},
-           "peaks": {"hbm_gbs": pk["hbm"], "tflops_sustained": pk["tf_sustained"]},
-           "timing": f"wall clock over {seconds} s windows, one host thread per role (a throughput figure, not a kernel time)"}
+                          "hbm_gbs_summed": both["rows_scanned"] * bytes_per_row / 1e9,
+                          "tflops_summed": both["segments"] * seg_flops / 1e12},
+           "concurrent_vs_alone": {"search": both["queries"] / max(alone_s["queries"], 1e-9),
+                                   "ingest": both["segments"] / max(alone_i["segments"], 1e-9)},
+           "peaks_per_gpu": {"hbm_gbs": pk["hbm"], "tflops_burst": pk["tf_burst"]},
+           "fresh_rows_searchable": found,
+           "timing": f"wall clock, ~{seconds} s windows, one host thread per role and rank, stream sync per batch (throughput, not kernel time)"}
     enc.close()
     st.close()
+    if part is not None:
+        torch.cuda.synchronize(device)
+        L.mx_sm_partition_destroy(part)
     return res
 
 
@@ -885,6 +954,12 @@ def run_ours(args):
         line["embed"] = {"workload": emb["workload"] + f", one replica per GPU x{world}", "value": world * 256 * 1e3 / ms.item(),
                          "unit": "segments/s", "ms_per_step": ms.item(), "dtype": "bf16", "scaling": "weak (replicas, no collective)",
                          "per_gpu_roofline": emb["roofline"]}
+    if not args.skip_extras and not args.skip_ingest:
+        # config 5: streamed ingest (embed + append) WHILE searching, SMs partitioned, every rank on its own shard
+        barrier()
+        ing = bench_ingest(device, pk, args.ingest_rows, args.ingest_seconds, rank, world, group)
+        if rank == 0:
+            line["ingest"] = ing
     if rank == 0 and world == 1:
         if not args.skip_extras:
             line["single_query"] = bench_single_query(device, max(50, args.steps * 5), max(20, args.warmup), pk)
@@ -926,8 +1001,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000)
-    ap.add_argument("--ingest-rows", type=int, default=6_250_000, help="--only ingest: rows of the 768-d shard (50 M / 8)")
-    ap.add_argument("--ingest-seconds", type=float, default=3.0, help="--only ingest: length of each timed window")
+    ap.add_argument("--ingest-rows", type=int, default=6_250_000, help="config 5: rows of the 768-d shard PER GPU (50 M / 8)")
+    ap.add_argument("--ingest-seconds", type=float, default=2.0, help="config 5: length of each timed window")
+    ap.add_argument("--skip-ingest", action="store_true", help="leave out the config-5 sub-bench (ingest while searching)")
     ap.add_argument("--skip-cpu", action="store_true", help="leave out the CPU baseline legs")
     ap.add_argument("--skip-extras", action="store_true", help="leave out the single_query / embed sub-benches")
     ap.add_argument("--skip-check", action="store_true", help="profiling aid: leave out the independent answer check")

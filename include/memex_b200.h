@@ -83,6 +83,26 @@ void mx_store_destroy(mx_store *s);
 int32_t mx_store_add(mx_store *s, const float *vecs, uint64_t n, uint64_t *first_id_out);
 /* same, rows already in DEVICE memory (ingest straight from the embedder's output) */
 int32_t mx_store_add_device(mx_store *s, const float *vecs_dev, uint64_t n, uint64_t *first_id_out);
+/* streamed ingest WHILE another host thread searches the same store (worker/src/tasks.rs:15-59 next to
+ * api handlers.rs:61-81): the rows are produced on `cuda_stream` (the embedder's), appended on it, and join the
+ * searchable range (the committed-rows watermark) when the append has completed.  The store never grows on this path:
+ * create it with the capacity it will reach. */
+int32_t mx_store_add_device_stream(mx_store *s, const float *vecs_dev, uint64_t n, uint64_t *first_id_out,
+                                   void *cuda_stream);
+/* SM partitioning between a store's scan and an embedder's forward pass running concurrently on one GPU: both are
+ * persistent kernels that otherwise fill every SM and could only take turns.  `sms` = the CTA budget of the scan grid
+ * (the scan stays HBM-bound far below the full chip) / of the embedder's grids; 0 = the whole device. */
+int32_t mx_store_set_sm_limit(mx_store *s, uint32_t sms);
+/* ... and the partition itself: two disjoint sets of SMs of one GPU (CUDA green contexts) with one stream each.  EVERY
+ * kernel launched into a partition's stream runs on its SMs only, so a scan on part 0 and a forward pass on part 1
+ * overlap instead of taking turns.  sms_first is rounded up to the hardware's granularity (8 SMs on sm_100); part 1 gets
+ * the rest.  MX_ERR_UNSUPPORTED where the driver has no green contexts (the caller then shares the GPU by grid budgets
+ * alone).  Pass mx_sm_partition_stream(p, i) as the cuda_stream argument of the *_device calls. */
+typedef struct mx_sm_partition mx_sm_partition;
+int32_t mx_sm_partition_create(int32_t device, uint32_t sms_first, mx_sm_partition **out);
+void mx_sm_partition_destroy(mx_sm_partition *p);
+void *mx_sm_partition_stream(mx_sm_partition *p, uint32_t which);
+uint32_t mx_sm_partition_sms(mx_sm_partition *p, uint32_t which);
 
 /* HnswStore::search (local.rs:71-91) for nq queries at once.  HOST buffers.
  *   ids_out [nq, k], scores_out [nq, k] best first, counts_out [nq] = min(k, len).
@@ -263,6 +283,7 @@ int32_t mx_embedder_encode(mx_embedder *e, const int32_t *ids, const int32_t *le
 int32_t mx_embedder_encode_device(mx_embedder *e, const int32_t *ids_dev, const int32_t *lens,
                                   uint32_t B, uint32_t S, float *out_dev, void *cuda_stream);
 int32_t mx_embedder_sync(mx_embedder *e);
+int32_t mx_embedder_set_sm_limit(mx_embedder *e, uint32_t sms);
 int32_t mx_embedder_set_timing(mx_embedder *e, int32_t on);
 int32_t mx_embedder_get_timing(mx_embedder *e, double *gemm_ms_total, uint64_t *gemm_launches,
                                double *other_ms_total, uint64_t *other_launches);

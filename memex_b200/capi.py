@@ -85,6 +85,13 @@ def lib() -> C.CDLL:
     sig("mx_store_destroy", None, vp)
     sig("mx_store_add", C.c_int32, vp, vp, C.c_uint64, u64p)
     sig("mx_store_add_device", C.c_int32, vp, vp, C.c_uint64, u64p)
+    sig("mx_store_add_device_stream", C.c_int32, vp, vp, C.c_uint64, u64p, vp)
+    sig("mx_store_set_sm_limit", C.c_int32, vp, C.c_uint32)
+    sig("mx_embedder_set_sm_limit", C.c_int32, vp, C.c_uint32)
+    sig("mx_sm_partition_create", C.c_int32, C.c_int32, C.c_uint32, C.POINTER(vp))
+    sig("mx_sm_partition_destroy", None, vp)
+    sig("mx_sm_partition_stream", vp, vp, C.c_uint32)
+    sig("mx_sm_partition_sms", C.c_uint32, vp, C.c_uint32)
     sig("mx_store_search", C.c_int32, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp)
     sig("mx_store_search_device", C.c_int32, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp)
     sig("mx_merge_topk_device", C.c_int32, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32,

@@ -240,6 +240,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_trigger();
+    pdl_wait();   // qkv is the previous kernel's output (lens / cu were copied in before the step)
 
     if (warp < kSoftmaxWarps) {
         // ================= softmax: thread = query row = TMEM lane =================
@@ -471,9 +473,12 @@ cudaError_t launch_at(const void *qkv, const int32_t *lens, void *ctx, uint32_t 
     const uint32_t n_units = B * heads * ceil_div<uint32_t>(S, kQT);
     const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count, ceil_div<uint32_t>(n_units, kGroups));
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)DH);
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, lens, (uint16_t *)ctx, B, S, H, heads, scale_log2e, cu);
+    LaunchAttrs attrs;
+    attrs.pdl();
+    e = launch_ex(kern, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, st, attrs, tm, lens, (uint16_t *)ctx, B, S, H,
+                  heads, scale_log2e, cu);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -124,6 +125,59 @@ inline T ceil_div(T a, T b)
     return (a + b - 1) / b;
 }
 
+// Programmatic dependent launch: a kernel launched with this attribute may be SCHEDULED while its predecessor in the
+// stream is still running (its CTAs start on SMs the predecessor has vacated, run their prologue -- barrier init, TMEM
+// allocation, descriptor prefetch -- and then block in pdl_wait() until the predecessor has completed and its writes are
+// visible).  Takes the launch latency and the prologue of every kernel of a chain off the critical path.  MX_PDL=0 turns
+// it off (A/B measurements).  A kernel launched WITH the attribute must call pdl_wait() before it reads anything the
+// predecessor wrote or writes anything it read.
+inline bool pdl_enabled()
+{
+    static const bool on = getenv("MX_PDL") == nullptr || atoi(getenv("MX_PDL")) != 0;
+    return on;
+}
+struct LaunchAttrs {
+    cudaLaunchAttribute a[3];
+    unsigned n = 0;
+    LaunchAttrs &pdl()
+    {
+        if (pdl_enabled()) {
+            a[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            a[n].val.programmaticStreamSerializationAllowed = 1;
+            ++n;
+        }
+        return *this;
+    }
+    LaunchAttrs &cluster(unsigned x)
+    {
+        a[n].id = cudaLaunchAttributeClusterDimension;
+        a[n].val.clusterDim.x = x;
+        a[n].val.clusterDim.y = 1;
+        a[n].val.clusterDim.z = 1;
+        ++n;
+        return *this;
+    }
+    LaunchAttrs &cooperative()
+    {
+        a[n].id = cudaLaunchAttributeCooperative;
+        a[n].val.cooperative = 1;
+        ++n;
+        return *this;
+    }
+};
+template <typename Kern, typename... Args>
+inline cudaError_t launch_ex(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, LaunchAttrs &attrs, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attrs.n ? attrs.a : nullptr;
+    cfg.numAttrs = attrs.n;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 }  // namespace mx
 
 // ------------------------------------------------------------------------------------------
@@ -154,6 +208,10 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const uint4 *p)
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// programmatic dependent launch (see LaunchAttrs::pdl): no-ops in a kernel that was launched without the attribute
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // "a ranks before b" for approximate candidates: higher score first, ties -> lower row
 __device__ __forceinline__ bool cand_before(float sa, uint32_t ra, float sb, uint32_t rb)

@@ -503,6 +503,17 @@ int32_t mx_embedder_sync(mx_embedder *e)
     return MX_OK;
 }
 
+int32_t mx_embedder_set_sm_limit(mx_embedder *e, uint32_t sms)
+{
+    if (!e) return MX_ERR_INVALID;
+    cudaDeviceProp prop{};
+    MX_CUDA(e, MX_ERR_CONNECTION, cudaGetDeviceProperties(&prop, e->device));
+    // the persistent kernels size their grids by this count; an even number keeps the 2-CTA clusters whole
+    const uint32_t all = (uint32_t)prop.multiProcessorCount;
+    e->sm_count = (int)(sms == 0 || sms >= all ? all : std::max<uint32_t>(2u, sms & ~1u));
+    return MX_OK;
+}
+
 int32_t mx_embedder_set_timing(mx_embedder *e, int32_t on)
 {
     if (!e) return MX_ERR_INVALID;

@@ -279,6 +279,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (MC || SPLIT || PAIR) cluster_sync_all();   // the peer's barriers exist before anything is sent at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // everything above is this kernel's own set-up; from here on it reads what the previous kernel of the stream wrote
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -637,31 +640,20 @@ static cudaError_t launch_cfg(const GemmParams &p, const CUtensorMap &tmA, const
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     const uint32_t tiles_m = ceil_div<uint32_t>(p.M, kBM), tiles_n = p.N / BN;
+    LaunchAttrs attrs;
+    attrs.pdl();
+    uint32_t grid;
     if constexpr (MC || SPLIT || PAIR) {
         const uint32_t units = SPLIT ? tiles_m : ceil_div<uint32_t>(tiles_m, 2) * tiles_n;
         const uint32_t clusters = std::min<uint32_t>(units, (uint32_t)sm_count / 2);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(2 * clusters);
-        cfg.blockDim = dim3(Cfg::kThreads);
-        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, p);
-        count_launch();
-        return e != cudaSuccess ? e : cudaGetLastError();
+        grid = 2 * clusters;
+        attrs.cluster(2);
     } else {
-        const uint32_t n_tiles = tiles_m * tiles_n;
-        const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)sm_count);
-        kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmO, p);
-        count_launch();
-        return cudaGetLastError();
+        grid = std::min<uint32_t>(tiles_m * tiles_n, (uint32_t)sm_count);
     }
+    e = launch_ex(kern, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, st, attrs, tmA, tmB, tmO, p);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // resident-weights variant: K <= 384, N a multiple of 192, enough tiles per CTA to amortise the weight load
@@ -705,8 +697,10 @@ cudaError_t launch_gemm_tc(const GemmParams &p, int epi, int sm_count, cudaStrea
     // run both settings).
     static const bool mc_on = getenv("MX_GEMM_MULTICAST") != nullptr;
     const bool mc = !res && mc_on && epi != EPI_BIAS_GELU_TANH && sm_count >= 2 && ceil_div<uint32_t>(p.M, 2 * kBM) * (p.N / bn) >= (uint32_t)sm_count / 2;
-    // CTA pairs (cta_group::2, GemmCfg): MX_GEMM_PAIR=0 turns them off (A/B measurements)
-    static const bool pair_on = getenv("MX_GEMM_PAIR") == nullptr || atoi(getenv("MX_GEMM_PAIR")) != 0;
+    // CTA pairs (cta_group::2, GemmCfg): parity-green, but MEASURED SLOWER than the single-CTA form on the encoder step
+    // (r2, one box, A/B: 97.9 / 97.5 k against 103.6 / 103.0 k segments/s; GEMM time 1.90 against 1.77 ms) -- the
+    // accumulator hand-over couples the two CTAs' epilogues -- so it is opt-in (MX_GEMM_PAIR=1)
+    static const bool pair_on = getenv("MX_GEMM_PAIR") != nullptr && atoi(getenv("MX_GEMM_PAIR")) != 0;
     const bool pair = pair_on && !res && !mc && (epi == EPI_BIAS || epi == EPI_BIAS_GELU) && (bn == 192 || bn == 256) &&
                       sm_count >= 2 && ceil_div<uint32_t>(p.M, 2 * kBM) * (p.N / bn) >= (uint32_t)sm_count / 2 &&
                       p.N <= (bn == 192 ? 2304u : 3072u);

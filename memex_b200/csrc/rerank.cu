@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
     __shared__ float sel_v_s, kth_key_s, red_s[kRerankWarps];
     __shared__ uint32_t sel_r_s;
 
+    pdl_trigger();
+    pdl_wait();   // the candidate lists (and, second pass, the flagged-query count) are the previous kernel's output
     // second pass (exact fallback): CTA b answers flagged query active_map[b] from candidate lists b
     const bool second_pass = p.active_n != nullptr;
     if (second_pass && blockIdx.x >= *p.active_n) return;
@@ -384,16 +386,29 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
             __syncthreads();
             if (folder && my_row != kNoRow && my_row < p.n_rows) {
                 const float *rb = rowbuf + (fb * 32 + lane) * kFoldPitch;
-                if (frole == 0) {
-#pragma unroll 4
-                    for (uint32_t i = 0; i < cn; ++i) acc = __dadd_rn(acc, (double)__fmul_rn(qs[i], rb[i]));
-                } else {
-#pragma unroll 4
-                    for (uint32_t i = 0; i < cn; ++i) acc = __dadd_rn(acc, (double)__fmul_rn(rb[i], rb[i]));
+                // 16 products and their f32 -> f64 conversions are computed ahead of the chain, so the chain itself is 16
+                // dependent DADDs (the conversion is an XU op with a long latency: interleaved with the adds it paced the fold
+                // at ~42 cycles per element, 8.3 us of the kernel's 18.6 -- scripts/rerank_prof.py)
+                const float *xa = frole == 0 ? qs : rb;
+                uint32_t i = 0;
+                for (; i + 16 <= cn; i += 16) {
+                    double t[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) t[j] = (double)__fmul_rn(xa[i + j], rb[i + j]);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc = __dadd_rn(acc, t[j]);
                 }
+                for (; i < cn; ++i) acc = __dadd_rn(acc, (double)__fmul_rn(xa[i], rb[i]));
             } else if (q_folder) {
-#pragma unroll 4
-                for (uint32_t i = 0; i < cn; ++i) acc = __dadd_rn(acc, (double)__fmul_rn(qs[i], qs[i]));
+                uint32_t i = 0;
+                for (; i + 16 <= cn; i += 16) {
+                    double t[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) t[j] = (double)__fmul_rn(qs[i + j], qs[i + j]);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc = __dadd_rn(acc, t[j]);
+                }
+                for (; i < cn; ++i) acc = __dadd_rn(acc, (double)__fmul_rn(qs[i], qs[i]));
             }
         }
         if (frole == 1 && folder) bb_s[fb * 32 + lane] = acc;
@@ -535,7 +550,10 @@ cudaError_t launch_rerank(const RerankParams &p, cudaStream_t st)
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                        \
         }                                                                                          \
-        kern<<<p.nq, kRerankThreads, smem, st>>>(p);                                               \
+        LaunchAttrs attrs;                                                                         \
+        attrs.pdl();                                                                               \
+        cudaError_t le = launch_ex(kern, dim3(p.nq), dim3(kRerankThreads), smem, st, attrs, p);    \
+        if (le != cudaSuccess) return le;                                                          \
     }
     switch (E) {
         case 1: MX_RR(1) break;
@@ -562,6 +580,8 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeParams p)
     __shared__ uint32_t total_s;
     const uint32_t q = blockIdx.x;
     if (threadIdx.x == 0) total_s = 0;
+    pdl_trigger();
+    pdl_wait();
     if (p.wait_flags != nullptr && threadIdx.x < p.n_shards) {
         // peer-memory exchange: shard g's answer was stored into this GPU's memory by rank g, followed by a release store of
         // the epoch into flag g.  Bounded wait: a lost peer must surface as a launch failure, not as a hung GPU.
@@ -616,6 +636,8 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeParams p)
 __global__ void __launch_bounds__(256) exchange_push_kernel(PushParams p)
 {
     const uint32_t peer = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const uint4 *src = reinterpret_cast<const uint4 *>(p.blob);
     uint4 *dst = reinterpret_cast<uint4 *>(p.peer_base[peer] + p.slot_offset);
     for (uint64_t i = threadIdx.x; i < p.blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
@@ -630,9 +652,11 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(PushParams p)
 cudaError_t launch_exchange_push(const PushParams &p, cudaStream_t st)
 {
     if (p.world == 0 || p.world > (uint32_t)kMaxPeers || p.blob_bytes % 16 != 0) return cudaErrorInvalidValue;
-    exchange_push_kernel<<<p.world, 256, 0, st>>>(p);
+    LaunchAttrs attrs;
+    attrs.pdl();
+    cudaError_t e = launch_ex(exchange_push_kernel, dim3(p.world), dim3(256), (size_t)0, st, attrs, p);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_merge(const MergeParams &p, cudaStream_t st)
@@ -643,9 +667,11 @@ cudaError_t launch_merge(const MergeParams &p, cudaStream_t st)
         cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    merge_kernel<<<p.nq, 256, smem, st>>>(p);
+    LaunchAttrs attrs;
+    attrs.pdl();
+    cudaError_t e = launch_ex(merge_kernel, dim3(p.nq), dim3(256), smem, st, attrs, p);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -124,6 +124,7 @@ struct TcScanState;
 TcScanState *tc_scan_create(int sm_count, uint32_t ld, uint32_t dim);  // nullptr if shape unsupported
 void tc_scan_destroy(TcScanState *t);
 void tc_scan_invalidate(TcScanState *t);  // the row matrix moved: tensor maps must be rebuilt
+void tc_scan_set_sms(TcScanState *t, int sm_count);   // the scan grid's CTA budget (SM partitioning with another kernel)
 bool tc_scan_supports(const TcScanState *t, uint32_t k);
 uint32_t tc_scan_max_k();
 uint32_t tc_scan_lists(const TcScanState *t, uint64_t n_rows);

@@ -244,6 +244,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_stream_kernel(ScanParams
 template <typename T, int LPR, int CPL, int R, int E>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_exact_kernel(ScanParams p, ExactExtra x, const uint32_t *active_n)
 {
+    pdl_trigger();
+    pdl_wait();   // the rerank's certificate counts the flagged queries
     const uint32_t n = *active_n;
     for (uint32_t slot = 0; slot < n; ++slot) scan_stream_body<T, LPR, CPL, R, 1, E, true>(p, x, slot);
 }
@@ -306,9 +308,12 @@ static cudaError_t launch_exact_one(const ExactScanParams &p, uint32_t n_ctas, c
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<n_ctas, kScanThreads, smem, st>>>(p.scan, ExactExtra{p.active_map, p.fb_thr, p.dim, p.metric}, p.active_n);
+    LaunchAttrs attrs;
+    attrs.pdl();
+    cudaError_t e = launch_ex(kern, dim3(n_ctas), dim3(kScanThreads), smem, st, attrs, p.scan,
+                              ExactExtra{p.active_map, p.fb_thr, p.dim, p.metric}, p.active_n);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 template <typename T, int E>

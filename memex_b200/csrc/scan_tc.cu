@@ -113,6 +113,8 @@ struct TcParams {
     uint32_t ldq, dim;
     float *qerr;            // [nq_pad] fp16 rounding radius of each prepared query (written by CTA x = 0)
     uint32_t *done;         // exit ticket: the LAST CTA out resets tau / sync / done for the next launch
+    uint32_t plain_barrier; // host-side only: launch the seeded form without the cooperative attribute (exclusive SM partition)
+    uint32_t diag;          // TIMING DIAGNOSTIC ONLY (MX_SCAN_TC_DIAG, wrong results): bit 0 = skip the query preparation
 };
 
 // QM = 128: TMEM lane = query.  QM = 64 (cta_group::1, M = 64): accumulator row r sits in TMEM lane
@@ -235,7 +237,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
         {
             const uint32_t n_chunks = p.k_blocks * 8;            // 8-element (16-byte) chunks per prepared row
             constexpr int kRowsInFlight = 4;                     // the loads of 4 rows are issued before the first reduction
-            for (uint32_t rb = quarter; rb < (uint32_t)QM; rb += 4 * kRowsInFlight) {
+            for (uint32_t rb = quarter; rb < (uint32_t)QM && !(p.diag & 1u); rb += 4 * kRowsInFlight) {
                 float4 va[kRowsInFlight][3], vb[kRowsInFlight][3];
 #pragma unroll
                 for (int j = 0; j < kRowsInFlight; ++j) {
@@ -512,6 +514,7 @@ __global__ void tc_init_state_kernel(float *tau, float *floor_out, float *qerr, 
 
 struct TcScanState {
     int sm_count;
+    int device_sms = 0;         // SMs of the whole device (a smaller sm_count = an SM budget, mx_store_set_sm_limit)
     uint32_t ld, dim, k_blocks;
     float *tau = nullptr;
     float *samp = nullptr;      // [sm_count][q_cap]
@@ -527,6 +530,7 @@ TcScanState *tc_scan_create(int sm_count, uint32_t ld, uint32_t dim)
     if (!encode_tiled_fn()) return nullptr;
     TcScanState *t = new TcScanState();
     t->sm_count = sm_count;
+    t->device_sms = sm_count;
     t->ld = ld;
     t->dim = dim;
     t->k_blocks = ceil_div<uint32_t>(dim, kBK);
@@ -545,6 +549,13 @@ void tc_scan_destroy(TcScanState *t)
 }
 
 void tc_scan_invalidate(TcScanState *) {}  // tensor maps are rebuilt on every launch
+void tc_scan_set_sms(TcScanState *t, int sm_count)
+{
+    if (t && sm_count > 0 && sm_count != t->sm_count) {
+        t->sm_count = sm_count;
+        t->q_cap = 0;   // samp is [sm_count][q_cap]: re-made (and the cross-launch state re-initialised) on the next launch
+    }
+}
 
 uint32_t tc_scan_max_k() { return 26; }
 bool tc_scan_supports(const TcScanState *t, uint32_t k) { return t != nullptr && k <= tc_scan_max_k(); }
@@ -568,6 +579,16 @@ static cudaError_t launch_tc_one(const CUtensorMap &tmC, TcParams tp, dim3 grid,
     auto kern = scan_tc_kernel<L, USE_INV, QM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
+    // A cooperative launch does not overlap with kernels of other streams (measured r2, config 5: scan and forward pass ran
+    // in lock-step, 5.8 ms per pair against 1.8 + 2.6 ms alone, with or without an SM partition).  When the store has been
+    // given an SM budget of its own (mx_store_set_sm_limit: one CTA per SM of an exclusive partition, nothing else ever
+    // resident there), co-residency holds by construction and the barrier runs under a plain launch; its bounded spin
+    // still turns a violated assumption into a launch failure rather than a hang.
+    if (tp.sample_tiles > 0 && tp.plain_barrier) {
+        kern<<<grid, kTcThreads, smem, st>>>(tmC, tp);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (tp.sample_tiles > 0) {
         // the grid barrier needs every CTA resident at once: cooperative launch (the driver refuses rather than deadlocks)
         cudaLaunchConfig_t cfg{};
@@ -663,6 +684,9 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
     tp.dim = t->dim;
     tp.qerr = t->qerr;
     tp.done = t->sync + 32;
+    static const uint32_t diag = getenv("MX_SCAN_TC_DIAG") ? (uint32_t)atoi(getenv("MX_SCAN_TC_DIAG")) : 0u;
+    tp.diag = diag;
+    tp.plain_barrier = t->sm_count < t->device_sms ? 1u : 0u;
     dim3 grid(p.n_lists, nq_pad / qm);
     // threshold seeding needs every CTA at the barrier: one query pass (grid.y == 1), a full grid, enough tiles per CTA
     // that scanning P of them twice is cheap; MX_SCAN_TC_SAMPLE=0 turns it off (A/B measurements)

@@ -49,6 +49,7 @@ struct mx_store : HandleBase {
     uint32_t ldq = 0;     // floats per staged query
     size_t elem = 4;
     uint64_t n = 0, capacity = 0;
+    uint64_t n_view = 0;   // the committed-rows watermark ONE search works with (another host thread may append meanwhile)
     void *rows = nullptr;
     float *inv_norm = nullptr;
     uint32_t *zero_rows = nullptr;  // [MX_MAX_K]
@@ -190,7 +191,7 @@ uint32_t pick_path(mx_store *s, uint32_t nq, uint32_t k)
 uint32_t stream_lists(const mx_store *s)
 {
     const uint64_t rows_per_cta = 16 * 16;  // a CTA iteration covers at least this many rows
-    return (uint32_t)std::min<uint64_t>((uint64_t)s->sm_count, ceil_div<uint64_t>(s->n, rows_per_cta));
+    return (uint32_t)std::min<uint64_t>((uint64_t)s->sm_count, ceil_div<uint64_t>(s->n_view, rows_per_cta));
 }
 
 // Second pass over the queries the certificate flagged (normally none: both kernels return at once).  The exact scan
@@ -206,7 +207,7 @@ int32_t search_fallback(mx_store *s, const float *q_use, uint32_t nq, uint32_t k
     ep.scan.queries = q_use;
     ep.scan.cand_s = s->cand_s;
     ep.scan.cand_r = s->cand_r;
-    ep.scan.n_rows = (uint32_t)s->n;
+    ep.scan.n_rows = (uint32_t)s->n_view;
     ep.scan.ld = s->ld;
     ep.scan.ldq = s->ldq;
     ep.scan.nq = nq;
@@ -233,7 +234,7 @@ int32_t search_fallback(mx_store *s, const float *q_use, uint32_t nq, uint32_t k
     rp.counts_out = counts_dev;
     rp.id_offset = s->cfg.id_offset;
     rp.id_stride = s->cfg.id_stride;
-    rp.n_rows = (uint32_t)s->n;
+    rp.n_rows = (uint32_t)s->n_view;
     rp.ld = s->ld;
     rp.ldq = s->ldq;
     rp.dim = s->cfg.dim;
@@ -261,7 +262,8 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
     if (!q_dev || !ids_dev || !scores_dev || !counts_dev) return fail(s, MX_ERR_INVALID, "null buffer");
     if (k == 0 || k > MX_MAX_K) return fail(s, MX_ERR_INVALID, "k must be in [1, %u]", MX_MAX_K);
     if (nq == 0) return MX_OK;
-    if (s->n == 0) {
+    s->n_view = s->n;
+    if (s->n_view == 0) {
         // empty index: HnswStore::search returns no neighbours (local.rs:76-90)
         MX_CUDA(s, MX_ERR_SEARCH, cudaMemsetAsync(counts_dev, 0, sizeof(uint32_t) * nq, st));
         MX_CUDA(s, MX_ERR_SEARCH, cudaMemsetAsync(ids_dev, 0, sizeof(uint64_t) * nq * k, st));
@@ -270,7 +272,7 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
         return MX_OK;
     }
     if (s->zero_dirty) {
-        MX_CUDA(s, MX_ERR_SEARCH, launch_collect_zero_rows(s->inv_norm, s->n, s->zero_rows, s->n_zero, st));
+        MX_CUDA(s, MX_ERR_SEARCH, launch_collect_zero_rows(s->inv_norm, s->n_view, s->zero_rows, s->n_zero, st));
         s->zero_dirty = false;
     }
     const uint32_t path = pick_path(s, nq, k);
@@ -300,7 +302,7 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
 
     uint32_t n_lists, lcap;
     if (path == 2) {
-        n_lists = tc_scan_lists(s->tc, s->n);
+        n_lists = tc_scan_lists(s->tc, s->n_view);
         lcap = tc_scan_lcap(k);
     } else {
         n_lists = stream_lists(s);
@@ -339,7 +341,7 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
     sp.queries = q_use;
     sp.cand_s = s->cand_s;
     sp.cand_r = s->cand_r;
-    sp.n_rows = (uint32_t)s->n;
+    sp.n_rows = (uint32_t)s->n_view;
     sp.ld = s->ld;
     sp.ldq = s->ldq;
     sp.nq = nq;
@@ -369,7 +371,7 @@ int32_t search_device_impl(mx_store *s, const float *q_dev, uint32_t nq, uint32_
     rp.counts_out = counts_dev;
     rp.id_offset = s->cfg.id_offset;
     rp.id_stride = s->cfg.id_stride;
-    rp.n_rows = (uint32_t)s->n;
+    rp.n_rows = (uint32_t)s->n_view;
     rp.ld = s->ld;
     rp.ldq = s->ldq;
     rp.dim = s->cfg.dim;
@@ -588,6 +590,54 @@ int32_t mx_store_add_device(mx_store *s, const float *vecs_dev, uint64_t n, uint
     return finish_add(s, n, s->stream, first_id_out);
 }
 
+int32_t mx_store_add_device_stream(mx_store *s, const float *vecs_dev, uint64_t n, uint64_t *first_id_out, void *cuda_stream)
+{
+    if (!s) return MX_ERR_INVALID;
+    if (n == 0) {
+        if (first_id_out) *first_id_out = s->cfg.id_offset + s->n * s->cfg.id_stride + 1;
+        return MX_OK;
+    }
+    if (!vecs_dev) return fail(s, MX_ERR_INVALID, "null vectors");
+    int32_t rc;
+    if ((rc = set_device(s)) != MX_OK) return rc;
+    // concurrent with searches of another host thread: the row matrix must not move (no growth on this path)
+    if (s->n + n > s->capacity)
+        return fail(s, MX_ERR_INSERTION, "capacity %llu exhausted (streamed ingest does not grow the store: create it with the "
+                                         "capacity it will reach)", (unsigned long long)s->capacity);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
+    IngestParams ip{};
+    ip.src = vecs_dev;
+    ip.rows = s->rows;
+    ip.inv_norm = s->inv_norm;
+    ip.zero_rows = s->zero_rows;
+    ip.n_zero = s->n_zero;
+    ip.bad_flag = s->flags;
+    ip.max_norm = s->max_norm;
+    ip.first_row = s->n;
+    ip.n = n;
+    ip.dim = s->cfg.dim;
+    ip.ld = s->ld;
+    ip.dtype = s->cfg.dtype;
+    ip.metric = s->cfg.metric;
+    MX_CUDA(s, MX_ERR_INSERTION, launch_ingest(ip, st));
+    // the rows become visible to searches (the committed-rows watermark s->n) only once they are in place
+    return finish_add(s, n, st, first_id_out);
+}
+
+int32_t mx_store_set_sm_limit(mx_store *s, uint32_t sms)
+{
+    if (!s) return MX_ERR_INVALID;
+    int32_t rc;
+    if ((rc = set_device(s)) != MX_OK) return rc;
+    cudaDeviceProp prop{};
+    MX_CUDA(s, MX_ERR_CONNECTION, cudaGetDeviceProperties(&prop, s->cfg.device));
+    const uint32_t all = (uint32_t)prop.multiProcessorCount;
+    s->sm_count = (int)(sms == 0 || sms >= all ? all : std::max<uint32_t>(1u, sms));
+    MX_CUDA(s, MX_ERR_CONNECTION, cudaStreamSynchronize(s->stream));
+    if (s->tc) tc_scan_set_sms(s->tc, s->sm_count);
+    return MX_OK;
+}
+
 int32_t mx_store_search_device(mx_store *s, const float *queries_dev, uint32_t nq, uint32_t k, uint64_t *ids_dev,
                                float *scores_dev, float *dists_dev, uint32_t *counts_dev, void *cuda_stream)
 {
@@ -626,7 +676,7 @@ int32_t mx_store_search(mx_store *s, const float *queries, uint32_t nq, uint32_t
             cudaMemcpyAsync(hp + off_i, dp + off_i, total - off_i, cudaMemcpyDeviceToHost, s->stream));
     uint32_t *flagged_h = reinterpret_cast<uint32_t *>(hp + total);
     *flagged_h = 0;
-    if (s->verify && s->n > 0)
+    if (s->verify && s->n_view > 0)
         MX_CUDA(s, MX_ERR_SEARCH, cudaMemcpyAsync(flagged_h, s->n_flagged, 4, cudaMemcpyDeviceToHost, s->stream));
     MX_CUDA(s, MX_ERR_SEARCH, cudaStreamSynchronize(s->stream));
     if (*flagged_h > 0) {

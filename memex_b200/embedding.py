@@ -271,22 +271,64 @@ class SentenceEmbedder:
         handle.start()
         return handle, cls(q)
 
+    MAX_BATCH_SEGMENTS = 256      # segments per forward pass (BASELINE.json config 3's batch)
+    MAX_BATCH_WAIT_S = 0.0005     # how long the first request of a batch waits for company
+
     @staticmethod
     def _runner(receiver, model_config, encoder, tokenizer):
+        """embedding.rs:94-135 processes ONE document per message: `model.encode(&segments)` sees a batch of ~50 segments
+        for a 42 KB text and of 1 for a query, far from the 256-segment batches the kernels are at their best with
+        (SURVEY.md 8(f) N4).  Here the runner drains the channel: whatever requests are queued when one arrives (plus what
+        arrives within MAX_BATCH_WAIT_S, up to MAX_BATCH_SEGMENTS segments) are segmented and tokenised on the host and go
+        through ONE forward pass; every caller gets exactly the rows of its own segments, in order.  Rows of a batch
+        are independent (padding is masked, the packed layout drops it), so a request's vectors do not depend on what it
+        was batched with."""
+        import time as _time
+        pending = None
         while True:
-            msg = receiver.get()
+            msg = pending if pending is not None else receiver.get()
+            pending = None
             if msg is None:
                 return
-            text, segment, reply = msg
-            try:
-                segments = segment_text(model_config, text, tokenizer) if segment else [text]
-                ids, lens = tokenize_batch(tokenizer, segments, encoder.arch.max_seq_length, encoder.arch.pad_id)
-                embeddings = encoder.encode_ids(ids, lens)        # <- model.encode(&segments), :109
-                if len(segments) != len(embeddings):
-                    raise EncodingFailure("# of embeddings doesn't match # of segments")
-                reply.put([EmbeddingResult(content=s, vector=v.tolist()) for s, v in zip(segments, embeddings)])
-            except Exception as e:  # the reference's runner dies; here the caller gets the error
-                reply.put(e)
+            batch, n_seg, stop = [], 0, False
+            deadline = _time.perf_counter() + SentenceEmbedder.MAX_BATCH_WAIT_S
+            while True:
+                text, segment, reply = msg
+                try:
+                    segments = segment_text(model_config, text, tokenizer) if segment else [text]
+                    batch.append((segments, reply))
+                    n_seg += len(segments)
+                except Exception as e:  # the reference's runner dies; here the caller gets the error
+                    reply.put(e)
+                if n_seg >= SentenceEmbedder.MAX_BATCH_SEGMENTS:
+                    break
+                try:
+                    msg = receiver.get(timeout=max(0.0, deadline - _time.perf_counter()))
+                except queue.Empty:
+                    break
+                if msg is None:
+                    stop = True
+                    break
+            if batch:
+                try:
+                    flat = [s for segs, _ in batch for s in segs]
+                    ids, lens = tokenize_batch(tokenizer, flat, encoder.arch.max_seq_length, encoder.arch.pad_id)
+                    embeddings = encoder.encode_ids(ids, lens)        # <- model.encode(&segments), :109
+                    if len(flat) != len(embeddings):
+                        raise EncodingFailure("# of embeddings doesn't match # of segments")
+                    at = 0
+                    for segs, reply in batch:
+                        reply.put([EmbeddingResult(content=s, vector=v.tolist())
+                                   for s, v in zip(segs, embeddings[at:at + len(segs)])])
+                        at += len(segs)
+                except Exception as e:
+                    for _, reply in batch:
+                        reply.put(e)
+            SentenceEmbedder.batches_run += 1
+            if stop:
+                return
+
+    batches_run = 0               # forward passes issued by runners of this process (tests)
 
     def _call(self, text: str, segment: bool):
         reply: queue.Queue = queue.Queue(maxsize=1)               # oneshot::channel

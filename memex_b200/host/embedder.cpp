@@ -1,5 +1,6 @@
 // embedder.cpp -- B200Encoder, SentenceEmbedder (the actor of reference llm/embedding.rs:77-152), model table and
 // the .safetensors reader.  See memex_host.hpp.
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -252,34 +253,75 @@ SentenceEmbedder::~SentenceEmbedder()
     if (handle_.joinable()) handle_.join();
 }
 
+// embedding.rs:94-135 embeds ONE document per message: `model.encode(&segments)` sees ~50 segments for a 42 KB text and 1 for a
+// query, far from the 256-segment batches the kernels are at their best with.  This runner drains the
+// channel: whatever is queued when a request arrives (plus what arrives within kBatchWaitUs, up to kBatchSegments
+// segments) is segmented and tokenised on the host and goes through ONE forward pass; every caller gets exactly the rows
+// of its own segments, in order.  Rows of a batch are independent (padding is masked, the packed layout drops it), so a
+// request's vectors do not depend on what it was batched with.
 void SentenceEmbedder::runner(ModelConfig model_config, std::shared_ptr<Encoder> encoder, std::shared_ptr<Tokenizer> tokenizer)
 {
-    while (true) {
+    struct Job {
         Message msg;
-        {
-            std::unique_lock<std::mutex> g(mu_);
-            not_empty_.wait(g, [this] { return closed_ || !channel_.empty(); });
-            if (channel_.empty()) return;
-            msg = std::move(channel_.front());
-            channel_.pop_front();
+        std::vector<std::string> segments;
+    };
+    while (true) {
+        std::vector<Job> jobs;
+        size_t n_seg = 0;
+        bool first = true;
+        std::chrono::steady_clock::time_point deadline;
+        while (n_seg < kBatchSegments) {
+            Message msg;
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                if (first) {
+                    not_empty_.wait(g, [this] { return closed_ || !channel_.empty(); });
+                    if (channel_.empty()) return;
+                    deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(kBatchWaitUs);
+                    first = false;
+                } else if (!not_empty_.wait_until(g, deadline, [this] { return closed_ || !channel_.empty(); }) || channel_.empty()) {
+                    break;
+                }
+                msg = std::move(channel_.front());
+                channel_.pop_front();
+            }
+            not_full_.notify_one();
+            try {
+                std::vector<std::string> segments =
+                    msg.segment ? segment_text(model_config, msg.text, *tokenizer) : std::vector<std::string>{msg.text};
+                n_seg += segments.size();
+                jobs.push_back(Job{std::move(msg), std::move(segments)});
+            } catch (...) {
+                // the reference's runner returns Err and dies; here the caller gets the error and the actor lives on
+                msg.sender.set_exception(std::current_exception());
+            }
         }
-        not_full_.notify_one();
+        if (jobs.empty()) continue;
         try {
-            std::vector<std::string> segments =
-                msg.segment ? segment_text(model_config, msg.text, *tokenizer) : std::vector<std::string>{msg.text};
-            const TokenBatch batch = tokenize_batch(*tokenizer, segments, encoder->max_seq_length());
+            std::vector<std::string> flat;
+            flat.reserve(n_seg);
+            for (const Job &j : jobs) flat.insert(flat.end(), j.segments.begin(), j.segments.end());
+            const TokenBatch batch = tokenize_batch(*tokenizer, flat, encoder->max_seq_length());
             const std::vector<float> embeddings = encoder->encode_ids(batch);   // <- model.encode(&segments), embedding.rs:109
+            ++batches_;
             const uint32_t H = encoder->hidden();
-            if (embeddings.size() != segments.size() * H)   // embedding.rs:110-115
+            if (embeddings.size() != flat.size() * H)   // embedding.rs:110-115
                 throw EmbeddingError(EmbeddingErrorKind::EncodingFailure, "# of embeddings doesn't match # of segments");
-            std::vector<EmbeddingResult> results;
-            results.reserve(segments.size());
-            for (size_t i = 0; i < segments.size(); ++i)
-                results.push_back({segments[i], std::vector<float>(embeddings.begin() + i * H, embeddings.begin() + (i + 1) * H)});
-            msg.sender.set_value(std::move(results));
+            size_t at = 0;
+            for (Job &j : jobs) {
+                std::vector<EmbeddingResult> results;
+                results.reserve(j.segments.size());
+                for (size_t i = 0; i < j.segments.size(); ++i, ++at)
+                    results.push_back({j.segments[i], std::vector<float>(embeddings.begin() + at * H, embeddings.begin() + (at + 1) * H)});
+                j.msg.sender.set_value(std::move(results));
+            }
         } catch (...) {
-            // the reference's runner returns Err and dies; here the caller gets the error and the actor lives on
-            msg.sender.set_exception(std::current_exception());
+            for (Job &j : jobs) {
+                try {
+                    j.msg.sender.set_exception(std::current_exception());
+                } catch (const std::future_error &) {   // already answered
+                }
+            }
         }
     }
 }

@@ -18,6 +18,7 @@
 // All arithmetic happens in libmemex_b200.so on the GPU; nothing here computes a distance or an embedding.
 #pragma once
 
+#include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
@@ -377,8 +378,12 @@ public:
     std::vector<EmbeddingResult> encode(const std::string &text);                    // segment + embed each window
     std::optional<EmbeddingResult> encode_single(const std::string &text);           // one shot, truncated by the model
     std::future<std::vector<EmbeddingResult>> encode_async(std::string text, bool segment);
+    uint64_t batches_run() const { return batches_; }   // forward passes issued (requests queued together share one)
 
 private:
+    static constexpr size_t kBatchSegments = 256;   // segments per forward pass (BASELINE.json config 3's batch)
+    static constexpr uint32_t kBatchWaitUs = 500;   // how long the first request of a batch waits for company
+    std::atomic<uint64_t> batches_{0};
     struct Message {
         std::string text;
         bool segment;

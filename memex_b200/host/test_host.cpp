@@ -254,8 +254,15 @@ static int run_cpu()
         CHECK(longer->vector[0] == 16.f);
         // many concurrent callers go through the bounded channel
         std::vector<std::future<std::vector<EmbeddingResult>>> futs;
-        for (int i = 0; i < 300; ++i) futs.push_back(emb->encode_async("a b", false));
-        for (auto &f : futs) CHECK(f.get().size() == 1);
+        const int calls_before = enc->calls;
+        for (int i = 0; i < 300; ++i) futs.push_back(emb->encode_async(i % 2 ? "a b" : "the fox a", false));
+        for (int i = 0; i < 300; ++i) {
+            auto r = futs[i].get();
+            // every caller gets ITS row out of the shared forward pass: token count of its own text (+ [CLS] + [SEP])
+            CHECK(r.size() == 1 && r[0].content == (i % 2 ? "a b" : "the fox a") && r[0].vector[0] == (i % 2 ? 4.f : 5.f));
+        }
+        // N4: requests queued together share forward passes (300 requests -> far fewer passes)
+        CHECK(enc->calls - calls_before < 300 && emb->batches_run() >= 1);
         // an unsupported model surfaces as SetupError to the caller and the actor survives
         ModelConfig bad;
         bad.model = EmbeddingsModelType::SentenceT5Base;

@@ -77,12 +77,16 @@ class ShardedStore:
     """
 
     def __init__(self, storage_path, dim: int, total_rows: int, dtype: str = "f16", metric: str = "cosine",
-                 device: int = 0, rank: int = 0, world: int = 1, group=None):
+                 device: int = 0, rank: int = 0, world: int = 1, group=None, id_stride: int = 1):
+        """id_stride = 1: contiguous row ranges (rank r owns global rows [start, start + count), a corpus known up front);
+        id_stride = world: round-robin ids (local row i of rank r is global row i * world + r) -- a corpus that GROWS on
+        every rank independently (streamed ingest), `total_rows` then only sizes the shards' capacity."""
         self.plan = ShardPlan(total_rows, world)
         self.rank, self.world, self.group = rank, world, group
         self.dim, self.metric, self.device = dim, metric, device
         self.local = B200Store.new(storage_path, dim=dim, dtype=dtype, metric=metric, device=device,
-                                   capacity=self.plan.count(rank), id_offset=self.plan.start(rank), id_stride=1)
+                                   capacity=self.plan.count(rank),
+                                   id_offset=self.plan.start(rank) if id_stride == 1 else rank, id_stride=id_stride)
         self._bufs = {}
         self.exchange = "none" if world == 1 else "nccl"
         self._want_p2p = world > 1 and os.environ.get("MX_EXCHANGE", "p2p") != "nccl"

@@ -144,3 +144,44 @@ def test_actor_reports_a_count_mismatch_and_survives(bert_tok):
     finally:
         embedder.shutdown()
         handle.join(timeout=10)
+
+
+def test_runner_batches_concurrent_requests_into_one_forward_pass(bert_tok):
+    """the reference's runner embeds one document per message (embedding.rs:102-132).  Here requests
+    that are queued together share ONE forward pass, and every caller still gets exactly its own rows, in order."""
+    import threading
+    import time
+    tok, g = bert_tok
+    arch = dataclasses.replace(ARCHITECTURES[EmbeddingsModelType.AllMiniLmL6V2], max_seq_length=32)
+
+    class SlowEncoder(FakeEncoder):
+        def encode_ids(self, ids, lens):
+            time.sleep(0.05)                 # while one pass runs, the other callers' requests pile up in the channel
+            return super().encode_ids(ids, lens)
+
+    enc = SlowEncoder(arch)
+    mc = ModelConfig(model=EmbeddingsModelType.AllMiniLmL6V2, max_length=24, stride=8)
+    texts = [c["text"] for c in g["cases"] if c["text"].strip()][:12]
+    handle, embedder = SentenceEmbedder.spawn(mc, enc, tok)
+    results = [None] * len(texts)
+
+    def call(i):
+        results[i] = embedder.encode(texts[i]) if i % 3 else [embedder.encode_single(texts[i])]
+
+    try:
+        threads = [threading.Thread(target=call, args=(i,)) for i in range(len(texts))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=30)
+        assert all(r is not None for r in results)
+        assert len(enc.calls) < len(texts)                       # fewer forward passes than requests
+        assert max(len(lens) for _, lens in enc.calls) > 1
+        # every caller got the rows of ITS segments: same content and same vectors as a call made alone
+        for i, text in enumerate(texts):
+            alone = embedder.encode(text) if i % 3 else [embedder.encode_single(text)]
+            assert [r.content for r in results[i]] == [r.content for r in alone]
+            assert [r.vector for r in results[i]] == [r.vector for r in alone]
+    finally:
+        embedder.shutdown()
+        handle.join(timeout=10)

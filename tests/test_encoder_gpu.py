@@ -295,7 +295,7 @@ def test_roberta_position_offset_limits_the_sequence_length():
 
 
 @pytest.mark.parametrize("switch", ["MX_GEMM_MULTICAST", "MX_GEMM_RESIDENT", "MX_GEMM_LN_NO_SPLIT", "MX_GEMM_EPI16", "MX_GEMM_LN_AMC", "MX_GEMM_QKV12",
-                                    "MX_GEMM_PAIR=0"])
+                                    "MX_GEMM_PAIR"])
 def test_gemm_opt_in_variants_in_a_fresh_process(switch):
     """the 2-CTA weight-multicast and resident-weight GEMM variants are selected by an environment switch that
     the library reads once, so they are exercised in a child process: same GEMM parity cases + the end-to-end
