@@ -432,7 +432,6 @@ def bench_single_query(device, steps: int, warmup: int, pk):
     for i in range(warmup):
         st.search_device(q[i % 64:i % 64 + 1], TOPK)
     torch.cuda.synchronize(device)
-    L.mx_store_set_timing(st.local.handle, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
@@ -440,6 +439,11 @@ def bench_single_query(device, steps: int, warmup: int, pk):
     e1.record()
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1) / steps
+    # second pass with the library's per-kernel events on: the scan / other split (see run_ours)
+    L.mx_store_set_timing(st.local.handle, 1)
+    for i in range(steps):
+        st.search_device(q[i % 64:i % 64 + 1], TOPK)
+    torch.cuda.synchronize(device)
     scan_ms, scan_n, oth_ms, oth_n = C.c_double(), C.c_uint64(), C.c_double(), C.c_uint64()
     L.mx_store_get_timing(st.local.handle, C.byref(scan_ms), C.byref(scan_n), C.byref(oth_ms), C.byref(oth_n))
     L.mx_store_set_timing(st.local.handle, 0)
@@ -693,13 +697,32 @@ def bench_ingest(device, pk, rows: int, seconds: float, rank: int = 0, world: in
                 counts["queries"] += NQ
                 counts["rows_scanned"] += n_now
 
+    diag_mode = [0]   # MX_INGEST_DIAG: which part of the ingest loop runs (measurement aid; 0 = all of it)
+    mm_a = torch.randn((4096, 4096), device=device, dtype=torch.bfloat16)
+
     def ingester(stop):
         torch.cuda.set_device(device)
         first = C.c_uint64()
         while not stop.is_set():
+            if diag_mode[0] == 3:      # no library call at all: plain torch matmuls on the ingest stream
+                with torch.cuda.stream(s_ingest):
+                    for _ in range(8):
+                        torch.matmul(mm_a, mm_a)
+                s_ingest.synchronize()
+                counts["segments"] += B
+                continue
+            if diag_mode[0] == 2:      # only the append
+                rc = L.mx_store_add_device_stream(st.local.handle, out_d.data_ptr(), B, C.byref(first), s_ingest.cuda_stream)
+                assert rc == 0, L.mx_last_error(st.local.handle)
+                counts["segments"] += B
+                continue
             rc = L.mx_embedder_encode_device(enc.handle, ids_d.data_ptr(), lens.ctypes.data, B, S, out_d.data_ptr(),
                                              s_ingest.cuda_stream)
             assert rc == 0, L.mx_last_error(enc.handle)
+            if diag_mode[0] == 1:      # only the forward pass
+                s_ingest.synchronize()
+                counts["segments"] += B
+                continue
             rc = L.mx_store_add_device_stream(st.local.handle, out_d.data_ptr(), B, C.byref(first), s_ingest.cuda_stream)
             assert rc == 0, L.mx_last_error(st.local.handle)
             counts["segments"] += B
@@ -767,6 +790,13 @@ def bench_ingest(device, pk, rows: int, seconds: float, rank: int = 0, world: in
             st.search_device(q, TOPK)
     torch.cuda.synchronize(device)
     both = window(True, True, max(10, n_alone * 2 // 3))
+    diag = {}
+    if os.environ.get("MX_INGEST_DIAG"):
+        for mode, name in ((1, "forward pass only"), (2, "append only"), (3, "torch matmuls only (no library call)")):
+            diag_mode[0] = mode
+            r = window(True, True, max(10, n_alone // 3))
+            diag[name] = {"queries_per_s": r["queries"], "ingest_iterations_per_s": r["segments"] / B}
+        diag_mode[0] = 0
     rows_end = torch.tensor([len(st)], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(rows_end, op=dist.ReduceOp.SUM, group=group)
@@ -793,7 +823,7 @@ def bench_ingest(device, pk, rows: int, seconds: float, rank: int = 0, world: in
            "concurrent_vs_alone": {"search": both["queries"] / max(alone_s["queries"], 1e-9),
                                    "ingest": both["segments"] / max(alone_i["segments"], 1e-9)},
            "peaks_per_gpu": {"hbm_gbs": pk["hbm"], "tflops_burst": pk["tf_burst"]},
-           "fresh_rows_searchable": found,
+           "fresh_rows_searchable": found, **({"diag": diag} if diag else {}),
            "timing": f"wall clock, ~{seconds} s windows, one host thread per role and rank, stream sync per batch (throughput, not kernel time)"}
     enc.close()
     st.close()
@@ -847,7 +877,9 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    L.mx_store_set_timing(store.local.handle, 1)
+    # two passes of `steps` steps: the first is the throughput -- nothing but the kernels on the stream (the library's
+    # per-kernel CUDA events sit between the launches, cost ~1 us each and keep a dependent launch from being scheduled
+    # early); the second runs with those events on and gives the scan / other split the roofline is computed from
     l0 = L.mx_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -860,6 +892,11 @@ def run_ours(args):
     t_end = sampler.mark()
     ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     launches = torch.tensor([L.mx_launch_count() - l0], dtype=torch.int64, device=device)
+    L.mx_store_set_timing(store.local.handle, 1)
+    barrier()
+    for _ in range(args.steps):
+        store.search_device(q_dev, TOPK)
+    barrier()
     scan_ms, scan_n, oth_ms, oth_n = C.c_double(), C.c_uint64(), C.c_double(), C.c_uint64()
     L.mx_store_get_timing(store.local.handle, C.byref(scan_ms), C.byref(scan_n), C.byref(oth_ms), C.byref(oth_n))
     L.mx_store_set_timing(store.local.handle, 0)

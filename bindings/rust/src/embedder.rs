@@ -60,7 +60,22 @@ pub fn architecture_of(model: EmbeddingsModelType) -> Option<Architecture> {
             a.ext.share_layers = 1;
             a
         }
-        EmbeddingsModelType::SentenceT5Base => return None, // T5 encoder: not built
+        EmbeddingsModelType::SentenceT5Base => {
+            // T5 v1.1 base encoder + mean pool + Dense(768 -> 768, no bias) + Normalize; weights under the HF
+            // T5EncoderModel names (include/memex_b200.h, mx_model_ext.family)
+            let mut a = bert(12, 768, 2048, 1, 256);
+            a.cfg.vocab = 32128;
+            a.cfg.type_vocab = 0;
+            a.cfg.ln_eps = 1e-6;
+            a.ext.family = ffi::MX_FAMILY_T5;
+            a.ext.d_kv = 64;
+            a.ext.rel_buckets = 32;
+            a.ext.rel_max_distance = 128;
+            a.ext.dense_out = 768;
+            a.ext.dense_bias = 0;
+            a.ext.ffn_act = ffi::MX_FFN_GELU_TANH; // gated: gelu_new(wi_0 x) * wi_1 x
+            a
+        }
     })
 }
 

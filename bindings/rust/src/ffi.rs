@@ -56,6 +56,10 @@ pub struct mx_model_ext {
     pub ffn_act: u32,
     pub embed_dim: u32,
     pub share_layers: u32,
+    pub family: u32,           // MX_FAMILY_*
+    pub d_kv: u32,             // T5: per-head width
+    pub rel_buckets: u32,      // T5: relative_attention_num_buckets
+    pub rel_max_distance: u32, // T5: relative_attention_max_distance
 }
 
 #[repr(C)]
@@ -88,6 +92,8 @@ pub const MX_ACT_IDENTITY: u32 = 0;
 pub const MX_ACT_TANH: u32 = 1;
 pub const MX_FFN_GELU_ERF: u32 = 0;
 pub const MX_FFN_GELU_TANH: u32 = 1;
+pub const MX_FAMILY_BERT: u32 = 0;
+pub const MX_FAMILY_T5: u32 = 1;
 
 extern "C" {
     pub fn mx_store_create(cfg: *const mx_store_cfg, out: *mut *mut mx_store) -> i32;

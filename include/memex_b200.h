@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MX_ABI_VERSION 1
+#define MX_ABI_VERSION 2
 
 /* status codes <-> reference error variants */
 #define MX_OK 0
@@ -268,7 +268,22 @@ typedef struct mx_model_ext {
     uint32_t ffn_act;       /* MX_FFN_* */
     uint32_t embed_dim;     /* > 0 and != hidden: factorised embeddings (ALBERT), projected to hidden */
     uint32_t share_layers;  /* 1: every layer uses the weights of "encoder.layer.0." (ALBERT) */
+    /* SentenceT5Base (embedding.rs:32,52): family = MX_FAMILY_T5 selects the T5 encoder stack -- pre-RMSNorm layers around an
+     * f32 residual stream, unscaled attention with a bucketed relative position bias shared by all layers, gated-GELU
+     * feed-forward, no biases.  Weights under the HF T5EncoderModel names: "shared.weight" [vocab, hidden],
+     * "encoder.block.{i}.layer.0.SelfAttention.{q,k,v,o}.weight", "encoder.block.0.layer.0.SelfAttention.
+     * relative_attention_bias.weight" [rel_buckets, heads], "encoder.block.{i}.layer.{0,1}.layer_norm.weight",
+     * "encoder.block.{i}.layer.1.DenseReluDense.{wi_0,wi_1,wo}.weight", "encoder.final_layer_norm.weight" (+ the Dense
+     * module's "dense.linear.weight").  heads * d_kv must equal hidden (T5-base: 12 x 64 = 768); cfg.max_pos bounds the
+     * sequence length (the bias table is built for it), ffn_act is read as gated gelu_new.  The tensor-core path runs the
+     * seven GEMMs of a layer on tcgen05; attention (score bias) and RMSNorm run on CUDA cores. */
+    uint32_t family;           /* MX_FAMILY_* */
+    uint32_t d_kv;             /* T5: per-head width */
+    uint32_t rel_buckets;      /* T5: relative_attention_num_buckets (32) */
+    uint32_t rel_max_distance; /* T5: relative_attention_max_distance (128) */
 } mx_model_ext;
+#define MX_FAMILY_BERT 0u /* BERT / RoBERTa / DistilBERT / ALBERT: post-LayerNorm layers */
+#define MX_FAMILY_T5 1u
 int32_t mx_embedder_create_ex(const mx_model_cfg *cfg, const mx_model_ext *ext, const mx_tensor *weights,
                               uint32_t n_weights, int32_t device, mx_embedder **out);
 /* width of one output row: dense_out when a Dense module is present, else hidden */

@@ -47,7 +47,11 @@ class ModelCfg(C.Structure):
 class ModelExt(C.Structure):
     _fields_ = [("pos_offset", C.c_uint32), ("no_token_type", C.c_uint32), ("dense_out", C.c_uint32),
                 ("dense_act", C.c_uint32), ("dense_bias", C.c_uint32), ("ffn_act", C.c_uint32),
-                ("embed_dim", C.c_uint32), ("share_layers", C.c_uint32)]
+                ("embed_dim", C.c_uint32), ("share_layers", C.c_uint32),
+                ("family", C.c_uint32), ("d_kv", C.c_uint32), ("rel_buckets", C.c_uint32), ("rel_max_distance", C.c_uint32)]
+
+
+FAMILY_BERT, FAMILY_T5 = 0, 1
 
 
 class Tensor(C.Structure):

@@ -19,6 +19,8 @@
 
 #include <cstdlib>
 
+#include <cmath>
+
 #include "common.cuh"
 #include "encoder.cuh"
 #include "gemm.cuh"
@@ -29,6 +31,7 @@ namespace {
 
 struct LayerWeights {
     void *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;  // activation dtype, [out, in]
+    void *w1g = nullptr;        // T5: wi_1 (the linear half of the gated feed-forward)
     float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
     float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
 };
@@ -50,6 +53,11 @@ struct mx_embedder : HandleBase {
     void *proj_w = nullptr;     // ALBERT: [hidden, embed_dim] in the activation dtype
     float *proj_b = nullptr;
     float *dense_w = nullptr, *dense_b = nullptr, *pooled_dev = nullptr;   // Dense module (f32)
+    // T5 stack
+    float *t5_rel_bias = nullptr;   // [heads][2 max_pos - 1] f32: bias of (key - query), from the bucket table
+    float *t5_final_g = nullptr, *t5_zero_bias = nullptr;
+    float *xr = nullptr;            // [max_tokens, H] f32 residual stream
+    void *hh2 = nullptr;            // [max_tokens, F] second half of the gated feed-forward
     std::vector<LayerWeights> layers;
     // workspaces sized for cfg.max_tokens
     void *x = nullptr, *x1 = nullptr, *qkv = nullptr, *ctx = nullptr, *hh = nullptr;
@@ -150,12 +158,174 @@ int32_t run_gemm(mx_embedder *e, const void *A, const void *W, const float *bias
     return MX_OK;
 }
 
+// HF T5Attention._relative_position_bucket, bidirectional, with torch's float32 arithmetic (the bucket boundaries are
+// decided by its rounding)
+int t5_bucket(int rel, int num_buckets, int max_distance)
+{
+    const int nb = num_buckets / 2;
+    const int ret = rel > 0 ? nb : 0;
+    const int n = rel < 0 ? -rel : rel;
+    const int max_exact = nb / 2;
+    if (n < max_exact) return ret + n;
+    const float v = logf((float)n / (float)max_exact) / (float)log((double)max_distance / (double)max_exact) * (float)(nb - max_exact);
+    const int large = max_exact + (int)v;
+    return ret + std::min(large, nb - 1);
+}
+
+// weights + workspaces of the T5 stack (HF T5EncoderModel names, include/memex_b200.h)
+int32_t load_t5(mx_embedder *e, const WeightTable &tab, float *staging)
+{
+    const mx_model_cfg &c = e->cfg;
+    const mx_model_ext &x = e->ext;
+    const uint64_t H = c.hidden, F = c.ffn;
+    const int act = e->act;
+    const size_t asz = act_size(act);
+    int32_t rc = MX_OK;
+    auto up_f32 = [&](const std::string &name, uint64_t numel, float **dst) -> int32_t {
+        int32_t r = MX_OK;
+        const mx_tensor *t = tab.get(name, numel, e, &r);
+        if (!t) return r;
+        if ((r = dev_alloc(e, dst, numel)) != MX_OK) return r;
+        return upload(e, t->data, numel, *dst, ACT_F32, staging);
+    };
+    auto up_act = [&](const std::string &name, uint64_t numel, void **dst) -> int32_t {
+        int32_t r = MX_OK;
+        const mx_tensor *t = tab.get(name, numel, e, &r);
+        if (!t) return r;
+        unsigned char *p = nullptr;
+        if ((r = dev_alloc(e, &p, numel * asz)) != MX_OK) return r;
+        *dst = p;
+        return upload(e, t->data, numel, p, act, staging);
+    };
+    if (tab.by_name.count("shared.weight") || !tab.by_name.count("encoder.embed_tokens.weight")) {
+        if ((rc = up_f32("shared.weight", (uint64_t)c.vocab * H, &e->word)) != MX_OK) return rc;
+    } else if ((rc = up_f32("encoder.embed_tokens.weight", (uint64_t)c.vocab * H, &e->word)) != MX_OK) {
+        return rc;
+    }
+    // relative position bias: bucket table [rel_buckets, heads] -> bias of every (key - query) in (-max_pos, max_pos)
+    {
+        const mx_tensor *t = tab.get("encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight",
+                                     (uint64_t)x.rel_buckets * c.heads, e, &rc);
+        if (!t) return rc;
+        const uint32_t P = c.max_pos, span = 2 * P - 1;
+        std::vector<float> table((size_t)c.heads * span);
+        for (uint32_t h = 0; h < c.heads; ++h)
+            for (uint32_t i = 0; i < span; ++i) {
+                const int rel = (int)i - (int)(P - 1);   // key - query
+                table[(size_t)h * span + i] = t->data[(size_t)t5_bucket(rel, (int)x.rel_buckets, (int)x.rel_max_distance) * c.heads + h];
+            }
+        if ((rc = dev_alloc(e, &e->t5_rel_bias, table.size())) != MX_OK) return rc;
+        MX_CUDA(e, MX_ERR_SETUP, cudaMemcpyAsync(e->t5_rel_bias, table.data(), table.size() * 4, cudaMemcpyHostToDevice, e->stream));
+        MX_CUDA(e, MX_ERR_SETUP, cudaStreamSynchronize(e->stream));
+    }
+    const uint64_t nz = std::max<uint64_t>(3 * H, F);
+    if ((rc = dev_alloc(e, &e->t5_zero_bias, nz)) != MX_OK) return rc;
+    MX_CUDA(e, MX_ERR_SETUP, cudaMemsetAsync(e->t5_zero_bias, 0, nz * 4, e->stream));
+    if ((rc = up_f32("encoder.final_layer_norm.weight", H, &e->t5_final_g)) != MX_OK) return rc;
+    if (x.dense_out) {
+        if ((rc = up_f32("dense.linear.weight", (uint64_t)x.dense_out * H, &e->dense_w)) != MX_OK) return rc;
+        if (x.dense_bias && (rc = up_f32("dense.linear.bias", x.dense_out, &e->dense_b)) != MX_OK) return rc;
+    }
+    e->layers.resize(c.layers);
+    for (uint32_t l = 0; l < c.layers; ++l) {
+        LayerWeights &w = e->layers[l];
+        const std::string p = "encoder.block." + std::to_string(l) + ".layer.";
+        unsigned char *wqkv = nullptr;
+        if ((rc = dev_alloc(e, &wqkv, 3 * H * H * asz)) != MX_OK) return rc;
+        w.wqkv = wqkv;
+        const char *names[3] = {"q", "k", "v"};
+        for (int j = 0; j < 3; ++j) {
+            int32_t r2 = MX_OK;
+            const mx_tensor *t = tab.get(p + "0.SelfAttention." + names[j] + ".weight", H * H, e, &r2);
+            if (!t) return r2;
+            if ((rc = upload(e, t->data, H * H, wqkv + (size_t)j * H * H * asz, act, staging)) != MX_OK) return rc;
+        }
+        if ((rc = up_act(p + "0.SelfAttention.o.weight", H * H, &w.wo)) != MX_OK) return rc;
+        if ((rc = up_f32(p + "0.layer_norm.weight", H, &w.ln1_g)) != MX_OK) return rc;
+        if ((rc = up_act(p + "1.DenseReluDense.wi_0.weight", F * H, &w.w1)) != MX_OK) return rc;
+        if ((rc = up_act(p + "1.DenseReluDense.wi_1.weight", F * H, &w.w1g)) != MX_OK) return rc;
+        if ((rc = up_act(p + "1.DenseReluDense.wo.weight", H * F, &w.w2)) != MX_OK) return rc;
+        if ((rc = up_f32(p + "1.layer_norm.weight", H, &w.ln2_g)) != MX_OK) return rc;
+    }
+    const uint64_t T = c.max_tokens;
+    unsigned char *ws = nullptr;
+    if ((rc = dev_alloc(e, &ws, T * H * asz)) != MX_OK) return rc;
+    e->x = ws;
+    if ((rc = dev_alloc(e, &ws, T * H * asz)) != MX_OK) return rc;
+    e->x1 = ws;
+    if ((rc = dev_alloc(e, &ws, T * 3 * H * asz)) != MX_OK) return rc;
+    e->qkv = ws;
+    if ((rc = dev_alloc(e, &ws, T * H * asz)) != MX_OK) return rc;
+    e->ctx = ws;
+    if ((rc = dev_alloc(e, &ws, T * F * asz)) != MX_OK) return rc;
+    e->hh = ws;
+    if ((rc = dev_alloc(e, &ws, T * F * asz)) != MX_OK) return rc;
+    e->hh2 = ws;
+    if ((rc = dev_alloc(e, &e->xr, T * H)) != MX_OK) return rc;
+    e->max_seqs = (uint32_t)std::min<uint64_t>(T, 8192);
+    if ((rc = dev_alloc(e, &e->ids_dev, T)) != MX_OK) return rc;
+    if ((rc = dev_alloc(e, &e->lens_dev, 2 * (uint64_t)e->max_seqs + 1)) != MX_OK) return rc;
+    if ((rc = dev_alloc(e, &e->out_dev, (uint64_t)e->max_seqs * e->out_dim)) != MX_OK) return rc;
+    if (x.dense_out && (rc = dev_alloc(e, &e->pooled_dev, (uint64_t)e->max_seqs * H)) != MX_OK) return rc;
+    MX_CUDA(e, MX_ERR_SETUP, cudaStreamSynchronize(e->stream));
+    return MX_OK;
+}
+
+// SentenceT5Base (embedding.rs:32,52): T5 encoder + mean pool + Dense + Normalize.  Padded layout; the residual stream xr
+// stays in f32 (pre-norm stacks accumulate into it layer after layer), the GEMMs read the RMS-normalised activations.
+int32_t forward_t5(mx_embedder *e, const int32_t *ids_dev, const int32_t *lens_dev, uint32_t B, uint32_t S, float *out_dev,
+                   cudaStream_t st)
+{
+    const mx_model_cfg &c = e->cfg;
+    const uint32_t T = B * S, H = c.hidden, F = c.ffn;
+    if (S > c.max_pos) return fail(e, MX_ERR_ENCODE, "sequence length %u exceeds max_pos %u", S, c.max_pos);
+    int32_t rc;
+    e->timer.begin(st, 1);
+    MX_CUDA(e, MX_ERR_ENCODE, launch_t5_embed(ids_dev, e->word, e->xr, T, H, c.vocab, st));
+    e->timer.end(st);
+    const void *delta = nullptr;
+    for (uint32_t l = 0; l < c.layers; ++l) {
+        const LayerWeights &w = e->layers[l];
+        e->timer.begin(st, 1);
+        MX_CUDA(e, MX_ERR_ENCODE, launch_t5_add_rmsnorm(e->xr, delta, w.ln1_g, c.ln_eps, e->x, e->act, T, H, st));
+        e->timer.end(st);
+        if ((rc = run_gemm(e, e->x, w.wqkv, e->t5_zero_bias, nullptr, nullptr, nullptr, e->qkv, T, 3 * H, H, EPI_BIAS, st)) != MX_OK) return rc;
+        e->timer.begin(st, 1);
+        MX_CUDA(e, MX_ERR_ENCODE, launch_attention_simt(e->qkv, lens_dev, e->ctx, e->act, B, S, H, c.heads, st, 1.0f, e->t5_rel_bias, c.max_pos));
+        e->timer.end(st);
+        if ((rc = run_gemm(e, e->ctx, w.wo, e->t5_zero_bias, nullptr, nullptr, nullptr, e->x1, T, H, H, EPI_BIAS, st)) != MX_OK) return rc;
+        e->timer.begin(st, 1);
+        MX_CUDA(e, MX_ERR_ENCODE, launch_t5_add_rmsnorm(e->xr, e->x1, w.ln2_g, c.ln_eps, e->x, e->act, T, H, st));
+        e->timer.end(st);
+        if ((rc = run_gemm(e, e->x, w.w1, e->t5_zero_bias, nullptr, nullptr, nullptr, e->hh, T, F, H, EPI_BIAS_GELU_TANH, st)) != MX_OK) return rc;
+        if ((rc = run_gemm(e, e->x, w.w1g, e->t5_zero_bias, nullptr, nullptr, nullptr, e->hh2, T, F, H, EPI_BIAS, st)) != MX_OK) return rc;
+        e->timer.begin(st, 1);
+        MX_CUDA(e, MX_ERR_ENCODE, launch_gated_mul(e->hh, e->hh2, e->act, (uint64_t)T * F, st));
+        e->timer.end(st);
+        if ((rc = run_gemm(e, e->hh, w.w2, e->t5_zero_bias, nullptr, nullptr, nullptr, e->x1, T, H, F, EPI_BIAS, st)) != MX_OK) return rc;
+        delta = e->x1;
+    }
+    e->timer.begin(st, 1);
+    MX_CUDA(e, MX_ERR_ENCODE, launch_t5_add_rmsnorm(e->xr, delta, e->t5_final_g, c.ln_eps, e->x, e->act, T, H, st));
+    if (e->ext.dense_out) {
+        MX_CUDA(e, MX_ERR_ENCODE, launch_pool_normalize(e->x, e->act, lens_dev, e->pooled_dev, B, S, H, 0, nullptr, st));
+        MX_CUDA(e, MX_ERR_ENCODE,
+                launch_dense_tail(e->pooled_dev, e->dense_w, e->dense_b, out_dev, B, H, e->ext.dense_out, e->ext.dense_act,
+                                  c.normalize, st));
+    } else {
+        MX_CUDA(e, MX_ERR_ENCODE, launch_pool_normalize(e->x, e->act, lens_dev, out_dev, B, S, H, c.normalize, nullptr, st));
+    }
+    e->timer.end(st);
+    return MX_OK;
+}
+
 // one forward pass over B sequences of S tokens already in ids_dev / lens_dev
 // cu_dev / n_rows: packed layout (encoder.cuh) -- the activations hold only the n_rows real tokens; nullptr = padded
 int32_t forward(mx_embedder *e, const int32_t *ids_dev, const int32_t *lens_dev, const int32_t *cu_dev, uint32_t n_rows,
                 uint32_t B, uint32_t S, float *out_dev, cudaStream_t st)
 {
     const mx_model_cfg &c = e->cfg;
+    if (e->ext.family == MX_FAMILY_T5) return forward_t5(e, ids_dev, lens_dev, B, S, out_dev, st);
     const uint32_t T = cu_dev ? n_rows : B * S, H = c.hidden, F = c.ffn;
     const uint32_t E = e->ext.embed_dim ? e->ext.embed_dim : H;
     const int epi_ffn = e->ext.ffn_act == MX_FFN_GELU_TANH ? EPI_BIAS_GELU_TANH : EPI_BIAS_GELU;
@@ -209,7 +379,7 @@ int32_t stage_lengths(mx_embedder *e, const int32_t *lens, uint32_t nb, uint32_t
     *cu_dev = nullptr;
     *n_rows = nb * S;
     MX_CUDA(e, MX_ERR_ENCODE, cudaMemcpyAsync(e->lens_dev, lens, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (!e->packing || e->act == ACT_F32 || !e->attention_tc || e->attention_tc4 ||
+    if (!e->packing || e->act == ACT_F32 || !e->attention_tc || e->attention_tc4 || e->ext.family == MX_FAMILY_T5 ||
         !attention_tc_supported(S, e->cfg.hidden, e->cfg.heads))
         return MX_OK;
     std::vector<int32_t> cu(nb + 1);
@@ -251,6 +421,14 @@ int32_t mx_embedder_create_ex(const mx_model_cfg *cfg, const mx_model_ext *ext_i
     if (ext.embed_dim == cfg->hidden) ext.embed_dim = 0;
     if (ext.pos_offset >= cfg->max_pos) return fail(nullptr, MX_ERR_SETUP, "pos_offset %u >= max_pos %u", ext.pos_offset, cfg->max_pos);
     if (ext.dense_out > 1024) return fail(nullptr, MX_ERR_SETUP, "dense_out %u > 1024", ext.dense_out);
+    if (ext.family > MX_FAMILY_T5) return fail(nullptr, MX_ERR_SETUP, "unknown model family %u", ext.family);
+    const bool t5 = ext.family == MX_FAMILY_T5;
+    if (t5 && (ext.d_kv == 0 || ext.d_kv * cfg->heads != cfg->hidden))
+        return fail(nullptr, MX_ERR_SETUP, "T5: heads (%u) x d_kv (%u) must equal hidden (%u)", cfg->heads, ext.d_kv, cfg->hidden);
+    if (t5 && (ext.rel_buckets < 4 || ext.rel_buckets % 2 != 0 || ext.rel_buckets > 256 || ext.rel_max_distance < ext.rel_buckets))
+        return fail(nullptr, MX_ERR_SETUP, "T5: bad relative attention shape (buckets %u, max distance %u)", ext.rel_buckets, ext.rel_max_distance);
+    if (t5 && (ext.embed_dim || ext.share_layers || ext.pos_offset))
+        return fail(nullptr, MX_ERR_SETUP, "T5: embed_dim / share_layers / pos_offset do not apply");
     if (ext.dense_act > MX_ACT_TANH || ext.ffn_act > MX_FFN_GELU_TANH)
         return fail(nullptr, MX_ERR_SETUP, "unknown activation code (dense_act %u, ffn_act %u)", ext.dense_act, ext.ffn_act);
     if (ext.embed_dim && (ext.embed_dim > cfg->hidden || ext.embed_dim % 64 != 0))
@@ -266,7 +444,7 @@ int32_t mx_embedder_create_ex(const mx_model_cfg *cfg, const mx_model_ext *ext_i
     const int act = cfg->precision == 1 ? ACT_F32 : (cfg->precision == 0 ? ACT_BF16 : ACT_F16);
     if (act != ACT_F32) {
         if (!gemm_tc_block_n(3 * cfg->hidden, EPI_BIAS) || !gemm_tc_block_n(cfg->ffn, EPI_BIAS_GELU) ||
-            !gemm_tc_block_n(cfg->hidden, EPI_BIAS_RES_LN) || (ext.embed_dim && !gemm_tc_block_n(cfg->hidden, EPI_BIAS)))
+            !gemm_tc_block_n(cfg->hidden, t5 ? EPI_BIAS : EPI_BIAS_RES_LN) || (ext.embed_dim && !gemm_tc_block_n(cfg->hidden, EPI_BIAS)))
             return fail(nullptr, MX_ERR_SETUP, "hidden %u / ffn %u have no tcgen05 tile configuration", cfg->hidden, cfg->ffn);
     }
     int ndev = 0;
@@ -331,6 +509,11 @@ int32_t mx_embedder_create_ex(const mx_model_cfg *cfg, const mx_model_ext *ext_i
         return upload(e, t->data, numel, dst, act, staging);
     };
 
+    if (t5) {
+        if ((rc = load_t5(e, tab, staging)) != MX_OK) return bail(rc);
+        *out = e;
+        return MX_OK;
+    }
     if ((rc = up_f32("embeddings.word_embeddings.weight", (uint64_t)cfg->vocab * E, &e->word)) != MX_OK) return bail(rc);
     if ((rc = up_f32("embeddings.position_embeddings.weight", (uint64_t)cfg->max_pos * E, &e->pos)) != MX_OK) return bail(rc);
     if (ext.no_token_type) {

@@ -20,8 +20,18 @@ cudaError_t launch_embed_ln(const int32_t *ids, const float *word, const float *
 
 // K6 (CUDA-core version): ctx = softmax(q k^T / sqrt(dh) + mask(lens)) v, from the fused qkv buffer
 // [T, 3H] (q | k | v, heads contiguous inside each).  Rows at or beyond lens[b] are written as zero.
+// scale <= 0 selects 1 / sqrt(dh); rel_bias (may be null): [heads][2 bias_span - 1] f32 added to the score of (query, key)
+// at index key - query + bias_span - 1 (T5's relative position bias; S <= bias_span)
 cudaError_t launch_attention_simt(const void *qkv, const int32_t *lens_dev, void *ctx, int act, uint32_t B, uint32_t S,
-                                  uint32_t H, uint32_t heads, cudaStream_t st);
+                                  uint32_t H, uint32_t heads, cudaStream_t st, float scale = 0.f,
+                                  const float *rel_bias = nullptr, uint32_t bias_span = 0);
+
+// T5 stack: f32 residual stream xr [T, H]; see encoder_kernels.cu
+cudaError_t launch_t5_embed(const int32_t *ids, const float *word, float *xr, uint32_t n_tokens, uint32_t H, uint32_t vocab,
+                            cudaStream_t st);
+cudaError_t launch_t5_add_rmsnorm(float *xr, const void *delta, const float *g, float eps, void *out, int act, uint32_t rows,
+                                  uint32_t H, cudaStream_t st);
+cudaError_t launch_gated_mul(void *a, const void *b, int act, uint64_t n, cudaStream_t st);
 
 // K6 (tensor-core version, attention_mma.cu): same contract, 16-bit activations only
 cudaError_t launch_attention_mma(const void *qkv, const int32_t *lens_dev, void *ctx, int act, uint32_t B, uint32_t S,

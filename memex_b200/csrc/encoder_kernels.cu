@@ -208,7 +208,8 @@ template <int ACT, int DH>
 __global__ void __launch_bounds__(kAttWarps * 32) attention_simt_kernel(const typename Act<ACT>::T *__restrict__ qkv,
                                                                        const int32_t *__restrict__ lens,
                                                                        typename Act<ACT>::T *__restrict__ ctx, uint32_t S,
-                                                                       uint32_t H, uint32_t heads, float scale)
+                                                                       uint32_t H, uint32_t heads, float scale,
+                                                                       const float *__restrict__ rel_bias, uint32_t bias_span)
 {
     using T = typename Act<ACT>::T;
     constexpr int DPL = DH / 32;  // output dims per lane
@@ -271,6 +272,9 @@ __global__ void __launch_bounds__(kAttWarps * 32) attention_simt_kernel(const ty
                 float s = 0.f;
 #pragma unroll 8
                 for (int d = 0; d < DH; ++d) s = fmaf(q[d], ks[kj * (DH + 1) + d], s);
+                // T5: additive relative position bias of this head, indexed by (key - query)
+                if (rel_bias != nullptr && kj < kn)
+                    s += rel_bias[(size_t)h * (2 * bias_span - 1) + (k0 + kj) + (bias_span - 1) - (q0 + warp * kAttQPW + i)];
                 sc[j] = kj < kn ? s : kNegInf;
                 bmax = fmaxf(bmax, sc[j]);
             }
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(kAttWarps * 32) attention_simt_kernel(const ty
 
 template <int ACT, int DH>
 static cudaError_t launch_att(const void *qkv, const int32_t *lens, void *ctx, uint32_t B, uint32_t S, uint32_t H,
-                              uint32_t heads, cudaStream_t st)
+                              uint32_t heads, cudaStream_t st, float scale, const float *rel_bias, uint32_t bias_span)
 {
     using T = typename Act<ACT>::T;
     auto kern = attention_simt_kernel<ACT, DH>;
@@ -322,21 +326,24 @@ static cudaError_t launch_att(const void *qkv, const int32_t *lens, void *ctx, u
         if (e != cudaSuccess) return e;
     }
     dim3 grid(B * heads, ceil_div<uint32_t>(S, kAttQ));
-    kern<<<grid, kAttWarps * 32, smem, st>>>((const T *)qkv, lens, (T *)ctx, S, H, heads, 1.0f / sqrtf((float)DH));
+    kern<<<grid, kAttWarps * 32, smem, st>>>((const T *)qkv, lens, (T *)ctx, S, H, heads,
+                                             scale > 0.f ? scale : 1.0f / sqrtf((float)DH), rel_bias, bias_span);
     count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t launch_attention_simt(const void *qkv, const int32_t *lens_dev, void *ctx, int act, uint32_t B, uint32_t S,
-                                  uint32_t H, uint32_t heads, cudaStream_t st)
+                                  uint32_t H, uint32_t heads, cudaStream_t st, float scale, const float *rel_bias,
+                                  uint32_t bias_span)
 {
     const uint32_t dh = H / heads;
-#define MX_A(A)                                                                       \
-    switch (dh) {                                                                     \
-        case 32: return launch_att<A, 32>(qkv, lens_dev, ctx, B, S, H, heads, st);    \
-        case 64: return launch_att<A, 64>(qkv, lens_dev, ctx, B, S, H, heads, st);    \
-        case 128: return launch_att<A, 128>(qkv, lens_dev, ctx, B, S, H, heads, st);  \
-        default: return cudaErrorInvalidValue;                                        \
+    if (rel_bias != nullptr && S > bias_span) return cudaErrorInvalidValue;
+#define MX_A(A)                                                                                                  \
+    switch (dh) {                                                                                                \
+        case 32: return launch_att<A, 32>(qkv, lens_dev, ctx, B, S, H, heads, st, scale, rel_bias, bias_span);   \
+        case 64: return launch_att<A, 64>(qkv, lens_dev, ctx, B, S, H, heads, st, scale, rel_bias, bias_span);   \
+        case 128: return launch_att<A, 128>(qkv, lens_dev, ctx, B, S, H, heads, st, scale, rel_bias, bias_span); \
+        default: return cudaErrorInvalidValue;                                                                   \
     }
     if (act == ACT_F32) { MX_A(ACT_F32) }
     if (act == ACT_BF16) { MX_A(ACT_BF16) }
@@ -630,6 +637,90 @@ cudaError_t launch_gemm_ref(const GemmRefParams &p, int epi, cudaStream_t st)
         if (e != cudaSuccess) return e;
         return launch_add_ln_f32(p.out, p.residual, p.gamma, p.beta, p.ln_eps, p.out, p.M, p.N, st);
     }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// T5 encoder stack (SentenceT5Base, reference lib/libmemex/src/llm/embedding.rs:32,52): pre-RMSNorm layers around an f32
+// residual stream.  xr [T, H] f32 is the stream; the GEMMs read / write the activation dtype.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) t5_embed_kernel(const int32_t *__restrict__ ids, const float *__restrict__ word,
+                                                       float *__restrict__ xr, uint32_t n_tokens, uint32_t H, uint32_t vocab)
+{
+    const uint32_t t = blockIdx.x;
+    if (t >= n_tokens) return;
+    const int32_t id = min(max(ids[t], 0), (int32_t)vocab - 1);
+    for (uint32_t c = threadIdx.x; c < H; c += blockDim.x) xr[(size_t)t * H + c] = word[(size_t)id * H + c];
+}
+
+cudaError_t launch_t5_embed(const int32_t *ids, const float *word, float *xr, uint32_t n_tokens, uint32_t H, uint32_t vocab,
+                            cudaStream_t st)
+{
+    if (n_tokens == 0) return cudaSuccess;
+    t5_embed_kernel<<<n_tokens, 256, 0, st>>>(ids, word, xr, n_tokens, H, vocab);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// xr += delta (the previous sub-layer's output, may be null); out = xr / sqrt(mean(xr^2) + eps) * g   (T5LayerNorm: no mean
+// subtraction, no bias).  One warp per row.
+template <int ACT>
+__global__ void __launch_bounds__(256) t5_add_rmsnorm_kernel(float *__restrict__ xr, const typename Act<ACT>::T *__restrict__ delta,
+                                                             const float *__restrict__ g, float eps,
+                                                             typename Act<ACT>::T *__restrict__ out, uint32_t rows, uint32_t H)
+{
+    const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = lane_id();
+    if (row >= rows) return;
+    float *x = xr + (size_t)row * H;
+    float ss = 0.f;
+    for (uint32_t c = lane; c < H; c += 32) {
+        float v = x[c];
+        if (delta != nullptr) {
+            v += Act<ACT>::ld(delta + (size_t)row * H + c);
+            x[c] = v;
+        }
+        ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    const float r = rsqrtf(ss / (float)H + eps);
+    for (uint32_t c = lane; c < H; c += 32) Act<ACT>::st(out + (size_t)row * H + c, x[c] * r * g[c]);
+}
+
+cudaError_t launch_t5_add_rmsnorm(float *xr, const void *delta, const float *g, float eps, void *out, int act, uint32_t rows,
+                                  uint32_t H, cudaStream_t st)
+{
+    if (rows == 0) return cudaSuccess;
+    const uint32_t grid = ceil_div<uint32_t>(rows, 8);
+    if (act == ACT_F32)
+        t5_add_rmsnorm_kernel<ACT_F32><<<grid, 256, 0, st>>>(xr, (const float *)delta, g, eps, (float *)out, rows, H);
+    else if (act == ACT_BF16)
+        t5_add_rmsnorm_kernel<ACT_BF16><<<grid, 256, 0, st>>>(xr, (const __nv_bfloat16 *)delta, g, eps, (__nv_bfloat16 *)out, rows, H);
+    else
+        t5_add_rmsnorm_kernel<ACT_F16><<<grid, 256, 0, st>>>(xr, (const __half *)delta, g, eps, (__half *)out, rows, H);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// gated feed-forward: a <- a * b  (a = gelu_new(wi_0 x) from the GEMM epilogue, b = wi_1 x)
+template <int ACT>
+__global__ void __launch_bounds__(256) gated_mul_kernel(typename Act<ACT>::T *__restrict__ a, const typename Act<ACT>::T *__restrict__ b,
+                                                        uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) Act<ACT>::st(a + i, Act<ACT>::ld(a + i) * Act<ACT>::ld(b + i));
+}
+
+cudaError_t launch_gated_mul(void *a, const void *b, int act, uint64_t n, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)ceil_div<uint64_t>(n, 256);
+    if (act == ACT_F32)
+        gated_mul_kernel<ACT_F32><<<grid, 256, 0, st>>>((float *)a, (const float *)b, n);
+    else if (act == ACT_BF16)
+        gated_mul_kernel<ACT_BF16><<<grid, 256, 0, st>>>((__nv_bfloat16 *)a, (const __nv_bfloat16 *)b, n);
+    else
+        gated_mul_kernel<ACT_F16><<<grid, 256, 0, st>>>((__half *)a, (const __half *)b, n);
+    count_launch();
     return cudaGetLastError();
 }
 

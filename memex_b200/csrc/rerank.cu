@@ -337,58 +337,67 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
     prof_mark(p, 4);
     const uint32_t n_batches = (n_entries + 31) / 32;
     const uint32_t frole = warp / kFoldBatches, fb = warp % kFoldBatches;   // role 0: a.b, 1: b.b, warp 2F: a.a
+    // entry e of a pass -> rowbuf[e][0 .. cn) as f32.  16-byte loads, all of a row's loads issued before the first use
+    // (a warp owns entries e = warp, warp + 16, ...); the query chunk goes to qs
+    auto stage = [&](uint32_t first, uint32_t n_here, uint32_t c0, uint32_t cn) {
+        __syncthreads();   // previous chunk fully consumed
+        for (uint32_t i = threadIdx.x; i < cn; i += blockDim.x) qs[i] = qg[c0 + i];
+        const uint32_t per16 = p.dtype == MX_DTYPE_F32 ? 4u : 8u;        // elements per 16-byte chunk
+        const uint32_t n16 = (cn + per16 - 1) / per16;                   // c0 and ld are multiples of per16
+        for (uint32_t e = warp; e < n_here; e += kRerankWarps) {
+            const uint32_t row = erow[first + e];
+            if (row == kNoRow || row >= p.n_rows) continue;
+            const uint4 *src = reinterpret_cast<const uint4 *>(
+                reinterpret_cast<const char *>(p.rows) + ((size_t)row * p.ld + c0) * (p.dtype == MX_DTYPE_F32 ? 4 : 2));
+            uint4 buf[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const uint32_t ch = lane + 32 * u;
+                buf[u] = ch < n16 ? src[ch] : make_uint4(0, 0, 0, 0);
+            }
+            float *dst = rowbuf + e * kFoldPitch;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const uint32_t ch = lane + 32 * u;
+                if (ch >= n16) continue;
+                if (p.dtype == MX_DTYPE_F32) {
+                    const float *f = reinterpret_cast<const float *>(&buf[u]);
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+                        if (ch * 4 + x < cn) dst[ch * 4 + x] = f[x];
+                } else {
+                    const __half *hh = reinterpret_cast<const __half *>(&buf[u]);
+#pragma unroll
+                    for (int x = 0; x < 8; ++x)
+                        if (ch * 8 + x < cn) dst[ch * 8 + x] = __half2float(hh[x]);
+                }
+            }
+        }
+        __syncthreads();
+    };
+    // (r2, measured: a "fast fold" that summed an entry's products with a warp-parallel tree whenever the sum is provably
+    // exact -- all non-zero products within 29 - log2(dim) binades, so that no f64 addition can round in ANY order -- was
+    // bit-identical but SLOWER, 13.4 us against 7.0: the fold is bound by the FP64 pipe's THROUGHPUT, ~16 cycles per
+    // warp-wide DADD and SM sub-partition, not by the chain's latency, and the tree does the same number of additions plus
+    // the bookkeeping.  What helps is spreading the three chains over three sub-partitions: a.b on warp 0, b.b on warp
+    // 2, a.a on warp 5 -- warp 4 would share warp 0's sub-partition and double the critical path.)
+    __shared__ int aa_known_s;
+    if (threadIdx.x == 0) aa_known_s = 0;
+    __syncthreads();
     for (uint32_t b0 = 0; b0 < n_batches; b0 += kFoldBatches) {
         const uint32_t first = b0 * 32;
         const uint32_t n_here = min((uint32_t)kFoldBatches * 32, n_entries - first);
         double acc = 0.0;
         const bool folder = frole < 2 && fb * 32 + lane < n_here;
-        const bool q_folder = warp == 2 * kFoldBatches && b0 == 0;
+        const bool q_folder = warp == 2 * kFoldBatches + 1 && !aa_known_s;
         const uint32_t my_row = folder ? erow[first + fb * 32 + lane] : kNoRow;
         for (uint32_t c0 = 0; c0 < p.dim; c0 += kFoldChunk) {
             const uint32_t cn = min((uint32_t)kFoldChunk, p.dim - c0);
-            __syncthreads();   // previous chunk fully consumed
-            for (uint32_t i = threadIdx.x; i < cn; i += blockDim.x) qs[i] = qg[c0 + i];
-            // stage: entry e of this pass -> rowbuf[e][0 .. cn) as f32.  16-byte loads, all of a row's loads issued
-            // before the first use (a warp owns entries e = warp, warp + 16, ...)
-            {
-                const uint32_t per16 = p.dtype == MX_DTYPE_F32 ? 4u : 8u;        // elements per 16-byte chunk
-                const uint32_t n16 = (cn + per16 - 1) / per16;                   // c0 and ld are multiples of per16
-                for (uint32_t e = warp; e < n_here; e += kRerankWarps) {
-                    const uint32_t row = erow[first + e];
-                    if (row == kNoRow || row >= p.n_rows) continue;
-                    const uint4 *src = reinterpret_cast<const uint4 *>(
-                        reinterpret_cast<const char *>(p.rows) + ((size_t)row * p.ld + c0) * (p.dtype == MX_DTYPE_F32 ? 4 : 2));
-                    uint4 buf[3];
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const uint32_t ch = lane + 32 * u;
-                        buf[u] = ch < n16 ? src[ch] : make_uint4(0, 0, 0, 0);
-                    }
-                    float *dst = rowbuf + e * kFoldPitch;
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const uint32_t ch = lane + 32 * u;
-                        if (ch >= n16) continue;
-                        if (p.dtype == MX_DTYPE_F32) {
-                            const float *f = reinterpret_cast<const float *>(&buf[u]);
-#pragma unroll
-                            for (int x = 0; x < 4; ++x)
-                                if (ch * 4 + x < cn) dst[ch * 4 + x] = f[x];
-                        } else {
-                            const __half *hh = reinterpret_cast<const __half *>(&buf[u]);
-#pragma unroll
-                            for (int x = 0; x < 8; ++x)
-                                if (ch * 8 + x < cn) dst[ch * 8 + x] = __half2float(hh[x]);
-                        }
-                    }
-                }
-            }
-            __syncthreads();
+            stage(first, n_here, c0, cn);
             if (folder && my_row != kNoRow && my_row < p.n_rows) {
                 const float *rb = rowbuf + (fb * 32 + lane) * kFoldPitch;
                 // 16 products and their f32 -> f64 conversions are computed ahead of the chain, so the chain itself is 16
-                // dependent DADDs (the conversion is an XU op with a long latency: interleaved with the adds it paced the fold
-                // at ~42 cycles per element, 8.3 us of the kernel's 18.6 -- scripts/rerank_prof.py)
+                // dependent DADDs
                 const float *xa = frole == 0 ? qs : rb;
                 uint32_t i = 0;
                 for (; i + 16 <= cn; i += 16) {
@@ -414,6 +423,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
         if (frole == 1 && folder) bb_s[fb * 32 + lane] = acc;
         if (q_folder && lane == 0) aa_s = acc;
         __syncthreads();
+        if (q_folder && lane == 0) aa_known_s = 1;
         if (frole == 0 && folder) {
             const uint32_t j = first + fb * 32 + lane;
             if (my_row != kNoRow && my_row < p.n_rows) {
@@ -430,6 +440,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p)
                 erow[j] = kNoRow;
             }
         }
+        __syncthreads();
     }
     if (threadIdx.x == 0) {
         // the query's own norm decides the degenerate case (DistCosine: aa == 0 -> d = 0 for all rows).

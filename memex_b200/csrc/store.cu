@@ -55,6 +55,8 @@ struct mx_store : HandleBase {
     uint32_t *zero_rows = nullptr;  // [MX_MAX_K]
     uint32_t *n_zero = nullptr;     // device scalar
     uint32_t *flags = nullptr;      // device scalar: bit0 non-finite, bit1 zero row seen
+    uint32_t *flags_host = nullptr; // PINNED copy target: a device-to-host copy into pageable memory holds a runtime lock until
+                                    // the stream has drained, which stalls the kernel launches of every other host thread
     bool zero_dirty = false;
     int32_t force_path = -1;
     // scratch
@@ -166,9 +168,9 @@ int32_t ingest_device(mx_store *s, const float *src_dev, uint64_t n, cudaStream_
 
 int32_t finish_add(mx_store *s, uint64_t n, cudaStream_t st, uint64_t *first_id_out)
 {
-    uint32_t flags = 0;
-    MX_CUDA(s, MX_ERR_INSERTION, cudaMemcpyAsync(&flags, s->flags, 4, cudaMemcpyDeviceToHost, st));
+    MX_CUDA(s, MX_ERR_INSERTION, cudaMemcpyAsync(s->flags_host, s->flags, 4, cudaMemcpyDeviceToHost, st));
     MX_CUDA(s, MX_ERR_INSERTION, cudaStreamSynchronize(st));
+    const uint32_t flags = *s->flags_host;
     if (flags) {
         cudaMemsetAsync(s->flags, 0, 4, st);
         cudaStreamSynchronize(st);
@@ -479,6 +481,8 @@ int32_t mx_store_create(const mx_store_cfg *cfg, mx_store **out)
     if ((e = cudaMalloc(&s->zero_rows, sizeof(uint32_t) * MX_MAX_K)) != cudaSuccess ||
         (e = cudaMalloc(&s->n_zero, 4)) != cudaSuccess || (e = cudaMalloc(&s->flags, 4)) != cudaSuccess)
         return bail(MX_ERR_CONNECTION, "cudaMalloc", e);
+    if ((e = cudaMallocHost(&s->flags_host, 64)) != cudaSuccess) return bail(MX_ERR_CONNECTION, "cudaMallocHost", e);
+    *s->flags_host = 0;
     if ((e = cudaMalloc(&s->n_flagged_buf, 8)) != cudaSuccess || (e = cudaMalloc(&s->stats, 16)) != cudaSuccess ||
         (e = cudaMalloc(&s->max_norm, 4)) != cudaSuccess)
         return bail(MX_ERR_CONNECTION, "cudaMalloc", e);
@@ -526,6 +530,7 @@ void mx_store_destroy(mx_store *s)
     cudaFree(s->max_norm);
     cudaFree(s->prof);
     if (s->pinned) cudaFreeHost(s->pinned);
+    if (s->flags_host) cudaFreeHost(s->flags_host);
     if (s->stream) cudaStreamDestroy(s->stream);
     s->magic = 0;
     delete s;

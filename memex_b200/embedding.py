@@ -72,16 +72,24 @@ class Architecture:
     ffn_act: str = "gelu"        # "gelu" (erf) | "gelu_new" (tanh form, ALBERT)
     embed_dim: int = 0           # ALBERT: factorised embedding width (0 = hidden)
     share_layers: bool = False   # ALBERT: one set of layer weights
+    # family "t5" (SentenceT5Base): T5 encoder stack, weights under the HF T5EncoderModel names
+    d_kv: int = 0
+    rel_buckets: int = 32
+    rel_max_distance: int = 128
 
     @property
     def out_dim(self) -> int:
         return self.dense_out or self.hidden
 
 
-# The models of the enum whose layer is BERT's post-LayerNorm block (embedding.rs:24-55; shapes from the
-# sentence-transformers model cards).  SentenceT5Base is a T5 encoder (relative position bias, RMSNorm, gated FFN)
-# and is not built; the reference can only segment L12 / L6 / distilroberta anyway (embedding.rs:156-161).
+# Every model of the enum (embedding.rs:24-55; shapes from the sentence-transformers model cards): six stacks around
+# BERT's post-LayerNorm block and SentenceT5Base, a T5 v1.1 encoder (pre-RMSNorm, relative position bias, gated-GELU
+# feed-forward) + mean pool + Dense(768 -> 768, no bias) + Normalize.  The reference can only SEGMENT L12 / L6 /
+# distilroberta (embedding.rs:156-161); the others embed single shots.
 ARCHITECTURES = {
+    EmbeddingsModelType.SentenceT5Base: Architecture(
+        12, 768, 12, 2048, vocab=32128, max_pos=512, type_vocab=0, ln_eps=1e-6, max_seq_length=256,
+        family="t5", d_kv=64, dense_out=768, dense_bias=False, ffn_act="gated-gelu"),
     EmbeddingsModelType.AllMiniLmL6V2: Architecture(6, 384, 12, 1536, max_seq_length=256),
     EmbeddingsModelType.AllMiniLmL12V2: Architecture(12, 384, 12, 1536, max_seq_length=128),
     EmbeddingsModelType.BertBaseNliMeanTokens: Architecture(12, 768, 12, 3072, normalize=False, max_seq_length=128),
@@ -155,7 +163,10 @@ class B200Encoder:
         self.arch = arch
         self._auto = precision == "auto"
         if self._auto:
-            precision = "bf16" if arch.layers <= 6 else "f16"
+            # (T5: the residual stream is f32 in the kernels, but every sub-layer output is added to it un-normalised, and
+            # bf16 measures 1 - 3.5e-4 at two layers; f16 meets the gate.  T5 v1.1 checkpoints are the ones known to
+            # overflow f16 in the feed-forward: that is what the bf16 twin below is for.)
+            precision = "bf16" if (arch.layers <= 6 and arch.family != "t5") else "f16"
         self._twin = None
         self._args = (arch, weights, device, max_tokens)
         names, tensors, keep = [], [], []
@@ -171,8 +182,11 @@ class B200Encoder:
                             precision=PRECISION[precision], max_tokens=max_tokens)
         ext = capi.ModelExt(pos_offset=arch.pos_offset, no_token_type=1 if arch.family == "distilbert" else 0,
                             dense_out=arch.dense_out, dense_act={"identity": 0, "tanh": 1}[arch.dense_act],
-                            dense_bias=1 if arch.dense_bias else 0, ffn_act={"gelu": 0, "gelu_new": 1}[arch.ffn_act],
-                            embed_dim=arch.embed_dim, share_layers=1 if arch.share_layers else 0)
+                            dense_bias=1 if arch.dense_bias else 0,
+                            ffn_act={"gelu": 0, "gelu_new": 1, "gated-gelu": 1}[arch.ffn_act],
+                            embed_dim=arch.embed_dim, share_layers=1 if arch.share_layers else 0,
+                            family=capi.FAMILY_T5 if arch.family == "t5" else capi.FAMILY_BERT, d_kv=arch.d_kv,
+                            rel_buckets=arch.rel_buckets, rel_max_distance=arch.rel_max_distance)
         h = C.c_void_p()
         rc = capi.lib().mx_embedder_create_ex(C.byref(cfg), C.byref(ext), arr_t, len(tensors), device, C.byref(h))
         if rc != capi.OK:

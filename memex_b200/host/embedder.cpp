@@ -47,7 +47,17 @@ std::optional<Architecture> architecture_of(EmbeddingsModelType model)
             a.share_layers = true;
             return a;
         }
-        default: return std::nullopt;   // SentenceT5Base: T5 encoder, not built
+        case EmbeddingsModelType::SentenceT5Base: {
+            // sentence-transformers/sentence-t5-base: T5 v1.1 base encoder + mean pool + Dense(768 -> 768, no bias) + Normalize
+            Architecture a{12, 768, 12, 2048, 32128, 512, 0, 1e-6f, true, 256};
+            a.family = Family::T5;
+            a.d_kv = 64;
+            a.dense_out = 768;
+            a.dense_bias = false;
+            a.ffn_gelu_new = true;   // gated: gelu_new(wi_0 x) * wi_1 x
+            return a;
+        }
+        default: return std::nullopt;
     }
 }
 
@@ -188,7 +198,8 @@ B200Encoder::B200Encoder(const Architecture &arch, const Weights &weights, Preci
     cfg.type_vocab = arch.type_vocab;
     cfg.ln_eps = arch.ln_eps;
     cfg.normalize = arch.normalize ? 1 : 0;
-    if (precision == Precision::AUTO) precision = arch.layers <= 6 ? Precision::BF16 : Precision::F16;
+    // (T5 measures 1 - 3.5e-4 in bf16 at two layers, f16 meets the gate; an f16 overflow surfaces as EncodingFailure below)
+    if (precision == Precision::AUTO) precision = (arch.layers <= 6 && arch.family != Family::T5) ? Precision::BF16 : Precision::F16;
     f16_ = precision == Precision::F16;
     cfg.precision = (uint32_t)precision;
     cfg.max_tokens = max_tokens;
@@ -201,6 +212,10 @@ B200Encoder::B200Encoder(const Architecture &arch, const Weights &weights, Preci
     ext.ffn_act = arch.ffn_gelu_new ? MX_FFN_GELU_TANH : MX_FFN_GELU_ERF;
     ext.embed_dim = arch.embed_dim;
     ext.share_layers = arch.share_layers ? 1 : 0;
+    ext.family = arch.family == Family::T5 ? MX_FAMILY_T5 : MX_FAMILY_BERT;
+    ext.d_kv = arch.d_kv;
+    ext.rel_buckets = arch.rel_buckets;
+    ext.rel_max_distance = arch.rel_max_distance;
     int32_t rc = mx_embedder_create_ex(&cfg, &ext, ts.data(), (uint32_t)ts.size(), device, &handle_);
     if (rc != MX_OK) {
         const char *m = mx_last_error(nullptr);

@@ -308,7 +308,7 @@ struct TokenBatch {
 };
 TokenBatch tokenize_batch(const Tokenizer &tokenizer, const std::vector<std::string> &segments, size_t max_seq_length);
 
-enum class Family { Bert, Roberta, DistilBert, Albert };   // the checkpoint's naming scheme / embedding layout
+enum class Family { Bert, Roberta, DistilBert, Albert, T5 };   // the checkpoint's naming scheme / embedding layout
 struct Architecture {
     uint32_t layers, hidden, heads, ffn, vocab = 30522, max_pos = 512, type_vocab = 2;
     float ln_eps = 1e-12f;
@@ -323,9 +323,11 @@ struct Architecture {
     bool ffn_gelu_new = false;       // ALBERT's tanh-form GELU
     uint32_t embed_dim = 0;          // ALBERT: factorised embedding width (0 = hidden)
     bool share_layers = false;       // ALBERT: one set of layer weights
+    // Family::T5 (SentenceT5Base): T5 encoder stack, weights under the HF T5EncoderModel names (include/memex_b200.h)
+    uint32_t d_kv = 0, rel_buckets = 32, rel_max_distance = 128;
     uint32_t out_dim() const { return dense_out ? dense_out : hidden; }
 };
-// every member of the enum whose layer is BERT's post-LayerNorm block; SentenceT5Base (a T5 encoder) has none
+// every member of the enum: six stacks around BERT's post-LayerNorm block and SentenceT5Base (T5 v1.1 encoder + Dense)
 std::optional<Architecture> architecture_of(EmbeddingsModelType model);
 
 // named f32 tensors (HF BertModel names); from_safetensors reads a model.safetensors file (F32 / F16 / BF16)

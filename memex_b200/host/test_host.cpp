@@ -293,7 +293,8 @@ static int run_cpu()
     // ---- architecture table
     CHECK(architecture_of(EmbeddingsModelType::AllMiniLmL6V2)->layers == 6);
     CHECK(architecture_of(EmbeddingsModelType::AllMiniLmL12V2)->max_seq_length == 128);
-    CHECK(!architecture_of(EmbeddingsModelType::SentenceT5Base).has_value());
+    CHECK(architecture_of(EmbeddingsModelType::SentenceT5Base)->family == Family::T5);
+    CHECK(architecture_of(EmbeddingsModelType::SentenceT5Base)->d_kv * 12 == 768 && !architecture_of(EmbeddingsModelType::SentenceT5Base)->dense_bias);
     CHECK(architecture_of(EmbeddingsModelType::AllDistilrobertaV1)->pos_offset == 2);
     CHECK(architecture_of(EmbeddingsModelType::DistiluseBaseMultilingualCased)->out_dim() == 512);
     CHECK(architecture_of(EmbeddingsModelType::ParaphraseAlbertSmallV2)->embed_dim == 128);

@@ -204,6 +204,13 @@ class ShardedStore:
             if rc != capi.OK:
                 _raise(rc, self._shard_group, SearchError)
             return b["ids"], b["scores"], b["counts"]
+        if self.world == 1:
+            # one shard: the store's own answer IS the answer (no blob, no merge launch)
+            rc = L.mx_store_search_device(self.local.handle, q_dev.data_ptr(), nq, k, b["ids"].data_ptr(), b["scores"].data_ptr(),
+                                          None, b["counts"].data_ptr(), st)
+            if rc != capi.OK:
+                _raise(rc, self.local.handle, SearchError)
+            return b["ids"], b["scores"], b["counts"]
         mine = b["mine"]
         rc = L.mx_store_search_blob_device(self.local.handle, q_dev.data_ptr(), nq, k, mine.data_ptr(), st)
         if rc != capi.OK:

@@ -53,6 +53,12 @@ class EncoderConfig:
     ffn_act: str = "gelu"         # "gelu" | "gelu_new"
     embed_dim: int = 0            # ALBERT factorised embeddings (0 = hidden)
     share_layers: bool = False    # ALBERT
+    # T5 encoder (SentenceT5Base, embedding.rs:32,52): pre-RMSNorm, unscaled attention with a bucketed relative position
+    # bias shared by all layers, gated-GELU feed-forward, no biases anywhere; weights under HF T5EncoderModel names
+    d_kv: int = 0                 # per-head width (T5: heads * d_kv need not equal hidden)
+    rel_buckets: int = 32
+    rel_max_distance: int = 128
+    dense_bias: bool = True       # sentence-t5's 2_Dense has none
 
     def to_dict(self):
         return asdict(self)
@@ -72,6 +78,11 @@ DISTILUSE = EncoderConfig(layers=6, hidden=768, heads=12, ffn=3072, vocab=119547
 # ParaphraseAlbertSmallV2: ALBERT (128-wide embeddings, one shared layer applied 6 times, gelu_new), no Normalize
 ALBERT_SMALL = EncoderConfig(layers=6, hidden=768, heads=12, ffn=3072, vocab=30000, max_pos=512, normalize=False,
                              family="albert", ffn_act="gelu_new", embed_dim=128, share_layers=True)
+# SentenceT5Base: sentence-transformers/sentence-t5-base = T5 v1.1 base encoder + mean pool + Dense(768 -> 768, no bias) + Normalize
+SENTENCE_T5_BASE = EncoderConfig(layers=12, hidden=768, heads=12, ffn=2048, vocab=32128, max_pos=512, type_vocab=0, ln_eps=1e-6,
+                                 family="t5", d_kv=64, dense_out=768, dense_bias=False, ffn_act="gated-gelu")
+TINY_T5 = EncoderConfig(layers=2, hidden=64, heads=2, ffn=128, vocab=200, max_pos=64, type_vocab=0, ln_eps=1e-6,
+                        family="t5", d_kv=32, dense_out=64, dense_bias=False, ffn_act="gated-gelu")
 # the same three stacks at a size the numpy restatement runs in milliseconds
 TINY_ROBERTA = EncoderConfig(layers=2, hidden=64, heads=2, ffn=128, vocab=200, max_pos=66, type_vocab=1, ln_eps=1e-5,
                              family="roberta", pos_offset=2, pad_id=1)
@@ -85,6 +96,21 @@ def weight_names(cfg: EncoderConfig):
     """Canonical (HF ``BertModel(add_pooling_layer=False)``) state_dict names -> shapes; the other families use the
     same names (``hf_state_dict`` renames them for the HF model of the family)."""
     H, F = cfg.hidden, cfg.ffn
+    if cfg.family == "t5":
+        inner = cfg.heads * cfg.d_kv
+        out = {"shared.weight": (cfg.vocab, H),
+               "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight": (cfg.rel_buckets, cfg.heads)}
+        for i in range(cfg.layers):
+            p = f"encoder.block.{i}.layer."
+            out.update({p + "0.SelfAttention.q.weight": (inner, H), p + "0.SelfAttention.k.weight": (inner, H),
+                        p + "0.SelfAttention.v.weight": (inner, H), p + "0.SelfAttention.o.weight": (H, inner),
+                        p + "0.layer_norm.weight": (H,),
+                        p + "1.DenseReluDense.wi_0.weight": (F, H), p + "1.DenseReluDense.wi_1.weight": (F, H),
+                        p + "1.DenseReluDense.wo.weight": (H, F), p + "1.layer_norm.weight": (H,)})
+        out["encoder.final_layer_norm.weight"] = (H,)
+        if cfg.dense_out:
+            out["dense.linear.weight"] = (cfg.dense_out, H)
+        return out
     E = cfg.embed_dim or H
     out = {
         "embeddings.word_embeddings.weight": (cfg.vocab, E),
@@ -111,7 +137,8 @@ def weight_names(cfg: EncoderConfig):
         })
     if cfg.dense_out:
         out["dense.linear.weight"] = (cfg.dense_out, H)
-        out["dense.linear.bias"] = (cfg.dense_out,)
+        if cfg.dense_bias:
+            out["dense.linear.bias"] = (cfg.dense_out,)
     return out
 
 
@@ -125,8 +152,15 @@ def make_weights(cfg: EncoderConfig, seed: int = 0) -> dict[str, np.ndarray]:
     rng = np.random.default_rng(seed)
     w = {}
     for name, shape in weight_names(cfg).items():
-        if name.endswith("LayerNorm.weight"):
+        if name.endswith("LayerNorm.weight") or name.endswith("layer_norm.weight"):
             a = 1.0 + 0.1 * rng.standard_normal(shape)
+        elif name.endswith("relative_attention_bias.weight"):
+            a = 1.0 * rng.standard_normal(shape)
+        elif name == "shared.weight":
+            a = 0.5 * rng.standard_normal(shape)
+        elif cfg.family == "t5" and name.endswith("SelfAttention.q.weight"):
+            # T5 does not scale q . k by 1 / sqrt(d_kv): the scale lives in the weights (keeps the softmax from saturating)
+            a = rng.standard_normal(shape) * (1.5 / np.sqrt(shape[1]) / np.sqrt(cfg.d_kv) ** 0.5)
         elif name.endswith("LayerNorm.bias") or name.endswith(".bias"):
             a = 0.1 * rng.standard_normal(shape)
         elif "embeddings." in name:
@@ -172,10 +206,67 @@ def _layer_norm(x, g, b, eps):
     return (x - mu) / np.sqrt(var + eps) * g + b
 
 
+def t5_relative_buckets(S: int, num_buckets: int = 32, max_distance: int = 128) -> np.ndarray:
+    """HF T5Attention._relative_position_bucket, bidirectional: [S (query), S (key)] bucket of (key - query)"""
+    rel = np.arange(S)[None, :] - np.arange(S)[:, None]
+    nb = num_buckets // 2
+    ret = (rel > 0).astype(np.int64) * nb
+    n = np.abs(rel)
+    max_exact = nb // 2
+    is_small = n < max_exact
+    with np.errstate(divide="ignore", invalid="ignore"):
+        # float32, as torch computes it (the bucket boundaries are decided by this rounding)
+        large = max_exact + (np.log(n.astype(np.float32) / max_exact) / np.log(max_distance / max_exact) * (nb - max_exact)).astype(np.int64)
+    large = np.minimum(large, nb - 1)
+    return ret + np.where(is_small, n, large)
+
+
+def _np_encode_t5(cfg: EncoderConfig, W: dict, ids, lens, dtype, return_hidden):
+    B, S = ids.shape
+    H, nh, dk = cfg.hidden, cfg.heads, cfg.d_kv
+    mask = (np.arange(S)[None, :] < lens[:, None])
+
+    def rms(x, g):
+        return x / np.sqrt((x ** 2).mean(-1, keepdims=True) + cfg.ln_eps) * g
+
+    x = W["shared.weight"][ids]
+    bias = W["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"][
+        t5_relative_buckets(S, cfg.rel_buckets, cfg.rel_max_distance)]            # [S, S, heads]
+    bias = bias.transpose(2, 0, 1)[None] + np.where(mask, 0.0, -1e30)[:, None, None, :]
+    for i in range(cfg.layers):
+        p = f"encoder.block.{i}.layer."
+        n = rms(x, W[p + "0.layer_norm.weight"])
+        q = (n @ W[p + "0.SelfAttention.q.weight"].T).reshape(B, S, nh, dk).transpose(0, 2, 1, 3)
+        k = (n @ W[p + "0.SelfAttention.k.weight"].T).reshape(B, S, nh, dk).transpose(0, 2, 1, 3)
+        v = (n @ W[p + "0.SelfAttention.v.weight"].T).reshape(B, S, nh, dk).transpose(0, 2, 1, 3)
+        s = q @ k.transpose(0, 1, 3, 2) + bias                                      # no 1 / sqrt(d_kv)
+        s = s - s.max(-1, keepdims=True)
+        pr = np.exp(s)
+        pr = pr / pr.sum(-1, keepdims=True)
+        ctx = (pr @ v).transpose(0, 2, 1, 3).reshape(B, S, nh * dk)
+        x = x + ctx @ W[p + "0.SelfAttention.o.weight"].T
+        n = rms(x, W[p + "1.layer_norm.weight"])
+        g = n @ W[p + "1.DenseReluDense.wi_0.weight"].T
+        g = 0.5 * g * (1.0 + np.tanh(np.sqrt(2.0 / np.pi) * (g + 0.044715 * g ** 3)))
+        x = x + (g * (n @ W[p + "1.DenseReluDense.wi_1.weight"].T)) @ W[p + "1.DenseReluDense.wo.weight"].T
+    x = rms(x, W["encoder.final_layer_norm.weight"])
+    m = mask[..., None].astype(dtype)
+    pooled = (x * m).sum(1) / np.maximum(m.sum(1), 1e-9)
+    if cfg.dense_out:
+        pooled = pooled @ W["dense.linear.weight"].T
+    if cfg.normalize:
+        pooled = pooled / np.maximum(np.linalg.norm(pooled, axis=1, keepdims=True), 1e-12)
+    if return_hidden:
+        return pooled.astype(np.float32), x
+    return pooled.astype(np.float32)
+
+
 def np_encode(cfg: EncoderConfig, w: dict, ids: np.ndarray, lens: np.ndarray, dtype=np.float64,
               return_hidden: bool = False):
     """BERT forward + masked mean-pool + L2 normalise in numpy (default float64)."""
     W = {k: v.astype(dtype) for k, v in w.items()}
+    if cfg.family == "t5":
+        return _np_encode_t5(cfg, W, ids, lens, dtype, return_hidden)
     B, S = ids.shape
     H, nh = cfg.hidden, cfg.heads
     dh = H // nh
@@ -295,6 +386,14 @@ def hf_model(cfg: EncoderConfig, w: dict):
                           layer_norm_eps=cfg.ln_eps, hidden_act=cfg.ffn_act, hidden_dropout_prob=0.0,
                           attention_probs_dropout_prob=0.0, pad_token_id=cfg.pad_id)
         make = lambda: AlbertModel(hc, add_pooling_layer=False)
+    elif cfg.family == "t5":
+        from transformers import T5Config, T5EncoderModel
+        hc = T5Config(vocab_size=cfg.vocab, d_model=cfg.hidden, d_kv=cfg.d_kv, d_ff=cfg.ffn, num_layers=cfg.layers,
+                      num_heads=cfg.heads, relative_attention_num_buckets=cfg.rel_buckets,
+                      relative_attention_max_distance=cfg.rel_max_distance, dropout_rate=0.0,
+                      layer_norm_epsilon=cfg.ln_eps, feed_forward_proj="gated-gelu", is_encoder_decoder=False,
+                      use_cache=False, pad_token_id=cfg.pad_id)
+        make = lambda: T5EncoderModel(hc)
     else:
         raise ValueError(cfg.family)
     try:
@@ -303,6 +402,8 @@ def hf_model(cfg: EncoderConfig, w: dict):
         pass
     model = make()
     sd = {k: torch.from_numpy(v.copy()) for k, v in hf_state_dict(cfg, w).items()}
+    if cfg.family == "t5":
+        sd["encoder.embed_tokens.weight"] = sd["shared.weight"]
     missing, unexpected = model.load_state_dict(sd, strict=False)
     real_missing = [m for m in missing if "position_ids" not in m and "token_type_ids" not in m]
     if real_missing or unexpected:
@@ -322,7 +423,7 @@ def hf_encode(cfg: EncoderConfig, w: dict, ids: np.ndarray, lens: np.ndarray, th
     t_ids = torch.from_numpy(ids.astype(np.int64))
     mask = (torch.arange(S)[None, :] < torch.from_numpy(lens.astype(np.int64))[:, None]).to(torch.int64)
     with torch.no_grad():
-        if cfg.family == "distilbert":
+        if cfg.family in ("distilbert", "t5"):
             h = model(input_ids=t_ids, attention_mask=mask).last_hidden_state
         else:   # RoBERTa derives its position ids from the pad id inside the model
             h = model(input_ids=t_ids, attention_mask=mask,
@@ -330,7 +431,9 @@ def hf_encode(cfg: EncoderConfig, w: dict, ids: np.ndarray, lens: np.ndarray, th
         m = mask[..., None].to(h.dtype)
         pooled = (h * m).sum(1) / m.sum(1).clamp(min=1e-9)
         if cfg.dense_out:
-            pooled = pooled @ torch.from_numpy(w["dense.linear.weight"]).T + torch.from_numpy(w["dense.linear.bias"])
+            pooled = pooled @ torch.from_numpy(w["dense.linear.weight"]).T
+            if cfg.dense_bias:
+                pooled = pooled + torch.from_numpy(w["dense.linear.bias"])
             if cfg.dense_act == "tanh":
                 pooled = torch.tanh(pooled)
         if cfg.normalize:

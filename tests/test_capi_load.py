@@ -23,7 +23,7 @@ def test_exports_every_declared_symbol():
 
 def test_abi_version_and_launch_counter():
     L = capi.lib()
-    assert L.mx_abi_version() == 1
+    assert L.mx_abi_version() == 2   # 2: mx_model_ext gained the T5 fields (family, d_kv, rel_buckets, rel_max_distance)
     assert L.mx_launch_count() >= 0
 
 

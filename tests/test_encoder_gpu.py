@@ -22,8 +22,9 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 def arch_of(cfg: enc_oracle.EncoderConfig) -> Architecture:
     return Architecture(cfg.layers, cfg.hidden, cfg.heads, cfg.ffn, cfg.vocab, cfg.max_pos, cfg.type_vocab,
                         cfg.ln_eps, cfg.normalize, family=cfg.family, pos_offset=cfg.pos_offset, pad_id=cfg.pad_id,
-                        dense_out=cfg.dense_out, dense_act=cfg.dense_act, ffn_act=cfg.ffn_act, embed_dim=cfg.embed_dim,
-                        share_layers=cfg.share_layers)
+                        dense_out=cfg.dense_out, dense_act=cfg.dense_act, dense_bias=cfg.dense_bias, ffn_act=cfg.ffn_act,
+                        embed_dim=cfg.embed_dim, share_layers=cfg.share_layers, d_kv=cfg.d_kv, rel_buckets=cfg.rel_buckets,
+                        rel_max_distance=cfg.rel_max_distance)
 
 
 def row_cosine(a, b):
@@ -281,6 +282,41 @@ def test_other_stacks_of_the_enum_tensor_core_path(name):
         if not cfg.normalize:   # the scale matters when the model has no Normalize module
             assert np.abs(out - ref).max() <= (5e-2 if precision == "bf16" else 5e-3) * max(1.0, np.abs(ref).max())
         e.close()
+
+
+def test_sentence_t5_stack():
+    """SentenceT5Base (embedding.rs:32,52): T5 v1.1 encoder (pre-RMSNorm, unscaled attention + bucketed relative position
+    bias, gated-GELU feed-forward, no biases) + mean pool + Dense(no bias) + Normalize, against HF T5EncoderModel on
+    torch-CPU.  The tiny shape runs the f32 path (every kernel of the stack on CUDA cores); the model's true width runs the
+    tensor-core path (the seven GEMMs of a layer on tcgen05) with sequences long enough to reach the logarithmic buckets."""
+    import dataclasses
+    cfg = enc_oracle.TINY_T5
+    w = enc_oracle.make_weights(cfg, seed=71)
+    ids, lens = enc_oracle.make_inputs(cfg, 5, 60, seed=72, ragged=True, min_len=2)
+    ref = enc_oracle.hf_encode(cfg, w, ids, lens)
+    e = B200Encoder(arch_of(cfg), w, precision="f32", max_tokens=5 * 60)
+    out = e.encode_ids(ids, lens)
+    e.close()
+    print(f"tiny T5 f32: max abs diff {np.abs(out - ref).max():.2e}")
+    assert np.abs(out - ref).max() <= 1e-4 and (row_cosine(out, ref) >= 1 - 1e-6).all()
+    cfg = dataclasses.replace(enc_oracle.SENTENCE_T5_BASE, layers=2, vocab=4000)
+    w = enc_oracle.make_weights(cfg, seed=73)
+    ids, lens = enc_oracle.make_inputs(cfg, 4, 200, seed=74, ragged=True, min_len=150)
+    lens[0] = 200
+    ref = enc_oracle.hf_encode(cfg, w, ids, lens)
+    # bf16 sits at 1 - 3.5e-4 here (measured): the stack adds sub-layer outputs to an un-normalised stream, and with 8
+    # mantissa bits every one of those additions carries the GEMM output's rounding; f16's 11 bits meet the 1e-4 gate and
+    # are the hosts' default for this stack ("auto"), with the bf16 twin as the fallback should a checkpoint overflow f16
+    for precision, min_cos in (("f32", 1 - 1e-6), ("f16", 1 - 1e-4), ("bf16", 1 - 1e-3)):
+        e = B200Encoder(arch_of(cfg), w, precision=precision, max_tokens=4 * 200)
+        out = e.encode_ids(ids, lens)
+        e.close()
+        cos = row_cosine(out, ref)
+        print(f"sentence-t5 shape {precision}: min cosine {cos.min():.7f}, max abs diff {np.abs(out - ref).max():.2e}")
+        assert out.shape == (4, 768) and (cos >= min_cos).all(), (precision, cos.min())
+    auto = B200Encoder(arch_of(cfg), w, max_tokens=4 * 200)
+    assert auto.precision == "f16"
+    auto.close()
 
 
 def test_roberta_position_offset_limits_the_sequence_length():

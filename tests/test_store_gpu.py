@@ -192,6 +192,33 @@ def test_unnormalised_rows_duplicates_and_zero_rows(tmp_path):
     assert scores[0][top.index(34)] == 1.0 and scores[0][top.index(4000)] == 1.0
 
 
+@pytest.mark.parametrize("dtype", ["f32", "f16"])
+def test_exact_fold_on_rows_spanning_many_decades(tmp_path, dtype):
+    """The exact re-score folds the f32 products left to right in f64, the reference's order.  On ordinary rows every
+    partial sum is exactly representable and any order would give the same bits; on rows whose elements span 18 decades
+    the order of the additions decides the last bits.  Both kinds, mixed in one candidate list, must give the oracle's
+    bits."""
+    rng = np.random.default_rng(77)
+    n, d = 6000, 200
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    wide = rng.random(n) < 0.5
+    decades = (-4, 4) if dtype == "f16" else (-12, 6)          # f16 rows: stay inside the format's range
+    x[wide] *= (10.0 ** rng.uniform(*decades, size=(int(wide.sum()), d))).astype(np.float32)
+    x[5] = 0.0
+    x[6, 1:] = 0.0                                             # a single non-zero product
+    queries = rng.standard_normal((12, d)).astype(np.float32)
+    queries[:6] *= (10.0 ** rng.uniform(-8, 4, size=(6, d))).astype(np.float32)
+    queries[11] = x[6]
+    store = B200Store.new(tmp_path, dim=d, dtype=dtype)
+    store.add_matrix(x)
+    stored = x if dtype == "f32" else x.astype(np.float16).astype(np.float32)
+    for k in (1, 10, 40):
+        check_parity(store, stored, queries, k)                # batch: every query against the oracle, bits and all
+        check_parity(store, stored, queries[3:4], k)
+        check_parity(store, stored, queries[8:9], k)
+    store.close()
+
+
 def test_zero_query_returns_first_rows(tmp_path):
     corpus = unit_rows(500, 16, 1)
     store = B200Store.new(tmp_path, dim=16)
