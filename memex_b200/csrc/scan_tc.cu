@@ -692,8 +692,12 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
     // that scanning P of them twice is cheap; MX_SCAN_TC_SAMPLE=0 turns it off (A/B measurements)
     static const int sample_cap = getenv("MX_SCAN_TC_SAMPLE") ? atoi(getenv("MX_SCAN_TC_SAMPLE")) : 4;
     const uint32_t tiles_per_cta = ceil_div<uint32_t>(p.n_rows, kTileN) / std::max<uint32_t>(1u, p.n_lists);
+    // sampled tiles = min(4, tiles per CTA / 4): measured r2 (scripts/diag_scan_fixed.py, k = 10): 4 tiles beat 1 / 2 / 3 / 6 / 8
+    // on shards of 1.25 M rows and more (216 / 198 / 181 / 180 / 182 / 186 us at 1.25 M), and sampling 4 instead of 1-2 on
+    // smaller shards is worth 10-14 % (625 k rows: 123 -> 111 us, 312 k: 91 -> 79 us)
+    static const uint32_t sample_div = getenv("MX_SCAN_TC_SAMPLE_DIV") ? (uint32_t)std::max(1, atoi(getenv("MX_SCAN_TC_SAMPLE_DIV"))) : 4u;
     tp.sample_tiles = (grid.y == 1 && p.n_lists == (uint32_t)t->sm_count && sample_cap > 0)
-                          ? std::min<uint32_t>((uint32_t)sample_cap, tiles_per_cta / 16)
+                          ? std::min<uint32_t>((uint32_t)sample_cap, tiles_per_cta / sample_div)
                           : 0u;
     if (timer) timer->begin(st, 0);
     cudaError_t e = tc_scan_lcap(k) == 16 ? launch_tc<16>(tmC, tp, p.use_inv != 0, qm, grid, st)

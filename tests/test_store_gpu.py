@@ -442,9 +442,10 @@ def test_tcgen05_scan_duplicates_and_growth(tmp_path):
 
 
 @pytest.mark.parametrize("n,d,nq,k,metric", [
-    (400_000, 64, 64, 10, "cosine"),    # 21 tiles per CTA -> 1 sample tile
-    (700_000, 64, 16, 26, "cosine"),    # 37 tiles per CTA -> 2 sample tiles, L = 32 lists (tau0 = 16th of the second bests)
+    (400_000, 64, 64, 10, "cosine"),    # 21 tiles per CTA -> 4 sample tiles (min(4, tiles / 4))
+    (700_000, 64, 16, 26, "cosine"),    # 37 tiles per CTA -> 4 sample tiles, L = 32 lists (tau0 = 16th of the second bests)
     (1_300_001, 32, 64, 10, "dot"),     # 68 tiles per CTA -> 4 sample tiles, ragged last tile, dot metric
+    (120_000, 96, 32, 10, "cosine"),    # 6 tiles per CTA -> 1 sample tile (the smallest seeded shape)
 ])
 def test_tcgen05_scan_threshold_seeding(tmp_path, n, d, nq, k, metric):
     """shards large enough for the seeded scan (two-best sampling pass + grid barrier + tau0): full oracle parity with
