@@ -128,6 +128,19 @@ class ShardedStore:
         dist.barrier(group=self.group)   # every member is connected before anyone pushes
         return True
 
+    def _ensure_group(self, nq: int, k: int):
+        import torch
+        import torch.distributed as dist
+        if self._shard_group is not None:        # a larger batch than the group was sized for: make a new one
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            capi.lib().mx_shard_group_destroy(self._shard_group)
+            self._shard_group = None
+        if self._setup_group(nq, k):
+            self.exchange = "p2p"
+        else:
+            self._want_p2p = False
+
     # ---- ingest: rows already on this rank's device (f32 [n, dim]); ids follow the plan ----
     def add_local_device(self, rows_dev_ptr: int, n: int) -> int:
         first = C.c_uint64()
@@ -187,15 +200,7 @@ class ShardedStore:
         st = torch.cuda.current_stream(self.device).cuda_stream or 1
         metric = capi.METRIC_DOT if self.metric == "dot" else capi.METRIC_COSINE
         if self._want_p2p and (self._shard_group is None or nq > self._group_nq or k > self._group_k):
-            if self._shard_group is not None:        # a larger batch than the group was sized for: make a new one
-                torch.cuda.synchronize(self.device)
-                dist.barrier(group=self.group)
-                L.mx_shard_group_destroy(self._shard_group)
-                self._shard_group = None
-            if self._setup_group(nq, k):
-                self.exchange = "p2p"
-            else:
-                self._want_p2p = False
+            self._ensure_group(nq, k)
         if self._shard_group is not None:
             # scan + rerank, push to every peer, merge-with-wait: all below the C ABI (csrc/shard_group.cu)
             rc = L.mx_shard_group_search_device(self._shard_group, self.local.handle,
@@ -238,17 +243,31 @@ class ShardedStore:
             nq = queries.shape[0]
             if queries.ndim != 2 or queries.shape[1] != self.dim:
                 raise SearchError(f"query has dimension {queries.shape[-1]}, store has {self.dim}")
+        L = capi.lib()
+        if self.world == 1:
+            # one shard: the store's own host-buffer call (pinned staging, one H2D, one D2H, fallback only when flagged)
+            return self.local.search_matrix(queries, k)
+        if self._want_p2p and (self._shard_group is None or nq > self._group_nq or k > self._group_k):
+            self._ensure_group(nq, k)
+        if self._shard_group is not None:
+            # the whole step below the C ABI (csrc/shard_group.cu): rank 0's block is staged through pinned memory and pushed
+            # to the peers' exchange buffers, every rank scans / pushes / merges, ONE device-to-host copy of the answer
+            ids = np.zeros((nq, k), dtype=np.uint64)
+            scores = np.zeros((nq, k), dtype=np.float32)
+            counts = np.zeros(nq, dtype=np.uint32)
+            rc = L.mx_shard_group_search(self._shard_group, self.local.handle,
+                                         queries.ctypes.data if queries is not None else None, 0, nq, k,
+                                         ids.ctypes.data, scores.ctypes.data, counts.ctypes.data)
+            if rc != capi.OK:
+                _raise(rc, self._shard_group, SearchError)
+            return ids, scores, counts
         b = self._buffers(nq, k)
         if queries is not None:
             b["q_pin"].numpy()[...] = queries
             b["q"].copy_(b["q_pin"], non_blocking=True)
-        if self.world > 1 and self._shard_group is not None and nq <= self._group_nq and k <= self._group_k:
-            # rank 0's block goes to the peers through the exchange buffers (one push kernel, no collective call)
-            self.search_device(b["q"] if self.rank == 0 else None, k, nq=nq, query_root=0)
-        else:
-            if self.world > 1:
-                dist.broadcast(b["q"], src=0, group=self.group)
-            self.search_device(b["q"], k)                 # fills b["out"] (ids | scores | counts)
+        if self.world > 1:
+            dist.broadcast(b["q"], src=0, group=self.group)    # collective form of the exchange (MX_EXCHANGE=nccl)
+        self.search_device(b["q"], k)                     # fills b["out"] (ids | scores | counts)
         b["out_pin"].copy_(b["out"], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return (b["ids_pin"].numpy().astype(np.uint64), b["scores_pin"].numpy().copy(),
