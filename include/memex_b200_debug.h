@@ -27,6 +27,9 @@ const char *mx_debug_last_error(void);
 /* rerank_kernel phase timestamps (%globaltimer ns of CTA 0: start, loads issued, sorted, merged + certified, entries
  * ready, folded, written) of the last search on a store created under MX_RERANK_PROF=1; `store` is an mx_store *. */
 int32_t mx_debug_rerank_prof(void *store, uint64_t *out8);
+/* scan_tc_kernel phase timestamps of CTA 0 (start, queries prepared, sampled, barrier passed + tau0, sampled tiles scanned
+ * again, last tile done) of the last tcgen05 scan on a store created under MX_SCAN_TC_PROF=1 */
+int32_t mx_debug_scan_tc_prof(void *store, uint64_t *out8);
 
 #ifdef __cplusplus
 }

@@ -131,6 +131,7 @@ uint32_t tc_scan_lists(const TcScanState *t, uint64_t n_rows);
 uint32_t tc_scan_lcap(uint32_t k);
 const float *tc_scan_qerr(const TcScanState *t);    // valid after tc_scan_launch, [nq]
 const float *tc_scan_floor(const TcScanState *t);
+const unsigned long long *tc_scan_prof(const TcScanState *t);   // MX_SCAN_TC_PROF=1: [8] phase timestamps of CTA 0, else null
 cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacity, uint32_t k, KernelTimer *timer,
                            cudaStream_t st, const char **why);
 

@@ -95,6 +95,15 @@ __device__ __forceinline__ void atomic_max_float(float *addr, float v)
         atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
 }
 
+__device__ __forceinline__ void tc_prof_mark(unsigned long long *prof, int slot)
+{
+    if (prof && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        prof[slot] = t;
+    }
+}
+
 struct TcParams {
     const float *inv_norm;  // [>= n_tiles * 128] (cosine) or nullptr (dot)
     float *tau;             // [nq_pad] global lower bounds, -inf on entry
@@ -114,6 +123,7 @@ struct TcParams {
     float *qerr;            // [nq_pad] fp16 rounding radius of each prepared query (written by CTA x = 0)
     uint32_t *done;         // exit ticket: the LAST CTA out resets tau / sync / done for the next launch
     uint32_t plain_barrier; // host-side only: launch the seeded form without the cooperative attribute (exclusive SM partition)
+    unsigned long long *prof;   // test-only (MX_SCAN_TC_PROF=1): %globaltimer of CTA 0's epilogue thread 64 at phase boundaries, [8]
     uint32_t diag;          // TIMING DIAGNOSTIC ONLY (MX_SCAN_TC_DIAG, wrong results): bit 0 = skip the query preparation
 };
 
@@ -229,6 +239,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
     } else {
         // ================= epilogue: thread = query (TMEM lane), columns = corpus rows =================
         const uint32_t quarter = warp & 3;
+        tc_prof_mark(p.prof, 0);
         // ---- query preparation (was a kernel of its own): rows q0 .. q0 + QM of the f32 query block -> unit norm ->
         // fp16 -> the K-major SWIZZLE_128B layout the UMMA descriptor expects ([k-block][QM rows][64 halfs], 16-byte chunk
         // index ^= row & 7), zero rows beyond nq.  Scaling a query by a positive constant changes neither ranking, and keeps
@@ -297,6 +308,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
             __syncwarp();
             if (lane == 0) mbar_arrive(q_full);
         }
+        tc_prof_mark(p.prof, 1);
         const uint32_t t = QM == 128 ? quarter * 32 + lane : quarter * 16 + (lane & 15);   // query row of this thread
         const bool q_ok = (QM == 128 || lane < 16) && q0 + t < p.nq;
         float *ls = list_s + quarter * 32 + lane;    // one list column per thread (idle lanes own an unused one)
@@ -344,6 +356,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[as]);
                 if (local + 1 == n_sample) {
+                    tc_prof_mark(p.prof, 2);
                     // ---- publish, ONE grid-wide barrier (all CTAs are co-resident: cooperative launch), take tau0 ----
                     if (q_ok) p.samp[(size_t)blockIdx.x * p.nq_pad + q0 + t] = b2;
                     __threadfence();
@@ -378,9 +391,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
                         g_floor = top[L / 2 - 1];
                     }
                     if (q_ok && blockIdx.x == 0) p.floor_out[q0 + t] = g_floor;   // rerank's certificate needs every threshold
+                    tc_prof_mark(p.prof, 3);
                 }
                 continue;
             }
+            if (local == 2 * n_sample) tc_prof_mark(p.prof, 4);
             float g = q_ok ? fmaxf(ld_relaxed(tau), g_floor) : kPosInf;
             if (USE_INV) mbar_wait(&inv_full[slot], sphase);
             mbar_wait(&tmem_full[as], aphase);
@@ -458,6 +473,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
         }
+        tc_prof_mark(p.prof, 5);
         if (q_ok) {
             const size_t o = ((size_t)(q0 + t) * p.n_lists + blockIdx.x) * L;
 #pragma unroll
@@ -519,6 +535,7 @@ struct TcScanState {
     float *tau = nullptr;
     float *samp = nullptr;      // [sm_count][q_cap]
     uint32_t *sync = nullptr;   // [0] grid barrier arrivals, [32] exit tickets (separate 128-byte lines)
+    unsigned long long *prof = nullptr;   // MX_SCAN_TC_PROF=1: phase timestamps of CTA 0
     float *qerr = nullptr;      // [q_cap] fp16 rounding radius of each prepared query
     float *floor_out = nullptr; // [q_cap] tau0 of the last launch
     uint32_t q_cap = 0;  // rows
@@ -534,12 +551,14 @@ TcScanState *tc_scan_create(int sm_count, uint32_t ld, uint32_t dim)
     t->ld = ld;
     t->dim = dim;
     t->k_blocks = ceil_div<uint32_t>(dim, kBK);
+    if (getenv("MX_SCAN_TC_PROF") && cudaMalloc(&t->prof, 64) == cudaSuccess) cudaMemset(t->prof, 0, 64);
     return t;
 }
 
 void tc_scan_destroy(TcScanState *t)
 {
     if (!t) return;
+    cudaFree(t->prof);
     cudaFree(t->tau);
     cudaFree(t->samp);
     cudaFree(t->sync);
@@ -562,6 +581,7 @@ bool tc_scan_supports(const TcScanState *t, uint32_t k) { return t != nullptr &&
 uint32_t tc_scan_lcap(uint32_t k) { return k <= 10 ? 16u : 32u; }
 const float *tc_scan_qerr(const TcScanState *t) { return t->qerr; }
 const float *tc_scan_floor(const TcScanState *t) { return t->floor_out; }
+const unsigned long long *tc_scan_prof(const TcScanState *t) { return t ? t->prof : nullptr; }
 uint32_t tc_scan_lists(const TcScanState *t, uint64_t n_rows)
 {
     return (uint32_t)std::min<uint64_t>((uint64_t)t->sm_count, ceil_div<uint64_t>(n_rows, kTileN));
@@ -686,6 +706,7 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
     tp.done = t->sync + 32;
     static const uint32_t diag = getenv("MX_SCAN_TC_DIAG") ? (uint32_t)atoi(getenv("MX_SCAN_TC_DIAG")) : 0u;
     tp.diag = diag;
+    tp.prof = t->prof;
     tp.plain_barrier = t->sm_count < t->device_sms ? 1u : 0u;
     dim3 grid(p.n_lists, nq_pad / qm);
     // threshold seeding needs every CTA at the barrier: one query pass (grid.y == 1), a full grid, enough tiles per CTA

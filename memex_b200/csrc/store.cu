@@ -803,6 +803,14 @@ int32_t mx_exchange_push_device(const void *blob_dev, uint64_t blob_bytes, const
     return MX_OK;
 }
 
+int32_t mx_debug_scan_tc_prof(void *store, uint64_t *out8)
+{
+    mx_store *s = static_cast<mx_store *>(store);
+    if (!s || !out8 || !s->tc || !tc_scan_prof(s->tc)) return MX_ERR_INVALID;
+    cudaSetDevice(s->cfg.device);
+    return cudaMemcpy(out8, tc_scan_prof(s->tc), 64, cudaMemcpyDeviceToHost) == cudaSuccess ? MX_OK : MX_ERR_CONNECTION;
+}
+
 int32_t mx_debug_rerank_prof(void *store, uint64_t *out8)
 {
     mx_store *s = static_cast<mx_store *>(store);
