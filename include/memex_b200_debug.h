@@ -27,9 +27,14 @@ const char *mx_debug_last_error(void);
 /* rerank_kernel phase timestamps (%globaltimer ns of CTA 0: start, loads issued, sorted, merged + certified, entries
  * ready, folded, written) of the last search on a store created under MX_RERANK_PROF=1; `store` is an mx_store *. */
 int32_t mx_debug_rerank_prof(void *store, uint64_t *out8);
-/* scan_tc_kernel phase timestamps of CTA 0 (start, queries prepared, sampled, barrier passed + tau0, sampled tiles scanned
- * again, last tile done) of the last tcgen05 scan on a store created under MX_SCAN_TC_PROF=1 */
-int32_t mx_debug_scan_tc_prof(void *store, uint64_t *out8);
+/* scan_tc_kernel phase timestamps of CTA 0 ([0] start, [1] queries prepared, [2] sampled, [3] barrier passed + tau0, [4]
+ * sampled tiles scanned again, [5] last tile done, [6] barrier passed; [8 + 4 i ..] the i-th real tile, i < 2: loop top, tau
+ * loaded, accumulator ready, tile filtered) of the last tcgen05 scan on a store created under MX_SCAN_TC_PROF=1; 32 values */
+int32_t mx_debug_scan_tc_prof(void *store, uint64_t *out32);
+/* wall-clock phases (us, summed over `*calls` calls) of mx_store_search under MX_HOST_PROF=1: [0] finiteness check,
+ * [1] device + staging buffers, [2] copy into pinned memory, [3] H2D enqueue, [4] kernel launches, [5] D2H enqueue,
+ * [6] stream synchronise (= the device's work), [7] copy out; reset != 0 zeroes the counters */
+int32_t mx_debug_host_prof(double *out12, uint64_t *calls, int32_t reset);
 
 #ifdef __cplusplus
 }

@@ -282,7 +282,7 @@ cudaError_t launch_am(const void *qkv, const int32_t *lens, void *ctx, uint32_t 
     const size_t smem = (size_t)(kAmQ + 2 * s_pad) * (DH + 8) * 2;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = set_max_smem(kern, (int)smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(B * heads, ceil_div<uint32_t>(S, kAmQ));

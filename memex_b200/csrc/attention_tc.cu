@@ -466,7 +466,7 @@ cudaError_t launch_at(const void *qkv, const int32_t *lens, void *ctx, uint32_t 
             default: break;
         }
     }
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = set_max_smem(kern, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     CUtensorMap tm;
     if (!make_tmap_qkv(&tm, qkv, cu ? (uint64_t)n_rows : (uint64_t)B * S, H, DH, BF16)) return cudaErrorInvalidValue;

@@ -429,7 +429,7 @@ cudaError_t launch_at4(const void *qkv, const int32_t *lens, void *ctx, uint32_t
                        int sm_count, cudaStream_t st)
 {
     auto kern = attention_tc4_kernel<BF16>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = set_max_smem(kern, kSmemBytes);
     if (e != cudaSuccess) return e;
     CUtensorMap tm;
     if (!make_tmap_qkv4(&tm, qkv, (uint64_t)B * S, H, BF16)) return cudaErrorInvalidValue;

@@ -125,6 +125,35 @@ inline T ceil_div(T a, T b)
     return (a + b - 1) / b;
 }
 
+// Copies [rows, dim] f32 into `dst` (the pinned staging buffer) and returns the first row holding a non-finite value, or
+// -1.  One pass, exponent test on the bit patterns with an OR-accumulator per row so that the compiler vectorises it
+// (the scalar isfinite loop with its early exit took 10 us per 64 x 384 block -- as long as the two kernel launches).
+inline int64_t copy_checking_finite(float *dst, const float *src, size_t rows, size_t dim)
+{
+    for (size_t r = 0; r < rows; ++r) {
+        const float *s = src + r * dim;
+        float *d = dst + r * dim;
+        uint32_t bad = 0;
+        for (size_t i = 0; i < dim; ++i) {
+            uint32_t b;
+            __builtin_memcpy(&b, s + i, 4);
+            bad |= ((b & 0x7f800000u) == 0x7f800000u) ? 1u : 0u;
+            __builtin_memcpy(d + i, &b, 4);
+        }
+        if (bad) return (int64_t)r;
+    }
+    return -1;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of once per launch: the call takes
+// ~1 us of host time, which the latency of a small search (two launches) and a 32-launch forward pass both pay for.
+cudaError_t set_max_smem_impl(const void *func, int bytes);
+template <typename Kern>
+inline cudaError_t set_max_smem(Kern kern, int bytes)
+{
+    return set_max_smem_impl(reinterpret_cast<const void *>(kern), bytes);
+}
+
 // Programmatic dependent launch: a kernel launched with this attribute may be SCHEDULED while its predecessor in the
 // stream is still running (its CTAs start on SMs the predecessor has vacated, run their prologue -- barrier init, TMEM
 // allocation, descriptor prefetch -- and then block in pdl_wait() until the predecessor has completed and its writes are

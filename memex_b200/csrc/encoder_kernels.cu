@@ -322,7 +322,7 @@ static cudaError_t launch_att(const void *qkv, const int32_t *lens, void *ctx, u
     auto kern = attention_simt_kernel<ACT, DH>;
     const size_t smem = sizeof(float) * (kAttQ * DH + kAttKB * (DH + 1) + kAttKB * DH);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = set_max_smem(kern, (int)smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(B * heads, ceil_div<uint32_t>(S, kAttQ));

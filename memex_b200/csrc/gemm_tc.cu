@@ -637,7 +637,7 @@ static cudaError_t launch_cfg(const GemmParams &p, const CUtensorMap &tmA, const
 {
     using Cfg = GemmCfg<BN, RES, EPI == EPI_BIAS_RES_LN, CG, PAIR>;
     auto kern = gemm_tc_kernel<BN, EPI, FMT, RES, MC, SPLIT, CG, AMC, PAIR>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = set_max_smem(kern, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     const uint32_t tiles_m = ceil_div<uint32_t>(p.M, kBM), tiles_n = p.N / BN;
     LaunchAttrs attrs;

@@ -558,7 +558,7 @@ cudaError_t launch_rerank(const RerankParams &p, cudaStream_t st)
     {                                                                                              \
         auto kern = rerank_kernel<EE>;                                                             \
         if (smem > 48 * 1024) {                                                                    \
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            cudaError_t e = set_max_smem(kern, (int)smem); \
             if (e != cudaSuccess) return e;                                                        \
         }                                                                                          \
         LaunchAttrs attrs;                                                                         \
@@ -675,7 +675,7 @@ cudaError_t launch_merge(const MergeParams &p, cudaStream_t st)
     const size_t T = (size_t)p.n_shards * p.k;
     const size_t smem = ((T * 4 + 7) & ~(size_t)7) + T * 8;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = set_max_smem(merge_kernel, (int)smem);
         if (e != cudaSuccess) return e;
     }
     LaunchAttrs attrs;

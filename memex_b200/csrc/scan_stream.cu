@@ -256,7 +256,7 @@ static cudaError_t launch_one(const ScanParams &p, uint32_t n_ctas, cudaStream_t
     auto kern = scan_stream_kernel<T, LPR, CPL, R, NQ, E>;
     size_t smem = std::max((size_t)NQ * p.ldq * sizeof(float), (size_t)kScanWarps * 32 * E * 8);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = set_max_smem(kern, (int)smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(n_ctas, ceil_div<uint32_t>(p.nq, NQ));
@@ -305,7 +305,7 @@ static cudaError_t launch_exact_one(const ExactScanParams &p, uint32_t n_ctas, c
     auto kern = scan_exact_kernel<T, LPR, CPL, R, E>;
     size_t smem = std::max((size_t)p.scan.ldq * sizeof(float), (size_t)kScanWarps * 32 * E * 8);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = set_max_smem(kern, (int)smem);
         if (e != cudaSuccess) return e;
     }
     LaunchAttrs attrs;

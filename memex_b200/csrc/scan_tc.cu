@@ -22,10 +22,10 @@
 //
 // Threshold seeding.  An insertion is the slow path (the warp diverges and rescans an L-entry list), and a cold list
 // takes ~L ln(n / L) of them per thread: ~100 us per launch at L = 16 whatever the shard size, 330 us at L = 32
-// (measured, scripts/diag_scan_fixed.py).  So every CTA first scans its first P tiles keeping only the two best scores
-// per query (no list), publishes the second best, and after ONE grid-wide barrier (cooperative launch) every thread
-// takes tau0 = the (L/2)-th largest of the published values: L/2 CTAs hold two rows each scoring >= tau0, so tau0 is a
-// valid lower bound for the top L, and it sits at the ~0.07 % quantile instead of -inf.  The P tiles are then scanned
+// (measured, scripts/diag_scan_fixed.py).  So every CTA first scans its first P tiles keeping only the best score per
+// query (no list), folds it into the maximum of its group with one atomic, and after ONE grid-wide barrier (cooperative launch) every thread takes tau0 = the
+// smallest of L group maxima (CTA c in group c % L): L different CTAs hold a row scoring >= tau0, so tau0 is a valid
+// lower bound for the top L, and it sits at the ~0.07 % quantile instead of -inf.  The P tiles are then scanned
 // again, normally, RIGHT AFTER the barrier (they are still in L2: the sampling pass loads them with the normal eviction
 // priority, everything after it evict-first), so a CTA visits its rows in increasing order and the strict `>` admission
 // of the list keeps the LOWER row of two equal scores -- the (distance, id) order of the reference's result.
@@ -54,6 +54,7 @@ constexpr int kAccStages = 4;       // 4 x 128 TMEM columns
 constexpr int kInvSlots = 24;        // inverse-norm tiles in flight: the producer runs up to kMaxStages + kAccStages tiles ahead (k_blocks = 1)
 constexpr int kKBBytes = kTileN * kBK * 2;  // 16 KB: one k-block of a corpus tile (a k-block of Q is QM x 128 bytes)
 
+constexpr int kSampLd = 32;         // group maxima per query of the threshold seeding (>= the longest list)
 constexpr int kMaxStages = 12;      // the corpus ring takes whatever shared memory the query block and the lists leave
 
 template <int L>
@@ -111,8 +112,9 @@ struct TcParams {
     uint32_t *cand_r;
     uint32_t n_rows, nq, n_lists, k_blocks;
     uint32_t stages;        // depth of the corpus ring (<= kMaxStages)
-    // threshold seeding (see the kernel): the first `sample_tiles` tiles of every CTA are scanned for their two best
-    // scores only; samp [n_lists][nq_pad] collects the second best, sync is the grid-wide arrival counter
+    // threshold seeding (see the kernel): the first `sample_tiles` tiles of every CTA are scanned for their best score
+    // only; samp [nq_pad][kSampLd] collects the maxima of the CTA groups (-inf on entry, like tau), sync is the grid-wide
+    // arrival counter
     uint32_t sample_tiles, nq_pad;
     float *samp;
     uint32_t *sync;
@@ -123,9 +125,78 @@ struct TcParams {
     float *qerr;            // [nq_pad] fp16 rounding radius of each prepared query (written by CTA x = 0)
     uint32_t *done;         // exit ticket: the LAST CTA out resets tau / sync / done for the next launch
     uint32_t plain_barrier; // host-side only: launch the seeded form without the cooperative attribute (exclusive SM partition)
-    unsigned long long *prof;   // test-only (MX_SCAN_TC_PROF=1): %globaltimer of CTA 0's epilogue thread 64 at phase boundaries, [8]
-    uint32_t diag;          // TIMING DIAGNOSTIC ONLY (MX_SCAN_TC_DIAG, wrong results): bit 0 = skip the query preparation
+    unsigned long long *prof;   // test-only (MX_SCAN_TC_PROF=1): %globaltimer of CTA 0's epilogue thread 64 at phase boundaries, [32]
+    uint32_t diag;          // TIMING / POWER DIAGNOSTIC ONLY (MX_SCAN_TC_DIAG, wrong results): bit 0 = skip the query preparation,
+                            // bit 1 = no tcgen05.mma (barriers only), bit 2 = no epilogue work on the real tiles
 };
+
+// Query preparation by the four epilogue warps of a CTA (warp `quarter` takes rows quarter, quarter + 4, ...): R rows in
+// flight per warp (all their loads are issued before the first reduction), U 32-lane rounds of 16-byte chunk pairs per row.
+template <int QM, int R, int U>
+__device__ __forceinline__ void prepare_queries(const TcParams &p, unsigned char *sq, uint32_t q0, uint32_t quarter, uint32_t lane)
+{
+    constexpr uint32_t kQKB = QM * kBK * 2;
+    const uint32_t n_chunks = p.k_blocks * 8;            // 8-element (16-byte) chunks per prepared row
+    // every CTA of the grid reads the same block at the same moment: each starts at a different group of rows so that the
+    // requests spread over the L2 slices instead of queueing on the same lines
+    constexpr uint32_t kGroups = QM / (4 * R);
+    for (uint32_t it = 0; it < kGroups; ++it) {
+        const uint32_t rb = quarter + 4 * R * ((it + blockIdx.x) % kGroups);
+        float4 va[R][U], vb[R][U];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const uint32_t gq = q0 + rb + 4 * j;
+            const bool live = gq < p.nq;
+            const float *src = p.queries + (size_t)gq * p.ldq;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t c = lane + 32 * u;
+                va[j][u] = vb[j][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live && c < n_chunks && c * 8 < p.ldq) {     // ldq is a multiple of 8, zero beyond dim
+                    va[j][u] = __ldg(reinterpret_cast<const float4 *>(src + c * 8));
+                    vb[j][u] = __ldg(reinterpret_cast<const float4 *>(src + c * 8 + 4));
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const uint32_t r = rb + 4 * j;
+            float ss = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                ss = fmaf(va[j][u].x, va[j][u].x, fmaf(va[j][u].y, va[j][u].y, fmaf(va[j][u].z, va[j][u].z, fmaf(va[j][u].w, va[j][u].w, ss))));
+                ss = fmaf(vb[j][u].x, vb[j][u].x, fmaf(vb[j][u].y, vb[j][u].y, fmaf(vb[j][u].z, vb[j][u].z, fmaf(vb[j][u].w, vb[j][u].w, ss))));
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+            float ee = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t c = lane + 32 * u;
+                if (c >= n_chunks) continue;
+                const float f[8] = {va[j][u].x * inv, va[j][u].y * inv, va[j][u].z * inv, va[j][u].w * inv,
+                                    vb[j][u].x * inv, vb[j][u].y * inv, vb[j][u].z * inv, vb[j][u].w * inv};
+                uint32_t w[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const __half2 h2 = __floats2half2_rn(f[2 * x], f[2 * x + 1]);
+                    const float2 back = __half22float2(h2);
+                    const float e0 = back.x - f[2 * x], e1 = back.y - f[2 * x + 1];
+                    ee = fmaf(e0, e0, fmaf(e1, e1, ee));
+                    w[x] = *reinterpret_cast<const uint32_t *>(&h2);
+                }
+                const uint32_t kb = c >> 3, cj = c & 7;
+                *reinterpret_cast<uint4 *>(sq + kb * kQKB + r * 128 + ((cj ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            if (blockIdx.x == 0) {
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) ee += __shfl_xor_sync(0xffffffffu, ee, o);
+                if (lane == 0) p.qerr[q0 + r] = sqrtf(ee) * 1.001f;
+            }
+        }
+    }
+}
 
 // QM = 128: TMEM lane = query.  QM = 64 (cta_group::1, M = 64): accumulator row r sits in TMEM lane
 // 32 * (r / 16) + r % 16, i.e. the first 16 lanes of each 32-lane quarter -- epilogue lanes 16..31 idle.
@@ -223,10 +294,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
                     tc_fence_after();
                     const uint32_t sa = sq_addr + kb * kQKB;
                     const uint32_t sb = smem_u32(ring + stage * kKBBytes);
+                    if (!(p.diag & 2u)) {
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k)
-                        umma(tmem_base + as * kTileN, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc,
-                             (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kBK / 16; ++k)
+                            umma(tmem_base + as * kTileN, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc,
+                                 (kb | k) != 0 ? 1u : 0u);
+                    }
                     umma_commit(&empty[stage]);
                     if (++stage == n_stages) {
                         stage = 0;
@@ -245,69 +318,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
         // index ^= row & 7), zero rows beyond nq.  Scaling a query by a positive constant changes neither ranking, and keeps
         // every fp16 component in [-1, 1].  qerr[row] = |q16 - q / |q||_2: by Cauchy-Schwarz the tensor-core score of ANY
         // unit row differs from the exact cosine by at most this -- the rerank's certificate uses it as the radius.
-        {
-            const uint32_t n_chunks = p.k_blocks * 8;            // 8-element (16-byte) chunks per prepared row
-            constexpr int kRowsInFlight = 4;                     // the loads of 4 rows are issued before the first reduction
-            for (uint32_t rb = quarter; rb < (uint32_t)QM && !(p.diag & 1u); rb += 4 * kRowsInFlight) {
-                float4 va[kRowsInFlight][3], vb[kRowsInFlight][3];
-#pragma unroll
-                for (int j = 0; j < kRowsInFlight; ++j) {
-                    const uint32_t gq = q0 + rb + 4 * j;
-                    const bool live = rb + 4 * j < (uint32_t)QM && gq < p.nq;
-                    const float *src = p.queries + (size_t)gq * p.ldq;
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const uint32_t c = lane + 32 * u;
-                        va[j][u] = vb[j][u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (live && c < n_chunks && c * 8 < p.ldq) {     // ldq is a multiple of 8, zero beyond dim
-                            va[j][u] = __ldg(reinterpret_cast<const float4 *>(src + c * 8));
-                            vb[j][u] = __ldg(reinterpret_cast<const float4 *>(src + c * 8 + 4));
-                        }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < kRowsInFlight; ++j) {
-                    const uint32_t r = rb + 4 * j;
-                    if (r >= (uint32_t)QM) break;
-                    float ss = 0.f;
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        ss = fmaf(va[j][u].x, va[j][u].x, fmaf(va[j][u].y, va[j][u].y, fmaf(va[j][u].z, va[j][u].z, fmaf(va[j][u].w, va[j][u].w, ss))));
-                        ss = fmaf(vb[j][u].x, vb[j][u].x, fmaf(vb[j][u].y, vb[j][u].y, fmaf(vb[j][u].z, vb[j][u].z, fmaf(vb[j][u].w, vb[j][u].w, ss))));
-                    }
-#pragma unroll
-                    for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                    const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
-                    float ee = 0.f;
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const uint32_t c = lane + 32 * u;
-                        if (c >= n_chunks) continue;
-                        const float f[8] = {va[j][u].x * inv, va[j][u].y * inv, va[j][u].z * inv, va[j][u].w * inv,
-                                            vb[j][u].x * inv, vb[j][u].y * inv, vb[j][u].z * inv, vb[j][u].w * inv};
-                        uint32_t w[4];
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) {
-                            const __half2 h2 = __floats2half2_rn(f[2 * x], f[2 * x + 1]);
-                            const float2 back = __half22float2(h2);
-                            const float e0 = back.x - f[2 * x], e1 = back.y - f[2 * x + 1];
-                            ee = fmaf(e0, e0, fmaf(e1, e1, ee));
-                            w[x] = *reinterpret_cast<const uint32_t *>(&h2);
-                        }
-                        const uint32_t kb = c >> 3, cj = c & 7;
-                        *reinterpret_cast<uint4 *>(sq + kb * kQKB + r * 128 + ((cj ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                    if (blockIdx.x == 0) {
-#pragma unroll
-                        for (int o = 16; o >= 1; o >>= 1) ee += __shfl_xor_sync(0xffffffffu, ee, o);
-                        if (lane == 0) p.qerr[q0 + r] = sqrtf(ee) * 1.001f;
-                    }
-                }
-            }
-            fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(q_full);
+        if (!(p.diag & 1u)) {
+            // 8 rows in flight when a row is at most 64 chunks (dim <= 512: two loads of two float4 per lane and row), else 4
+            if (p.k_blocks <= 8)
+                prepare_queries<QM, 8, 2>(p, sq, q0, quarter, lane);
+            else
+                prepare_queries<QM, 4, 3>(p, sq, q0, quarter, lane);
         }
+        fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(q_full);
         tc_prof_mark(p.prof, 1);
         const uint32_t t = QM == 128 ? quarter * 32 + lane : quarter * 16 + (lane & 15);   // query row of this thread
         const bool q_ok = (QM == 128 || lane < 16) && q0 + t < p.nq;
@@ -325,13 +345,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
         const float kPosInf = __int_as_float(0x7f800000);
         float g_floor = kNegInf;          // tau0 from the sampling pass
         if (n_sample == 0 && q_ok && blockIdx.x == 0) p.floor_out[q0 + t] = kNegInf;
-        float b1 = kNegInf, b2 = kNegInf; // two best scores of the sampling pass
+        float b1 = kNegInf;               // best score of the sampling pass
         for (uint32_t local = 0; local < n_seq; ++local) {
             const uint32_t tile = tile_of(local);
             const uint32_t as = local % kAccStages, aphase = (local / kAccStages) & 1;
             const uint32_t slot = local % kInvSlots, sphase = (local / kInvSlots) & 1;
             if (local < n_sample) {
-                // ---- sampling pass: the two best scores of this query over the tile, nothing else ----
+                // ---- sampling pass: the best score of this query over the tile, nothing else ----
                 if (USE_INV) mbar_wait(&inv_full[slot], sphase);
                 mbar_wait(&tmem_full[as], aphase);
                 tc_fence_after();
@@ -348,7 +368,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
                         float s = __uint_as_float(v[j]);
                         if (USE_INV) s *= inv[c * 32 + j];
                         if (row0 + c * 32 + j >= p.n_rows) s = kNegInf;
-                        b2 = fmaxf(b2, fminf(b1, s));
                         b1 = fmaxf(b1, s);
                     }
                 }
@@ -358,7 +377,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
                 if (local + 1 == n_sample) {
                     tc_prof_mark(p.prof, 2);
                     // ---- publish, ONE grid-wide barrier (all CTAs are co-resident: cooperative launch), take tau0 ----
-                    if (q_ok) p.samp[(size_t)blockIdx.x * p.nq_pad + q0 + t] = b2;
+                    if (q_ok) atomic_max_float(p.samp + (size_t)(q0 + t) * kSampLd + blockIdx.x % L, b1);
                     __threadfence();
                     bar_sync(1, 128);
                     if (threadIdx.x == 64) {
@@ -373,22 +392,22 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
                         } while (seen < gridDim.x);
                     }
                     bar_sync(1, 128);
-                    if (q_ok && gridDim.x >= (uint32_t)(L / 2)) {
-                        float top[L / 2];
+                    tc_prof_mark(p.prof, 6);
+                    if (q_ok && gridDim.x >= (uint32_t)L) {
+                        // CTA c belongs to group c % L and has folded its best score into samp[query][group] with an atomic
+                        // max; tau0 = the smallest of the L group maxima: L different CTAs each hold a row scoring >= tau0.
+                        // One round trip of L / 4 float4 loads per thread.  (r2 history, scripts/scan_tc_prof.py: the exact
+                        // (L/2)-th largest of the CTAs' second-best scores, kept as a sorted list per thread over a
+                        // [query][CTA] matrix, bounded the same 0.07 % quantile (simulated) but took 8.9 us of dependent
+                        // compares; reading the matrix branch-free still took 5 us -- every SM reads all of it.)
+                        const float4 *sp = reinterpret_cast<const float4 *>(p.samp + (size_t)(q0 + t) * kSampLd);
+                        float4 vv[L / 4];
 #pragma unroll
-                        for (int e = 0; e < L / 2; ++e) top[e] = kNegInf;
-                        for (uint32_t c = 0; c < gridDim.x; ++c) {
-                            float v = __ldcg(p.samp + (size_t)c * p.nq_pad + q0 + t);
-                            if (v > top[L / 2 - 1]) {
+                        for (int j = 0; j < L / 4; ++j) vv[j] = __ldcg(sp + j);
+                        float lo = vv[0].x;
 #pragma unroll
-                                for (int e = 0; e < L / 2; ++e) {   // sorted insertion, best first
-                                    const float hi = fmaxf(top[e], v);
-                                    v = fminf(top[e], v);
-                                    top[e] = hi;
-                                }
-                            }
-                        }
-                        g_floor = top[L / 2 - 1];
+                        for (int j = 0; j < L / 4; ++j) lo = fminf(fminf(lo, vv[j].x), fminf(fminf(vv[j].y, vv[j].z), vv[j].w));
+                        g_floor = lo;
                     }
                     if (q_ok && blockIdx.x == 0) p.floor_out[q0 + t] = g_floor;   // rerank's certificate needs every threshold
                     tc_prof_mark(p.prof, 3);
@@ -396,10 +415,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
                 continue;
             }
             if (local == 2 * n_sample) tc_prof_mark(p.prof, 4);
+            const bool fine = p.prof != nullptr && local - n_sample < 2u;   // test-only: the first two real tiles in detail
+            if (fine) tc_prof_mark(p.prof, 8 + 4 * (local - n_sample));
             float g = q_ok ? fmaxf(ld_relaxed(tau), g_floor) : kPosInf;
+            if (fine) {
+                if (g == 12345.678f) p.prof[31] = 1;   // the mark below must wait for the load
+                tc_prof_mark(p.prof, 9 + 4 * (local - n_sample));
+            }
             if (USE_INV) mbar_wait(&inv_full[slot], sphase);
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
+            if (fine) tc_prof_mark(p.prof, 10 + 4 * (local - n_sample));
             // s >= g  <=>  s > gm
             const float gm = (g == kNegInf) ? kNegInf : nextafterf(g, kNegInf);
             float thr = fmaxf(lthr, gm);
@@ -407,7 +433,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
             const uint32_t row0 = tile * kTileN;
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * kTileN;
 #pragma unroll 1
-            for (int c = 0; c < kTileN / 32; ++c) {
+            for (int c = 0; c < kTileN / 32 && !(p.diag & 4u); ++c) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c * 32, v);
                 tmem_ld_wait();
@@ -445,7 +471,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
                             ls[lpos * kQM] = s;
                             lr[lpos * kQM] = row;
                             if (filled < L) ++filled;
-                            // new eviction entry: minimal score, ties -> maximal row (empty slots first)
+                            if (filled < L) {
+                                // the list still has empty slots: append, nothing to evict, the threshold does not move.
+                                // With a seeded threshold a shard of ~1 M rows leaves ~6 rows per (CTA, query) above it:
+                                // its lists never fill, and EVERY insertion used to pay for the 16-entry scan below
+                                lpos = filled;
+                                continue;
+                            }
+                            // new eviction entry: minimal score, ties -> maximal row
                             float ms = ls[0];
                             uint32_t mr = lr[0], mp = 0;
 #pragma unroll
@@ -460,7 +493,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
                             }
                             lpos = mp;
                             lthr = ms;
-                            if (filled == L && lthr > g) {
+                            if (lthr > g) {
                                 atomic_max_float(p.tau + q0 + t, lthr);
                                 g = lthr;
                             }
@@ -472,6 +505,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (fine) tc_prof_mark(p.prof, 11 + 4 * (local - n_sample));
         }
         tc_prof_mark(p.prof, 5);
         if (q_ok) {
@@ -501,6 +535,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket == gridDim.x * gridDim.y - 1) {
             for (uint32_t i = lane; i < p.nq_pad; i += 32) p.tau[i] = kNegInf;
+            if (n_sample > 0)
+                for (uint32_t i = lane; i < p.nq_pad * kSampLd; i += 32) p.samp[i] = kNegInf;
             if (lane == 0) {
                 *p.sync = 0;
                 __threadfence();
@@ -512,9 +548,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
 
 // cross-launch state of a freshly (re)allocated query capacity: tau = -inf, counters zero.  Every launch's last CTA puts
 // it back, so this runs once per allocation, not once per search.
-__global__ void tc_init_state_kernel(float *tau, float *floor_out, float *qerr, uint32_t n, uint32_t *sync, uint32_t *done)
+__global__ void tc_init_state_kernel(float *tau, float *floor_out, float *qerr, uint32_t n, uint32_t *sync, uint32_t *done,
+                                     float *samp)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        for (uint32_t c = 0; c < (uint32_t)kSampLd; ++c) samp[(size_t)i * kSampLd + c] = kNegInf;
     if (i < n) {
         tau[i] = kNegInf;
         floor_out[i] = kNegInf;
@@ -533,7 +572,7 @@ struct TcScanState {
     int device_sms = 0;         // SMs of the whole device (a smaller sm_count = an SM budget, mx_store_set_sm_limit)
     uint32_t ld, dim, k_blocks;
     float *tau = nullptr;
-    float *samp = nullptr;      // [sm_count][q_cap]
+    float *samp = nullptr;      // [q_cap][kSampLd] group maxima of the threshold seeding
     uint32_t *sync = nullptr;   // [0] grid barrier arrivals, [32] exit tickets (separate 128-byte lines)
     unsigned long long *prof = nullptr;   // MX_SCAN_TC_PROF=1: phase timestamps of CTA 0
     float *qerr = nullptr;      // [q_cap] fp16 rounding radius of each prepared query
@@ -551,7 +590,7 @@ TcScanState *tc_scan_create(int sm_count, uint32_t ld, uint32_t dim)
     t->ld = ld;
     t->dim = dim;
     t->k_blocks = ceil_div<uint32_t>(dim, kBK);
-    if (getenv("MX_SCAN_TC_PROF") && cudaMalloc(&t->prof, 64) == cudaSuccess) cudaMemset(t->prof, 0, 64);
+    if (getenv("MX_SCAN_TC_PROF") && cudaMalloc(&t->prof, 256) == cudaSuccess) cudaMemset(t->prof, 0, 256);
     return t;
 }
 
@@ -572,7 +611,7 @@ void tc_scan_set_sms(TcScanState *t, int sm_count)
 {
     if (t && sm_count > 0 && sm_count != t->sm_count) {
         t->sm_count = sm_count;
-        t->q_cap = 0;   // samp is [sm_count][q_cap]: re-made (and the cross-launch state re-initialised) on the next launch
+        t->q_cap = 0;   // the cross-launch state is re-made (and re-initialised) on the next launch
     }
 }
 
@@ -597,7 +636,7 @@ static cudaError_t launch_tc_one(const CUtensorMap &tmC, TcParams tp, dim3 grid,
     tp.stages = (uint32_t)n_stages;
     const int smem = TcCfg<L>::smem_bytes((int)tp.k_blocks, QM, n_stages);
     auto kern = scan_tc_kernel<L, USE_INV, QM>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = set_max_smem(kern, smem);
     if (e != cudaSuccess) return e;
     // A cooperative launch does not overlap with kernels of other streams (measured r2, config 5: scan and forward pass ran
     // in lock-step, 5.8 ms per pair against 1.8 + 2.6 ms alone, with or without an SM partition).  When the store has been
@@ -666,7 +705,7 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
         t->floor_out = nullptr;
         t->q_cap = 0;
         cudaError_t e = cudaMalloc(&t->tau, (size_t)nq_pad * sizeof(float));
-        if (e == cudaSuccess) e = cudaMalloc(&t->samp, (size_t)t->sm_count * nq_pad * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&t->samp, (size_t)kSampLd * nq_pad * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&t->sync, 256);
         if (e == cudaSuccess) e = cudaMalloc(&t->qerr, (size_t)nq_pad * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&t->floor_out, (size_t)nq_pad * sizeof(float));
@@ -674,7 +713,8 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
             if (why) *why = "query staging allocation failed";
             return e;
         }
-        tc_init_state_kernel<<<ceil_div<uint32_t>(nq_pad, 128), 128, 0, st>>>(t->tau, t->floor_out, t->qerr, nq_pad, t->sync, t->sync + 32);
+        tc_init_state_kernel<<<ceil_div<uint32_t>(nq_pad, 128), 128, 0, st>>>(t->tau, t->floor_out, t->qerr, nq_pad, t->sync, t->sync + 32,
+                                                                              t->samp);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -704,7 +744,7 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
     tp.dim = t->dim;
     tp.qerr = t->qerr;
     tp.done = t->sync + 32;
-    static const uint32_t diag = getenv("MX_SCAN_TC_DIAG") ? (uint32_t)atoi(getenv("MX_SCAN_TC_DIAG")) : 0u;
+    const uint32_t diag = getenv("MX_SCAN_TC_DIAG") ? (uint32_t)atoi(getenv("MX_SCAN_TC_DIAG")) : 0u;   // read per launch: scripts flip it
     tp.diag = diag;
     tp.prof = t->prof;
     tp.plain_barrier = t->sm_count < t->device_sms ? 1u : 0u;

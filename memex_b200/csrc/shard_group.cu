@@ -310,17 +310,16 @@ int32_t mx_shard_group_search(mx_shard_group *g, mx_store *s, const float *queri
     }
     char *hp = static_cast<char *>(g->pinned), *dp = static_cast<char *>(g->dev_io);
     if (have_q) {
-        for (size_t i = 0; i < (size_t)nq * g->dim; ++i)
-            if (!std::isfinite(queries[i])) return fail(g, MX_ERR_SEARCH, "non-finite value in query %zu", i / g->dim);
-        memcpy(hp, queries, qb);
+        const int64_t bad_row = copy_checking_finite(reinterpret_cast<float *>(hp), queries, nq, g->dim);
+        if (bad_row >= 0) return fail(g, MX_ERR_SEARCH, "non-finite value in query %lld", (long long)bad_row);
         MX_CUDA(g, MX_ERR_SEARCH, cudaMemcpyAsync(dp, hp, qb, cudaMemcpyHostToDevice, g->stream));
     }
+    // the merge kernel stores the answer straight into the pinned host buffer (posted PCIe writes, never read back by the
+    // device): no device-to-host copy operation at the end of the step
     rc = mx_shard_group_search_device(g, s, have_q ? reinterpret_cast<const float *>(dp) : nullptr, query_root, nq, k,
-                                      reinterpret_cast<uint64_t *>(dp + off_i), reinterpret_cast<float *>(dp + off_s),
-                                      reinterpret_cast<uint32_t *>(dp + off_c), g->stream);
+                                      reinterpret_cast<uint64_t *>(hp + off_i), reinterpret_cast<float *>(hp + off_s),
+                                      reinterpret_cast<uint32_t *>(hp + off_c), g->stream);
     if (rc != MX_OK) return rc;
-    // ids | scores | counts are contiguous: ONE device-to-host copy
-    MX_CUDA(g, MX_ERR_SEARCH, cudaMemcpyAsync(hp + off_i, dp + off_i, total - off_i, cudaMemcpyDeviceToHost, g->stream));
     MX_CUDA(g, MX_ERR_SEARCH, cudaStreamSynchronize(g->stream));
     memcpy(ids_out, hp + off_i, ib);
     memcpy(scores_out, hp + off_s, sb);
@@ -342,8 +341,15 @@ int32_t mx_shard_group_search_local(mx_shard_group *const *groups, mx_store *con
     if (!queries || !ids_out || !scores_out || !counts_out) return fail(g0, MX_ERR_INVALID, "null buffer");
     if (nq == 0) return MX_OK;
     if (nq > g0->max_nq || k == 0 || k > g0->max_k) return fail(g0, MX_ERR_INVALID, "batch of %u x top-%u exceeds the group's %u x %u", nq, k, g0->max_nq, g0->max_k);
-    for (size_t i = 0; i < (size_t)nq * g0->dim; ++i)
-        if (!std::isfinite(queries[i])) return fail(g0, MX_ERR_SEARCH, "non-finite value in query %zu", i / g0->dim);
+    for (size_t r = 0; r < nq; ++r) {
+        uint32_t bad = 0;
+        for (size_t i = 0; i < g0->dim; ++i) {
+            uint32_t b;
+            memcpy(&b, queries + r * g0->dim + i, 4);
+            bad |= ((b & 0x7f800000u) == 0x7f800000u) ? 1u : 0u;
+        }
+        if (bad) return fail(g0, MX_ERR_SEARCH, "non-finite value in query %zu", r);
+    }
     const size_t qb = (size_t)nq * g0->dim * sizeof(float);
     const size_t ib = (size_t)nq * k * sizeof(uint64_t), sb = (size_t)nq * k * sizeof(float), cb = (size_t)nq * 4;
     const size_t off_i = (qb + 255) & ~(size_t)255, off_s = off_i + ib, off_c = off_s + sb, total = off_c + cb;

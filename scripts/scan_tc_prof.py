@@ -27,17 +27,24 @@ for rows in (1_250_000, 5_000_000):
         st.search_device(q, 10)
     torch.cuda.synchronize()
     acc = np.zeros(5)
+    fine = np.zeros(10)
     reps = 20
     for _ in range(reps):
         st.search_device(q, 10)
         torch.cuda.synchronize()
-        out = (C.c_uint64 * 8)()
+        out = (C.c_uint64 * 32)()
         assert L.mx_debug_scan_tc_prof(st.local.handle, out) == 0
         t = np.array(list(out)[:6], dtype=np.float64)
         acc += np.diff(t)
+        f = np.array([out[2], out[6], out[3]] + list(out)[8:16], dtype=np.float64)
+        fine += np.diff(f)
     tiles = (rows + 127) // 128 / 148
     print(f"{rows} rows ({tiles:.0f} tiles per CTA, ideal {rows * 772 / 6552.3e3:.1f} us at the copy peak): CTA 0 phases (us, mean of {reps})")
     for nm, v in zip(names, acc / reps / 1e3):
         print(f"   {nm:30s} {v:8.2f}")
     print(f"   {'total first mark -> last tile':30s} {acc.sum() / reps / 1e3:8.2f}")
+    fnames = ["sampled -> barrier passed", "tau0 from the samples", "(to the first real tile)", "tile A: tau load", "tile A: accumulator wait",
+              "tile A: filter 128 columns", "(loop)", "tile B: tau load", "tile B: accumulator wait", "tile B: filter 128 columns"]
+    for nm, v in zip(fnames, fine / reps / 1e3):
+        print(f"      {nm:30s} {v:8.2f}")
     st.close()

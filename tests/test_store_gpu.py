@@ -268,6 +268,14 @@ def test_empty_store_and_bad_arguments(tmp_path):
     with pytest.raises(VectorStoreError) as ei:
         store.search_matrix(qn, 1)
     assert ei.value.variant == "SearchError"
+    # the vectorised finiteness check names the FIRST bad query of a batch (NaN, +-inf, any position) and leaves the
+    # store usable
+    qb = np.ones((5, 8), np.float32); qb[3, 7] = -np.inf; qb[4, 0] = np.nan
+    with pytest.raises(VectorStoreError) as ei:
+        store.search_matrix(qb, 1)
+    assert ei.value.variant == "SearchError" and "query 3" in str(ei.value)
+    ids, _, counts = store.search_matrix(np.ones((5, 8), np.float32), 1)
+    assert (counts == 1).all() and (ids[:, 0] == 1).all()
 
 
 def test_sharded_ids_and_device_merge(tmp_path):
