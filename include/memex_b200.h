@@ -110,6 +110,15 @@ uint32_t mx_sm_partition_sms(mx_sm_partition *p, uint32_t which);
  * scores are bit-identical to DistCosine + local.rs:86 evaluated on the stored rows. */
 int32_t mx_store_search(mx_store *s, const float *queries, uint32_t nq, uint32_t k,
                         uint64_t *ids_out, float *scores_out, uint32_t *counts_out);
+/* The same call split in two, so that TWO searches may be in flight on a store: submit stages the queries, enqueues the
+ * copy and the kernels on the store's stream and returns a ticket at once; collect waits for that search and copies its
+ * answer out.  While the device works on search i the host prepares search i + 1 -- a server with several requests
+ * outstanding (memex's handlers are async, lib/api/src/endpoints/collections/handlers.rs:61-81) keeps the GPU busy instead
+ * of alternating with it.  Tickets are collected in the order they were issued; a third submit before a collect is
+ * MX_ERR_INVALID.  Same results, bit for bit, as mx_store_search.  Not thread-safe (as every other call on a handle): the
+ * host's VectorStorage mutex (storage/mod.rs:68) covers each half. */
+int32_t mx_store_search_submit(mx_store *s, const float *queries, uint32_t nq, uint32_t k, uint64_t *ticket_out);
+int32_t mx_store_search_collect(mx_store *s, uint64_t ticket, uint64_t *ids_out, float *scores_out, uint32_t *counts_out);
 /* same with DEVICE buffers, asynchronous on `cuda_stream` (a cudaStream_t; NULL = the store's
  * own stream).  dists_out (may be NULL) receives the raw sort keys (cosine distance, or -dot)
  * that mx_merge_topk_device consumes. */
@@ -185,6 +194,12 @@ int32_t mx_shard_group_search_device(mx_shard_group *g, mx_store *s, const float
 /* HOST buffers: H2D of the queries (where this member has them), the search, ONE D2H of the answer */
 int32_t mx_shard_group_search(mx_shard_group *g, mx_store *s, const float *queries, int32_t query_root, uint32_t nq,
                               uint32_t k, uint64_t *ids_out, float *scores_out, uint32_t *counts_out);
+/* the host-buffer call split in two (see mx_store_search_submit): two searches in flight per member, every member submits
+ * and collects in the same order */
+int32_t mx_shard_group_search_submit(mx_shard_group *g, mx_store *s, const float *queries, int32_t query_root, uint32_t nq,
+                                     uint32_t k, uint64_t *ticket_out);
+int32_t mx_shard_group_search_collect(mx_shard_group *g, uint64_t ticket, uint64_t *ids_out, float *scores_out,
+                                      uint32_t *counts_out);
 /* single-process form: `world` members / stores in rank order; HOST buffers; the answer is member 0's */
 int32_t mx_shard_group_search_local(mx_shard_group *const *groups, mx_store *const *stores, uint32_t world,
                                     const float *queries, uint32_t nq, uint32_t k, uint64_t *ids_out,

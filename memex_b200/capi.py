@@ -75,12 +75,19 @@ def lib() -> C.CDLL:
     path = _build.LIB
     if not os.path.exists(path):
         _build.build()
+    # measurement aid: MX_B200_LIB=<another build of the library> (same-box A/B of two builds, scripts/ab_builds.sh);
+    # symbols that build lacks are skipped, every other use loads the in-tree build and nothing else
+    override = os.environ.get("MX_B200_LIB")
+    if override:
+        path = override
     L = C.CDLL(path)
     vp, f32p, u64p, u32p, i32p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64), \
         C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
     f64p = C.POINTER(C.c_double)
 
     def sig(name, res, *args):
+        if override and not hasattr(L, name):
+            return
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = list(args)
@@ -97,6 +104,8 @@ def lib() -> C.CDLL:
     sig("mx_sm_partition_stream", vp, vp, C.c_uint32)
     sig("mx_sm_partition_sms", C.c_uint32, vp, C.c_uint32)
     sig("mx_store_search", C.c_int32, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp)
+    sig("mx_store_search_submit", C.c_int32, vp, vp, C.c_uint32, C.c_uint32, u64p)
+    sig("mx_store_search_collect", C.c_int32, vp, C.c_uint64, vp, vp, vp)
     sig("mx_store_search_device", C.c_int32, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp)
     sig("mx_merge_topk_device", C.c_int32, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32,
         C.c_uint32, vp, vp, vp, C.c_int32, vp)
@@ -115,6 +124,8 @@ def lib() -> C.CDLL:
     sig("mx_shard_group_connect_local", C.c_int32, C.POINTER(vp), C.c_uint32)
     sig("mx_shard_group_search_device", C.c_int32, vp, vp, vp, C.c_int32, C.c_uint32, C.c_uint32, vp, vp, vp, vp)
     sig("mx_shard_group_search", C.c_int32, vp, vp, vp, C.c_int32, C.c_uint32, C.c_uint32, vp, vp, vp)
+    sig("mx_shard_group_search_submit", C.c_int32, vp, vp, vp, C.c_int32, C.c_uint32, C.c_uint32, u64p)
+    sig("mx_shard_group_search_collect", C.c_int32, vp, C.c_uint64, vp, vp, vp)
     sig("mx_shard_group_search_local", C.c_int32, C.POINTER(vp), C.POINTER(vp), C.c_uint32, vp, C.c_uint32, C.c_uint32, vp, vp, vp)
     sig("mx_shard_group_info", C.c_int32, vp, u32p, u32p, u32p, i32p)
     sig("mx_store_len", C.c_int32, vp, u64p)

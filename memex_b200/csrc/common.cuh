@@ -125,6 +125,61 @@ inline T ceil_div(T a, T b)
     return (a + b - 1) / b;
 }
 
+// One in-flight host-buffer search of the submit / collect pair (two per handle): its own pinned block {queries | ids |
+// scores | counts} (the kernels store the answer straight into it), its own device copy of the queries, and the event the
+// collect call waits for.
+struct IoSlot {
+    void *pinned = nullptr;
+    void *dev = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    uint64_t ticket = 0;
+    uint32_t nq = 0, k = 0;
+    size_t off_i = 0, off_s = 0, off_c = 0;
+    bool busy = false, empty = false;
+
+    cudaError_t reserve(size_t bytes)
+    {
+        cudaError_t e = cudaSuccess;
+        if (!done && (e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if (bytes <= cap) return cudaSuccess;
+        if (pinned) cudaFreeHost(pinned);
+        cudaFree(dev);
+        pinned = dev = nullptr;
+        cap = 0;
+        if ((e = cudaMallocHost(&pinned, bytes)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&dev, bytes)) != cudaSuccess) return e;
+        cap = bytes;
+        return cudaSuccess;
+    }
+    void layout(size_t qb, uint32_t nq_, uint32_t k_)
+    {
+        nq = nq_;
+        k = k_;
+        off_i = (qb + 255) & ~(size_t)255;
+        off_s = off_i + (((size_t)nq * k * sizeof(uint64_t) + 255) & ~(size_t)255);
+        off_c = off_s + (((size_t)nq * k * sizeof(float) + 255) & ~(size_t)255);
+    }
+    size_t total() const { return off_c + (((size_t)nq * 4 + 255) & ~(size_t)255); }
+    void copy_out(uint64_t *ids_out, float *scores_out, uint32_t *counts_out) const
+    {
+        const char *hp = static_cast<const char *>(pinned);
+        __builtin_memcpy(ids_out, hp + off_i, (size_t)nq * k * sizeof(uint64_t));
+        __builtin_memcpy(scores_out, hp + off_s, (size_t)nq * k * sizeof(float));
+        __builtin_memcpy(counts_out, hp + off_c, (size_t)nq * sizeof(uint32_t));
+    }
+    void release()
+    {
+        if (pinned) cudaFreeHost(pinned);
+        cudaFree(dev);
+        if (done) cudaEventDestroy(done);
+        pinned = dev = nullptr;
+        done = nullptr;
+        cap = 0;
+        busy = false;
+    }
+};
+
 // Copies [rows, dim] f32 into `dst` (the pinned staging buffer) and returns the first row holding a non-finite value, or
 // -1.  One pass, exponent test on the bit patterns with an OR-accumulator per row so that the compiler vectorises it
 // (the scalar isfinite loop with its early exit took 10 us per 64 x 384 block -- as long as the two kernel launches).

@@ -127,7 +127,7 @@ struct TcParams {
     uint32_t plain_barrier; // host-side only: launch the seeded form without the cooperative attribute (exclusive SM partition)
     unsigned long long *prof;   // test-only (MX_SCAN_TC_PROF=1): %globaltimer of CTA 0's epilogue thread 64 at phase boundaries, [32]
     uint32_t diag;          // TIMING / POWER DIAGNOSTIC ONLY (MX_SCAN_TC_DIAG, wrong results): bit 0 = skip the query preparation,
-                            // bit 1 = no tcgen05.mma (barriers only), bit 2 = no epilogue work on the real tiles
+                            // and, in a -DMX_TC_DIAG build only: bit 1 = no tcgen05.mma (barriers only), bit 2 = no epilogue work
 };
 
 // Query preparation by the four epilogue warps of a CTA (warp `quarter` takes rows quarter, quarter + 4, ...): R rows in
@@ -253,6 +253,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();   // launched as a programmatic dependent (plain-barrier form): the queries are the previous kernel's output
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -285,6 +286,15 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
             tc_fence_after();
             const uint32_t sq_addr = smem_u32(sq);
             uint32_t stage = 0, phase = 0;
+            // diagnostic switches 2 and 4 exist only in a -DMX_TC_DIAG build (scripts/power_probe.py): testing the kernel
+            // parameter here put a constant-bank load + branch between the barrier wait and the first MMA of every k-block,
+            // +6 % on the main loop of a 1.25 M-row shard (measured on one box with scripts/ab_builds.sh), and hoisting
+            // the test does not help -- the compiler rematerialises it inside the loop
+#ifdef MX_TC_DIAG
+            const bool diag_no_mma = (p.diag & 2u) != 0;
+#else
+            constexpr bool diag_no_mma = false;
+#endif
             for (uint32_t local = 0; local < n_seq; ++local) {
                 const uint32_t as = local % kAccStages, aphase = (local / kAccStages) & 1;
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -294,7 +304,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
                     tc_fence_after();
                     const uint32_t sa = sq_addr + kb * kQKB;
                     const uint32_t sb = smem_u32(ring + stage * kKBBytes);
-                    if (!(p.diag & 2u)) {
+                    if (!diag_no_mma) {
 #pragma unroll
                         for (int k = 0; k < kBK / 16; ++k)
                             umma(tmem_base + as * kTileN, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc,
@@ -320,9 +330,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
         // unit row differs from the exact cosine by at most this -- the rerank's certificate uses it as the radius.
         if (!(p.diag & 1u)) {
             // 8 rows in flight when a row is at most 64 chunks (dim <= 512: two loads of two float4 per lane and row), else 4
+#ifndef MX_TC_PREP4
             if (p.k_blocks <= 8)
                 prepare_queries<QM, 8, 2>(p, sq, q0, quarter, lane);
             else
+#endif
                 prepare_queries<QM, 4, 3>(p, sq, q0, quarter, lane);
         }
         fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
@@ -346,6 +358,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
         float g_floor = kNegInf;          // tau0 from the sampling pass
         if (n_sample == 0 && q_ok && blockIdx.x == 0) p.floor_out[q0 + t] = kNegInf;
         float b1 = kNegInf;               // best score of the sampling pass
+#ifdef MX_TC_DIAG
+        const int n_chunks_real = (p.diag & 4u) ? 0 : kTileN / 32;   // diagnostic switch (see the MMA issuer)
+#else
+        constexpr int n_chunks_real = kTileN / 32;
+#endif
         for (uint32_t local = 0; local < n_seq; ++local) {
             const uint32_t tile = tile_of(local);
             const uint32_t as = local % kAccStages, aphase = (local / kAccStages) & 1;
@@ -415,7 +432,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
                 continue;
             }
             if (local == 2 * n_sample) tc_prof_mark(p.prof, 4);
-            const bool fine = p.prof != nullptr && local - n_sample < 2u;   // test-only: the first two real tiles in detail
+#ifdef MX_TC_DIAG
+            const bool fine = p.prof != nullptr && local - n_sample < 2u;   // diagnostic build: the first two real tiles in detail
+#else
+            constexpr bool fine = false;
+#endif
             if (fine) tc_prof_mark(p.prof, 8 + 4 * (local - n_sample));
             float g = q_ok ? fmaxf(ld_relaxed(tau), g_floor) : kPosInf;
             if (fine) {
@@ -433,7 +454,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
             const uint32_t row0 = tile * kTileN;
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * kTileN;
 #pragma unroll 1
-            for (int c = 0; c < kTileN / 32 && !(p.diag & 4u); ++c) {
+            for (int c = 0; c < n_chunks_real; ++c) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c * 32, v);
                 tmem_ld_wait();
@@ -471,6 +492,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
                             ls[lpos * kQM] = s;
                             lr[lpos * kQM] = row;
                             if (filled < L) ++filled;
+#ifndef MX_TC_NO_APPEND
                             if (filled < L) {
                                 // the list still has empty slots: append, nothing to evict, the threshold does not move.
                                 // With a seeded threshold a shard of ~1 M rows leaves ~6 rows per (CTA, query) above it:
@@ -478,6 +500,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
                                 lpos = filled;
                                 continue;
                             }
+#endif
                             // new eviction entry: minimal score, ties -> maximal row
                             float ms = ls[0];
                             uint32_t mr = lr[0], mp = 0;
@@ -508,6 +531,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmC, TcParams p)
             if (fine) tc_prof_mark(p.prof, 11 + 4 * (local - n_sample));
         }
         tc_prof_mark(p.prof, 5);
+        // the rerank is launched as a programmatic dependent: its CTAs may be scheduled (and run their prologue) as soon as
+        // every CTA of this grid is past its last tile; its pdl_wait() still waits for this grid to complete
+        if (threadIdx.x == 64) pdl_trigger();
         if (q_ok) {
             const size_t o = ((size_t)(q0 + t) * p.n_lists + blockIdx.x) * L;
 #pragma unroll
@@ -644,6 +670,13 @@ static cudaError_t launch_tc_one(const CUtensorMap &tmC, TcParams tp, dim3 grid,
     // resident there), co-residency holds by construction and the barrier runs under a plain launch; its bounded spin
     // still turns a violated assumption into a launch failure rather than a hang.
     if (tp.sample_tiles > 0 && tp.plain_barrier) {
+        if (tp.plain_barrier == 2) {   // measurement aid (MX_SCAN_TC_PLAIN=2): plain launch as a programmatic dependent
+            LaunchAttrs attrs;
+            attrs.pdl();
+            e = launch_ex(kern, grid, dim3(kTcThreads), (size_t)smem, st, attrs, tmC, tp);
+            count_launch();
+            return e != cudaSuccess ? e : cudaGetLastError();
+        }
         kern<<<grid, kTcThreads, smem, st>>>(tmC, tp);
         count_launch();
         return cudaGetLastError();
@@ -748,10 +781,11 @@ cudaError_t tc_scan_launch(TcScanState *t, const ScanParams &p, uint64_t capacit
     tp.diag = diag;
     tp.prof = t->prof;
     tp.plain_barrier = t->sm_count < t->device_sms ? 1u : 0u;
+    if (const char *pl = getenv("MX_SCAN_TC_PLAIN")) tp.plain_barrier = (uint32_t)atoi(pl);   // measurement aid, read per launch
     dim3 grid(p.n_lists, nq_pad / qm);
     // threshold seeding needs every CTA at the barrier: one query pass (grid.y == 1), a full grid, enough tiles per CTA
     // that scanning P of them twice is cheap; MX_SCAN_TC_SAMPLE=0 turns it off (A/B measurements)
-    static const int sample_cap = getenv("MX_SCAN_TC_SAMPLE") ? atoi(getenv("MX_SCAN_TC_SAMPLE")) : 4;
+    const int sample_cap = getenv("MX_SCAN_TC_SAMPLE") ? atoi(getenv("MX_SCAN_TC_SAMPLE")) : 4;   // read per launch: sweeps flip it
     const uint32_t tiles_per_cta = ceil_div<uint32_t>(p.n_rows, kTileN) / std::max<uint32_t>(1u, p.n_lists);
     // sampled tiles = min(4, tiles per CTA / 4): measured r2 (scripts/diag_scan_fixed.py, k = 10): 4 tiles beat 1 / 2 / 3 / 6 / 8
     // on shards of 1.25 M rows and more (216 / 198 / 181 / 180 / 182 / 186 us at 1.25 M), and sampling 4 instead of 1-2 on

@@ -63,6 +63,8 @@ struct mx_shard_group : HandleBase {
     size_t pinned_cap = 0;
     void *dev_io = nullptr;     // host-buffer call: queries in, answer out
     size_t dev_io_cap = 0;
+    IoSlot slots[2];            // mx_shard_group_search_submit / _collect: two host-buffer searches in flight
+    uint64_t submit_seq = 0;
 };
 
 namespace {
@@ -129,6 +131,7 @@ void mx_shard_group_destroy(mx_shard_group *g)
     cudaFree(g->mine);
     cudaFree(g->dev_io);
     if (g->pinned) cudaFreeHost(g->pinned);
+    for (IoSlot &sl : g->slots) sl.release();
     if (g->stream) cudaStreamDestroy(g->stream);
     g->magic = 0;
     delete g;
@@ -324,6 +327,59 @@ int32_t mx_shard_group_search(mx_shard_group *g, mx_store *s, const float *queri
     memcpy(ids_out, hp + off_i, ib);
     memcpy(scores_out, hp + off_s, sb);
     memcpy(counts_out, hp + off_c, cb);
+    return MX_OK;
+}
+
+// The same step split in two so that TWO may be in flight per member (every member submits and collects in the same order):
+// while the device works on search i the host stages, copies in and enqueues search i + 1, and the GPUs never wait for a
+// host.  The exchange buffers already allow it -- slots and flags alternate between two parities, and a member's push of
+// epoch e + 2 is stream-ordered after its merge of e + 1 -- it is what the device-buffer call does when it is called in a loop.
+int32_t mx_shard_group_search_submit(mx_shard_group *g, mx_store *s, const float *queries, int32_t query_root, uint32_t nq,
+                                     uint32_t k, uint64_t *ticket_out)
+{
+    if (!g || !s) return MX_ERR_INVALID;
+    if (!ticket_out) return fail(g, MX_ERR_INVALID, "null buffer");
+    if (nq == 0 || nq > g->max_nq || k == 0 || k > g->max_k)
+        return fail(g, MX_ERR_INVALID, "batch of %u x top-%u outside the group's %u x %u", nq, k, g->max_nq, g->max_k);
+    const bool have_q = query_root < 0 || (uint32_t)query_root == g->rank;
+    if (have_q && !queries) return fail(g, MX_ERR_INVALID, "null queries");
+    IoSlot &sl = g->slots[g->submit_seq & 1];
+    if (sl.busy)
+        return fail(g, MX_ERR_INVALID, "two searches are already in flight: collect ticket %llu first", (unsigned long long)sl.ticket);
+    int32_t rc;
+    if ((rc = group_set_device(g)) != MX_OK) return rc;
+    const size_t qb = (size_t)nq * g->dim * sizeof(float);
+    sl.layout(qb, nq, k);
+    sl.empty = false;
+    MX_CUDA(g, MX_ERR_CONNECTION, sl.reserve(sl.total()));
+    char *hp = static_cast<char *>(sl.pinned), *dp = static_cast<char *>(sl.dev);
+    if (have_q) {
+        const int64_t bad_row = copy_checking_finite(reinterpret_cast<float *>(hp), queries, nq, g->dim);
+        if (bad_row >= 0) return fail(g, MX_ERR_SEARCH, "non-finite value in query %lld", (long long)bad_row);
+        MX_CUDA(g, MX_ERR_SEARCH, cudaMemcpyAsync(dp, hp, qb, cudaMemcpyHostToDevice, g->stream));
+    }
+    rc = mx_shard_group_search_device(g, s, have_q ? reinterpret_cast<const float *>(dp) : nullptr, query_root, nq, k,
+                                      reinterpret_cast<uint64_t *>(hp + sl.off_i), reinterpret_cast<float *>(hp + sl.off_s),
+                                      reinterpret_cast<uint32_t *>(hp + sl.off_c), g->stream);
+    if (rc != MX_OK) return rc;
+    MX_CUDA(g, MX_ERR_SEARCH, cudaEventRecord(sl.done, g->stream));
+    sl.busy = true;
+    sl.ticket = g->submit_seq;
+    *ticket_out = g->submit_seq++;
+    return MX_OK;
+}
+
+int32_t mx_shard_group_search_collect(mx_shard_group *g, uint64_t ticket, uint64_t *ids_out, float *scores_out, uint32_t *counts_out)
+{
+    if (!g) return MX_ERR_INVALID;
+    if (!ids_out || !scores_out || !counts_out) return fail(g, MX_ERR_INVALID, "null buffer");
+    IoSlot &sl = g->slots[ticket & 1];
+    if (!sl.busy || sl.ticket != ticket) return fail(g, MX_ERR_INVALID, "no search with ticket %llu is in flight", (unsigned long long)ticket);
+    sl.busy = false;
+    int32_t rc;
+    if ((rc = group_set_device(g)) != MX_OK) return rc;
+    MX_CUDA(g, MX_ERR_SEARCH, cudaEventSynchronize(sl.done));
+    sl.copy_out(ids_out, scores_out, counts_out);
     return MX_OK;
 }
 

@@ -109,6 +109,8 @@ struct mx_store : HandleBase {
     float *max_norm = nullptr;       // device scalar
     unsigned long long *prof = nullptr;   // test-only: rerank phase timestamps (MX_RERANK_PROF=1)
     KernelTimer timer;
+    IoSlot slots[2];                 // mx_store_search_submit / _collect: two host-buffer searches in flight
+    uint64_t submit_seq = 0;
 };
 
 namespace {
@@ -578,6 +580,7 @@ void mx_store_destroy(mx_store *s)
     cudaFree(s->prof);
     if (s->pinned) cudaFreeHost(s->pinned);
     if (s->flags_host) cudaFreeHost(s->flags_host);
+    for (IoSlot &sl : s->slots) sl.release();
     if (s->stream) cudaStreamDestroy(s->stream);
     s->magic = 0;
     delete s;
@@ -757,6 +760,59 @@ int32_t mx_store_search(mx_store *s, const float *queries, uint32_t nq, uint32_t
     memcpy(counts_out, hp + off_c, cb);
     g_host_prof.mark(7);
     g_host_prof.calls++;
+    return MX_OK;
+}
+
+int32_t mx_store_search_submit(mx_store *s, const float *queries, uint32_t nq, uint32_t k, uint64_t *ticket_out)
+{
+    if (!s) return MX_ERR_INVALID;
+    if (!queries || !ticket_out) return fail(s, MX_ERR_INVALID, "null buffer");
+    if (k == 0 || k > MX_MAX_K) return fail(s, MX_ERR_INVALID, "k must be in [1, %u]", MX_MAX_K);
+    IoSlot &sl = s->slots[s->submit_seq & 1];
+    if (sl.busy)
+        return fail(s, MX_ERR_INVALID, "two searches are already in flight: collect ticket %llu first", (unsigned long long)sl.ticket);
+    const size_t qb = (size_t)nq * s->cfg.dim * sizeof(float);
+    sl.layout(qb, nq, k);
+    sl.empty = nq == 0 || s->n == 0;     // HnswStore::search on an empty index returns no neighbours (local.rs:76-90)
+    if (!sl.empty) {
+        int32_t rc;
+        if ((rc = set_device(s)) != MX_OK) return rc;
+        MX_CUDA(s, MX_ERR_CONNECTION, sl.reserve(sl.total()));
+        char *hp = static_cast<char *>(sl.pinned), *dp = static_cast<char *>(sl.dev);
+        const int64_t bad_row = copy_checking_finite(reinterpret_cast<float *>(hp), queries, nq, s->cfg.dim);
+        if (bad_row >= 0) return fail(s, MX_ERR_SEARCH, "non-finite value in query %lld", (long long)bad_row);
+        MX_CUDA(s, MX_ERR_SEARCH, cudaMemcpyAsync(dp, hp, qb, cudaMemcpyHostToDevice, s->stream));
+        // nobody looks at the flagged-query counter between the rerank and the fallback here (the call returns at once): the
+        // exact-scan pair is always enqueued and exits immediately when no query was flagged
+        rc = search_device_impl(s, reinterpret_cast<const float *>(dp), nq, k, reinterpret_cast<uint64_t *>(hp + sl.off_i),
+                                reinterpret_cast<float *>(hp + sl.off_s), nullptr, reinterpret_cast<uint32_t *>(hp + sl.off_c),
+                                s->stream);
+        if (rc != MX_OK) return rc;
+        MX_CUDA(s, MX_ERR_SEARCH, cudaEventRecord(sl.done, s->stream));
+    }
+    sl.busy = true;
+    sl.ticket = s->submit_seq;
+    *ticket_out = s->submit_seq++;
+    return MX_OK;
+}
+
+int32_t mx_store_search_collect(mx_store *s, uint64_t ticket, uint64_t *ids_out, float *scores_out, uint32_t *counts_out)
+{
+    if (!s) return MX_ERR_INVALID;
+    if (!ids_out || !scores_out || !counts_out) return fail(s, MX_ERR_INVALID, "null buffer");
+    IoSlot &sl = s->slots[ticket & 1];
+    if (!sl.busy || sl.ticket != ticket) return fail(s, MX_ERR_INVALID, "no search with ticket %llu is in flight", (unsigned long long)ticket);
+    sl.busy = false;
+    if (sl.empty) {
+        memset(ids_out, 0, (size_t)sl.nq * sl.k * sizeof(uint64_t));
+        memset(scores_out, 0, (size_t)sl.nq * sl.k * sizeof(float));
+        memset(counts_out, 0, (size_t)sl.nq * sizeof(uint32_t));
+        return MX_OK;
+    }
+    int32_t rc;
+    if ((rc = set_device(s)) != MX_OK) return rc;
+    MX_CUDA(s, MX_ERR_SEARCH, cudaEventSynchronize(sl.done));
+    sl.copy_out(ids_out, scores_out, counts_out);
     return MX_OK;
 }
 

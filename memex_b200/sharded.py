@@ -273,6 +273,44 @@ class ShardedStore:
         return (b["ids_pin"].numpy().astype(np.uint64), b["scores_pin"].numpy().copy(),
                 b["counts_pin"].numpy().astype(np.uint32))
 
+    def search_submit(self, queries: np.ndarray | None, k: int, nq: int | None = None):
+        """First half of `search`: enqueues the step and returns a ticket; two may be in flight, collected in order.  Every
+        rank submits and collects the same sequence (rank 0 passes the queries, the others None and `nq`)."""
+        if queries is not None:
+            queries = np.ascontiguousarray(queries, dtype=np.float32)
+            nq = queries.shape[0]
+            if queries.ndim != 2 or queries.shape[1] != self.dim:
+                raise SearchError(f"query has dimension {queries.shape[-1]}, store has {self.dim}")
+        if self.world == 1:
+            return ("local", self.local.search_submit(queries, k))
+        if self._want_p2p and (self._shard_group is None or nq > self._group_nq or k > self._group_k):
+            self._ensure_group(nq, k)
+        if self._shard_group is None:
+            # collective exchange (MX_EXCHANGE=nccl): no split form, the step runs here and collect hands the answer over
+            return ("done", self.search(queries, k, nq=nq))
+        ticket = C.c_uint64()
+        rc = capi.lib().mx_shard_group_search_submit(self._shard_group, self.local.handle,
+                                                     queries.ctypes.data if queries is not None else None, 0, nq, k,
+                                                     C.byref(ticket))
+        if rc != capi.OK:
+            _raise(rc, self._shard_group, SearchError)
+        return ("group", (ticket.value, nq, k))
+
+    def search_collect(self, ticket):
+        kind, t = ticket
+        if kind == "local":
+            return self.local.search_collect(t)
+        if kind == "done":
+            return t
+        tv, nq, k = t
+        ids = np.zeros((nq, k), dtype=np.uint64)
+        scores = np.zeros((nq, k), dtype=np.float32)
+        counts = np.zeros(nq, dtype=np.uint32)
+        rc = capi.lib().mx_shard_group_search_collect(self._shard_group, tv, ids.ctypes.data, scores.ctypes.data, counts.ctypes.data)
+        if rc != capi.OK:
+            _raise(rc, self._shard_group, SearchError)
+        return ids, scores, counts
+
     def close(self):
         if self._shard_group is not None:
             capi.lib().mx_shard_group_destroy(self._shard_group)

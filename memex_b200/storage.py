@@ -255,6 +255,31 @@ class B200Store(VectorStore):
             _raise(rc, self._h, SearchError)
         return ids, scores, counts
 
+    def search_submit(self, queries: np.ndarray, k: int):
+        """First half of search_matrix (mx_store_search_submit): stages and enqueues the search, returns a ticket at once.
+        Two searches may be in flight; collect them in the order they were submitted."""
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        if queries.ndim != 2 or queries.shape[1] != self._dim:
+            raise SearchError(f"query has dimension {queries.shape[-1]}, store has {self._dim}")
+        if k > capi.MAX_K:
+            raise SearchError(f"limit {k} exceeds the store's maximum of {capi.MAX_K} neighbours per query")
+        ticket = C.c_uint64()
+        rc = capi.lib().mx_store_search_submit(self._h, queries.ctypes.data, queries.shape[0], k, C.byref(ticket))
+        if rc != capi.OK:
+            _raise(rc, self._h, SearchError)
+        return (ticket.value, queries.shape[0], k)
+
+    def search_collect(self, ticket):
+        """Second half: waits for the search behind `ticket` -> (ids [nq,k] u64, scores [nq,k] f32, counts [nq] u32)"""
+        t, nq, k = ticket
+        ids = np.zeros((nq, k), dtype=np.uint64)
+        scores = np.zeros((nq, k), dtype=np.float32)
+        counts = np.zeros(nq, dtype=np.uint32)
+        rc = capi.lib().mx_store_search_collect(self._h, t, ids.ctypes.data, scores.ctypes.data, counts.ctypes.data)
+        if rc != capi.OK:
+            _raise(rc, self._h, SearchError)
+        return ids, scores, counts
+
     def get_nb_point(self) -> int:
         """hnsw.get_nb_point() (local.rs:238)"""
         if self._h is None:

@@ -1,5 +1,7 @@
 """Where the scan's power goes: sustained loops of the 10 M-row scan with parts switched off (MX_SCAN_TC_DIAG; results are
-wrong in those runs, only GB/s and the board power are read)."""
+wrong in those runs, only GB/s and the board power are read).  Needs a diagnostic build of the library:
+    nvcc ... -DMX_TC_DIAG -c memex_b200/csrc/scan_tc.cu -o memex_b200/_lib/DIAG/scan_tc.o, linked with the other objects into
+    memex_b200/_lib/DIAG/libmemex_b200.so, and MX_B200_LIB pointing at it (the switches are compiled out of the product)."""
 import os
 import sys
 import threading

@@ -68,6 +68,24 @@ def main():
                       file=sys.stderr, flush=True)
                 os._exit(3)
             checked += nq
+    # the split call: two searches in flight on every rank, collected in order, same answers as the oracle
+    batches = []
+    for i in range(5):
+        qrng = np.random.default_rng(77 + i)
+        batches.append((corpus[qrng.integers(0, n, 64)] + 0.2 * qrng.standard_normal((64, d))).astype(np.float32))
+    got, prev = [], None
+    for q in batches:
+        t = store.search_submit(q if rank == 0 else None, k, nq=64)
+        if prev is not None:
+            got.append(store.search_collect(prev))
+        prev = t
+    got.append(store.search_collect(prev))
+    for q, (ids, scores, counts) in zip(batches, got):
+        oi, os_, oc = cosine.exact_topk(stored, q, k)
+        if not ((ids == oi).all() and (counts == oc).all() and (scores.view(np.uint32) == os_.view(np.uint32)).all()):
+            print(f"rank {rank} MISMATCH in the submit / collect form, exchange {store.exchange}", file=sys.stderr, flush=True)
+            os._exit(4)
+        checked += 64
     exchange = store.exchange
     store.close()
     dist.barrier()

@@ -662,3 +662,39 @@ def test_ordinary_corpus_is_never_flagged(tmp_path):
     check_parity(store, stored, queries[:1], k)
     qn, flagged = _verify_stats(store)
     assert qn == nq + 1 and flagged == 0
+
+
+def test_submit_collect_two_in_flight_equals_the_blocking_call(tmp_path):
+    """mx_store_search_submit / _collect: same answer, bit for bit, as mx_store_search, with two searches in flight; a third
+    submit is refused; an empty store and a non-finite query behave as in the blocking call."""
+    n, d, k = 300_000, 384, 10
+    x = unit_rows(n, d, 31)
+    store = B200Store.new(tmp_path, dim=d, dtype="f16")
+    empty = store.search_collect(store.search_submit(x[:3], k))
+    assert (empty[2] == 0).all() and (empty[0] == 0).all()
+    store.add_matrix(x)
+    batches = [unit_rows(nq, d, 40 + i) for i, nq in enumerate((64, 64, 8, 1, 64))]   # tcgen05 and stream paths
+    want = [store.search_matrix(q, k) for q in batches]
+    got, prev = [], None
+    for q in batches:
+        t = store.search_submit(q, k)
+        if prev is not None:
+            got.append(store.search_collect(prev))
+        prev = t
+    got.append(store.search_collect(prev))
+    for (wi, ws, wc), (gi, gs, gc) in zip(want, got):
+        assert (wi == gi).all() and (ws.view(np.uint32) == gs.view(np.uint32)).all() and (wc == gc).all()
+    t0 = store.search_submit(batches[0], k)
+    t1 = store.search_submit(batches[1], k)
+    with pytest.raises(VectorStoreError):
+        store.search_submit(batches[2], k)
+    with pytest.raises(VectorStoreError):
+        store.search_collect((t0[0] + 7, 64, k))
+    a, b = store.search_collect(t0), store.search_collect(t1)
+    assert (a[0] == want[0][0]).all() and (b[0] == want[1][0]).all()
+    bad = batches[0].copy(); bad[5, 9] = np.nan
+    with pytest.raises(VectorStoreError) as ei:
+        store.search_submit(bad, k)
+    assert "query 5" in str(ei.value)
+    again = store.search_collect(store.search_submit(batches[3], k))
+    assert (again[0] == want[3][0]).all()
