@@ -103,6 +103,11 @@ extern "C" {
         s: *mut mx_store, queries: *const f32, nq: u32, k: u32, ids_out: *mut u64, scores_out: *mut f32,
         counts_out: *mut u32,
     ) -> i32;
+    // the same call in two halves: two searches may be in flight on a store (tickets are collected in issue order)
+    pub fn mx_store_search_submit(s: *mut mx_store, queries: *const f32, nq: u32, k: u32, ticket_out: *mut u64) -> i32;
+    pub fn mx_store_search_collect(
+        s: *mut mx_store, ticket: u64, ids_out: *mut u64, scores_out: *mut f32, counts_out: *mut u32,
+    ) -> i32;
     pub fn mx_store_len(s: *mut mx_store, n_out: *mut u64) -> i32;
     pub fn mx_store_info(s: *mut mx_store, dim: *mut u32, dtype: *mut u32, metric: *mut u32, capacity: *mut u64) -> i32;
     pub fn mx_store_clear(s: *mut mx_store) -> i32;
@@ -124,6 +129,13 @@ extern "C" {
     pub fn mx_shard_group_search(
         g: *mut mx_shard_group, s: *mut mx_store, queries: *const f32, query_root: i32, nq: u32, k: u32,
         ids_out: *mut u64, scores_out: *mut f32, counts_out: *mut u32,
+    ) -> i32;
+    pub fn mx_shard_group_search_submit(
+        g: *mut mx_shard_group, s: *mut mx_store, queries: *const f32, query_root: i32, nq: u32, k: u32,
+        ticket_out: *mut u64,
+    ) -> i32;
+    pub fn mx_shard_group_search_collect(
+        g: *mut mx_shard_group, ticket: u64, ids_out: *mut u64, scores_out: *mut f32, counts_out: *mut u32,
     ) -> i32;
     pub fn mx_shard_group_search_local(
         groups: *const *mut mx_shard_group, stores: *const *mut mx_store, world: u32, queries: *const f32, nq: u32,
