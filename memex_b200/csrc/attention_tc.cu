@@ -32,7 +32,10 @@
 // warps (140-165 us; kept as experiments/attention_tc_pingpong.cu.txt), a rolled 8-key software pipeline (184 us).
 // Also measured slower (r1): announcing a P chunk half a chunk late so that tcgen05.wait::st never stalls the softmax warp
 // (+6 % kernel time: the last two chunks' P V products then queue up behind the final announcement and lengthen the unit's
-// tail).  Next step: 128-key sub-units (four score tiles in TMEM -> four independent streams per sub-partition).
+// tail).  Also tried (r2): 128-key sub-units -- four score tiles in TMEM, four independent softmax streams per sub-partition,
+// the two key blocks of a row combined through shared memory as in split-KV decoding; correct, but slower at the benchmark
+// shape (768 threads leave 85 registers per thread, and the pair combination adds a hand-over per unit).  Kept, not compiled,
+// as experiments/attention_tc4.cu.txt.
 #include <cstdlib>
 
 #include "common.cuh"

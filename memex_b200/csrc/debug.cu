@@ -56,16 +56,12 @@ int32_t mx_debug_attention(const void *qkv, const int32_t *lens_dev, void *ctx, 
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) {
         const int act = fmt == 1 ? ACT_BF16 : ACT_F16;
-        if (impl == 2 || impl == 3) {
+        if (impl == 2) {
             cudaDeviceProp prop;
             e = cudaGetDeviceProperties(&prop, device);
-            if (e == cudaSuccess && impl == 2)
+            if (e == cudaSuccess)
                 e = attention_tc_supported(S, H, heads)
                         ? launch_attention_tc(qkv, lens_dev, ctx, act, B, S, H, heads, prop.multiProcessorCount, nullptr, 0, nullptr)
-                        : cudaErrorNotSupported;
-            else if (e == cudaSuccess)
-                e = attention_tc4_supported(S, H, heads)
-                        ? launch_attention_tc4(qkv, lens_dev, ctx, act, B, S, H, heads, prop.multiProcessorCount, nullptr)
                         : cudaErrorNotSupported;
         } else {
             e = impl == 0 ? launch_attention_simt(qkv, lens_dev, ctx, act, B, S, H, heads, nullptr)

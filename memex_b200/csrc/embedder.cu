@@ -46,7 +46,6 @@ struct mx_embedder : HandleBase {
     int sm_count = kNumSMsDefault;
     int act = ACT_BF16;
     bool attention_tc = true;   // MX_ATTENTION_MMA=1 keeps the mma.sync kernel (A/B measurements)
-    bool attention_tc4 = false; // MX_ATTENTION_TC4=1: the four-stream tcgen05 form (attention_tc4.cu)
     cudaStream_t stream = nullptr;
     std::vector<void *> allocs;
     float *word = nullptr, *pos = nullptr, *type0 = nullptr, *emb_g = nullptr, *emb_b = nullptr;
@@ -346,8 +345,7 @@ int32_t forward(mx_embedder *e, const int32_t *ids_dev, const int32_t *lens_dev,
         e->timer.begin(st, 1);
         if (e->act == ACT_F32)
             MX_CUDA(e, MX_ERR_ENCODE, launch_attention_simt(e->qkv, lens_dev, e->ctx, e->act, B, S, H, c.heads, st));
-        else if (e->attention_tc4 && attention_tc4_supported(S, H, c.heads))
-            MX_CUDA(e, MX_ERR_ENCODE, launch_attention_tc4(e->qkv, lens_dev, e->ctx, e->act, B, S, H, c.heads, e->sm_count, st));
+
         else if (e->attention_tc && attention_tc_supported(S, H, c.heads))
             MX_CUDA(e, MX_ERR_ENCODE, launch_attention_tc(e->qkv, lens_dev, e->ctx, e->act, B, S, H, c.heads, e->sm_count, cu_dev, n_rows, st));
         else
@@ -379,7 +377,7 @@ int32_t stage_lengths(mx_embedder *e, const int32_t *lens, uint32_t nb, uint32_t
     *cu_dev = nullptr;
     *n_rows = nb * S;
     MX_CUDA(e, MX_ERR_ENCODE, cudaMemcpyAsync(e->lens_dev, lens, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (!e->packing || e->act == ACT_F32 || !e->attention_tc || e->attention_tc4 || e->ext.family == MX_FAMILY_T5 ||
+    if (!e->packing || e->act == ACT_F32 || !e->attention_tc || e->ext.family == MX_FAMILY_T5 ||
         !attention_tc_supported(S, e->cfg.hidden, e->cfg.heads))
         return MX_OK;
     std::vector<int32_t> cu(nb + 1);
@@ -472,7 +470,6 @@ int32_t mx_embedder_create_ex(const mx_model_cfg *cfg, const mx_model_ext *ext_i
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     e->attention_tc = getenv("MX_ATTENTION_MMA") == nullptr;
-    e->attention_tc4 = e->attention_tc && getenv("MX_ATTENTION_TC4") != nullptr;
     e->packing = getenv("MX_ENCODER_NO_PACKING") == nullptr;
     e->act = act;
     auto bail = [&](int32_t rc) {

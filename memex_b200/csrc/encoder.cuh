@@ -43,11 +43,6 @@ bool attention_tc_supported(uint32_t S, uint32_t H, uint32_t heads);
 cudaError_t launch_attention_tc(const void *qkv, const int32_t *lens_dev, void *ctx, int act, uint32_t B, uint32_t S,
                                 uint32_t H, uint32_t heads, int sm_count, const int32_t *cu, uint32_t n_rows, cudaStream_t st);
 
-// K6 (tcgen05, four-stream form, attention_tc4.cu): same contract; head_dim 32 and S <= 256 only
-bool attention_tc4_supported(uint32_t S, uint32_t H, uint32_t heads);
-cudaError_t launch_attention_tc4(const void *qkv, const int32_t *lens_dev, void *ctx, int act, uint32_t B, uint32_t S,
-                                 uint32_t H, uint32_t heads, int sm_count, cudaStream_t st);
-
 // fp32 path only: x = LayerNorm(y + residual) (the GEMM already added the bias)
 cudaError_t launch_add_ln_f32(const float *y, const float *residual, const float *gamma, const float *beta, float eps,
                               float *out, uint32_t rows, uint32_t H, cudaStream_t st);
