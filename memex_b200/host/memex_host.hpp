@@ -75,6 +75,15 @@ public:
     // not in the trait: nq queries in one scan (what the micro-batcher calls); default = a loop over search()
     virtual std::vector<std::vector<VectorSearchResult>> search_batch(const std::vector<std::vector<float>> &vecs,
                                                                       size_t limit) const;
+    // search_batch in two halves, so that two batches may be in flight (the micro-batcher stages batch i + 1 while the
+    // device answers batch i): submit returns a ticket, collect takes tickets in the order they were issued.
+    // Default = the whole search at submit time, the answer parked until collect (any store works behind the batcher).
+    virtual uint64_t search_batch_submit(const std::vector<std::vector<float>> &vecs, size_t limit) const;
+    virtual std::vector<std::vector<VectorSearchResult>> search_batch_collect(uint64_t ticket) const;
+
+protected:
+    mutable std::unordered_map<uint64_t, std::vector<std::vector<VectorSearchResult>>> parked_;
+    mutable uint64_t next_ticket_ = 0;
 };
 
 // HnswStore (local.rs:21-166) with the index replaced by the GPU row matrix.  Keeps `_id_map` exactly as the
@@ -103,6 +112,9 @@ public:
     std::vector<VectorSearchResult> search(const std::vector<float> &vec, size_t limit) const override;   // local.rs:71-91
     std::vector<std::vector<VectorSearchResult>> search_batch(const std::vector<std::vector<float>> &vecs,
                                                               size_t limit) const override;
+    // mx_store_search_submit / _collect: the device works on one batch while the next is staged
+    uint64_t search_batch_submit(const std::vector<std::vector<float>> &vecs, size_t limit) const override;
+    std::vector<std::vector<VectorSearchResult>> search_batch_collect(uint64_t ticket) const override;
 
     uint64_t len() const;   // hnsw.get_nb_point(), local.rs:238
     std::string storage_path;
@@ -112,7 +124,16 @@ public:
 private:
     B200Store() = default;
     void create_handle(uint32_t dim);   // the device store is made when the width is known (Options::dim or first insert)
+    std::vector<std::vector<VectorSearchResult>> map_results(const uint64_t *ids, const float *scores, const uint32_t *counts,
+                                                             size_t nq, uint32_t k) const;
+    std::vector<float> pack_queries(const std::vector<std::vector<float>> &vecs, size_t limit) const;
     mx_store *handle_ = nullptr;
+    struct InFlight {
+        uint64_t device_ticket;
+        size_t nq;
+        uint32_t k;
+    };
+    mutable std::unordered_map<uint64_t, InFlight> in_flight_;   // host ticket -> the device search behind it
 };
 
 // The same store over SEVERAL GPUs of one box, driven by ONE process (memex's server is one process: mod.rs:68-93).
@@ -166,6 +187,9 @@ public:
     void delete_collection();
     std::vector<VectorSearchResult> search(const std::vector<float> &query, size_t limit) const;
     std::vector<std::vector<VectorSearchResult>> search_batch(const std::vector<std::vector<float>> &queries, size_t limit) const;
+    // the two halves of search_batch, each under the mutex (the device answers between them with the mutex free)
+    uint64_t search_batch_submit(const std::vector<std::vector<float>> &queries, size_t limit) const;
+    std::vector<std::vector<VectorSearchResult>> search_batch_collect(uint64_t ticket) const;
     std::shared_ptr<VectorStore> client;
 
 private:
@@ -182,7 +206,8 @@ VectorStorage get_vector_storage(const std::string &uri, const std::string &coll
 void drop_vector_storage_registry();   // tests
 
 // N4: concurrent single-query searches -> one batched scan.  submit() returns a future; a worker thread collects
-// up to max_batch queries (waiting at most max_wait_us after the first) and issues ONE search_batch.
+// up to max_batch queries (waiting at most max_wait_us after the first) and issues ONE search_batch -- in its split
+// form: while the device answers batch i the worker is already collecting, staging and submitting batch i + 1.
 class SearchBatcher {
 public:
     SearchBatcher(VectorStorage storage, size_t max_batch = 64, uint32_t max_wait_us = 200);

@@ -96,6 +96,22 @@ std::vector<std::vector<VectorSearchResult>> VectorStore::search_batch(const std
     return out;
 }
 
+uint64_t VectorStore::search_batch_submit(const std::vector<std::vector<float>> &vecs, size_t limit) const
+{
+    const uint64_t t = next_ticket_++;
+    parked_.emplace(t, search_batch(vecs, limit));
+    return t;
+}
+
+std::vector<std::vector<VectorSearchResult>> VectorStore::search_batch_collect(uint64_t ticket) const
+{
+    auto it = parked_.find(ticket);
+    if (it == parked_.end()) throw VectorStoreError(StoreErrorKind::SearchError, "no search with ticket " + std::to_string(ticket));
+    auto out = std::move(it->second);
+    parked_.erase(it);
+    return out;
+}
+
 // ------------------------------------------------------------------------------------------------
 // B200Store
 // ------------------------------------------------------------------------------------------------
@@ -250,16 +266,13 @@ void B200Store::bulk_insert(const std::vector<VectorData> &data)
 
 void B200Store::insert(const VectorData &data) { bulk_insert({data}); }
 
-std::vector<std::vector<VectorSearchResult>> B200Store::search_batch(const std::vector<std::vector<float>> &vecs, size_t limit) const
+std::vector<float> B200Store::pack_queries(const std::vector<std::vector<float>> &vecs, size_t limit) const
 {
-    std::vector<std::vector<VectorSearchResult>> out(vecs.size());
-    if (vecs.empty() || limit == 0 || _id_map.empty() || !handle_) return out;
     // one behaviour in every host (C++, Python, Rust): more than MX_MAX_K neighbours is an error, never a silent cut
     if (limit > MX_MAX_K)
         throw VectorStoreError(StoreErrorKind::SearchError, "limit " + std::to_string(limit) + " exceeds the store's maximum of " +
                                                                 std::to_string(MX_MAX_K) + " neighbours per query");
     const size_t dim = options.dim, nq = vecs.size();
-    const uint32_t k = (uint32_t)limit;
     std::vector<float> q(nq * dim);
     for (size_t i = 0; i < nq; ++i) {
         if (vecs[i].size() != dim)
@@ -267,11 +280,13 @@ std::vector<std::vector<VectorSearchResult>> B200Store::search_batch(const std::
                                                                     ", store has " + std::to_string(dim));
         std::copy(vecs[i].begin(), vecs[i].end(), q.begin() + i * dim);
     }
-    std::vector<uint64_t> ids(nq * k);
-    std::vector<float> scores(nq * k);
-    std::vector<uint32_t> counts(nq);
-    int32_t rc = mx_store_search(handle_, q.data(), (uint32_t)nq, k, ids.data(), scores.data(), counts.data());
-    if (rc != MX_OK) raise(rc, handle_, StoreErrorKind::SearchError);
+    return q;
+}
+
+std::vector<std::vector<VectorSearchResult>> B200Store::map_results(const uint64_t *ids, const float *scores,
+                                                                    const uint32_t *counts, size_t nq, uint32_t k) const
+{
+    std::vector<std::vector<VectorSearchResult>> out(nq);
     for (size_t i = 0; i < nq; ++i) {
         out[i].reserve(counts[i]);
         for (uint32_t j = 0; j < counts[i]; ++j) {
@@ -282,6 +297,48 @@ std::vector<std::vector<VectorSearchResult>> B200Store::search_batch(const std::
         }
     }
     return out;
+}
+
+std::vector<std::vector<VectorSearchResult>> B200Store::search_batch(const std::vector<std::vector<float>> &vecs, size_t limit) const
+{
+    std::vector<std::vector<VectorSearchResult>> out(vecs.size());
+    if (vecs.empty() || limit == 0 || _id_map.empty() || !handle_) return out;
+    const std::vector<float> q = pack_queries(vecs, limit);
+    const size_t nq = vecs.size();
+    const uint32_t k = (uint32_t)limit;
+    std::vector<uint64_t> ids(nq * k);
+    std::vector<float> scores(nq * k);
+    std::vector<uint32_t> counts(nq);
+    int32_t rc = mx_store_search(handle_, q.data(), (uint32_t)nq, k, ids.data(), scores.data(), counts.data());
+    if (rc != MX_OK) raise(rc, handle_, StoreErrorKind::SearchError);
+    return map_results(ids.data(), scores.data(), counts.data(), nq, k);
+}
+
+uint64_t B200Store::search_batch_submit(const std::vector<std::vector<float>> &vecs, size_t limit) const
+{
+    // nothing for the device to do: park the empty answer (same ticket space as the device searches)
+    if (vecs.empty() || limit == 0 || _id_map.empty() || !handle_) return VectorStore::search_batch_submit(vecs, limit);
+    const std::vector<float> q = pack_queries(vecs, limit);
+    uint64_t dev_ticket = 0;
+    int32_t rc = mx_store_search_submit(handle_, q.data(), (uint32_t)vecs.size(), (uint32_t)limit, &dev_ticket);
+    if (rc != MX_OK) raise(rc, handle_, StoreErrorKind::SearchError);
+    const uint64_t t = next_ticket_++;
+    in_flight_.emplace(t, InFlight{dev_ticket, vecs.size(), (uint32_t)limit});
+    return t;
+}
+
+std::vector<std::vector<VectorSearchResult>> B200Store::search_batch_collect(uint64_t ticket) const
+{
+    auto it = in_flight_.find(ticket);
+    if (it == in_flight_.end()) return VectorStore::search_batch_collect(ticket);
+    const InFlight f = it->second;
+    in_flight_.erase(it);
+    std::vector<uint64_t> ids(f.nq * f.k);
+    std::vector<float> scores(f.nq * f.k);
+    std::vector<uint32_t> counts(f.nq);
+    int32_t rc = mx_store_search_collect(handle_, f.device_ticket, ids.data(), scores.data(), counts.data());
+    if (rc != MX_OK) raise(rc, handle_, StoreErrorKind::SearchError);
+    return map_results(ids.data(), scores.data(), counts.data(), f.nq, f.k);
 }
 
 std::vector<VectorSearchResult> B200Store::search(const std::vector<float> &vec, size_t limit) const
@@ -584,6 +641,16 @@ std::vector<std::vector<VectorSearchResult>> VectorStorage::search_batch(const s
     std::lock_guard<std::mutex> g(*lock_);
     return client->search_batch(queries, limit);
 }
+uint64_t VectorStorage::search_batch_submit(const std::vector<std::vector<float>> &queries, size_t limit) const
+{
+    std::lock_guard<std::mutex> g(*lock_);
+    return client->search_batch_submit(queries, limit);
+}
+std::vector<std::vector<VectorSearchResult>> VectorStorage::search_batch_collect(uint64_t ticket) const
+{
+    std::lock_guard<std::mutex> g(*lock_);
+    return client->search_batch_collect(ticket);
+}
 
 namespace {
 std::mutex g_registry_mu;
@@ -689,16 +756,40 @@ std::future<std::vector<VectorSearchResult>> SearchBatcher::submit(std::vector<f
 
 void SearchBatcher::run()
 {
+    struct Pending {
+        uint64_t ticket;
+        std::vector<Req> batch;
+    };
+    std::unique_ptr<Pending> pending;   // the batch the device is answering while the next one is gathered
+    auto deliver = [this](Pending &p) {
+        ++batches_;   // before the promises: a caller that has its answer sees the batch counted
+        try {
+            auto res = storage_.search_batch_collect(p.ticket);
+            for (size_t i = 0; i < p.batch.size(); ++i) p.batch[i].done.set_value(std::move(res[i]));
+        } catch (...) {
+            for (auto &r : p.batch) r.done.set_exception(std::current_exception());
+        }
+    };
     while (true) {
         std::vector<Req> batch;
         {
             std::unique_lock<std::mutex> g(mu_);
-            cv_.wait(g, [this] { return stop_ || !queue_.empty(); });
-            if (queue_.empty()) return;   // stop requested and nothing left
-            // the first request opens a window of max_wait_us for others to join
-            const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(max_wait_us_);
-            while (queue_.size() < max_batch_ && !stop_) {
-                if (cv_.wait_until(g, deadline) == std::cv_status::timeout) break;
+            if (pending) {
+                // a batch is on the device: take whatever has queued up meanwhile, but do not sit here waiting for more
+                if (queue_.empty()) {
+                    g.unlock();
+                    deliver(*pending);
+                    pending.reset();
+                    continue;
+                }
+            } else {
+                cv_.wait(g, [this] { return stop_ || !queue_.empty(); });
+                if (queue_.empty()) return;   // stop requested and nothing left
+                // the first request opens a window of max_wait_us for others to join
+                const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(max_wait_us_);
+                while (queue_.size() < max_batch_ && !stop_) {
+                    if (cv_.wait_until(g, deadline) == std::cv_status::timeout) break;
+                }
             }
             // one scan serves one `limit`: take the head's and everyone who asked for the same
             const size_t limit = queue_.front().limit;
@@ -714,13 +805,16 @@ void SearchBatcher::run()
         std::vector<std::vector<float>> qs;
         qs.reserve(batch.size());
         for (auto &r : batch) qs.push_back(std::move(r.q));
+        std::unique_ptr<Pending> next;
         try {
-            auto res = storage_.search_batch(qs, batch[0].limit);
-            for (size_t i = 0; i < batch.size(); ++i) batch[i].done.set_value(std::move(res[i]));
+            const uint64_t ticket = storage_.search_batch_submit(qs, batch[0].limit);   // staged + enqueued, returns at once
+            next.reset(new Pending{ticket, std::move(batch)});
         } catch (...) {
+            ++batches_;
             for (auto &r : batch) r.done.set_exception(std::current_exception());
         }
-        ++batches_;
+        if (pending) deliver(*pending);   // the older batch's answer (tickets are collected in issue order)
+        pending = std::move(next);
     }
 }
 

@@ -442,6 +442,26 @@ static int run_gpu(const std::string &tmp)
             if (i % 50 == 0) CHECK(r == c.search(pts[i].vector, 5));
         }
         CHECK(batcher.batches_issued() < 200);
+        // the split call (two batches in flight, collected in order) gives the blocking call's answers; a third submit
+        // before a collect is refused
+        {
+            std::vector<std::vector<float>> qa, qb;
+            for (int i = 0; i < 64; ++i) qa.push_back(pts[i].vector);
+            for (int i = 64; i < 73; ++i) qb.push_back(pts[i].vector);
+            const auto want_a = c.search_batch(qa, 7), want_b = c.search_batch(qb, 7);
+            const uint64_t ta = c.search_batch_submit(qa, 7), tb = c.search_batch_submit(qb, 7);
+            bool refused = false;
+            try {
+                c.search_batch_submit(qa, 7);
+            } catch (const VectorStoreError &e) {
+                refused = e.kind == StoreErrorKind::SearchError;
+            }
+            CHECK(refused);
+            CHECK(c.search_batch_collect(ta) == want_a);
+            CHECK(c.search_batch_collect(tb) == want_b);
+            const uint64_t tc = c.search_batch_submit(qb, 7);
+            CHECK(c.search_batch_collect(tc) == want_b);
+        }
         // more than MX_MAX_K neighbours: an error in every host, never a silent cut
         try {
             c.search(pts[0].vector, 257);
