@@ -132,6 +132,10 @@ struct TcParams {
 
 // Query preparation by the four epilogue warps of a CTA (warp `quarter` takes rows quarter, quarter + 4, ...): R rows in
 // flight per warp (all their loads are issued before the first reduction), U 32-lane rounds of 16-byte chunk pairs per row.
+// ~7 us per launch at 64 x 384, and not for want of loads in flight: 148 CTAs pull the SAME 98 KB out of L2 at the same
+// moment.  Measured r2 (profiles/r02b_query_staging_ab.txt): ONE cp.async.bulk of the raw block per CTA into the ring's upper
+// stages + conversion from shared memory took 7.9 us against 7.3 -- the broadcast is what costs, whoever issues it; only
+// fewer bytes per SM (a pre-converted fp16 block, cluster multicast) would shorten it.
 template <int QM, int R, int U>
 __device__ __forceinline__ void prepare_queries(const TcParams &p, unsigned char *sq, uint32_t q0, uint32_t quarter, uint32_t lane)
 {
