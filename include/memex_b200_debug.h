@@ -24,6 +24,9 @@ int32_t mx_debug_gemm(const void *A, const void *W, const float *bias, const voi
 int32_t mx_debug_attention(const void *qkv, const int32_t *lens_dev, void *ctx, uint32_t B, uint32_t S, uint32_t H,
                            uint32_t heads, uint32_t fmt, uint32_t impl, int32_t device);
 const char *mx_debug_last_error(void);
+/* HOST ONLY (runs without a device): the one-pass staging copy + finiteness check of mx_store_search / _submit and the
+ * shard-group calls -- copies [rows, dim] f32 to dst and returns the first row holding a NaN or an infinity, or -1 */
+int64_t mx_debug_copy_checking_finite(float *dst, const float *src, uint64_t rows, uint64_t dim);
 /* rerank_kernel phase timestamps (%globaltimer ns of CTA 0: start, loads issued, sorted, merged + certified, entries
  * ready, folded, written) of the last search on a store created under MX_RERANK_PROF=1; `store` is an mx_store *. */
 int32_t mx_debug_rerank_prof(void *store, uint64_t *out8);

@@ -50,6 +50,12 @@ int32_t mx_debug_gemm(const void *A, const void *W, const float *bias, const voi
     return MX_OK;
 }
 
+// host-only: the staging copy + finiteness check of the host-buffer search calls (no device needed)
+int64_t mx_debug_copy_checking_finite(float *dst, const float *src, uint64_t rows, uint64_t dim)
+{
+    return copy_checking_finite(dst, src, (size_t)rows, (size_t)dim);
+}
+
 int32_t mx_debug_attention(const void *qkv, const int32_t *lens_dev, void *ctx, uint32_t B, uint32_t S, uint32_t H,
                            uint32_t heads, uint32_t fmt, uint32_t impl, int32_t device)
 {

@@ -91,3 +91,29 @@ def test_factory_rejects_unknown_schemes():
         with pytest.raises(storage.VectorStoreError) as ei:
             storage.get_vector_storage(uri, "c")
         assert ei.value.variant == "Unsupported"
+
+
+def test_staging_copy_names_the_first_non_finite_row():
+    """Host logic of the host-buffer search calls (no device): one pass copies the query block into the staging buffer and
+    finds the first row with a NaN / +-inf at ANY position, for widths that do and do not fill whole SIMD vectors."""
+    import numpy as np
+    L = capi.lib()
+    fn = L.mx_debug_copy_checking_finite
+    fn.restype = C.c_int64
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
+    rng = np.random.default_rng(5)
+    for rows, dim in ((1, 1), (3, 7), (64, 384), (5, 33), (2, 1000)):
+        src = rng.standard_normal((rows, dim)).astype(np.float32)
+        src[0, 0] = np.float32(3.4e38)          # the largest finite magnitudes and denormals are fine
+        src[-1, -1] = np.float32(1e-45)
+        dst = np.full_like(src, -7.0)
+        assert fn(dst.ctypes.data, src.ctypes.data, rows, dim) == -1
+        np.testing.assert_array_equal(dst, src)
+        for bad in (np.nan, np.inf, -np.inf):
+            for r, c in {(0, 0), (rows - 1, dim - 1), (rows // 2, dim // 2), (rows - 1, 0)}:
+                x = src.copy()
+                x[r, c] = bad
+                if rows > 1 and r + 1 < rows:
+                    x[rows - 1, 0] = np.nan    # a later bad row does not change the answer
+                assert fn(dst.ctypes.data, x.ctypes.data, rows, dim) == r, (rows, dim, r, c, bad)
+    assert fn(None, None, 0, 384) == -1
